@@ -1,0 +1,103 @@
+/* srbtrack_b200.h -- C-ABI of the B200-native batched SRBTrack environment step.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of the reference
+ * (taesoobear/IPCDNNwalk).  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repository root).  All functions return 0 on success and a
+ * negative code on failure; the message is available from srb_last_error().  No exceptions cross
+ * the ABI.  One handle per GPU; a handle is not thread-safe.
+ *
+ * Pointers suffixed _dev are CUDA device pointers (caller-owned, e.g. torch tensors' data_ptr());
+ * pointers suffixed _host are host pointers.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream); device entry points are asynchronous on that stream.
+ */
+#ifndef SRBTRACK_B200_H
+#define SRBTRACK_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct srb_env srb_env; /* opaque: N batched `SRBEnv` instances on one device */
+
+#define SRB_OBS_DIM 150   /* observation_space Box(25*6)   env/SRBEnv5_mocap_list_window.py:175 */
+#define SRB_ACT_DIM 22    /* action_space Box(22)          env/SRBEnv5_mocap_list_window.py:174 */
+#define SRB_RINFO_DIM 8   /* info['reward_info'] entries   env/SRBEnv5_mocap_list_window.py:792-801 */
+#define SRB_PLAN_DIM 9    /* reset draws: clip, start frame, vel noise(3), noise quaternion wxyz(4) */
+#define SRB_DBG_DIM 256   /* per-env debug record: 4 sub-steps x [qdd(6) nu(6) qfrc(6) iters(1) pad(5) lambda(40)] */
+
+enum { SRB_VARIANT_TEST = 0,      /* env/SRBEnv5_mocap_list_window.py          (SDS foot filter, force clamp) */
+       SRB_VARIANT_TRAINING = 1   /* env/SRBEnv5_mocap_list_window_training.py (what PPO trains on)           */ };
+
+typedef struct srb_config {
+  int32_t num_envs;       /* replaces make_vec_env(SRBEnv, n_envs=...)  walk_SRBTrack2025_train_delta.py:94-100 */
+  int32_t variant;        /* SRB_VARIANT_*                                                                    */
+  int32_t precision;      /* 64: fp64 state+arithmetic (reference precision); 32: fp32                        */
+  int32_t lanes_per_env;  /* 0 = default; 1,2,4,8,16,32 lanes of a warp cooperate on one environment           */
+  int32_t auto_reset;     /* 1: a terminated env is reset inside the step (SubprocVecEnv semantics)            */
+  int32_t device;         /* CUDA device ordinal                                                               */
+  uint64_t seed;          /* stream for device-side reset draws (random.randrange / np.random in SRBEnv.reset) */
+} srb_config;
+
+/* SRBEnv.__init__ (env/SRBEnv5_mocap_list_window.py:123-189) for num_envs environments. */
+int srb_create(const srb_config* cfg, srb_env** out);
+int srb_destroy(srb_env* env);
+const char* srb_last_error(void);
+
+/* SRBEnv.loadMocap (env/SRBEnv5_mocap_list_window.py:1171-1197): install the reference tables of one
+ * clip.  All arrays are HOST, row-major, nframes = 2*cycle_length-1 rows:
+ *   pos_com[n][3], ori_com[n][9], vel_com[n][6], root_quat[n][4] (wxyz), feet_pos[n][2][3] (z==0 <=> contact),
+ *   feet_yaw[n][2][2] = (cos, sin) of the pure-yaw feet_ori_list matrices.
+ * The 25 look-ahead observation features per frame (get_obs_window :1096-1161) are computed on the device here. */
+int srb_upload_clip(srb_env* env, int32_t clip_id, int32_t nframes, int32_t cycle_length, int32_t is_stand,
+                    const double* pos_com, const double* ori_com, const double* vel_com, const double* root_quat,
+                    const double* feet_pos, const double* feet_yaw);
+
+/* SRBEnv.reset / set_state (env/SRBEnv5_mocap_list_window.py:805-911) for `count` environments.
+ * env_idx_host NULL = environments 0..count-1.  plan_host[count][SRB_PLAN_DIM] gives the draws explicitly
+ * (noise quaternion w = NaN reproduces testing_mode: no noise); NULL = draw on the device.
+ * obs_dev (may be NULL) is the full [num_envs][SRB_OBS_DIM] observation array; rows of the reset envs are written. */
+int srb_reset(srb_env* env, const int32_t* env_idx_host, int32_t count, const double* plan_host, float* obs_dev, void* stream);
+
+/* SRBEnv.step (env/SRBEnv5_mocap_list_window.py:208-494) for all environments:
+ *   act_dev[N][22] -> obs_dev[N][150], rew_dev[N], done_dev[N] (0/1), rinfo_dev[N][8] (may be NULL). */
+int srb_step(srb_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream);
+
+/* Same step through HOST buffers (what a per-process gym caller holds): copies actions host->device and
+ * results device->host on the handle's own stream and synchronises.  NULL pointers = use the handle's
+ * pinned staging buffers in place (see srb_pinned_buffers). */
+int srb_step_host(srb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host);
+int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint8_t** done, float** rinfo);
+
+/* Optional side channels (any may be NULL = detach):
+ *   contact_prob_dev[N][2]  Policy_prior_posterior_MoE_window._last_contact_prob hysteresis input
+ *                           (env/SRBEnv5_mocap_list_window.py:239-275); NaN = None
+ *   term_obs_dev[N][150]    observation of the terminal step when auto_reset replaces it
+ *   reset_plan_dev[N][9]    explicit draws for the next auto-reset of each env (parity tests)
+ *   dbg_dev[N][SRB_DBG_DIM] per-sub-step QP intermediates (qdd, nu, qfrc, iterations, lambda) */
+int srb_set_aux(srb_env* env, const float* contact_prob_dev, float* term_obs_dev, const double* reset_plan_dev, double* dbg_dev);
+
+/* Reward weights (w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c; :561-569) and the external-push schedule
+ * (impulse_interval / impulse_duration / force; :182-206). */
+int srb_set_reward_weights(srb_env* env, const double w[9]);
+int srb_set_impulse(srb_env* env, int32_t interval, int32_t duration, const double force[3]);
+
+/* SRBEnv.getFullState / restoreFullState (env/SRBEnv5_mocap_list_window.py:1005-1053) of one environment.
+ * reals[srb_state_dims real count], ints[int count], hist[slots*width]; layout in srb_state_dims(). */
+int srb_state_dims(int32_t* n_real, int32_t* n_int, int32_t* hist_slots, int32_t* hist_width);
+int srb_get_state(srb_env* env, int32_t env_index, double* reals, int32_t* ints, double* hist);
+int srb_set_state(srb_env* env, int32_t env_index, const double* reals, const int32_t* ints, const double* hist);
+
+/* Running statistics for the one collective of the path (VecNormalize obs_rms, gym_cdm2/train_gym.py:98):
+ * acc_dev[1 + 2*150] += (count, sum x, sum x^2) over the N rows of obs_dev.  The caller all-reduces acc. */
+int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* stream);
+/* Episode statistics accumulated by auto-reset: out[3] = sum of returns, sum of lengths, count. */
+int srb_episode_stats(srb_env* env, double out[3], int32_t clear);
+
+/* Number of kernels this handle has launched so far (for launch accounting). */
+int64_t srb_launch_count(srb_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRBTRACK_B200_H */

@@ -1,0 +1,4 @@
+"""ipcdnnwalk_b200 -- B200-native batched simulator for the SRB character-tracking hot path of
+taesoobear/IPCDNNwalk.  Hand-written sm_100a CUDA behind a C-ABI; no CPU fallback."""
+from ._lib import OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM, LIB_PATH, SrbError  # noqa: F401
+from .srb_vec_env import SRBVecEnv, REWARD_INFO_KEYS  # noqa: F401

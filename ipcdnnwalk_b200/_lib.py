@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI in include/srbtrack_b200.h (libsrbtrack_b200.so, built in-tree).
+
+There is no CPU fallback: if the shared library has not been built the import fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrbtrack_b200.so")
+
+OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM = 150, 22, 8, 9, 256
+VARIANT_TEST, VARIANT_TRAINING = 0, 1
+
+
+class SrbConfig(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("variant", C.c_int32), ("precision", C.c_int32), ("lanes_per_env", C.c_int32),
+                ("auto_reset", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "srb_create": (C.c_int, [C.POINTER(SrbConfig), C.POINTER(_P)]),
+    "srb_destroy": (C.c_int, [_P]),
+    "srb_last_error": (C.c_char_p, []),
+    "srb_upload_clip": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "srb_reset": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
+    "srb_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "srb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "srb_pinned_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "srb_set_aux": (C.c_int, [_P, _P, _P, _P, _P]),
+    "srb_set_reward_weights": (C.c_int, [_P, _P]),
+    "srb_set_impulse": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "srb_state_dims": (C.c_int, [C.POINTER(C.c_int32)] * 4),
+    "srb_get_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "srb_set_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "srb_obs_stats": (C.c_int, [_P, _P, _P, _P]),
+    "srb_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
+    "srb_launch_count": (C.c_int64, [_P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed to load it; compute entry points need one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class SrbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise SrbError(f"libsrbtrack_b200 error {rc}: {load().srb_last_error().decode()}")

@@ -1,0 +1,404 @@
+// C-ABI of the batched SRBTrack step (declared in include/srbtrack_b200.h).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "../../include/srbtrack_b200.h"
+#include "srb_kernels.cuh"
+
+using namespace srb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+struct ClipStore { void* frames = nullptr; float* feat = nullptr; int nframes = 0, cycle = 0, is_stand = 0; };
+
+struct srb_env {
+  srb_config cfg;
+  int N = 0, Npad = 0, G = 8;
+  size_t rsz = 8;
+  void* st = nullptr; int* ist = nullptr; void* hist = nullptr;
+  void* clips_dev = nullptr;            // ClipDesc<real>[MAX_CLIPS]
+  std::vector<ClipStore> clips;
+  int nclips = 0;
+  double* ep_stats = nullptr;
+  const float* contact_prob = nullptr; float* term_obs = nullptr; const double* reset_plan = nullptr; double* dbg = nullptr;
+  Params<double> p;
+  cudaStream_t stream = nullptr;
+  // pinned host staging + device I/O for the host-buffer path
+  float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
+  float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
+  int64_t launches = 0;
+};
+static const int MAX_CLIPS = 64;
+
+template <typename real> static Params<real> convert_params(const Params<double>& p) {
+  Params<real> q;
+  q.h = (real)p.h; q.nsub = p.nsub; q.mass = (real)p.mass;
+  for (int i = 0; i < 3; i++) { q.inertia[i] = (real)p.inertia[i]; q.impulse_force[i] = (real)p.impulse_force[i]; }
+  q.armature = (real)p.armature; q.damping = (real)p.damping; q.grav = (real)p.grav; q.mu_b = (real)p.mu_b;
+  q.kp = (real)p.kp; q.kd = (real)p.kd; q.w_lambda = (real)p.w_lambda; q.force_thr = (real)p.force_thr;
+  for (int i = 0; i < 9; i++) q.w[i] = (real)p.w[i];
+  q.use_filter = p.use_filter; q.use_clamp = p.use_clamp; q.use_impulse = p.use_impulse; q.obs_after_inc = p.obs_after_inc;
+  q.impulse_interval = p.impulse_interval; q.impulse_duration = p.impulse_duration; q.impulse_trigger_at_end = p.impulse_trigger_at_end;
+  q.max_frame = p.max_frame;
+  return q;
+}
+
+static void default_params(Params<double>& p, int variant) {
+  // gym_trackSRB/Characters/SRB5.xml:1-37
+  const double hx = 0.19557607215607947, hy = 0.25406692031825, hz = 0.667757440991862;
+  p.h = 0.0083332;
+  p.nsub = (int)std::lround(0.033333 / 0.0083332);     // round(self.mocap_dt / self.model.opt.timestep)
+  p.mass = 60.0;
+  p.inertia[0] = p.mass / 3.0 * (hy * hy + hz * hz);
+  p.inertia[1] = p.mass / 3.0 * (hx * hx + hz * hz);
+  p.inertia[2] = p.mass / 3.0 * (hx * hx + hy * hy);
+  p.armature = 1.0; p.damping = 1.0; p.grav = 9.81;
+  p.mu_b = 1.2 * (1.2 * 1.0);                           // b = (1.2*mu, 0, 1), mu = 1.2 * floor friction
+  p.kp = 120.0; p.kd = 35.0; p.w_lambda = 0.001; p.force_thr = 10000.0;
+  p.max_frame = 512;
+  if (variant == SRB_VARIANT_TEST) {
+    const double w[9] = {5, 0.1, 0.5, 0, 50, 20, 700, 50, 1};
+    memcpy(p.w, w, sizeof(w));
+    p.use_filter = 1; p.use_clamp = 1; p.use_impulse = 1; p.obs_after_inc = 0;
+    p.impulse_interval = 1000000000; p.impulse_duration = 24; p.impulse_trigger_at_end = 1;
+    p.impulse_force[0] = 700; p.impulse_force[1] = 700; p.impulse_force[2] = -350;
+  } else {
+    const double w[9] = {5, 1, 0.5, 0.01, 5, 1.5, 25, 1.5, 0.1};
+    memcpy(p.w, w, sizeof(w));
+    p.use_filter = 0; p.use_clamp = 0; p.use_impulse = 0; p.obs_after_inc = 1;
+    p.impulse_interval = 100000000; p.impulse_duration = 24; p.impulse_trigger_at_end = 0;
+    p.impulse_force[0] = 1000 / std::sqrt(2.0) * 0.5; p.impulse_force[1] = -1000 / std::sqrt(2.0) * 0.5; p.impulse_force[2] = 0;
+  }
+}
+
+extern "C" const char* srb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
+  if (!cfg || !out) return fail(-1, "srb_create: null argument");
+  if (cfg->num_envs <= 0) return fail(-1, "srb_create: num_envs must be positive");
+  if (cfg->precision != 32 && cfg->precision != 64) return fail(-1, "srb_create: precision must be 32 or 64");
+  int G = cfg->lanes_per_env == 0 ? 8 : cfg->lanes_per_env;
+  if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(-1, "srb_create: lanes_per_env must be 1,2,4,8,16 or 32");
+  if (cfg->variant != SRB_VARIANT_TEST && cfg->variant != SRB_VARIANT_TRAINING) return fail(-1, "srb_create: unknown variant");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(-3, std::string("srb_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(-1, "srb_create: bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  srb_env* h = new srb_env();
+  h->cfg = *cfg; h->N = cfg->num_envs; h->G = G;
+  h->Npad = (h->N + 31) / 32 * 32;
+  h->rsz = cfg->precision == 64 ? 8 : 4;
+  default_params(h->p, cfg->variant);
+  CK(cudaMalloc(&h->st, h->rsz * NF_REAL * h->Npad));
+  CK(cudaMemset(h->st, 0, h->rsz * NF_REAL * h->Npad));
+  CK(cudaMalloc(&h->ist, sizeof(int) * NF_INT * h->Npad));
+  CK(cudaMemset(h->ist, 0, sizeof(int) * NF_INT * h->Npad));
+  CK(cudaMalloc(&h->hist, h->rsz * (size_t)h->N * HIST_SLOTS * HIST_W));
+  CK(cudaMemset(h->hist, 0, h->rsz * (size_t)h->N * HIST_SLOTS * HIST_W));
+  CK(cudaMalloc(&h->clips_dev, sizeof(ClipDesc<double>) * MAX_CLIPS));
+  CK(cudaMemset(h->clips_dev, 0, sizeof(ClipDesc<double>) * MAX_CLIPS));
+  h->clips.resize(MAX_CLIPS);
+  CK(cudaMalloc(&h->ep_stats, sizeof(double) * 3));
+  CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  return 0;
+}
+
+extern "C" int srb_destroy(srb_env* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->st); cudaFree(h->ist); cudaFree(h->hist); cudaFree(h->clips_dev); cudaFree(h->ep_stats);
+  for (auto& c : h->clips) { cudaFree(c.frames); cudaFree(c.feat); }
+  cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_rinfo); cudaFreeHost(h->h_done);
+  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rinfo); cudaFree(h->d_done);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int srb_upload_clip(srb_env* h, int32_t clip_id, int32_t nframes, int32_t cycle_length, int32_t is_stand,
+                               const double* pos_com, const double* ori_com, const double* vel_com, const double* root_quat,
+                               const double* feet_pos, const double* feet_yaw) {
+  if (!h) return fail(-1, "srb_upload_clip: null handle");
+  if (clip_id < 0 || clip_id >= MAX_CLIPS) return fail(-1, "srb_upload_clip: clip_id out of range");
+  if (nframes <= 0 || !pos_com || !ori_com || !vel_com || !root_quat || !feet_pos || !feet_yaw) return fail(-1, "srb_upload_clip: bad arguments");
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<double> rec((size_t)nframes * CLIP_W);
+  for (int f = 0; f < nframes; f++) {
+    double* r = &rec[(size_t)f * CLIP_W];
+    for (int i = 0; i < 3; i++) r[i] = pos_com[3 * f + i];
+    for (int i = 0; i < 9; i++) r[3 + i] = ori_com[9 * f + i];
+    for (int i = 0; i < 6; i++) r[12 + i] = vel_com[6 * f + i];
+    for (int i = 0; i < 6; i++) r[18 + i] = feet_pos[6 * f + i];
+    for (int i = 0; i < 4; i++) r[24 + i] = feet_yaw[4 * f + i];
+    for (int i = 0; i < 4; i++) r[28 + i] = root_quat[4 * f + i];
+  }
+  ClipStore& cs = h->clips[clip_id];
+  cudaFree(cs.frames); cudaFree(cs.feat);
+  cs.frames = nullptr; cs.feat = nullptr;
+  // features are always computed from the fp64 table
+  double* dfr = nullptr;
+  CK(cudaMalloc(&dfr, sizeof(double) * rec.size()));
+  CK(cudaMemcpy(dfr, rec.data(), sizeof(double) * rec.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&cs.feat, sizeof(float) * (size_t)nframes * FEAT_W));
+  srb_clip_features_kernel<<<(nframes + 127) / 128, 128, 0, h->stream>>>(dfr, nframes, cs.feat);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->cfg.precision == 64) {
+    cs.frames = dfr;
+  } else {
+    std::vector<float> recf(rec.size());
+    for (size_t i = 0; i < rec.size(); i++) recf[i] = (float)rec[i];
+    CK(cudaMalloc(&cs.frames, sizeof(float) * recf.size()));
+    CK(cudaMemcpy(cs.frames, recf.data(), sizeof(float) * recf.size(), cudaMemcpyHostToDevice));
+    cudaFree(dfr);
+  }
+  cs.nframes = nframes; cs.cycle = cycle_length; cs.is_stand = is_stand;
+  ClipDesc<double> d;   // same layout for float/double instantiations (pointer, pointer, 4 ints)
+  d.frames = (const double*)cs.frames; d.feat = cs.feat; d.nframes = nframes; d.cycle_length = cycle_length; d.is_stand = is_stand; d.pad = 0;
+  CK(cudaMemcpy((char*)h->clips_dev + sizeof(ClipDesc<double>) * clip_id, &d, sizeof(d), cudaMemcpyHostToDevice));
+  if (clip_id + 1 > h->nclips) h->nclips = clip_id + 1;
+  return 0;
+}
+
+template <typename real> static int do_reset(srb_env* h, const int* idx_dev, int count, const double* plan_dev, float* obs_dev, cudaStream_t s) {
+  ResetArgs<real> A;
+  A.N = h->N; A.Npad = h->Npad; A.count = count; A.idx = idx_dev;
+  A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist;
+  A.clips = (const ClipDesc<real>*)h->clips_dev; A.nclips = h->nclips;
+  A.plan = plan_dev; A.obs = obs_dev; A.seed = h->cfg.seed; A.p = convert_params<real>(h->p);
+  srb_reset_kernel<real><<<(count + 127) / 128, 128, 0, s>>>(A);
+  h->launches++;
+  return 0;
+}
+
+extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count, const double* plan_host, float* obs_dev, void* stream) {
+  if (!h) return fail(-1, "srb_reset: null handle");
+  if (h->nclips == 0) return fail(-1, "srb_reset: no clip uploaded");
+  if (count <= 0 || count > h->N) return fail(-1, "srb_reset: bad count");
+  for (int c = 0; c < h->nclips; c++) if (h->clips[c].frames == nullptr) return fail(-1, "srb_reset: clip ids must be contiguous from 0");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int* idx_dev = nullptr; double* plan_dev = nullptr;
+  if (env_idx_host) {
+    for (int i = 0; i < count; i++) if (env_idx_host[i] < 0 || env_idx_host[i] >= h->N) return fail(-1, "srb_reset: env index out of range");
+    CK(cudaMalloc(&idx_dev, sizeof(int) * count));
+    CK(cudaMemcpyAsync(idx_dev, env_idx_host, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+  }
+  if (plan_host) {
+    CK(cudaMalloc(&plan_dev, sizeof(double) * 9 * count));
+    CK(cudaMemcpyAsync(plan_dev, plan_host, sizeof(double) * 9 * count, cudaMemcpyHostToDevice, s));
+  }
+  if (h->cfg.precision == 64) do_reset<double>(h, idx_dev, count, plan_dev, obs_dev, s);
+  else do_reset<float>(h, idx_dev, count, plan_dev, obs_dev, s);
+  CK(cudaGetLastError());
+  if (idx_dev || plan_dev) {
+    CK(cudaStreamSynchronize(s));
+    cudaFree(idx_dev); cudaFree(plan_dev);
+  }
+  return 0;
+}
+
+template <typename real, int G> static void launch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
+  StepArgs<real> A;
+  A.N = h->N; A.Npad = h->Npad;
+  A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist;
+  A.clips = (const ClipDesc<real>*)h->clips_dev; A.nclips = h->nclips;
+  A.act = act; A.obs = obs; A.rew = rew; A.done = done; A.rinfo = rinfo; A.term_obs = h->term_obs;
+  A.contact_prob = h->contact_prob; A.reset_plan = h->reset_plan; A.dbg = h->dbg; A.ep_stats = h->ep_stats;
+  A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p);
+  constexpr int EPW = 32 / G;
+  int blocks = (h->N + EPW - 1) / EPW;
+  srb_step_kernel<real, G><<<blocks, 32, 0, s>>>(A);
+  h->launches++;
+}
+
+template <typename real> static int dispatch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
+  switch (h->G) {
+    case 1: launch_step<real, 1>(h, act, obs, rew, done, rinfo, s); break;
+    case 2: launch_step<real, 2>(h, act, obs, rew, done, rinfo, s); break;
+    case 4: launch_step<real, 4>(h, act, obs, rew, done, rinfo, s); break;
+    case 8: launch_step<real, 8>(h, act, obs, rew, done, rinfo, s); break;
+    case 16: launch_step<real, 16>(h, act, obs, rew, done, rinfo, s); break;
+    case 32: launch_step<real, 32>(h, act, obs, rew, done, rinfo, s); break;
+    default: return fail(-1, "bad lanes_per_env");
+  }
+  return 0;
+}
+
+extern "C" int srb_step(srb_env* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream) {
+  if (!h) return fail(-1, "srb_step: null handle");
+  if (!act_dev || !obs_dev || !rew_dev || !done_dev) return fail(-1, "srb_step: null buffer");
+  if (h->nclips == 0) return fail(-1, "srb_step: no clip uploaded");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = h->cfg.precision == 64 ? dispatch_step<double>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s)
+                                  : dispatch_step<float>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_host_buffers(srb_env* h) {
+  if (h->h_act) return 0;
+  size_t N = h->N;
+  CK(cudaMallocHost(&h->h_act, sizeof(float) * N * ACT_W));
+  CK(cudaMallocHost(&h->h_obs, sizeof(float) * N * OBS_W));
+  CK(cudaMallocHost(&h->h_rew, sizeof(float) * N));
+  CK(cudaMallocHost(&h->h_rinfo, sizeof(float) * N * RINFO_W));
+  CK(cudaMallocHost(&h->h_done, N));
+  CK(cudaMalloc(&h->d_act, sizeof(float) * N * ACT_W));
+  CK(cudaMalloc(&h->d_obs, sizeof(float) * N * OBS_W));
+  CK(cudaMalloc(&h->d_rew, sizeof(float) * N));
+  CK(cudaMalloc(&h->d_rinfo, sizeof(float) * N * RINFO_W));
+  CK(cudaMalloc(&h->d_done, N));
+  return 0;
+}
+
+extern "C" int srb_pinned_buffers(srb_env* h, float** act, float** obs, float** rew, uint8_t** done, float** rinfo) {
+  if (!h) return fail(-1, "srb_pinned_buffers: null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_host_buffers(h);
+  if (rc) return rc;
+  if (act) *act = h->h_act; if (obs) *obs = h->h_obs; if (rew) *rew = h->h_rew; if (done) *done = h->h_done; if (rinfo) *rinfo = h->h_rinfo;
+  return 0;
+}
+
+extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host) {
+  if (!h) return fail(-1, "srb_step_host: null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_host_buffers(h);
+  if (rc) return rc;
+  size_t N = h->N;
+  if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
+  cudaStream_t s = h->stream;
+  CK(cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * N * ACT_W, cudaMemcpyHostToDevice, s));
+  rc = srb_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_rinfo, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * OBS_W, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_rinfo, h->d_rinfo, sizeof(float) * N * RINFO_W, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (obs_host && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, sizeof(float) * N * OBS_W);
+  if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, sizeof(float) * N);
+  if (done_host && done_host != h->h_done) memcpy(done_host, h->h_done, N);
+  if (rinfo_host && rinfo_host != h->h_rinfo) memcpy(rinfo_host, h->h_rinfo, sizeof(float) * N * RINFO_W);
+  return 0;
+}
+
+extern "C" int srb_set_aux(srb_env* h, const float* contact_prob_dev, float* term_obs_dev, const double* reset_plan_dev, double* dbg_dev) {
+  if (!h) return fail(-1, "srb_set_aux: null handle");
+  h->contact_prob = contact_prob_dev; h->term_obs = term_obs_dev; h->reset_plan = reset_plan_dev; h->dbg = dbg_dev;
+  return 0;
+}
+
+extern "C" int srb_set_reward_weights(srb_env* h, const double w[9]) {
+  if (!h || !w) return fail(-1, "srb_set_reward_weights: null argument");
+  memcpy(h->p.w, w, sizeof(double) * 9);
+  return 0;
+}
+
+extern "C" int srb_set_impulse(srb_env* h, int32_t interval, int32_t duration, const double force[3]) {
+  if (!h || !force) return fail(-1, "srb_set_impulse: null argument");
+  if (interval <= 0) return fail(-1, "srb_set_impulse: interval must be positive");
+  h->p.impulse_interval = interval; h->p.impulse_duration = duration;
+  for (int i = 0; i < 3; i++) h->p.impulse_force[i] = force[i];
+  h->p.use_impulse = 1;
+  return 0;
+}
+
+extern "C" int srb_state_dims(int32_t* n_real, int32_t* n_int, int32_t* hist_slots, int32_t* hist_width) {
+  if (n_real) *n_real = NF_REAL; if (n_int) *n_int = NF_INT; if (hist_slots) *hist_slots = HIST_SLOTS; if (hist_width) *hist_width = HIST_W;
+  return 0;
+}
+
+template <typename real> static int get_state_t(srb_env* h, int e, double* reals, int32_t* ints, double* hist) {
+  std::vector<real> col(NF_REAL);
+  CK(cudaMemcpy2D(col.data(), sizeof(real), (const real*)h->st + e, sizeof(real) * h->Npad, sizeof(real), NF_REAL, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < NF_REAL; i++) reals[i] = (double)col[i];
+  CK(cudaMemcpy2D(ints, sizeof(int), h->ist + e, sizeof(int) * h->Npad, sizeof(int), NF_INT, cudaMemcpyDeviceToHost));
+  if (hist) {
+    std::vector<real> hb(HIST_SLOTS * HIST_W);
+    CK(cudaMemcpy(hb.data(), (const real*)h->hist + (size_t)e * HIST_SLOTS * HIST_W, sizeof(real) * hb.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < hb.size(); i++) hist[i] = (double)hb[i];
+  }
+  return 0;
+}
+template <typename real> static int set_state_t(srb_env* h, int e, const double* reals, const int32_t* ints, const double* hist) {
+  std::vector<real> col(NF_REAL);
+  for (int i = 0; i < NF_REAL; i++) col[i] = (real)reals[i];
+  CK(cudaMemcpy2D((real*)h->st + e, sizeof(real) * h->Npad, col.data(), sizeof(real), sizeof(real), NF_REAL, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(h->ist + e, sizeof(int) * h->Npad, ints, sizeof(int), sizeof(int), NF_INT, cudaMemcpyHostToDevice));
+  if (hist) {
+    std::vector<real> hb(HIST_SLOTS * HIST_W);
+    for (size_t i = 0; i < hb.size(); i++) hb[i] = (real)hist[i];
+    CK(cudaMemcpy((real*)h->hist + (size_t)e * HIST_SLOTS * HIST_W, hb.data(), sizeof(real) * hb.size(), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int srb_get_state(srb_env* h, int32_t e, double* reals, int32_t* ints, double* hist) {
+  if (!h || !reals || !ints) return fail(-1, "srb_get_state: null argument");
+  if (e < 0 || e >= h->N) return fail(-1, "srb_get_state: env index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  return h->cfg.precision == 64 ? get_state_t<double>(h, e, reals, ints, hist) : get_state_t<float>(h, e, reals, ints, hist);
+}
+extern "C" int srb_set_state(srb_env* h, int32_t e, const double* reals, const int32_t* ints, const double* hist) {
+  if (!h || !reals || !ints) return fail(-1, "srb_set_state: null argument");
+  if (e < 0 || e >= h->N) return fail(-1, "srb_set_state: env index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  return h->cfg.precision == 64 ? set_state_t<double>(h, e, reals, ints, hist) : set_state_t<float>(h, e, reals, ints, hist);
+}
+
+// ---- observation statistics: acc[0] += N, acc[1+j] += sum_i obs[i][j], acc[1+150+j] += sum_i obs[i][j]^2
+__global__ void srb_obs_stats_kernel(const float* __restrict__ obs, int N, double* __restrict__ acc) {
+  // one CTA handles a strip of rows; thread j (<150) owns column j -> coalesced row reads
+  int j = threadIdx.x;
+  int rows_per = (N + gridDim.x - 1) / gridDim.x;
+  int r0 = blockIdx.x * rows_per, r1 = min(N, r0 + rows_per);
+  if (j < OBS_W) {
+    double s = 0, q = 0;
+    for (int r = r0; r < r1; r++) { double v = (double)obs[(size_t)r * OBS_W + j]; s += v; q += v * v; }
+    if (r1 > r0) { atomicAdd(acc + 1 + j, s); atomicAdd(acc + 1 + OBS_W + j, q); }
+  }
+  if (j == 0 && r1 > r0) atomicAdd(acc, (double)(r1 - r0));
+}
+
+extern "C" int srb_obs_stats(srb_env* h, const float* obs_dev, double* acc_dev, void* stream) {
+  if (!h || !obs_dev || !acc_dev) return fail(-1, "srb_obs_stats: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  int blocks = h->N < 148 * 4 ? (h->N + 7) / 8 : 148 * 4;
+  if (blocks < 1) blocks = 1;
+  srb_obs_stats_kernel<<<blocks, 160, 0, (cudaStream_t)stream>>>(obs_dev, h->N, acc_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srb_episode_stats(srb_env* h, double out[3], int32_t clear) {
+  if (!h || !out) return fail(-1, "srb_episode_stats: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, h->ep_stats, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+  if (clear) CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
+  return 0;
+}
+
+extern "C" int64_t srb_launch_count(srb_env* h) { return h ? h->launches : 0; }

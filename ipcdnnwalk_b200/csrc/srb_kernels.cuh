@@ -1,0 +1,910 @@
+// SRBTrack batched environment step for sm_100a.
+//
+// Mapping: G lanes (a power of two, 1..32) cooperate on one environment, 32/G environments per warp,
+// one warp per CTA (no CTA-level sharing is needed, and 1-warp CTAs give the finest SM load balance at
+// the 4096-environment batch the headline config uses).  The scalar part of the step (kinematics,
+// action decoding, swing-foot filter, integration, observation, reward, termination) is computed
+// redundantly by the G lanes (same instruction stream, no extra issue slots); the contact-force QP --
+// the dominant cost -- is spread over the lanes: each lane owns 40/G friction-basis columns, the 6x6
+// semismooth-Newton Hessian is all-reduced with xor-shuffles and factorised (LDL^T) in registers.
+//
+// Reference for every block is cited inline (paths relative to the reference repository root).
+#pragma once
+#include "srb_math.cuh"
+#include "srb_types.h"
+
+namespace srb {
+
+// ------------------------------------------------------------------------------------------------
+// state in registers
+template <typename real> struct EnvState {
+  V3<real> pos; Q4<real> quat; V3<real> vlin, vang; Q4<real> qlag;
+  V3<real> foot[2]; real yc[2], ys[2];
+  real filt_yaw[2]; real ballx[4]; real ballv[4];
+  real ep_ret;
+  int flags, frame, rif, clip, fcount, impulse, episode;
+};
+
+template <typename real> __device__ __forceinline__ void load_state(EnvState<real>& s, const real* __restrict__ st,
+                                                                   const int* __restrict__ ist, int Npad, int e) {
+#define LD(f) st[(size_t)(f) * Npad + e]
+  s.pos = {LD(F_POS), LD(F_POS + 1), LD(F_POS + 2)};
+  s.quat = {LD(F_QUAT), LD(F_QUAT + 1), LD(F_QUAT + 2), LD(F_QUAT + 3)};
+  s.vlin = {LD(F_QVEL), LD(F_QVEL + 1), LD(F_QVEL + 2)};
+  s.vang = {LD(F_QVEL + 3), LD(F_QVEL + 4), LD(F_QVEL + 5)};
+  s.qlag = {LD(F_QLAG), LD(F_QLAG + 1), LD(F_QLAG + 2), LD(F_QLAG + 3)};
+  s.foot[0] = {LD(F_FOOTL), LD(F_FOOTL + 1), LD(F_FOOTL + 2)};
+  s.foot[1] = {LD(F_FOOTR), LD(F_FOOTR + 1), LD(F_FOOTR + 2)};
+  s.yc[0] = LD(F_FYAWL); s.ys[0] = LD(F_FYAWL + 1); s.yc[1] = LD(F_FYAWR); s.ys[1] = LD(F_FYAWR + 1);
+  s.filt_yaw[0] = LD(F_FILTYAW); s.filt_yaw[1] = LD(F_FILTYAW + 1);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { s.ballx[i] = LD(F_BALLX + i); s.ballv[i] = LD(F_BALLV + i); }
+  s.ep_ret = LD(F_EPRET);
+#undef LD
+#define LDI(f) ist[(size_t)(f) * Npad + e]
+  s.flags = LDI(I_FLAGS); s.frame = LDI(I_FRAME); s.rif = LDI(I_RIF); s.clip = LDI(I_CLIP);
+  s.fcount = LDI(I_FCOUNT); s.impulse = LDI(I_IMPULSE); s.episode = LDI(I_EPISODE);
+#undef LDI
+}
+
+template <typename real> __device__ __forceinline__ void store_state(const EnvState<real>& s, real* __restrict__ st,
+                                                                    int* __restrict__ ist, int Npad, int e) {
+#define ST(f, v) st[(size_t)(f) * Npad + e] = (v)
+  ST(F_POS, s.pos.x); ST(F_POS + 1, s.pos.y); ST(F_POS + 2, s.pos.z);
+  ST(F_QUAT, s.quat.w); ST(F_QUAT + 1, s.quat.x); ST(F_QUAT + 2, s.quat.y); ST(F_QUAT + 3, s.quat.z);
+  ST(F_QVEL, s.vlin.x); ST(F_QVEL + 1, s.vlin.y); ST(F_QVEL + 2, s.vlin.z);
+  ST(F_QVEL + 3, s.vang.x); ST(F_QVEL + 4, s.vang.y); ST(F_QVEL + 5, s.vang.z);
+  ST(F_QLAG, s.qlag.w); ST(F_QLAG + 1, s.qlag.x); ST(F_QLAG + 2, s.qlag.y); ST(F_QLAG + 3, s.qlag.z);
+  ST(F_FOOTL, s.foot[0].x); ST(F_FOOTL + 1, s.foot[0].y); ST(F_FOOTL + 2, s.foot[0].z);
+  ST(F_FOOTR, s.foot[1].x); ST(F_FOOTR + 1, s.foot[1].y); ST(F_FOOTR + 2, s.foot[1].z);
+  ST(F_FYAWL, s.yc[0]); ST(F_FYAWL + 1, s.ys[0]); ST(F_FYAWR, s.yc[1]); ST(F_FYAWR + 1, s.ys[1]);
+  ST(F_FILTYAW, s.filt_yaw[0]); ST(F_FILTYAW + 1, s.filt_yaw[1]);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { ST(F_BALLX + i, s.ballx[i]); ST(F_BALLV + i, s.ballv[i]); }
+  ST(F_EPRET, s.ep_ret);
+#undef ST
+#define STI(f, v) ist[(size_t)(f) * Npad + e] = (v)
+  STI(I_FLAGS, s.flags); STI(I_FRAME, s.frame); STI(I_RIF, s.rif); STI(I_CLIP, s.clip);
+  STI(I_FCOUNT, s.fcount); STI(I_IMPULSE, s.impulse); STI(I_EPISODE, s.episode);
+#undef STI
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG (Philox-4x32-10) for device-side episode resets
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit uniform in [0,1)
+  return (double)((((unsigned long long)a << 32 | b) >> 11)) * (1.0 / 9007199254740992.0);
+}
+
+// draws of SRBEnv.reset / set_state (SRBEnv5_mocap_list_window.py:810,823,860-867, viewer.py:719-731):
+// plan = clip, start frame, uniform(-.05,.05)^3 velocity noise, small random quaternion.
+template <typename real>
+__device__ inline void draw_reset_plan(unsigned long long seed, int env, int episode, const ClipDesc<real>* clips, int nclips, double plan[9]) {
+  uint32_t c[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB0u, 0u};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t d[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB1u, 0u};
+  philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t g[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB2u, 0u};
+  philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
+  int clip = (int)(u01(c[0], c[1]) * nclips);                       // random.randrange(n)
+  if (clip >= nclips) clip = nclips - 1;
+  int cyc = clips[clip].cycle_length;
+  int hi = max(cyc - 2, 512);                                        // random.randint(0, hi) inclusive
+  int frame = (int)(u01(c[2], c[3]) * (hi + 1));
+  if (frame > hi) frame = hi;
+  plan[0] = clip; plan[1] = frame;
+  plan[2] = (2.0 * u01(d[0], d[1]) - 1.0) * 5e-2;
+  plan[3] = (2.0 * u01(d[2], d[3]) - 1.0) * 5e-2;
+  uint32_t e[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB3u, 0u};
+  philox4x32(e, (uint32_t)seed, (uint32_t)(seed >> 32));
+  plan[4] = (2.0 * u01(e[0], e[1]) - 1.0) * 5e-2;
+  // axis ~ normalised N(0,I) (Box-Muller), angle ~ U(-.05,.05)
+  double u1 = 1.0 - u01(g[0], g[1]), u2 = u01(g[2], g[3]);
+  double r = sqrt(-2.0 * log(u1));
+  double n0 = r * cos(6.283185307179586 * u2), n1 = r * sin(6.283185307179586 * u2);
+  double u3 = 1.0 - u01(e[2], e[3]);
+  uint32_t f[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB4u, 0u};
+  philox4x32(f, (uint32_t)seed, (uint32_t)(seed >> 32));
+  double n2 = sqrt(-2.0 * log(u3)) * cos(6.283185307179586 * u01(f[0], f[1]));
+  double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+  if (nn < 1e-300) { n0 = 1; n1 = 0; n2 = 0; nn = 1; }
+  double ang = (2.0 * u01(f[2], f[3]) - 1.0) * 5e-2;
+  double sh = sin(0.5 * ang) / nn;
+  plan[5] = cos(0.5 * ang); plan[6] = n0 * sh; plan[7] = n1 * sh; plan[8] = n2 * sh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SRBEnv.set_state (SRBEnv5_mocap_list_window.py:847-911) from an explicit plan.
+// plan[5] (noise quat w) == NaN selects testing_mode (no noise).
+template <typename real>
+__device__ inline void apply_reset(EnvState<real>& s, const ClipDesc<real>* clips, int nclips, const double plan[9],
+                                   real* __restrict__ hist_env) {
+  int clip = min(max((int)plan[0], 0), nclips - 1);
+  const ClipDesc<real> cd = clips[clip];
+  int f = min(max((int)plan[1], 0), cd.nframes - 1);
+  const real* fr = cd.frames + (size_t)f * CLIP_W;
+  s.clip = clip; s.rif = f; s.frame = 0;
+  s.pos = {fr[0], fr[1], fr[2]};
+  Q4<real> mq = {fr[28], fr[29], fr[30], fr[31]};
+  s.vlin = {fr[12], fr[13], fr[14]};
+  s.vang = {fr[15], fr[16], fr[17]};
+  if (plan[5] == plan[5]) {
+    Q4<real> nq = {(real)plan[5], (real)plan[6], (real)plan[7], (real)plan[8]};
+    Q4<real> pq = quat_mul(nq, mq);
+    real inv = real(1) / num<real>::sqrt(pq.w * pq.w + pq.x * pq.x + pq.y * pq.y + pq.z * pq.z);
+    s.quat = {pq.w * inv, pq.x * inv, pq.y * inv, pq.z * inv};
+    s.vlin = {s.vlin.x + (real)plan[2], s.vlin.y + (real)plan[3], s.vlin.z + (real)plan[4]};
+  } else {
+    s.quat = mq;
+  }
+  s.qlag = s.quat;                                 // mj_forward refreshes xmat (:892)
+  bool lc = (fr[20] == real(0)), rc = (fr[23] == real(0));
+  s.foot[0] = {fr[18], fr[19], real(0)};
+  s.foot[1] = {fr[21], fr[22], real(0)};
+  s.yc[0] = fr[24]; s.ys[0] = fr[25]; s.yc[1] = fr[26]; s.ys[1] = fr[27];
+  // legacy slices [:3] / [3:] of the 10-entry site list (Q2): right = left OR right
+  s.flags = (lc ? FLAG_L : 0) | ((lc || rc) ? FLAG_R : 0) | (cd.is_stand ? FLAG_STAND : 0);
+  s.filt_yaw[0] = s.filt_yaw[1] = real(0);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { s.ballx[i] = real(0); s.ballv[i] = real(0); }
+  s.ep_ret = real(0);
+  s.episode += 1;     // frame_counter / impulse persist across resets, as in the reference
+  // history entry 0 (:895-911)
+  real* h0 = hist_env;
+  h0[0] = s.pos.x; h0[1] = s.pos.y; h0[2] = s.pos.z;
+  h0[3] = s.qlag.w; h0[4] = s.qlag.x; h0[5] = s.qlag.y; h0[6] = s.qlag.z; h0[7] = real(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// observation (SRBEnv.get_obs_window, SRBEnv5_mocap_list_window.py:1055-1168).
+// Self part (25) from the state; look-ahead part = 5 precomputed 25-float records of the clip table
+// (they depend on the reference frame only).  `lane`/`G`: cooperative copy of the window.
+template <typename real, int G>
+__device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDesc<real>& cd, float* __restrict__ o, int lane, bool active) {
+  M3<real> R = quat2mat_normalized(s.qlag);
+  real fx, fy;
+  yaw_frame(R, &fx, &fy);
+  if (active && lane == 0) {
+    o[0] = (float)s.pos.z;
+    // (proj^T R)[:, :2] flattened column-major
+    o[1] = (float)(fx * R.m[0] + fy * R.m[3]); o[2] = (float)(-fy * R.m[0] + fx * R.m[3]); o[3] = (float)R.m[6];
+    o[4] = (float)(fx * R.m[1] + fy * R.m[4]); o[5] = (float)(-fy * R.m[1] + fx * R.m[4]); o[6] = (float)R.m[7];
+    V3<real> vl = yawT(fx, fy, s.vlin);
+    V3<real> va = yawT(fx, fy, mul(R, s.vang));
+    o[7] = (float)vl.x; o[8] = (float)vl.y; o[9] = (float)vl.z;
+    o[10] = (float)va.x; o[11] = (float)va.y; o[12] = (float)va.z;
+    V3<real> lf = yawT(fx, fy, s.foot[0] - s.pos);
+    V3<real> rf = yawT(fx, fy, s.foot[1] - s.pos);
+    real l00 = fx * s.yc[0] + fy * s.ys[0], l10 = -fy * s.yc[0] + fx * s.ys[0];
+    real r10 = -fy * s.yc[1] + fx * s.ys[1];
+    o[13] = (float)lf.x; o[14] = (float)lf.y; o[15] = (float)lf.z; o[16] = (float)num<real>::atan2(l10, l00);
+    o[17] = (float)rf.x; o[18] = (float)rf.y; o[19] = (float)rf.z; o[20] = (float)num<real>::atan2(r10, l00);   // Q1
+    int c = s.flags & 3;
+    o[21] = c == 0 ? 1.f : 0.f; o[22] = c == 1 ? 1.f : 0.f; o[23] = c == 2 ? 1.f : 0.f; o[24] = c == 3 ? 1.f : 0.f;
+  }
+  if (active) {
+    int f0 = s.frame + s.rif + 1;
+    for (int i = lane; i < 5 * FEAT_W; i += G) {
+      int f = min(f0 + i / FEAT_W, cd.nframes - 1);
+      o[FEAT_W + i] = __ldg(cd.feat + (size_t)f * FEAT_W + (i % FEAT_W));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group helpers
+template <int G> __device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G> __device__ __forceinline__ double gsum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 6x6 SPD solve H x = rhs by LDL^T, fully unrolled in registers.  H: lower triangle, index i*(i+1)/2+j.
+template <typename real> __device__ __forceinline__ void ldl_solve6(const real* Hl, const real* rhs, real* x) {
+  real L[6][6];      // unit lower factor
+  real W[6][6];      // W[i][k] = L[i][k] * d[k]
+  real dinv[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    real d = Hl[j * (j + 1) / 2 + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[j][k] * W[j][k];
+    dinv[j] = real(1) / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      real v = Hl[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= L[i][k] * W[j][k];
+      W[i][j] = v;
+      L[i][j] = v * dinv[j];
+    }
+  }
+  real z[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    real v = rhs[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) v -= L[i][k] * z[k];
+    z[i] = v;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    real v = z[i] * dinv[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
+    x[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contact-force QP (solve_qp_for_contact_forces, testSRB_mujoco_original_viewer.py:515-599):
+//     min |qdd - qdd_d|^2 + w |lam|^2   s.t.  M qdd - C lam = -b,  lam >= 0.
+// qdd is eliminated (M is diagonal and constant for the free body):  with A = M^-1 C, y = qdd_d + M^-1 b
+//     min_{lam>=0} |A lam - y|^2 + w |lam|^2.
+// Its dual is an unconstrained, strictly convex piecewise-quadratic in nu = A lam - y (= qdd - qdd_d):
+//     phi(nu) = 1/2|nu|^2 + nu.y + 1/(2w) |max(0, -A^T nu)|^2 ,   lam = max(0, -A^T nu)/w,
+// minimised by a semismooth Newton iteration on 6 unknowns: on the active set S={j: a_j.nu<0},
+// (I + A_S A_S^T / w) nu = -y.  A full step is accepted when S is reproduced (exact optimum) or phi
+// decreases, otherwise it is halved (globally convergent, finite termination).
+// Columns: c = s*8 + f*4 + d  (site s of 5, foot f, friction direction d), lane owns c = lane + k*G.
+template <typename real, int G> struct QP {
+  static constexpr int NC = (40 + G - 1) / G;
+  real a[NC][6];
+
+  __device__ __forceinline__ void build(int lane, const M3<real>& R, V3<real> p, const V3<real> foot[2], const real yc[2],
+                                        const real ys[2], int contact_mask, real fx, real fy, real mu_b, const real Minv[6]) {
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      int c = lane + k * G;
+      int sidx = c >> 3, f = (c >> 2) & 1, d = c & 3;
+      bool valid = (c < 40) && ((contact_mask >> f) & 1);
+      real bx = d == 0 ? mu_b : (d == 1 ? -mu_b : real(0));
+      real by = d == 2 ? mu_b : (d == 3 ? -mu_b : real(0));
+      V3<real> B = {fx * bx - fy * by, fy * bx + fx * by, real(1)};     // curr_projSRB_ori @ b_d
+      real ox = sidx == 0 ? real(0) : ((sidx == 1 || sidx == 2) ? real(0.12) : real(-0.12));
+      real oy = sidx == 0 ? real(0) : ((sidx == 1 || sidx == 3) ? real(0.06) : real(-0.06));
+      V3<real> ft = f ? foot[1] : foot[0];
+      real c_ = f ? yc[1] : yc[0], s_ = f ? ys[1] : ys[0];
+      V3<real> site = {ft.x + (c_ * ox - s_ * oy), ft.y + (s_ * ox + c_ * oy), ft.z};   // set_feet_site_this_step_env
+      V3<real> r = site - p;
+      V3<real> tau = mulT(R, cross(r, B));                              // jacp^T B, rotational rows (body frame)
+      real m = valid ? real(1) : real(0);
+      a[k][0] = m * Minv[0] * B.x; a[k][1] = m * Minv[1] * B.y; a[k][2] = m * Minv[2] * B.z;
+      a[k][3] = m * Minv[3] * tau.x; a[k][4] = m * Minv[4] * tau.y; a[k][5] = m * Minv[5] * tau.z;
+    }
+  }
+
+  __device__ __forceinline__ void tvals(const real nu[6], real t[NC]) const {
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+      t[k] = a[k][0] * nu[0] + a[k][1] * nu[1] + a[k][2] * nu[2] + a[k][3] * nu[3] + a[k][4] * nu[4] + a[k][5] * nu[5];
+  }
+  __device__ __forceinline__ real phi(const real nu[6], const real y[6], const real t[NC], real inv2w) const {
+    real ps = 0;
+#pragma unroll
+    for (int k = 0; k < NC; k++) { real m = t[k] < 0 ? t[k] : real(0); ps += m * m; }
+    ps = gsum<G>(ps);
+    real q = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) q += nu[i] * (real(0.5) * nu[i] + y[i]);
+    return q + inv2w * ps;
+  }
+
+  // returns number of Newton systems solved; nu in: initial guess, out: solution; t out: A^T nu
+  __device__ __forceinline__ int solve(int lane, const real y[6], real w, real nu[6], real t[NC]) {
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_id() / G) * G));
+    const real invw = real(1) / w, inv2w = real(0.5) * invw;
+    tvals(nu, t);
+    real ph = phi(nu, y, t, inv2w);
+    bool done = false;
+    int iters = 0;
+    real rhs[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) rhs[i] = -y[i];
+    for (int it = 0; it < 40; it++) {
+      if (!__any_sync(0xffffffffu, !done)) break;
+      real H[21];
+#pragma unroll
+      for (int i = 0; i < 21; i++) H[i] = 0;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        real m = t[k] < 0 ? real(1) : real(0);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          real ai = m * a[k][i];
+#pragma unroll
+          for (int j = 0; j <= i; j++) H[i * (i + 1) / 2 + j] += ai * a[k][j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 21; i++) H[i] = gsum<G>(H[i]) * invw;
+#pragma unroll
+      for (int i = 0; i < 6; i++) H[i * (i + 1) / 2 + i] += real(1);
+      real nn[6], tn[NC];
+      ldl_solve6(H, rhs, nn);
+      tvals(nn, tn);
+      bool same = true;
+#pragma unroll
+      for (int k = 0; k < NC; k++) same = same && ((tn[k] < 0) == (t[k] < 0));
+      unsigned bal = __ballot_sync(0xffffffffu, same);
+      same = (bal & gmask) == gmask;
+      real phn = phi(nn, y, tn, inv2w);
+      bool accept = same || (phn < ph);
+      bool need_bt = !done && !accept;
+      real alpha = real(0.5);
+      real nt[6], tt[NC];
+      real pht = phn;
+      while (__any_sync(0xffffffffu, need_bt)) {          // halve the step until phi decreases
+#pragma unroll
+        for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
+        tvals(nt, tt);
+        pht = phi(nt, y, tt, inv2w);
+        if (need_bt && (pht < ph || alpha < real(1e-6))) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) nn[i] = nt[i];
+#pragma unroll
+          for (int k = 0; k < NC; k++) tn[k] = tt[k];
+          phn = pht;
+          need_bt = false;
+        }
+        alpha *= real(0.5);
+      }
+      if (!done) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = nn[i];
+#pragma unroll
+        for (int k = 0; k < NC; k++) t[k] = tn[k];
+        ph = phn;
+        iters++;
+        if (same) done = true;
+      }
+    }
+    return iters;
+  }
+  static __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// SDS swing-foot LQR filter (work/controlmodule.py:962-1086, gains: useKpreset :1041-1057 with
+// sop.piecewiseLinearMap (module.lua:5203) and matrixn::sampleRow (matrixn.cpp:781, float32 `t`)).
+template <typename real> __device__ __forceinline__ void sds_gain(real speed, real* K0, real* K1) {
+  const double KP[7][2] = {{262.685, 127.410}, {942.739, 281.657}, {3103.828, 553.238}, {9941.174, 1033.866},
+                           {31563.832, 1887.117}, {99941.017, 3403.601}, {316168.772, 6099.859}};
+  if (speed < real(3)) { *K0 = (real)KP[4][0]; *K1 = (real)KP[4][1]; return; }     // logQ = 9 -> row 4 exactly
+  double logQ = speed > real(6) ? 11.0 : 9.0 + (((double)speed - 3.0) / 3.0) * (11.0 - 9.0);
+  logQ = fmax(9.0, logQ);
+  double Q = ::pow(10.0, logQ);
+  // piecewiseLinearMap(Q, 10^5..10^12, 0..7)
+  const double KT[8] = {1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12};
+  double index = 7.0;
+  for (int i = 0; i < 7; i++) {
+    double t1 = KT[i + 1];
+    double d = t1 - KT[i];
+    if (t1 >= Q - 1e-10) {
+      double lo = t1 - d;
+      double wgt = (Q - lo) / (t1 - lo);
+      wgt = 0.0 * (1.0 - wgt) + 1.0 * wgt;
+      index = (double)i * (1.0 - wgt) + (double)(i + 1) * wgt;
+      break;
+    }
+  }
+  int a = (int)::floor(index);
+  float t = (float)(index - (double)(float)a);
+  double k0, k1;
+  if (t < 0.005) { k0 = KP[a][0]; k1 = KP[a][1]; }
+  else if (t > 0.995) { k0 = KP[min(a + 1, 6)][0]; k1 = KP[min(a + 1, 6)][1]; }
+  else if (a + 1 >= 7) { double tt = (double)t + 1.0; k0 = KP[a - 1][0] * (1.0 - tt) + KP[a][0] * tt; k1 = KP[a - 1][1] * (1.0 - tt) + KP[a][1] * tt; }
+  else { double tt = (double)t; k0 = KP[a][0] * (1.0 - tt) + KP[a + 1][0] * tt; k1 = KP[a][1] * (1.0 - tt) + KP[a + 1][1] * tt; }
+  *K0 = (real)k0; *K1 = (real)k1;
+}
+
+template <typename real> __device__ __forceinline__ void sds_4steps(real& x, real& v, real xd, real K0, real K1) {
+  const real invM = real(1) / real(60.0), dt = real(1) / real(120.0);
+  const real C = real(0.001) * invM, Gc = real(1) * invM, H = real(1) * invM;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    real U = K0 * xd + K1 * real(0);
+    real cf = U - (K0 * x + K1 * v);
+    real dd = H * cf - Gc - C * v;
+    v += dd * dt;
+    x += v * dt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reward (SRBEnv._get_reward, SRBEnv5_mocap_list_window.py:496-803); returns r_t and the 8 info terms
+template <typename real> struct RefFrame { V3<real> pos; M3<real> R; };
+template <typename real> __device__ __forceinline__ RefFrame<real> load_ref(const ClipDesc<real>& cd, int f) {
+  f = min(max(f, 0), cd.nframes - 1);
+  const real* fr = cd.frames + (size_t)f * CLIP_W;
+  RefFrame<real> o;
+  o.pos = {fr[0], fr[1], fr[2]};
+#pragma unroll
+  for (int i = 0; i < 9; i++) o.R.m[i] = fr[3 + i];
+  return o;
+}
+// L1 norm of the 6-D rotation difference  |(Pa^T Ra)[:, :2] - (Pb^T Rb)[:, :2]|_1 for yaw frames Pa, Pb
+template <typename real> __device__ __forceinline__ real rot6_l1_yaw(real ax, real ay, const M3<real>& Ra, real bx, real by, const M3<real>& Rb) {
+  real s = 0;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    real a0 = ax * Ra.m[c] + ay * Ra.m[3 + c], a1 = -ay * Ra.m[c] + ax * Ra.m[3 + c], a2 = Ra.m[6 + c];
+    real b0 = bx * Rb.m[c] + by * Rb.m[3 + c], b1 = -by * Rb.m[c] + bx * Rb.m[3 + c], b2 = Rb.m[6 + c];
+    s += num<real>::abs(a0 - b0) + num<real>::abs(a1 - b1) + num<real>::abs(a2 - b2);
+  }
+  return s;
+}
+template <typename real> __device__ __forceinline__ real rot6_l1_full(const M3<real>& Pa, const M3<real>& Ra, const M3<real>& Pb, const M3<real>& Rb) {
+  M3<real> A = matmulTN(Pa, Ra), B = matmulTN(Pb, Rb);
+  real s = 0;
+#pragma unroll
+  for (int c = 0; c < 2; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) s += num<real>::abs(A.m[3 * r + c] - B.m[3 * r + c]);
+  return s;
+}
+
+template <typename real>
+__device__ __forceinline__ real compute_reward(const EnvState<real>& s, const ClipDesc<real>& cd, const real* __restrict__ hist_env,
+                                               int pred_contact, const Params<real>& p, float info[8]) {
+  const int cf = s.frame, f0 = cf + s.rif;
+  M3<real> X = quat2mat_normalized(s.qlag);            // data.xmat (stale by one sub-step)
+  real cx, cy;
+  yaw_frame(X, &cx, &cy);
+  RefFrame<real> cur = load_ref(cd, f0), nxt = load_ref(cd, f0 + 1);
+  real mcx, mcy, mnx, mny;
+  yaw_frame(cur.R, &mcx, &mcy);
+  yaw_frame(nxt.R, &mnx, &mny);
+  const real* nfr = cd.frames + (size_t)min(f0 + 1, cd.nframes - 1) * CLIP_W;
+
+  // contact timing
+  int mocap_next = (nfr[20] == real(0) ? 1 : 0) + (nfr[23] == real(0) ? 2 : 0);
+  real r_c = (pred_contact == mocap_next) ? real(0) : real(10);
+
+  // end-effector term
+  real r_e = 0;
+  {
+    V3<real> origin = {s.pos.x, s.pos.y, real(0)};
+    V3<real> morigin = {nxt.pos.x, nxt.pos.y, real(0)};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      V3<real> ref_xy = {nfr[18 + 3 * i], nfr[19 + 3 * i], real(0)};
+      V3<real> dv = yawT(cx, cy, s.foot[i] - origin) - yawT(mnx, mny, ref_xy - morigin);
+      bool on = (pred_contact == 3) || (pred_contact == (i == 0 ? 1 : 2));
+      real nrm = norm(dv);
+      r_e += (on ? real(1.9) : real(0.1)) * (nrm * nrm);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      // (proj^T foot_ori)[:, :2] vs (mproj^T ref_foot_ori)[:, :2]; both foot matrices are pure yaw
+      real c_ = s.yc[i], s_ = s.ys[i], rc = nfr[24 + 2 * i], rs = nfr[25 + 2 * i];
+      real a00 = cx * c_ + cy * s_, a10 = -cy * c_ + cx * s_, a01 = cx * (-s_) + cy * c_, a11 = -cy * (-s_) + cx * c_;
+      real b00 = mnx * rc + mny * rs, b10 = -mny * rc + mnx * rs, b01 = mnx * (-rs) + mny * rc, b11 = -mny * (-rs) + mnx * rc;
+      r_e += num<real>::abs(a00 - b00) + num<real>::abs(a10 - b10) + num<real>::abs(a01 - b01) + num<real>::abs(a11 - b11);
+    }
+  }
+
+  // delta terms vs history at -1, -5, -15 steps
+  real dp = 0, dR = 0;
+  auto hist_entry = [&](int e, V3<real>* hp, M3<real>* hR) {
+    const real* h = hist_env + (size_t)(e & (HIST_SLOTS - 1)) * HIST_W;
+    *hp = {h[0], h[1], h[2]};
+    *hR = quat2mat_normalized(Q4<real>{h[3], h[4], h[5], h[6]});
+  };
+  if (cf >= 15) {
+    V3<real> hp; M3<real> hR;
+    hist_entry(cf - 15, &hp, &hR);
+    RefFrame<real> m15 = load_ref(cd, f0 - 15);
+    real hx, hy, mx, my;
+    yaw_frame(hR, &hx, &hy);
+    yaw_frame(m15.R, &mx, &my);
+    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m15.pos));
+    dR += rot6_l1_full(hR, X, m15.R, nxt.R);
+  }
+  if (cf >= 5) {
+    V3<real> hp; M3<real> hR;
+    hist_entry(cf - 5, &hp, &hR);
+    RefFrame<real> m5 = load_ref(cd, f0 - 5);
+    real hx, hy, mx, my;
+    yaw_frame(hR, &hx, &hy);
+    yaw_frame(m5.R, &mx, &my);
+    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m5.pos));
+    dR += rot6_l1_yaw(hx, hy, X, mx, my, nxt.R);
+  }
+  {
+    V3<real> hp; M3<real> hR;
+    hist_entry(cf, &hp, &hR);
+    real hx, hy;
+    yaw_frame(hR, &hx, &hy);
+    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mcx, mcy, nxt.pos - cur.pos));
+    dR += rot6_l1_yaw(hx, hy, X, mcx, mcy, nxt.R);
+  }
+  // absolute terms
+  V3<real> pa = {real(0), real(0), s.pos.z}, pb = {real(0), real(0), nxt.pos.z};
+  real p_term = norm(yawT(cx, cy, pa) - yawT(mnx, mny, pb));
+  real R_term = rot6_l1_yaw(cx, cy, X, mnx, mny, nxt.R);
+
+  const real w_s = p.w[0], w_m = p.w[1], w_p = p.w[2], w_e = p.w[3], w_p1 = p.w[4], w_p2 = p.w[5], w_p3 = p.w[6], w_p4 = p.w[7], w_c = p.w[8];
+  real r_p = w_p1 * dp + w_p2 * dR + w_p3 * p_term + w_p4 * R_term;
+  real r_m = w_p * r_p + w_e * r_e + w_c * r_c;
+  real r_t = w_s * real(1) - w_m * r_m;
+  info[0] = (float)(w_s * real(1));
+  info[1] = (float)(-w_m * w_c * r_c);
+  info[2] = (float)(-w_m * w_e * r_e);
+  info[3] = (float)(-w_m * w_p * w_p1 * dp);
+  info[4] = (float)(-w_m * w_p * w_p2 * dR);
+  info[5] = (float)(-w_m * w_p * w_p3 * p_term);
+  info[6] = (float)(-w_m * w_p * w_p4 * R_term);
+  info[7] = (float)r_t;
+  return r_t;
+}
+
+// SRBEnv._get_done (:916-1003)
+template <typename real> __device__ __forceinline__ bool compute_done(const EnvState<real>& s, const ClipDesc<real>& cd, const Params<real>& p) {
+  int f1 = min(s.frame + 1 + s.rif, cd.nframes - 1);
+  real ref_h = cd.frames[(size_t)f1 * CLIP_W + 2];
+  real h = s.pos.z;
+  if (ref_h - h > real(0.2) || h - ref_h > real(0.2) || h < real(0.50) || h > real(1.2)) return true;
+  M3<real> X = quat2mat_normalized(s.qlag);
+  real zn = num<real>::sqrt(X.m[2] * X.m[2] + X.m[5] * X.m[5] + X.m[8] * X.m[8]);
+  real ca = X.m[8] / (zn * real(1));
+  ca = num<real>::fmin(real(1), num<real>::fmax(real(-1), ca));
+  real deg = num<real>::acos(ca) * real(57.29577951308232);
+  if (deg > real(65)) return true;
+  return s.frame >= p.max_frame - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step kernel
+template <typename real, int G>
+__global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
+  constexpr int EPW = 32 / G;
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 % G;
+  const int e_raw = (blockIdx.x * EPW) + lane32 / G;
+  const bool active = e_raw < A.N;
+  const int e = active ? e_raw : A.N - 1;
+  const Params<real>& P = A.p;
+
+  EnvState<real> s;
+  load_state(s, A.st, A.ist, A.Npad, e);
+  const ClipDesc<real> cd = A.clips[s.clip];
+  real* hist_env = A.hist + (size_t)e * HIST_SLOTS * HIST_W;
+  const float* act = A.act + (size_t)e * ACT_W;
+  real a[ACT_W];
+#pragma unroll
+  for (int i = 0; i < ACT_W; i++) a[i] = (real)__ldg(act + i);
+
+  // ---- frames from the (stale) xmat, action decoding (SRBEnv.step :209-231)
+  const M3<real> R0 = quat2mat_normalized(s.qlag);
+  real fx, fy;
+  yaw_frame(R0, &fx, &fy);
+  const V3<real> origin = {s.pos.x, s.pos.y, real(0)};
+  const V3<real> tv_lin = mul(R0, V3<real>{a[4], a[5], a[6]});
+  const V3<real> tv_ang = {a[7], a[8], a[9]};
+  const V3<real> p_hat = mul(R0, V3<real>{a[10], a[11], a[12]}) + s.pos;
+  const M3<real> R_hat = matmul(R0, exp_so3(V3<real>{a[13], a[14], a[15]}));
+
+  // ---- contact decision (:234-311): first arg-max of the one-hot, or policy-probability hysteresis
+  int sig = 0;
+  {
+    real best = a[18];
+#pragma unroll
+    for (int i = 1; i < 4; i++) if (a[18 + i] > best) { best = a[18 + i]; sig = i; }
+  }
+  const int pred_contact = sig;                         // np.argmax(self.next_contact_one_hot) in _get_reward
+  if (!P.use_filter && (s.flags & FLAG_STAND)) sig = 3;  // training variant, stand clip
+  bool lc = (sig & 1) != 0, rc = (sig & 2) != 0;
+  if (P.use_filter && A.contact_prob != nullptr) {
+    float p0 = __ldg(A.contact_prob + 2 * (size_t)e), p1 = __ldg(A.contact_prob + 2 * (size_t)e + 1);
+    if (p0 == p0) {
+      bool l0 = (s.flags & FLAG_L) != 0, r0 = (s.flags & FLAG_R) != 0;
+      const double conf = 0.7;
+      lc = (l0 && (double)p0 < (1.0 - conf)) ? false : ((!l0 && (double)p0 > conf) ? true : l0);
+      rc = (r0 && (double)p1 < (1.0 - conf)) ? false : ((!r0 && (double)p1 > conf) ? true : r0);
+    }
+  }
+  s.flags = (s.flags & ~(FLAG_L | FLAG_R)) | (lc ? FLAG_L : 0) | (rc ? FLAG_R : 0);
+
+  // ---- feet (:320-371; training: ..._training.py:231-258)
+  if (P.use_filter) {
+    if (!(s.flags & FLAG_FILT)) {                       // initFilter (:1209-1234)
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        s.filt_yaw[i] = a[16 + i];
+        V3<real> g = yawR(fx, fy, V3<real>{a[2 * i], a[2 * i + 1], real(0)}) + origin;
+        s.ballx[2 * i] = g.x; s.ballx[2 * i + 1] = g.y;
+        s.ballv[2 * i] = real(0); s.ballv[2 * i + 1] = real(0);
+      }
+      s.flags |= FLAG_FILT;
+    }
+    real speed = num<real>::sqrt(s.vlin.x * s.vlin.x + s.vlin.y * s.vlin.y);
+    real K0, K1;
+    sds_gain(speed, &K0, &K1);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      bool in_contact = i == 0 ? lc : rc;
+      if (!in_contact) {                                // filterFoot (:1238-1285)
+        s.filt_yaw[i] = s.filt_yaw[i] * real(0.5) + a[16 + i] * (real(1.0) - real(0.5));
+        V3<real> g = yawR(fx, fy, V3<real>{a[2 * i], a[2 * i + 1], real(0)}) + origin;
+        sds_4steps(s.ballx[2 * i], s.ballv[2 * i], g.x, K0, K1);
+        sds_4steps(s.ballx[2 * i + 1], s.ballv[2 * i + 1], g.y, K0, K1);
+        s.foot[i] = {s.ballx[2 * i], s.ballx[2 * i + 1], real(0)};
+        real sa, ca;
+        num<real>::sincos(s.filt_yaw[i], &sa, &ca);
+        s.yc[i] = fx * ca - fy * sa; s.ys[i] = fy * ca + fx * sa;     // ffSRB_ori @ Rz(filter yaw)
+      } else {                                          // updateFilter (:1289-1299): rows 0 of both matrices
+        real v1x = s.yc[i], v1y = -s.ys[i], v2x = fx, v2y = -fy;
+        real n1 = num<real>::sqrt(v1x * v1x + v1y * v1y), n2 = num<real>::sqrt(v2x * v2x + v2y * v2y);
+        v1x /= n1; v1y /= n1; v2x /= n2; v2y /= n2;
+        s.filt_yaw[i] = num<real>::atan2(v1x * v2y - v1y * v2x, v1x * v2x + v1y * v2y);
+        s.ballv[2 * i] = real(0); s.ballv[2 * i + 1] = real(0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      bool in_contact = i == 0 ? lc : rc;
+      if (!in_contact) {
+        s.foot[i] = yawR(fx, fy, V3<real>{a[2 * i], a[2 * i + 1], real(0)}) + origin;
+        real sa, ca;
+        num<real>::sincos(a[16 + i], &sa, &ca);
+        s.yc[i] = fx * ca - fy * sa; s.ys[i] = fy * ca + fx * sa;
+      }
+    }
+  }
+  const int contact_mask = (lc ? 1 : 0) | (rc ? 2 : 0);
+
+  // ---- 4 physics sub-steps (:382-450)
+  real Mdiag[6] = {P.mass + P.armature, P.mass + P.armature, P.mass + P.armature,
+                   P.inertia[0] + P.armature, P.inertia[1] + P.armature, P.inertia[2] + P.armature};
+  real Minv[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) Minv[i] = real(1) / Mdiag[i];
+  real nu[6] = {0, 0, 0, 0, 0, 0};
+  bool warm = false;
+  double* dbg = (A.dbg != nullptr && active) ? A.dbg + (size_t)e * DBG_W : nullptr;
+
+  for (int sub = 0; sub < P.nsub; sub++) {
+    // mj_step1: kinematics + bias
+    const M3<real> R = quat2mat_normalized(s.quat);
+    s.qlag = s.quat;
+    V3<real> Iw = {P.inertia[0] * s.vang.x, P.inertia[1] * s.vang.y, P.inertia[2] * s.vang.z};
+    V3<real> bw = cross(s.vang, Iw);
+    real bias[6] = {real(0), real(0), P.mass * P.grav, bw.x, bw.y, bw.z};
+    // update_impulse (:191-206)
+    real xf[3] = {0, 0, 0};
+    if (P.use_impulse) {
+      bool trig = P.impulse_trigger_at_end ? (s.fcount % P.impulse_interval == P.impulse_interval - 1)
+                                           : (s.fcount % P.impulse_interval == 0);
+      if (trig) s.impulse = P.impulse_duration;
+      if (s.impulse > 0) { s.impulse -= 1; xf[0] = P.impulse_force[0]; xf[1] = P.impulse_force[1]; xf[2] = P.impulse_force[2]; }
+      s.fcount += 1;
+    }
+    real qfrc[6] = {0, 0, 0, 0, 0, 0};
+    if (__any_sync(0xffffffffu, contact_mask != 0)) {
+      // desired acceleration (viewer.py:534-538)
+      real pfx, pfy;
+      yaw_frame(R, &pfx, &pfy);
+      V3<real> v_tw, w_tw;
+      log_se3(matmulTN(R, R_hat), mulT(R, p_hat - s.pos), &v_tw, &w_tw);
+      V3<real> vw = mul(R, v_tw);
+      real y[6];
+      y[0] = P.kp * vw.x + P.kd * (tv_lin.x - s.vlin.x) + Minv[0] * bias[0];
+      y[1] = P.kp * vw.y + P.kd * (tv_lin.y - s.vlin.y) + Minv[1] * bias[1];
+      y[2] = P.kp * vw.z + P.kd * (tv_lin.z - s.vlin.z) + Minv[2] * bias[2];
+      y[3] = P.kp * w_tw.x + P.kd * (tv_ang.x - s.vang.x) + Minv[3] * bias[3];
+      y[4] = P.kp * w_tw.y + P.kd * (tv_ang.y - s.vang.y) + Minv[4] * bias[4];
+      y[5] = P.kp * w_tw.z + P.kd * (tv_ang.z - s.vang.z) + Minv[5] * bias[5];
+      QP<real, G> qp;
+      qp.build(lane, R, s.pos, s.foot, s.yc, s.ys, contact_mask, pfx, pfy, P.mu_b, Minv);
+      if (!warm) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = -y[i];
+      }
+      real t[QP<real, G>::NC];
+      int iters = qp.solve(lane, y, P.w_lambda, nu, t);
+      warm = true;
+      const real invw = real(1) / P.w_lambda;
+      bool clamped = false;
+      if (P.use_clamp) {
+        // per-foot force sums and the 1e4 N clamp (:402-443, Q3)
+        real FL[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < QP<real, G>::NC; k++) {
+          int c = lane + k * G;
+          bool left = ((c >> 2) & 1) == 0;
+          real lam = (t[k] < 0 ? -t[k] : real(0)) * invw;
+          real m = left ? lam : real(0);
+          FL[0] += m * qp.a[k][0] * Mdiag[0]; FL[1] += m * qp.a[k][1] * Mdiag[1]; FL[2] += m * qp.a[k][2] * Mdiag[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) FL[i] = gsum<G>(FL[i]);
+        real FT[3] = {Mdiag[0] * (nu[0] + y[0]), Mdiag[1] * (nu[1] + y[1]), Mdiag[2] * (nu[2] + y[2])};
+        real nL = num<real>::sqrt(FL[0] * FL[0] + FL[1] * FL[1] + FL[2] * FL[2]);
+        real nR = num<real>::sqrt((FT[0] - FL[0]) * (FT[0] - FL[0]) + (FT[1] - FL[1]) * (FT[1] - FL[1]) + (FT[2] - FL[2]) * (FT[2] - FL[2]));
+        clamped = (nL > P.force_thr) || (nR > P.force_thr);
+        if (__any_sync(0xffffffffu, clamped)) {
+          real sL = nL > P.force_thr ? P.force_thr / nL : real(1), sR = nR > P.force_thr ? P.force_thr / nR : real(1);
+          real W[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < QP<real, G>::NC; k++) {
+            int c = lane + k * G;
+            int site = ((c >> 2) & 1) * 5 + (c >> 3);
+            real lam = (t[k] < 0 ? -t[k] : real(0)) * invw * (site > 5 ? sR : sL);
+#pragma unroll
+            for (int i = 0; i < 6; i++) W[i] += lam * qp.a[k][i] * Mdiag[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) W[i] = gsum<G>(W[i]);
+          if (clamped) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) qfrc[i] = W[i];
+          }
+        }
+      }
+      if (!clamped && contact_mask != 0) {
+        // sum_i J_i^T f_i = C lam = M (nu + y) at the optimum
+#pragma unroll
+        for (int i = 0; i < 6; i++) qfrc[i] = Mdiag[i] * (nu[i] + y[i]);
+      }
+      if (dbg != nullptr && contact_mask != 0) {
+        double* d = dbg + sub * DBG_SUB;
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) { d[i] = (double)(nu[i] + y[i] - Minv[i] * bias[i]); d[6 + i] = (double)nu[i]; d[12 + i] = (double)qfrc[i]; }
+          d[18] = (double)iters;
+        }
+#pragma unroll
+        for (int k = 0; k < QP<real, G>::NC; k++) {
+          int c = lane + k * G;
+          if (c < 40) {
+            int site = ((c >> 2) & 1) * 5 + (c >> 3);
+            d[24 + site * 4 + (c & 3)] = (double)((t[k] < 0 ? -t[k] : real(0)) * invw);
+          }
+        }
+      }
+    }
+    // mj_step2: acceleration + semi-implicit Euler with implicit joint damping
+    real xfq[6] = {xf[0], xf[1], xf[2], real(0), real(0), real(0)};
+    real qv[6] = {s.vlin.x, s.vlin.y, s.vlin.z, s.vang.x, s.vang.y, s.vang.z};
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      real f = (-P.damping * qv[i]) - bias[i] + qfrc[i] + xfq[i];
+      qv[i] += P.h * (f / (Mdiag[i] + P.h * P.damping));
+    }
+    s.vlin = {qv[0], qv[1], qv[2]};
+    s.vang = {qv[3], qv[4], qv[5]};
+    s.pos = {s.pos.x + P.h * s.vlin.x, s.pos.y + P.h * s.vlin.y, s.pos.z + P.h * s.vlin.z};
+    s.quat = quat_integrate(s.quat, s.vang, P.h);
+  }
+
+  // ---- history push (:453-474): entry frame+1 = (qpos[:3], stale xmat)
+  if (active && lane == 0) {
+    real* h = hist_env + (size_t)((s.frame + 1) & (HIST_SLOTS - 1)) * HIST_W;
+    h[0] = s.pos.x; h[1] = s.pos.y; h[2] = s.pos.z; h[3] = s.qlag.w; h[4] = s.qlag.x; h[5] = s.qlag.y; h[6] = s.qlag.z;
+  }
+
+  // ---- obs / reward / done (:477-494; training variant takes the obs after the frame increment)
+  float* obs = A.obs + (size_t)e * OBS_W;
+  if (!P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active);
+  float info[8];
+  real r = compute_reward(s, cd, hist_env, pred_contact, P, info);
+  bool done = compute_done(s, cd, P);
+  s.frame += 1;
+  if (P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active);
+  s.ep_ret += r;
+  if (active && lane == 0) {
+    A.rew[e] = (float)r;
+    A.done[e] = done ? 1 : 0;
+    if (A.rinfo != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) A.rinfo[(size_t)e * RINFO_W + i] = info[i];
+    }
+  }
+  // ---- fused auto-reset (what SB3's VecEnv does after a terminal step)
+  if (A.auto_reset && __any_sync(0xffffffffu, done)) {
+    __syncwarp();                                        // obs row of this env was written by sibling lanes
+    if (done && active && A.term_obs != nullptr) {
+      float* to = A.term_obs + (size_t)e * OBS_W;
+      for (int i = lane; i < OBS_W; i += G) to[i] = obs[i];
+    }
+    __syncwarp();                                        // ... and is overwritten by the reset observation below
+    if (done) {
+      if (active && lane == 0 && A.ep_stats != nullptr) {
+        atomicAdd(A.ep_stats + 0, (double)s.ep_ret);
+        atomicAdd(A.ep_stats + 1, (double)s.frame);
+        atomicAdd(A.ep_stats + 2, 1.0);
+      }
+      double plan[9];
+      if (A.reset_plan != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) plan[i] = A.reset_plan[(size_t)e * 9 + i];
+      } else {
+        draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan);
+      }
+      EnvState<real> ns = s;
+      real h0[HIST_W];
+      apply_reset(ns, A.clips, A.nclips, plan, h0);
+      s = ns;
+      if (active && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < HIST_W; i++) hist_env[i] = h0[i];
+      }
+      const ClipDesc<real> ncd = A.clips[s.clip];
+      write_obs<real, G>(s, ncd, obs, lane, active);
+    }
+  }
+  if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// explicit / random reset kernel: one thread per environment
+template <typename real> __global__ void srb_reset_kernel(const ResetArgs<real> A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.count) return;
+  int e = A.idx ? A.idx[i] : i;
+  if (e < 0 || e >= A.N) return;
+  EnvState<real> s;
+  load_state(s, A.st, A.ist, A.Npad, e);
+  double plan[9];
+  if (A.plan != nullptr) {
+    for (int k = 0; k < 9; k++) plan[k] = A.plan[(size_t)i * 9 + k];
+  } else {
+    draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan);
+  }
+  real* hist_env = A.hist + (size_t)e * HIST_SLOTS * HIST_W;
+  apply_reset(s, A.clips, A.nclips, plan, hist_env);
+  store_state(s, A.st, A.ist, A.Npad, e);
+  if (A.obs != nullptr) {
+    const ClipDesc<real> cd = A.clips[s.clip];
+    write_obs<real, 1>(s, cd, A.obs + (size_t)e * OBS_W, 0, true);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// look-ahead feature precompute: 25 floats per reference frame (get_obs_window :1096-1161), fp64.
+__global__ void srb_clip_features_kernel(const double* __restrict__ frames, int nframes, float* __restrict__ feat) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  const double* fr = frames + (size_t)f * CLIP_W;
+  M3<double> R;
+  for (int i = 0; i < 9; i++) R.m[i] = fr[3 + i];
+  V3<double> pos = {fr[0], fr[1], fr[2]};
+  double fx, fy;
+  yaw_frame(R, &fx, &fy);
+  float* o = feat + (size_t)f * FEAT_W;
+  o[0] = (float)pos.z;
+  o[1] = (float)(fx * R.m[0] + fy * R.m[3]); o[2] = (float)(-fy * R.m[0] + fx * R.m[3]); o[3] = (float)R.m[6];
+  o[4] = (float)(fx * R.m[1] + fy * R.m[4]); o[5] = (float)(-fy * R.m[1] + fx * R.m[4]); o[6] = (float)R.m[7];
+  V3<double> vl = yawT(fx, fy, V3<double>{fr[12], fr[13], fr[14]});
+  V3<double> va = yawT(fx, fy, mul(R, V3<double>{fr[15], fr[16], fr[17]}));
+  o[7] = (float)vl.x; o[8] = (float)vl.y; o[9] = (float)vl.z;
+  o[10] = (float)va.x; o[11] = (float)va.y; o[12] = (float)va.z;
+  int c = 0;
+  for (int i = 0; i < 2; i++) {
+    V3<double> fp = {fr[18 + 3 * i], fr[19 + 3 * i], 0.0};
+    if (fr[20 + 3 * i] == 0.0) c |= (1 << i);
+    V3<double> l = yawT(fx, fy, fp - pos);
+    double yc = fr[24 + 2 * i], ys = fr[25 + 2 * i];
+    double m00 = fx * yc + fy * ys, m10 = -fy * yc + fx * ys;
+    o[13 + 4 * i] = (float)l.x; o[14 + 4 * i] = (float)l.y; o[15 + 4 * i] = (float)l.z; o[16 + 4 * i] = (float)atan2(m10, m00);
+  }
+  o[21] = c == 0 ? 1.f : 0.f; o[22] = c == 1 ? 1.f : 0.f; o[23] = c == 2 ? 1.f : 0.f; o[24] = c == 3 ? 1.f : 0.f;
+}
+
+}  // namespace srb
