@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- SRB env-steps/s of the batched SRBTrack step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA step through the C-ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU oracle port of the
+                                                           reference's SRBEnv.step on all host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- SRBEnv5_mocap_list_window flat ground,
+4096 environments per GPU (weak scaling: N GPUs step N*4096 environments, no data-path collective;
+the per-rollout NCCL all-reduce of observation-normaliser statistics is inside the timed region).
+One "step" = one SRBEnv.step of every environment = 4 physics sub-steps + obs/reward/done (+ fused
+auto-reset).  Actions come from the device-side reference-tracking controller + N(0, 0.1^2) noise and
+are produced outside the timed events, like a policy would.
+
+Timing: CUDA events on the launching stream around every step launch; L2 is flushed (256 MiB write)
+between steps because one step's working set (~6 MB) is far below the 126 MB L2; max over ranks.
+"""
+import argparse
+import json
+import os
+
+# one BLAS/OpenMP thread per process, as the reference's trainer sets (walk_SRBTrack2025_train_delta.py:6-10);
+# must happen before numpy is imported.  The CPU arm parallelises over forked workers instead.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+ENVS_PER_GPU = 4096
+SIGMA = 0.1
+ROLLOUT = 128                 # steps between observation-statistics all-reduces (one per PPO rollout chunk)
+BYTES_PER_STEP = {32: 1008, 64: 1320}   # algorithmic HBM bytes per env-step, SURVEY.md 8(d) / DESIGN.md
+METRIC = "SRB env-steps/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("SRB_BENCH_PRECISION", "32")), choices=[32, 64])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--variant", default="test", choices=["test", "training"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(float(q[0]) / float(q[1]))))
+    except Exception:
+        pass
+    return n
+
+
+def _oracle_worker(args):
+    """One host core: `n_env` oracle environments; `warmup` passes, then `steps` passes (or until
+    `budget_s` seconds when steps is None).  Returns (env-steps, seconds)."""
+    wid, n_env, warmup, steps, budget_s, variant = args
+    import helpers
+    from oracle.srb_env import OracleSRBEnv
+    rng = np.random.default_rng(1000 + wid)
+    clips = helpers.fresh_clips()
+    envs = []
+    for _ in range(n_env):
+        e = OracleSRBEnv(helpers.fresh_clips(), variant)
+        helpers.oracle_reset(e, helpers.random_plan(rng, clips))
+        envs.append(e)
+
+    def one_pass():
+        for e in envs:
+            a = helpers.tracking_action(e, rng, SIGMA)
+            _, _, done, _, _ = e.step(a)
+            if done:
+                helpers.oracle_reset(e, helpers.random_plan(rng, clips))
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    n = 0
+    while (steps is not None and n < steps) or (steps is None and time.perf_counter() - t0 < budget_s):
+        one_pass()
+        n += 1
+    return n_env * n, time.perf_counter() - t0
+
+
+def cpu_oracle_throughput(cores, n_env_per_core, warmup, steps, variant, budget_s=None):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_oracle_worker, [(w, n_env_per_core, warmup, steps, budget_s, variant) for w in range(cores)])
+    total = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    return total / tmax, total, tmax
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = usable_cores()
+    # calibrate one pass (1 env per core), then size the per-step sample so that warmup+steps passes take ~40 s
+    _, _, t1 = cpu_oracle_throughput(cores, 1, 1, 2, args.variant)
+    per_pass = max(t1 / 2, 1e-3)
+    per_core = int(max(1, min(16, 40.0 / (per_pass * max(args.steps + args.warmup, 1)))))
+    value, total, tmax = cpu_oracle_throughput(cores, per_core, args.warmup, args.steps, args.variant)
+    sample = (f"{cores} forked single-thread workers x {per_core} envs x {args.steps} steps of the oracle port of SRBEnv.step "
+              f"(variant {args.variant}, clips stand1+aiming_show, tracking actions + N(0,{SIGMA}^2)); {total} env-steps in {tmax:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), bounded sample of {cores * per_core} envs per step on {cores} host cores"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import helpers
+    from ipcdnnwalk_b200 import SRBVecEnv, OBS_DIM, ACT_DIM, RINFO_DIM
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N = args.envs
+    clips = helpers.fresh_clips()
+    env = SRBVecEnv(clips, N, variant=args.variant, precision=args.precision, lanes_per_env=args.lanes, auto_reset=True,
+                    device=local_rank, seed=1234 + rank)
+    env.reset()
+    act = torch.zeros(N, ACT_DIM, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    acc = torch.zeros(1 + 2 * OBS_DIM, dtype=torch.float64, device=dev)
+    K, W = args.steps, args.warmup
+
+    def one_step(k, timed):
+        env.tracking_action(act, sigma=SIGMA, seed=99 + rank, step=k)      # the "policy": outside the timed events
+        flush.fill_(k & 0xFF)                                               # L2 flush between steps
+        ev = None
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        env.step(act)
+        if timed:
+            ev[1].record()
+        cev = None
+        if (k + 1) % ROLLOUT == 0:                                          # the path's one collective
+            if timed:
+                cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                cev[0].record()
+            env.obs_stats(acc)
+            if dist is not None:
+                dist.all_reduce(acc)
+            if timed:
+                cev[1].record()
+        return ev, cev
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for k in range(W):
+        one_step(k, False)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = env.launch_count()
+    t_wall0 = time.perf_counter()
+    evs, cevs = [], []
+    for k in range(W, W + K):
+        ev, cev = one_step(k, True)
+        evs.append(ev)
+        if cev is not None:
+            cevs.append(cev)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    coll_ms = float(sum(a.elapsed_time(b) for a, b in cevs))
+    total_ms = float(step_ms.sum()) + coll_ms
+    n_tracking = K
+    step_launches = env.launch_count() - launches0 - n_tracking - len(cevs)
+
+    # ---- end to end through the host-buffer C-ABI call (srb_step_host): pinned host actions in, obs/rew/done out
+    e2e_ms = None
+    Ke = min(K, 200)
+    if not args.no_e2e:
+        pin = env.pinned()
+        for k in range(3):
+            env.step_host()
+        tt = 0.0
+        for k in range(Ke):
+            env.tracking_action(act, sigma=SIGMA, seed=7 + rank, step=10_000 + k)
+            pin["act"][...] = act.cpu().numpy()          # the policy's output lands in pinned host memory (untimed)
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            env.step_host()                               # H2D actions + kernel + D2H obs/rew/done/info + sync
+            tt += time.perf_counter() - t0
+        e2e_ms = 1e3 * tt
+    clocks = sampler.stop() if rank == 0 else None     # sampled from warm-up through the end-to-end loop
+    # ---- max over ranks
+    tvec = torch.tensor([total_ms, e2e_ms if e2e_ms is not None else 0.0, float(np.median(step_ms))], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max, med_ms_max = (float(x) for x in tvec.cpu())
+    ep = env.episode_stats()
+
+    if rank == 0:
+        peaks = {}
+        src = "measured"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak = float(peaks["hbm_gbs"])
+        except Exception:
+            peak, src = 6650.0, "fallback"
+        bytes_step = BYTES_PER_STEP[args.precision] * N
+        kern_ms = float(step_ms.mean())
+        achieved = bytes_step / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj.get(f"fp{args.precision}_n{N}")
+            except Exception:
+                traffic = None
+        value = world * N * K / (total_ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+            "config": {"workload": f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), {N} envs per GPU x {world} GPU",
+                       "envs_per_gpu": N, "clips": "stand1 + aiming_show (shipped clips; walk/run clips are absent from the reference mount)",
+                       "actions": f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done",
+                       "l2": "flushed between steps (256 MiB write); per-step CUDA events on the launching stream",
+                       "collective": f"obs-normaliser statistics kernel + NCCL all-reduce every {ROLLOUT} steps, inside the timed total",
+                       "lanes_per_env": env_lanes(args), "median_step_ms": med_ms_max, "wall_s_timed_loop": t_wall,
+                       "episodes_finished": int(ep[2]), "mean_episode_len": float(ep[1] / max(ep[2], 1))},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_env_step": BYTES_PER_STEP[args.precision],
+                         "kernel": "srb_step_kernel", "avg_launch_ms": kern_ms},
+            "clocks": clocks,
+            "gpu_launches": int(step_launches),
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": world * N * Ke / (e2e_ms_max * 1e-3), "unit": "env-steps/s",
+                           "h2d_bytes_per_step": N * ACT_DIM * 4, "d2h_bytes_per_step": N * (OBS_DIM * 4 + 4 + 1 + RINFO_DIM * 4),
+                           "steps": Ke, "api": "srb_step_host (pinned host buffers, H2D + kernel + D2H + sync per step)"}
+        if not args.no_cpu_baseline:
+            cores = usable_cores()
+            v, total, tmax = cpu_oracle_throughput(cores, 1, 1, None, args.variant, budget_s=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cores} forked single-thread workers x 1 env, oracle port of SRBEnv.step for 15 s ({total} env-steps in {tmax:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def env_lanes(args):
+    return args.lanes if args.lanes else 8
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "RANK" not in os.environ:      # convenience: launch the ranks ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

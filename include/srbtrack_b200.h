@@ -94,6 +94,10 @@ int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* str
 /* Episode statistics accumulated by auto-reset: out[3] = sum of returns, sum of lengths, count. */
 int srb_episode_stats(srb_env* env, double out[3], int32_t clear);
 
+/* Benchmark / roll-out driver (not in the reference; stands in for the policy, walk_SRBTrack2025.py:424):
+ * act_dev[N][22] = reference-tracking action for the next reference frame + N(0, sigma^2) noise. */
+int srb_tracking_action(srb_env* env, float sigma, uint64_t seed, uint32_t step, float* act_dev, void* stream);
+
 /* Number of kernels this handle has launched so far (for launch accounting). */
 int64_t srb_launch_count(srb_env* env);
 

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "srb_set_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "srb_obs_stats": (C.c_int, [_P, _P, _P, _P]),
     "srb_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
+    "srb_tracking_action": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_uint32, _P, _P]),
     "srb_launch_count": (C.c_int64, [_P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

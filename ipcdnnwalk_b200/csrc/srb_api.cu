@@ -401,4 +401,18 @@ extern "C" int srb_episode_stats(srb_env* h, double out[3], int32_t clear) {
   return 0;
 }
 
+extern "C" int srb_tracking_action(srb_env* h, float sigma, uint64_t seed, uint32_t step, float* act_dev, void* stream) {
+  if (!h || !act_dev) return fail(-1, "srb_tracking_action: null argument");
+  if (h->nclips == 0) return fail(-1, "srb_tracking_action: no clip uploaded");
+  CK(cudaSetDevice(h->cfg.device));
+  int blocks = (h->N + 127) / 128;
+  if (h->cfg.precision == 64)
+    srb_tracking_action_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const double*)h->st, h->ist, (const ClipDesc<double>*)h->clips_dev, sigma, seed, step, act_dev);
+  else
+    srb_tracking_action_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const float*)h->st, h->ist, (const ClipDesc<float>*)h->clips_dev, sigma, seed, step, act_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int64_t srb_launch_count(srb_env* h) { return h ? h->launches : 0; }

@@ -343,7 +343,13 @@ template <typename real, int G> struct QP {
       unsigned bal = __ballot_sync(0xffffffffu, same);
       same = (bal & gmask) == gmask;
       real phn = phi(nn, y, tn, inv2w);
-      bool accept = same || (phn < ph);
+      // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker)
+      real dmax = 0, nmax = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) { dmax = num<real>::fmax(dmax, num<real>::abs(nn[i] - nu[i])); nmax = num<real>::fmax(nmax, num<real>::abs(nn[i])); }
+      same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
+      const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + num<real>::abs(ph));   // phi resolution
+      bool accept = same || (phn < ph + ph_tol);
       bool need_bt = !done && !accept;
       real alpha = real(0.5);
       real nt[6], tt[NC];
@@ -353,7 +359,7 @@ template <typename real, int G> struct QP {
         for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
         tvals(nt, tt);
         pht = phi(nt, y, tt, inv2w);
-        if (need_bt && (pht < ph || alpha < real(1e-6))) {
+        if (need_bt && (pht < ph + ph_tol || alpha < real(1e-3))) {
 #pragma unroll
           for (int i = 0; i < 6; i++) nn[i] = nt[i];
 #pragma unroll
@@ -873,6 +879,61 @@ template <typename real> __global__ void srb_reset_kernel(const ResetArgs<real> 
   if (A.obs != nullptr) {
     const ClipDesc<real> cd = A.clips[s.clip];
     write_obs<real, 1>(s, cd, A.obs + (size_t)e * OBS_W, 0, true);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Reference-tracking controller used to drive benchmarks and roll-out tests on the device: the action
+// that asks the QP to reach the next reference frame (feet, yaw and contact from the clip, pose and
+// velocity targets = next reference frame expressed in the current body frame) plus N(0, sigma^2) noise.
+// Not part of the reference; it plays the role of the policy (walk_SRBTrack2025.py:424 `ppo predict`).
+template <typename real>
+__global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restrict__ st, const int* __restrict__ ist,
+                                           const ClipDesc<real>* __restrict__ clips, float sigma, unsigned long long seed,
+                                           unsigned int step, float* __restrict__ act) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  EnvState<real> s;
+  load_state(s, st, ist, Npad, e);
+  const ClipDesc<real> cd = clips[s.clip];
+  int f = min(s.frame + s.rif + 1, cd.nframes - 1);
+  const real* fr = cd.frames + (size_t)f * CLIP_W;
+  M3<real> R = quat2mat_normalized(s.qlag);
+  real fx, fy;
+  yaw_frame(R, &fx, &fy);
+  real a[ACT_W];
+#pragma unroll
+  for (int i = 0; i < ACT_W; i++) a[i] = real(0);
+  V3<real> origin = {s.pos.x, s.pos.y, real(0)};
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    V3<real> l = yawT(fx, fy, V3<real>{fr[18 + 3 * i], fr[19 + 3 * i], real(0)} - origin);
+    a[2 * i] = l.x; a[2 * i + 1] = l.y;
+    real yc = fr[24 + 2 * i], ys = fr[25 + 2 * i];
+    a[16 + i] = num<real>::atan2(-fy * yc + fx * ys, fx * yc + fy * ys);
+  }
+  M3<real> Rr;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rr.m[i] = fr[3 + i];
+  V3<real> vl = mulT(R, V3<real>{fr[12], fr[13], fr[14]});
+  a[4] = vl.x; a[5] = vl.y; a[6] = vl.z; a[7] = fr[15]; a[8] = fr[16]; a[9] = fr[17];
+  V3<real> v_tw, w_tw;
+  V3<real> dp = mulT(R, V3<real>{fr[0], fr[1], fr[2]} - s.pos);
+  log_se3(matmulTN(R, Rr), dp, &v_tw, &w_tw);
+  a[10] = dp.x; a[11] = dp.y; a[12] = dp.z; a[13] = w_tw.x; a[14] = w_tw.y; a[15] = w_tw.z;
+  int c = (fr[20] == real(0) ? 1 : 0) + (fr[23] == real(0) ? 2 : 0);
+  a[18 + c] = real(1);
+  float* o = act + (size_t)e * ACT_W;
+  for (int i = 0; i < ACT_W; i += 2) {
+    uint32_t cnt[4] = {(uint32_t)e, step, (uint32_t)i, 0xAC7u};
+    philox4x32(cnt, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float u1 = 1.0f - (float)(cnt[0] >> 8) * (1.0f / 16777216.0f), u2 = (float)(cnt[1] >> 8) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.2831853f * u2, &sn, &cs);
+    o[i] = (float)a[i] + sigma * r * cs;
+    o[i + 1] = (float)a[i + 1] + sigma * r * sn;
   }
 }
 

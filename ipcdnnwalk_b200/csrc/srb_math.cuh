@@ -20,6 +20,7 @@ template <> struct num<float> {
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float tiny() { return 1e-4f; }   // series threshold for small angles
   static __device__ __forceinline__ float series_below() { return 0.3f; }
+  static __device__ __forceinline__ float eps_conv() { return 2e-6f; }
 };
 template <> struct num<double> {
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
@@ -34,6 +35,7 @@ template <> struct num<double> {
   static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
   static __device__ __forceinline__ double tiny() { return 1e-6; }
   static __device__ __forceinline__ double series_below() { return 0.02; }
+  static __device__ __forceinline__ double eps_conv() { return 1e-13; }
 };
 
 template <typename T> struct V3 { T x, y, z; };

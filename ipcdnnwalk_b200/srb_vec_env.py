@@ -232,5 +232,10 @@ class SRBVecEnv:
         check(self.lib.srb_episode_stats(self._h, _ptr(out), int(clear)))
         return out
 
+    def tracking_action(self, out, sigma=0.1, seed=1234, step=0):
+        """out (float32 [N,22], device) = reference-tracking action + N(0, sigma^2) noise (bench / roll-out driver)."""
+        check(self.lib.srb_tracking_action(self._h, float(sigma), int(seed), int(step), _ptr(out), self._stream()))
+        return out
+
     def launch_count(self):
         return int(self.lib.srb_launch_count(self._h))

@@ -1,0 +1,54 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol the
+public header declares; the host layer fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+import helpers
+
+HEADER = os.path.join(helpers.ROOT, "include", "srbtrack_b200.h")
+
+
+def _declared():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(srb_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(built_lib):
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in include/srbtrack_b200.h but not exported"
+
+
+def test_binding_table_matches_header(built_lib):
+    from ipcdnnwalk_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == _declared()
+
+
+def test_state_dims_and_errors_without_gpu(built_lib):
+    import ctypes as C
+    d = [C.c_int32() for _ in range(4)]
+    assert built_lib.srb_state_dims(*[C.byref(x) for x in d]) == 0
+    assert [x.value for x in d] == [38, 7, 32, 8]
+    import torch
+    if not torch.cuda.is_available():
+        from ipcdnnwalk_b200 import _lib
+        cfg = _lib.SrbConfig(16, 0, 64, 8, 1, 0, 0)
+        h = C.c_void_p()
+        rc = built_lib.srb_create(C.byref(cfg), C.byref(h))
+        assert rc != 0 and b"no CPU fallback" in built_lib.srb_last_error()
+        from ipcdnnwalk_b200 import SRBVecEnv
+        with pytest.raises(RuntimeError):
+            SRBVecEnv(helpers.fresh_clips(), 4)
+
+
+def test_bad_config_rejected(built_lib):
+    import ctypes as C
+    from ipcdnnwalk_b200 import _lib
+    h = C.c_void_p()
+    for cfg in (_lib.SrbConfig(0, 0, 64, 8, 1, 0, 0), _lib.SrbConfig(4, 0, 16, 8, 1, 0, 0), _lib.SrbConfig(4, 0, 64, 3, 1, 0, 0),
+                _lib.SrbConfig(4, 7, 64, 8, 1, 0, 0)):
+        assert built_lib.srb_create(C.byref(cfg), C.byref(h)) != 0
