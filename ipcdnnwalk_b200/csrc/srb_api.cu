@@ -51,6 +51,10 @@ template <typename real> static Params<real> convert_params(const Params<double>
   q.use_filter = p.use_filter; q.use_clamp = p.use_clamp; q.use_impulse = p.use_impulse; q.obs_after_inc = p.obs_after_inc;
   q.impulse_interval = p.impulse_interval; q.impulse_duration = p.impulse_duration; q.impulse_trigger_at_end = p.impulse_trigger_at_end;
   q.max_frame = p.max_frame;
+  q.inv_w_lambda = (real)(1.0 / p.w_lambda);
+  const double Md[6] = {p.mass + p.armature, p.mass + p.armature, p.mass + p.armature,
+                        p.inertia[0] + p.armature, p.inertia[1] + p.armature, p.inertia[2] + p.armature};
+  for (int i = 0; i < 6; i++) { q.inv_M[i] = (real)(1.0 / Md[i]); q.inv_Mh[i] = (real)(1.0 / (Md[i] + p.h * p.damping)); }
   return q;
 }
 

@@ -22,6 +22,7 @@ template <typename real> struct EnvState {
   V3<real> foot[2]; real yc[2], ys[2];
   real filt_yaw[2]; real ballx[4]; real ballv[4];
   real ep_ret;
+  real nu[6];        // QP dual from the last sub-step (warm start only; the optimum is unique)
   int flags, frame, rif, clip, fcount, impulse, episode;
 };
 
@@ -40,6 +41,8 @@ template <typename real> __device__ __forceinline__ void load_state(EnvState<rea
 #pragma unroll
   for (int i = 0; i < 4; i++) { s.ballx[i] = LD(F_BALLX + i); s.ballv[i] = LD(F_BALLV + i); }
   s.ep_ret = LD(F_EPRET);
+#pragma unroll
+  for (int i = 0; i < 6; i++) s.nu[i] = LD(F_NU + i);
 #undef LD
 #define LDI(f) ist[(size_t)(f) * Npad + e]
   s.flags = LDI(I_FLAGS); s.frame = LDI(I_FRAME); s.rif = LDI(I_RIF); s.clip = LDI(I_CLIP);
@@ -62,6 +65,8 @@ template <typename real> __device__ __forceinline__ void store_state(const EnvSt
 #pragma unroll
   for (int i = 0; i < 4; i++) { ST(F_BALLX + i, s.ballx[i]); ST(F_BALLV + i, s.ballv[i]); }
   ST(F_EPRET, s.ep_ret);
+#pragma unroll
+  for (int i = 0; i < 6; i++) ST(F_NU + i, s.nu[i]);
 #undef ST
 #define STI(f, v) ist[(size_t)(f) * Npad + e] = (v)
   STI(I_FLAGS, s.flags); STI(I_FRAME, s.frame); STI(I_RIF, s.rif); STI(I_CLIP, s.clip);
@@ -89,37 +94,37 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit unif
 // plan = clip, start frame, uniform(-.05,.05)^3 velocity noise, small random quaternion.
 template <typename real>
 __device__ inline void draw_reset_plan(unsigned long long seed, int env, int episode, const ClipDesc<real>* clips, int nclips, double plan[9]) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB0u, 0u};
-  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  philox4x32(c, k0, k1);
   uint32_t d[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB1u, 0u};
-  philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+  philox4x32(d, k0, k1);
   uint32_t g[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB2u, 0u};
-  philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
-  int clip = (int)(u01(c[0], c[1]) * nclips);                       // random.randrange(n)
-  if (clip >= nclips) clip = nclips - 1;
+  philox4x32(g, k0, k1);
+  const float U32 = 2.3283064365386963e-10f;                         // 2^-32
+  int clip = min((int)(__umulhi(c[0], (uint32_t)nclips)), nclips - 1);   // random.randrange(n)
   int cyc = clips[clip].cycle_length;
   int hi = max(cyc - 2, 512);                                        // random.randint(0, hi) inclusive
-  int frame = (int)(u01(c[2], c[3]) * (hi + 1));
-  if (frame > hi) frame = hi;
+  int frame = min((int)__umulhi(c[1], (uint32_t)(hi + 1)), hi);
   plan[0] = clip; plan[1] = frame;
-  plan[2] = (2.0 * u01(d[0], d[1]) - 1.0) * 5e-2;
-  plan[3] = (2.0 * u01(d[2], d[3]) - 1.0) * 5e-2;
-  uint32_t e[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB3u, 0u};
-  philox4x32(e, (uint32_t)seed, (uint32_t)(seed >> 32));
-  plan[4] = (2.0 * u01(e[0], e[1]) - 1.0) * 5e-2;
-  // axis ~ normalised N(0,I) (Box-Muller), angle ~ U(-.05,.05)
-  double u1 = 1.0 - u01(g[0], g[1]), u2 = u01(g[2], g[3]);
-  double r = sqrt(-2.0 * log(u1));
-  double n0 = r * cos(6.283185307179586 * u2), n1 = r * sin(6.283185307179586 * u2);
-  double u3 = 1.0 - u01(e[2], e[3]);
-  uint32_t f[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB4u, 0u};
-  philox4x32(f, (uint32_t)seed, (uint32_t)(seed >> 32));
-  double n2 = sqrt(-2.0 * log(u3)) * cos(6.283185307179586 * u01(f[0], f[1]));
-  double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
-  if (nn < 1e-300) { n0 = 1; n1 = 0; n2 = 0; nn = 1; }
-  double ang = (2.0 * u01(f[2], f[3]) - 1.0) * 5e-2;
-  double sh = sin(0.5 * ang) / nn;
-  plan[5] = cos(0.5 * ang); plan[6] = n0 * sh; plan[7] = n1 * sh; plan[8] = n2 * sh;
+  plan[2] = (double)((((float)c[2] + 0.5f) * U32 * 2.0f - 1.0f) * 5e-2f);
+  plan[3] = (double)((((float)c[3] + 0.5f) * U32 * 2.0f - 1.0f) * 5e-2f);
+  plan[4] = (double)((((float)d[0] + 0.5f) * U32 * 2.0f - 1.0f) * 5e-2f);
+  float ang = (((float)d[1] + 0.5f) * U32 * 2.0f - 1.0f) * 5e-2f;
+  // axis ~ normalised N(0,I) (Box-Muller), angle ~ U(-.05,.05)   (viewer.py:719-731)
+  float u1 = ((float)(d[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(d[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.2831853f * u2, &sn, &cs);
+  float n0 = r * cs, n1 = r * sn;
+  float u3 = ((float)(g[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = ((float)(g[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float n2 = sqrtf(-2.0f * __logf(u3)) * __cosf(6.2831853f * u4);
+  float nn = sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+  if (nn < 1e-20f) { n0 = 1.f; n1 = 0.f; n2 = 0.f; nn = 1.f; }
+  float sh, ch;
+  __sincosf(0.5f * ang, &sh, &ch);
+  sh /= nn;
+  plan[5] = (double)ch; plan[6] = (double)(n0 * sh); plan[7] = (double)(n1 * sh); plan[8] = (double)(n2 * sh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -152,11 +157,13 @@ __device__ inline void apply_reset(EnvState<real>& s, const ClipDesc<real>* clip
   s.foot[1] = {fr[21], fr[22], real(0)};
   s.yc[0] = fr[24]; s.ys[0] = fr[25]; s.yc[1] = fr[26]; s.ys[1] = fr[27];
   // legacy slices [:3] / [3:] of the 10-entry site list (Q2): right = left OR right
-  s.flags = (lc ? FLAG_L : 0) | ((lc || rc) ? FLAG_R : 0) | (cd.is_stand ? FLAG_STAND : 0);
+  s.flags = (lc ? FLAG_L : 0) | ((lc || rc) ? FLAG_R : 0) | (cd.is_stand ? FLAG_STAND : 0);   // clears FLAG_FILT / FLAG_NU
   s.filt_yaw[0] = s.filt_yaw[1] = real(0);
 #pragma unroll
   for (int i = 0; i < 4; i++) { s.ballx[i] = real(0); s.ballv[i] = real(0); }
   s.ep_ret = real(0);
+#pragma unroll
+  for (int i = 0; i < 6; i++) s.nu[i] = real(0);
   s.episode += 1;     // frame_counter / impulse persist across resets, as in the reference
   // history entry 0 (:895-911)
   real* h0 = hist_env;
@@ -192,10 +199,19 @@ __device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDes
     o[21] = c == 0 ? 1.f : 0.f; o[22] = c == 1 ? 1.f : 0.f; o[23] = c == 2 ? 1.f : 0.f; o[24] = c == 3 ? 1.f : 0.f;
   }
   if (active) {
-    int f0 = s.frame + s.rif + 1;
-    for (int i = lane; i < 5 * FEAT_W; i += G) {
-      int f = min(f0 + i / FEAT_W, cd.nframes - 1);
-      o[FEAT_W + i] = __ldg(cd.feat + (size_t)f * FEAT_W + (i % FEAT_W));
+    // 5 consecutive frame records are contiguous in the feature table (clamped only at the table end)
+    int f0 = min(s.frame + s.rif + 1, max(cd.nframes - 5, 0));
+    const float* __restrict__ src = cd.feat + (size_t)f0 * FEAT_W;
+    constexpr int PER = (5 * FEAT_W + G - 1) / G;
+    if constexpr (PER <= 32) {
+      float v[PER];
+#pragma unroll
+      for (int k = 0; k < PER; k++) { int i = lane + k * G; v[k] = (i < 5 * FEAT_W) ? __ldg(src + i) : 0.f; }
+#pragma unroll
+      for (int k = 0; k < PER; k++) { int i = lane + k * G; if (i < 5 * FEAT_W) o[FEAT_W + i] = v[k]; }
+    } else {
+#pragma unroll 5
+      for (int i = lane; i < 5 * FEAT_W; i += G) o[FEAT_W + i] = __ldg(src + i);
     }
   }
 }
@@ -213,6 +229,72 @@ template <int G> __device__ __forceinline__ double gsum(double v) {
   return v;
 }
 
+// All-reduce of the 21 lower-triangle Hessian partials over the G lanes of a group.
+// Generic: xor-shuffle butterfly (21 * log2 G shuffles + adds).
+// G == 8: staged through shared memory with 128-bit accesses -- every lane stores its 21 partials (padded row,
+// stride chosen so a quarter-warp's 16-byte chunks fall in distinct bank groups), lanes 0..5 of a group each sum
+// 4 entries over the 8 rows, the 24 sums are read back by all lanes: ~20 (fp32) / ~41 (fp64) LSU instructions
+// + 28 adds instead of 63 / 126 SHFL + 63 adds.
+template <typename real, int G> struct HReduce {
+  static constexpr int SMEM_WORDS = 1;
+  static __device__ __forceinline__ void run(real H[21], real* sm, int lane32) {
+#pragma unroll
+    for (int i = 0; i < 21; i++) H[i] = gsum<G>(H[i]);
+  }
+};
+template <> struct HReduce<float, 8> {
+  static constexpr int ROW = 28, RES = 32 * ROW, SMEM_WORDS = RES + 4 * 24;
+  static __device__ __forceinline__ void run(float H[21], float* sm, int lane32) {
+    float4* row = reinterpret_cast<float4*>(sm + lane32 * ROW);
+    row[0] = make_float4(H[0], H[1], H[2], H[3]); row[1] = make_float4(H[4], H[5], H[6], H[7]);
+    row[2] = make_float4(H[8], H[9], H[10], H[11]); row[3] = make_float4(H[12], H[13], H[14], H[15]);
+    row[4] = make_float4(H[16], H[17], H[18], H[19]); row[5] = make_float4(H[20], 0.f, 0.f, 0.f);
+    __syncwarp();
+    const int j = lane32 & 7, base = lane32 & ~7, grp = lane32 >> 3;
+    if (j < 6) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        float4 v = *reinterpret_cast<const float4*>(sm + (base + r) * ROW + 4 * j);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(sm + RES + grp * 24 + 4 * j) = acc;
+    }
+    __syncwarp();
+    const float4* res = reinterpret_cast<const float4*>(sm + RES + grp * 24);
+#pragma unroll
+    for (int q = 0; q < 5; q++) { float4 v = res[q]; H[4 * q] = v.x; H[4 * q + 1] = v.y; H[4 * q + 2] = v.z; H[4 * q + 3] = v.w; }
+    H[20] = res[5].x;
+  }
+};
+template <> struct HReduce<double, 8> {
+  static constexpr int ROW = 26, RES = 32 * ROW, SMEM_WORDS = RES + 4 * 24;
+  static __device__ __forceinline__ void run(double H[21], double* sm, int lane32) {
+    double2* row = reinterpret_cast<double2*>(sm + lane32 * ROW);
+#pragma unroll
+    for (int q = 0; q < 10; q++) row[q] = make_double2(H[2 * q], H[2 * q + 1]);
+    row[10] = make_double2(H[20], 0.0); row[11] = make_double2(0.0, 0.0);
+    __syncwarp();
+    const int j = lane32 & 7, base = lane32 & ~7, grp = lane32 >> 3;
+    if (j < 6) {
+      double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const double2* src = reinterpret_cast<const double2*>(sm + (base + r) * ROW + 4 * j);
+        double2 v0 = src[0], v1 = src[1];
+        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
+      }
+      double2* dst = reinterpret_cast<double2*>(sm + RES + grp * 24 + 4 * j);
+      dst[0] = a0; dst[1] = a1;
+    }
+    __syncwarp();
+    const double2* res = reinterpret_cast<const double2*>(sm + RES + grp * 24);
+#pragma unroll
+    for (int q = 0; q < 10; q++) { double2 v = res[q]; H[2 * q] = v.x; H[2 * q + 1] = v.y; }
+    H[20] = res[10].x;
+  }
+};
+
 // 6x6 SPD solve H x = rhs by LDL^T, fully unrolled in registers.  H: lower triangle, index i*(i+1)/2+j.
 template <typename real> __device__ __forceinline__ void ldl_solve6(const real* Hl, const real* rhs, real* x) {
   real L[6][6];      // unit lower factor
@@ -223,7 +305,7 @@ template <typename real> __device__ __forceinline__ void ldl_solve6(const real* 
     real d = Hl[j * (j + 1) / 2 + j];
 #pragma unroll
     for (int k = 0; k < j; k++) d -= L[j][k] * W[j][k];
-    dinv[j] = real(1) / d;
+    dinv[j] = num<real>::rcp(d);
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
       real v = Hl[i * (i + 1) / 2 + j];
@@ -304,10 +386,36 @@ template <typename real, int G> struct QP {
     return q + inv2w * ps;
   }
 
-  // returns number of Newton systems solved; nu in: initial guess, out: solution; t out: A^T nu
-  __device__ __forceinline__ int solve(int lane, const real y[6], real w, real nu[6], real t[NC]) {
+  // H (lower triangle, 21) = I + (1/w) sum_{k: t_k<0} a_k a_k^T, all-reduced over the group
+  __device__ __forceinline__ void hessian(const real t[NC], real invw, real H[21], real* sm) const {
+#pragma unroll
+    for (int i = 0; i < 21; i++) H[i] = 0;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      real m = t[k] < 0 ? real(1) : real(0);
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        real ai = m * a[k][i];
+#pragma unroll
+        for (int j = 0; j <= i; j++) H[i * (i + 1) / 2 + j] += ai * a[k][j];
+      }
+    }
+    HReduce<real, G>::run(H, sm, lane_id());
+#pragma unroll
+    for (int i = 0; i < 21; i++) H[i] *= invw;
+#pragma unroll
+    for (int i = 0; i < 6; i++) H[i * (i + 1) / 2 + i] += real(1);
+  }
+
+  // returns number of Newton systems solved; nu in: initial guess, out: solution; t out: A^T nu.
+  // Semismooth Newton with full steps; a step is accepted when it reproduces the active set (exact optimum of
+  // the piece), is below rounding level, or decreases the dual objective phi; otherwise it is halved until phi
+  // decreases (globally convergent; also keeps the iteration-count tail short, which matters because the
+  // environments of a warp iterate in lock-step).
+  __device__ __forceinline__ int solve(int lane, const real y[6], real inv_w, real nu[6], real t[NC], real* sm) {
+    constexpr int MAX_IT = 48;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_id() / G) * G));
-    const real invw = real(1) / w, inv2w = real(0.5) * invw;
+    const real invw = inv_w, inv2w = real(0.5) * invw;
     tvals(nu, t);
     real ph = phi(nu, y, t, inv2w);
     bool done = false;
@@ -315,25 +423,10 @@ template <typename real, int G> struct QP {
     real rhs[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) rhs[i] = -y[i];
-    for (int it = 0; it < 40; it++) {
+    for (int it = 0; it < MAX_IT; it++) {
       if (!__any_sync(0xffffffffu, !done)) break;
       real H[21];
-#pragma unroll
-      for (int i = 0; i < 21; i++) H[i] = 0;
-#pragma unroll
-      for (int k = 0; k < NC; k++) {
-        real m = t[k] < 0 ? real(1) : real(0);
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-          real ai = m * a[k][i];
-#pragma unroll
-          for (int j = 0; j <= i; j++) H[i * (i + 1) / 2 + j] += ai * a[k][j];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 21; i++) H[i] = gsum<G>(H[i]) * invw;
-#pragma unroll
-      for (int i = 0; i < 6; i++) H[i * (i + 1) / 2 + i] += real(1);
+      hessian(t, invw, H, sm);
       real nn[6], tn[NC];
       ldl_solve6(H, rhs, nn);
       tvals(nn, tn);
@@ -346,28 +439,32 @@ template <typename real, int G> struct QP {
       // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker)
       real dmax = 0, nmax = 0;
 #pragma unroll
-      for (int i = 0; i < 6; i++) { dmax = num<real>::fmax(dmax, num<real>::abs(nn[i] - nu[i])); nmax = num<real>::fmax(nmax, num<real>::abs(nn[i])); }
+      for (int i = 0; i < 6; i++) {
+        real dd = nn[i] - nu[i]; dd = dd < 0 ? -dd : dd;
+        real av = nn[i] < 0 ? -nn[i] : nn[i];
+        dmax = dd > dmax ? dd : dmax; nmax = av > nmax ? av : nmax;
+      }
       same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
-      const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + num<real>::abs(ph));   // phi resolution
-      bool accept = same || (phn < ph + ph_tol);
-      bool need_bt = !done && !accept;
-      real alpha = real(0.5);
-      real nt[6], tt[NC];
-      real pht = phn;
-      while (__any_sync(0xffffffffu, need_bt)) {          // halve the step until phi decreases
+      const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + (ph < 0 ? -ph : ph));   // phi resolution
+      bool need_bt = !done && !same && !(phn < ph + ph_tol);
+      if (__any_sync(0xffffffffu, need_bt)) {                 // rare
+        real alpha = real(0.5);
+        while (__any_sync(0xffffffffu, need_bt)) {
+          real nt[6], tt[NC];
 #pragma unroll
-        for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
-        tvals(nt, tt);
-        pht = phi(nt, y, tt, inv2w);
-        if (need_bt && (pht < ph + ph_tol || alpha < real(1e-3))) {
+          for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
+          tvals(nt, tt);
+          real pht = phi(nt, y, tt, inv2w);
+          if (need_bt && (pht < ph + ph_tol || alpha < real(1e-3))) {
 #pragma unroll
-          for (int i = 0; i < 6; i++) nn[i] = nt[i];
+            for (int i = 0; i < 6; i++) nn[i] = nt[i];
 #pragma unroll
-          for (int k = 0; k < NC; k++) tn[k] = tt[k];
-          phn = pht;
-          need_bt = false;
+            for (int k = 0; k < NC; k++) tn[k] = tt[k];
+            phn = pht;
+            need_bt = false;
+          }
+          alpha *= real(0.5);
         }
-        alpha *= real(0.5);
       }
       if (!done) {
 #pragma unroll
@@ -387,15 +484,21 @@ template <typename real, int G> struct QP {
 // ------------------------------------------------------------------------------------------------
 // SDS swing-foot LQR filter (work/controlmodule.py:962-1086, gains: useKpreset :1041-1057 with
 // sop.piecewiseLinearMap (module.lua:5203) and matrixn::sampleRow (matrixn.cpp:781, float32 `t`)).
+__constant__ double SDS_KP[7][2] = {{262.685, 127.410}, {942.739, 281.657}, {3103.828, 553.238}, {9941.174, 1033.866},
+                                    {31563.832, 1887.117}, {99941.017, 3403.601}, {316168.772, 6099.859}};
+__constant__ double SDS_KT[8] = {1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12};
+template <typename real> __device__ __noinline__ void sds_gain_slow(real speed, real* K0, real* K1);
 template <typename real> __device__ __forceinline__ void sds_gain(real speed, real* K0, real* K1) {
-  const double KP[7][2] = {{262.685, 127.410}, {942.739, 281.657}, {3103.828, 553.238}, {9941.174, 1033.866},
-                           {31563.832, 1887.117}, {99941.017, 3403.601}, {316168.772, 6099.859}};
-  if (speed < real(3)) { *K0 = (real)KP[4][0]; *K1 = (real)KP[4][1]; return; }     // logQ = 9 -> row 4 exactly
+  if (speed < real(3)) { *K0 = real(31563.832); *K1 = real(1887.117); return; }     // logQ = 9 -> row 4 exactly
+  sds_gain_slow(speed, K0, K1);
+}
+template <typename real> __device__ __noinline__ void sds_gain_slow(real speed, real* K0, real* K1) {
+  const double (*KP)[2] = SDS_KP;
   double logQ = speed > real(6) ? 11.0 : 9.0 + (((double)speed - 3.0) / 3.0) * (11.0 - 9.0);
   logQ = fmax(9.0, logQ);
   double Q = ::pow(10.0, logQ);
   // piecewiseLinearMap(Q, 10^5..10^12, 0..7)
-  const double KT[8] = {1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12};
+  const double* KT = SDS_KT;
   double index = 7.0;
   for (int i = 0; i < 7; i++) {
     double t1 = KT[i + 1];
@@ -586,6 +689,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   const int e = active ? e_raw : A.N - 1;
   const Params<real>& P = A.p;
 
+  __shared__ __align__(16) real hsm[HReduce<real, G>::SMEM_WORDS];
   EnvState<real> s;
   load_state(s, A.st, A.ist, A.Npad, e);
   const ClipDesc<real> cd = A.clips[s.clip];
@@ -680,9 +784,11 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
                    P.inertia[0] + P.armature, P.inertia[1] + P.armature, P.inertia[2] + P.armature};
   real Minv[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) Minv[i] = real(1) / Mdiag[i];
-  real nu[6] = {0, 0, 0, 0, 0, 0};
-  bool warm = false;
+  for (int i = 0; i < 6; i++) Minv[i] = P.inv_M[i];
+  real nu[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) nu[i] = s.nu[i];
+  bool warm = (s.flags & FLAG_NU) != 0;
   double* dbg = (A.dbg != nullptr && active) ? A.dbg + (size_t)e * DBG_W : nullptr;
 
   for (int sub = 0; sub < P.nsub; sub++) {
@@ -723,9 +829,14 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         for (int i = 0; i < 6; i++) nu[i] = -y[i];
       }
       real t[QP<real, G>::NC];
-      int iters = qp.solve(lane, y, P.w_lambda, nu, t);
+      int iters = qp.solve(lane, y, P.inv_w_lambda, nu, t, hsm);
       warm = true;
-      const real invw = real(1) / P.w_lambda;
+      if (contact_mask != 0) {
+        s.flags |= FLAG_NU;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.nu[i] = nu[i];
+      }
+      const real invw = P.inv_w_lambda;
       bool clamped = false;
       if (P.use_clamp) {
         // per-foot force sums and the 1e4 N clamp (:402-443, Q3)
@@ -791,7 +902,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 #pragma unroll
     for (int i = 0; i < 6; i++) {
       real f = (-P.damping * qv[i]) - bias[i] + qfrc[i] + xfq[i];
-      qv[i] += P.h * (f / (Mdiag[i] + P.h * P.damping));
+      qv[i] += P.h * (f * P.inv_Mh[i]);
     }
     s.vlin = {qv[0], qv[1], qv[2]};
     s.vang = {qv[3], qv[4], qv[5]};

@@ -21,6 +21,9 @@ template <> struct num<float> {
   static __device__ __forceinline__ float tiny() { return 1e-4f; }   // series threshold for small angles
   static __device__ __forceinline__ float series_below() { return 0.3f; }
   static __device__ __forceinline__ float eps_conv() { return 2e-6f; }
+  // MUFU-based approximations (<= 2 ulp): the fp32 mode's tolerance is 1e-3
+  static __device__ __forceinline__ float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static __device__ __forceinline__ float rsqrt_pos(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 };
 template <> struct num<double> {
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
@@ -36,6 +39,21 @@ template <> struct num<double> {
   static __device__ __forceinline__ double tiny() { return 1e-6; }
   static __device__ __forceinline__ double series_below() { return 0.02; }
   static __device__ __forceinline__ double eps_conv() { return 1e-13; }
+  // MUFU seed (2^-23) + two Newton steps: relative error ~1e-16 without the IEEE-division slow path
+  static __device__ __forceinline__ double rcp(double d) {
+    double x; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0); x = fma(x, e, x);
+    e = fma(-d, x, 1.0); x = fma(x, e, x);
+    return x;
+  }
+  static __device__ __forceinline__ double rsqrt_pos(double d) {
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double hd = 0.5 * d;
+    double e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-hd * y, y, 0.5); y = fma(y, e, y);
+    return y;
+  }
 };
 
 template <typename T> struct V3 { T x, y, z; };
@@ -81,7 +99,7 @@ template <typename T> __device__ __forceinline__ M3<T> matmulTN(const M3<T>& A, 
 
 // mju_quat2Mat of the normalised quaternion (what mj_kinematics stores in xmat).
 template <typename T> __device__ __forceinline__ M3<T> quat2mat_normalized(Q4<T> q) {
-  T inv = T(1) / num<T>::sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  T inv = num<T>::rsqrt_pos(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
   q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
   T q00 = q.w * q.w, q01 = q.w * q.x, q02 = q.w * q.y, q03 = q.w * q.z;
   T q11 = q.x * q.x, q12 = q.x * q.y, q13 = q.x * q.z, q22 = q.y * q.y, q23 = q.y * q.z, q33 = q.z * q.z;
@@ -106,10 +124,10 @@ template <typename T> __device__ __forceinline__ Q4<T> quat_integrate(Q4<T> q, V
   } else {
     T s, c;
     num<T>::sincos(T(0.5) * h * n, &s, &c);
-    T k = s / n;
+    T k = s * num<T>::rcp(n);
     r = {c, k * w.x, k * w.y, k * w.z};
   }
-  T inv = T(1) / num<T>::sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  T inv = num<T>::rsqrt_pos(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
   q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
   return quat_mul(q, r);
 }
@@ -184,8 +202,8 @@ template <typename T> __device__ __forceinline__ void log_se3(const M3<T>& Rr, V
 // testSRB_mujoco_original_viewer.py:83-114): columns x=(fx,fy,0), y=(-fy,fx,0), z=(0,0,1).
 template <typename T> __device__ __forceinline__ void yaw_frame(const M3<T>& R, T* fx, T* fy) {
   T x = R.m[0], y = R.m[3];
-  T n = num<T>::sqrt(x * x + y * y);
-  if (n != T(0)) { x = x / n; y = y / n; }
+  T n2 = x * x + y * y;
+  if (n2 > T(1e-30)) { T inv = num<T>::rsqrt_pos(n2); x = x * inv; y = y * inv; }
   *fx = x; *fy = y;
 }
 // ff^T v and ff v for the yaw frame (fx, fy)

@@ -18,7 +18,8 @@ enum RealField {
   F_BALLX = 29,   // 4  SDS position state  (left x, left y, right x, right y)
   F_BALLV = 33,   // 4  SDS velocity state
   F_EPRET = 37,   // 1  running episode return
-  NF_REAL = 38
+  F_NU = 38,      // 6  QP dual of the last sub-step (warm start)
+  NF_REAL = 44
 };
 enum IntField {
   I_FLAGS = 0,    // bit0 left_foot_in_contact, bit1 right_foot_in_contact, bit2 filter initialised, bit3 is_stand
@@ -30,7 +31,7 @@ enum IntField {
   I_EPISODE = 6,  // episodes started (RNG stream position)
   NF_INT = 7
 };
-enum { FLAG_L = 1, FLAG_R = 2, FLAG_FILT = 4, FLAG_STAND = 8 };
+enum { FLAG_L = 1, FLAG_R = 2, FLAG_FILT = 4, FLAG_STAND = 8, FLAG_NU = 16 };
 
 // history ring: hist[(env * HIST_SLOTS + slot) * HIST_W + k] ; entry e lives in slot e % HIST_SLOTS
 enum { HIST_SLOTS = 32, HIST_W = 8 };   // pos(3) quat_lag(4) pad(1)
@@ -58,6 +59,7 @@ template <typename real> struct Params {
   real mass, inertia[3], armature, damping, grav;
   real mu_b;            // 1.2 * self.mu = 1.2 * (1.2 * floor friction)
   real kp, kd, w_lambda;
+  real inv_w_lambda, inv_M[6], inv_Mh[6];   // 1/w, 1/(M+armature), 1/(M+armature+h*damping)
   real force_thr;
   real w[9];            // w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c
   int use_filter, use_clamp, use_impulse, obs_after_inc;

@@ -198,7 +198,7 @@ class SRBVecEnv:
                     left_foot_contact_pos_global=r[17:20].copy(), right_foot_contact_pos_global=r[20:23].copy(),
                     left_foot_yaw_cs=r[23:25].copy(), right_foot_yaw_cs=r[25:27].copy(),
                     contactFilter_yaw=r[27:29].copy(), sds_x=r[29:33].copy(), sds_v=r[33:37].copy(),
-                    episode_return=float(r[37]),
+                    episode_return=float(r[37]), qp_dual_warm_start=r[38:44].copy(),
                     left_foot_in_contact=bool(k[0] & 1), right_foot_in_contact=bool(k[0] & 2),
                     filter_initialised=bool(k[0] & 4), is_stand=bool(k[0] & 8),
                     current_frame=int(k[1]), random_initial_frame=int(k[2]), clip=int(k[3]),

@@ -359,6 +359,7 @@ class OracleSRBEnv:
         for _ in range(round(self.mocap_dt / m.timestep)):
             d.qfrc_applied = np.zeros(6)
             mj.mj_step1(m, d)
+            self.xquat_lagged = d.qpos[3:7].copy()        # the quaternion data.xmat now corresponds to (Q14)
             if self.variant == "test":
                 self.update_impulse()
             set_feet_site_this_step_env(d, next_predicted_feet_pos, curr_feet_ori, des_l, des_r)
@@ -401,6 +402,7 @@ class OracleSRBEnv:
         set_feet_site_this_step_env(d, next_predicted_feet_pos, curr_feet_ori, des_l, des_r)
         self.SRB_pos_list.append(d.qpos[:3].copy())
         self.SRB_ori_list.append(self._xmat().copy())            # stale by one sub-step (Q14)
+        self.SRB_quat_list.append(self.xquat_lagged.copy())
         self.simulated_feet_pos_list.append([d.site_xpos[s].copy() for s in self.site_id_list])
         self.simulated_feet_ori_list.append([d.site_xmat[s].copy().reshape(3, 3) for s in self.site_id_list])
         self.contact_signal_list.append(next_contact_signal)
@@ -538,7 +540,7 @@ class OracleSRBEnv:
     # -- :847-911
     def set_state(self, initial_frame, vel_noise, noise_quat):
         d, m = self.data, self.model
-        self.SRB_pos_list, self.SRB_ori_list = [], []
+        self.SRB_pos_list, self.SRB_ori_list, self.SRB_quat_list = [], [], []
         self.simulated_feet_pos_list, self.simulated_feet_ori_list = [], []
         self.contact_signal_list = []
         if vel_noise is not None:
@@ -565,9 +567,11 @@ class OracleSRBEnv:
         d.xfrc_applied = np.zeros(6)
         d.qfrc_applied = np.zeros(6)
         mj.mj_forward(m, d)
+        self.xquat_lagged = d.qpos[3:7].copy()
         set_feet_site_this_step_env(d, feet_pos, feet_ori, self.left_foot_contact_pos_global, self.right_foot_contact_pos_global)
         self.SRB_pos_list.append(d.qpos[:3].copy())
         self.SRB_ori_list.append(self._xmat().copy())
+        self.SRB_quat_list.append(self.xquat_lagged.copy())
         self.simulated_feet_pos_list.append([d.site_xpos[s].copy() for s in self.site_id_list])
         self.simulated_feet_ori_list.append([d.site_xmat[s].copy().reshape(3, 3) for s in self.site_id_list])
         sig = (1 if self.left_foot_in_contact else 0) + (2 if self.right_foot_in_contact else 0)

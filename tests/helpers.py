@@ -97,3 +97,28 @@ def cuda_state_vector(named):
     return np.concatenate([named["qpos"], named["qvel"], named["left_foot_contact_pos_global"], named["right_foot_contact_pos_global"],
                            named["left_foot_yaw_cs"], named["right_foot_yaw_cs"],
                            [float(named["left_foot_in_contact"]), float(named["right_foot_in_contact"])], [float(named["current_frame"])]])
+
+
+def oracle_to_cuda_state(env, n_real=44, n_int=7, slots=32, width=8):
+    """Pack an OracleSRBEnv's full state in the layout of srb_get_state / srb_set_state
+    (ipcdnnwalk_b200/csrc/srb_types.h)."""
+    d = env.data
+    r = np.zeros(n_real)
+    r[0:7] = d.qpos; r[7:13] = d.qvel; r[13:17] = env.xquat_lagged
+    r[17:20] = env.left_foot_contact_pos_global; r[20:23] = env.right_foot_contact_pos_global
+    lo, ro = env.left_foot_contact_ori, env.right_foot_contact_ori
+    r[23:27] = [lo[0, 0], lo[1, 0], ro[0, 0], ro[1, 0]]
+    inited = env.variant == "test" and env.contactFilter[0] is not None
+    if inited:
+        r[27:29] = [float(env.contactFilter[0]), float(env.contactFilter[1])]
+        balls = [env.contactFilter[2][0], env.contactFilter[2][1], env.contactFilter[3][0], env.contactFilter[3][1]]
+        r[29:33] = [b.x[0] for b in balls]; r[33:37] = [b.x[1] for b in balls]
+    k = np.zeros(n_int, dtype=np.int32)
+    k[0] = (1 if env.left_foot_in_contact else 0) | (2 if env.right_foot_in_contact else 0) | (4 if inited else 0) | (8 if env.is_stand else 0)
+    k[1] = env.current_frame; k[2] = env.random_initial_frame; k[3] = env.clip_id
+    k[4] = env.frame_counter; k[5] = env.impulse; k[6] = 1
+    h = np.zeros((slots, width))
+    n = len(env.SRB_pos_list)
+    for e in range(max(0, n - slots), n):
+        h[e % slots, 0:3] = env.SRB_pos_list[e]; h[e % slots, 3:7] = env.SRB_quat_list[e]
+    return dict(reals=r, ints=k, hist=h)
