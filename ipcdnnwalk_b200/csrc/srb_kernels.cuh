@@ -682,6 +682,7 @@ template <typename real> __device__ __forceinline__ bool compute_done(const EnvS
 template <typename real, int G>
 __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   constexpr int EPW = 32 / G;
+  const long long tk_entry = clock64();
   const int lane32 = threadIdx.x & 31;
   const int lane = lane32 % G;
   const int e_raw = (blockIdx.x * EPW) + lane32 / G;
@@ -695,6 +696,28 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   const ClipDesc<real> cd = A.clips[s.clip];
   real* hist_env = A.hist + (size_t)e * HIST_SLOTS * HIST_W;
   const float* act = A.act + (size_t)e * ACT_W;
+  // Everything the post-step phase reads (history entries, reference frames, look-ahead features) is known now:
+  // prefetch those lines into L1 so their DRAM latency overlaps the four sub-steps instead of stalling the reward.
+  {
+    const int f0 = s.frame + s.rif;
+    for (int id = lane; id < 16; id += G) {
+      const char* ptr;
+      if (id < 3) {
+        int back = id == 0 ? 0 : (id == 1 ? 5 : 15);
+        ptr = (const char*)(hist_env + (size_t)((s.frame - back) & (HIST_SLOTS - 1)) * HIST_W);
+      } else if (id < 11) {
+        int k = (id - 3) >> 1;                              // two 128-byte lines per record (fp64 records are 256 B)
+        int fr = k == 0 ? f0 : (k == 1 ? f0 + 1 : (k == 2 ? f0 - 5 : f0 - 15));
+        fr = min(max(fr, 0), cd.nframes - 1);
+        ptr = (const char*)(cd.frames + (size_t)fr * CLIP_W) + ((id - 3) & 1) * 128;
+        if (sizeof(real) == 4 && ((id - 3) & 1)) ptr -= 128;
+      } else {
+        int fw = min(f0 + 1 + (P.obs_after_inc ? 1 : 0), max(cd.nframes - 5, 0));
+        ptr = (const char*)(cd.feat + (size_t)fw * FEAT_W) + (id - 11) * 128;
+      }
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+    }
+  }
   real a[ACT_W];
 #pragma unroll
   for (int i = 0; i < ACT_W; i++) a[i] = (real)__ldg(act + i);
@@ -790,8 +813,12 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   for (int i = 0; i < 6; i++) nu[i] = s.nu[i];
   bool warm = (s.flags & FLAG_NU) != 0;
   double* dbg = (A.dbg != nullptr && active) ? A.dbg + (size_t)e * DBG_W : nullptr;
+  long long tk0 = 0, tk_pre = 0;
+  if (A.dbg != nullptr) { tk_pre = clock64(); tk0 = tk_pre; }   // phase clocks land in the debug record's pad slots
 
   for (int sub = 0; sub < P.nsub; sub++) {
+    long long tk_sub = 0;
+    if (A.dbg != nullptr) tk_sub = clock64();
     // mj_step1: kinematics + bias
     const M3<real> R = quat2mat_normalized(s.quat);
     s.qlag = s.quat;
@@ -885,6 +912,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 #pragma unroll
           for (int i = 0; i < 6; i++) { d[i] = (double)(nu[i] + y[i] - Minv[i] * bias[i]); d[6 + i] = (double)nu[i]; d[12 + i] = (double)qfrc[i]; }
           d[18] = (double)iters;
+          d[19] = (double)(clock64() - tk_sub);           // cycles: sub-step start .. QP solved
         }
 #pragma unroll
         for (int k = 0; k < QP<real, G>::NC; k++) {
@@ -910,6 +938,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     s.quat = quat_integrate(s.quat, s.vang, P.h);
   }
 
+  if (dbg != nullptr && lane == 0) { dbg[20] = (double)(clock64() - tk_pre); }    // cycles: 4 sub-steps
   // ---- history push (:453-474): entry frame+1 = (qpos[:3], stale xmat)
   if (active && lane == 0) {
     real* h = hist_env + (size_t)((s.frame + 1) & (HIST_SLOTS - 1)) * HIST_W;
@@ -967,6 +996,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     }
   }
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
+  if (dbg != nullptr && lane == 0) { dbg[21] = (double)(clock64() - tk0); dbg[22] = (double)(tk_pre - tk_entry); dbg[23] = (double)tk_entry; }
 }
 
 // ------------------------------------------------------------------------------------------------
