@@ -38,7 +38,15 @@ _SIGNATURES = {
     "srb_tracking_action": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_uint32, _P, _P]),
     "srb_launch_count": (C.c_int64, [_P]),
 }
+_FK_SIGNATURES = {          # include/bonefk_b200.h
+    "fk_create": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "fk_destroy": (C.c_int, [_P]),
+    "fk_dims": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fk_forward_f32": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "fk_forward_f64": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+FK_EXPORTED_SYMBOLS = tuple(_FK_SIGNATURES)
 
 _lib = None
 
@@ -53,7 +61,7 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in _SIGNATURES.items():
+    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

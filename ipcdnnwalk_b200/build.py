@@ -8,7 +8,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 TARGETS = {
-    "libsrbtrack_b200.so": ["srb_api.cu"],
+    "libsrbtrack_b200.so": ["srb_api.cu", "fk_api.cu"],
 }
 
 
@@ -21,7 +21,7 @@ def _stale(out, deps):
 
 def build(force=False, verbose=True):
     nvcc = os.environ.get("NVCC", "nvcc")
-    deps_all = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "srbtrack_b200.h")]
+    deps_all = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "srbtrack_b200.h"), os.path.join(HERE, "..", "include", "bonefk_b200.h")]
     built = []
     for lib, srcs in TARGETS.items():
         out = os.path.join(HERE, lib)

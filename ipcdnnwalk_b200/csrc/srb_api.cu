@@ -14,6 +14,7 @@ using namespace srb;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int srb_set_error(int code, const std::string& msg) { return fail(code, msg); }   // shared with fk_api.cu
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \

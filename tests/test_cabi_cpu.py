@@ -28,6 +28,26 @@ def test_binding_table_matches_header(built_lib):
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared()
 
 
+def test_fk_header_symbols_exported(built_lib):
+    from ipcdnnwalk_b200 import _lib
+    txt = open(os.path.join(helpers.ROOT, "include", "bonefk_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fk_[a-z_0-9]+)\s*\(", txt)))
+    assert names == sorted(_lib.FK_EXPORTED_SYMBOLS) and len(names) == 5
+    for n in names:
+        assert hasattr(built_lib, n)
+
+
+def test_skeleton_parser_matches_builtin_tables():
+    from ipcdnnwalk_b200 import vrml_skeleton
+    s = vrml_skeleton.builtin()
+    assert len(s["names"]) == 20 and s["n_pose"] == 60 and s["n_dq"] == 59 and max(s["depth"]) == 7
+    assert s["channels"][2] == "X" and s["channels"][11] == "XYZ" and s["channels"][12] == "ZXY"
+    wrl = "/root/reference/gym_trackSRB/taesooLib/hanyang_lowdof_T_sh.wrl"
+    if os.path.exists(wrl):
+        assert vrml_skeleton.parse_wrl(wrl) == s
+
+
 def test_state_dims_and_errors_without_gpu(built_lib):
     import ctypes as C
     d = [C.c_int32() for _ in range(4)]

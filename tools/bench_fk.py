@@ -1,0 +1,39 @@
+"""GPU throughput of the batched FK / CoM / momentum kernel (BASELINE config 5: 1M humanoid poses).
+Prints poses/s and the HBM-roofline fraction (836 B/pose fp32, 1672 B/pose fp64: pose in, 20x7 transforms + CoM + momentum out;
+dq input adds 236/472 B and is reported separately)."""
+import json, os, sys
+import torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+from ipcdnnwalk_b200 import vrml_skeleton, Skeleton
+
+skel = vrml_skeleton.builtin()
+sk = Skeleton(skel)
+n = 1 << 20
+peak = 6547.8
+try:
+    peak = json.load(open(os.path.join(R, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+g = torch.Generator(device="cuda"); g.manual_seed(4)
+for dt, name in ((torch.float32, "f32"), (torch.float64, "f64")):
+    q = torch.randn(n, 4, device="cuda", generator=g, dtype=dt); q = q / q.norm(dim=1, keepdim=True)
+    pose = torch.cat([torch.rand(n, 3, device="cuda", generator=g, dtype=dt) * 10 - 5, q, torch.rand(n, 53, device="cuda", generator=g, dtype=dt) * 2 - 1], 1).contiguous()
+    dq = (torch.rand(n, 59, device="cuda", generator=g, dtype=dt) * 2 - 1).contiguous()
+    out = sk.forward(pose, dq)
+    for mode, d in (("fk+com (no velocities)", None), ("fk+com+momentum", dq)):
+        for _ in range(3):
+            sk.forward(pose, d, out=out)
+        ts = []
+        for _ in range(10):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); sk.forward(pose, d, out=out); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        es = pose.element_size()
+        alg = (60 + 140 + 3 + (6 if d is not None else 0)) * es
+        tot = alg + (59 * es if d is not None else 0)
+        print(json.dumps({"kernel": "fk_forward_kernel", "dtype": name, "mode": mode, "poses": n, "ms": ms, "poses_per_s": n / ms * 1e3,
+                          "algorithmic_bytes_per_pose": alg, "achieved_GBps_algorithmic": alg * n / ms / 1e6,
+                          "achieved_GBps_incl_dq": tot * n / ms / 1e6, "peak_GBps": peak, "frac": alg * n / ms / 1e6 / peak}))
+sk.close()

@@ -1,0 +1,11 @@
+import os, sys, torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
+from ipcdnnwalk_b200 import vrml_skeleton, Skeleton
+dt = torch.float32 if sys.argv[1] == "32" else torch.float64
+sk = Skeleton(vrml_skeleton.builtin()); n = 1 << 20
+g = torch.Generator(device="cuda"); g.manual_seed(4)
+q = torch.randn(n, 4, device="cuda", generator=g, dtype=dt); q = q / q.norm(dim=1, keepdim=True)
+pose = torch.cat([torch.rand(n, 3, device="cuda", generator=g, dtype=dt) * 10 - 5, q, torch.rand(n, 53, device="cuda", generator=g, dtype=dt) * 2 - 1], 1).contiguous()
+dq = (torch.rand(n, 59, device="cuda", generator=g, dtype=dt) * 2 - 1).contiguous()
+for _ in range(4): sk.forward(pose, dq)
+torch.cuda.synchronize(); print("ok")
