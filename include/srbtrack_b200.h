@@ -27,7 +27,8 @@ typedef struct srb_env srb_env; /* opaque: N batched `SRBEnv` instances on one d
 #define SRB_DBG_DIM 256   /* per-env debug record: 4 sub-steps x [qdd(6) nu(6) qfrc(6) iters(1) pad(5) lambda(40)] */
 
 enum { SRB_VARIANT_TEST = 0,      /* env/SRBEnv5_mocap_list_window.py          (SDS foot filter, force clamp) */
-       SRB_VARIANT_TRAINING = 1   /* env/SRBEnv5_mocap_list_window_training.py (what PPO trains on)           */ };
+       SRB_VARIANT_TRAINING = 1,  /* env/SRBEnv5_mocap_list_window_training.py (what PPO trains on)           */
+       SRB_VARIANT_TERRAIN = 2    /* env/SRBEnv5_mocap_list_terrain_window.py  (height-field / pyramid contacts) */ };
 
 typedef struct srb_config {
   int32_t num_envs;       /* replaces make_vec_env(SRBEnv, n_envs=...)  walk_SRBTrack2025_train_delta.py:94-100 */
@@ -93,6 +94,21 @@ int srb_set_state(srb_env* env, int32_t env_index, const double* reals, const in
 int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* stream);
 /* Episode statistics accumulated by auto-reset: out[3] = sum of returns, sum of lengths, count. */
 int srb_episode_stats(srb_env* env, double out[3], int32_t clear);
+
+/* ---- terrain variant (env/SRBEnv5_mocap_list_terrain_window.py, model gym_trackSRB/Characters/SRB5_playground.xml) ----
+ * The group-0 geoms the reference ray-casts against (terrain_height_ray, env/testSRB_mujoco_original_viewer_terrain.py:741-752):
+ * one plane, height fields (elevation data already normalised to [0,1], row 0 at -y, as mujoco stores hfield_data) and
+ * axis-aligned boxes (consecutive geoms in model order, grouped by body, tops ascending inside a body). */
+typedef struct srb_hfield { const float* data_host; int32_t nrow, ncol; double size[4]; double pos[3]; int32_t geom_id; } srb_hfield;
+typedef struct srb_box { double pos[3]; double size[3]; int32_t geom_id; int32_t body_id; } srb_box;
+typedef struct srb_terrain_body { double xpos[3]; int32_t body_id; int32_t snap; /* 1: pyramid body followed by a pyramid body (:349,:410) */ } srb_terrain_body;
+int srb_upload_terrain(srb_env* env, const double plane_size[2], int32_t plane_geom, int32_t n_hf, const srb_hfield* hfs,
+                       int32_t n_box, const srb_box* boxes, int32_t n_body, const srb_terrain_body* bodies);
+/* initial_pos_planar of every environment's reference motion (SRBEnv.reset(..., initial_pos_planar), :528,:636); xy_host[N][2].
+ * Takes effect at the next reset of each environment. */
+int srb_set_planar_offsets(srb_env* env, const double* xy_host);
+/* Batched terrain_height_ray: xy_dev[n][2] -> height_dev[n]; hit_dev[n][4] (may be NULL) = geom id, hfield cell column, row, triangle. */
+int srb_terrain_height(srb_env* env, int32_t n, const double* xy_dev, double* height_dev, int32_t* hit_dev, void* stream);
 
 /* Benchmark / roll-out driver (not in the reference; stands in for the policy, walk_SRBTrack2025.py:424):
  * act_dev[N][22] = reference-tracking action for the next reference frame + N(0, sigma^2) noise. */

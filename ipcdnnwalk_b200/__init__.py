@@ -4,3 +4,4 @@ from ._lib import OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM, LIB_PATH, SrbE
 from .srb_vec_env import SRBVecEnv, REWARD_INFO_KEYS  # noqa: F401
 from . import vrml_skeleton  # noqa: F401
 from .bone_fk import Skeleton, BoneForwardKinematics, LoaderToTree  # noqa: F401
+from .terrain import TerrainModel  # noqa: F401

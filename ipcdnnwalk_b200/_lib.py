@@ -9,12 +9,24 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrbtrack_b200.so")
 
 OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM = 150, 22, 8, 9, 256
-VARIANT_TEST, VARIANT_TRAINING = 0, 1
+VARIANT_TEST, VARIANT_TRAINING, VARIANT_TERRAIN = 0, 1, 2
 
 
 class SrbConfig(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("variant", C.c_int32), ("precision", C.c_int32), ("lanes_per_env", C.c_int32),
                 ("auto_reset", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64)]
+
+
+class SrbHField(C.Structure):
+    _fields_ = [("data_host", C.c_void_p), ("nrow", C.c_int32), ("ncol", C.c_int32), ("size", C.c_double * 4), ("pos", C.c_double * 3), ("geom_id", C.c_int32)]
+
+
+class SrbBox(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("size", C.c_double * 3), ("geom_id", C.c_int32), ("body_id", C.c_int32)]
+
+
+class SrbTerrainBody(C.Structure):
+    _fields_ = [("xpos", C.c_double * 3), ("body_id", C.c_int32), ("snap", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -36,6 +48,9 @@ _SIGNATURES = {
     "srb_obs_stats": (C.c_int, [_P, _P, _P, _P]),
     "srb_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
     "srb_tracking_action": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_uint32, _P, _P]),
+    "srb_upload_terrain": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P]),
+    "srb_set_planar_offsets": (C.c_int, [_P, _P]),
+    "srb_terrain_height": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "srb_launch_count": (C.c_int64, [_P]),
 }
 _FK_SIGNATURES = {          # include/bonefk_b200.h

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <algorithm>
 
 #include "../../include/srbtrack_b200.h"
 #include "srb_kernels.cuh"
@@ -39,6 +40,8 @@ struct srb_env {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
   int64_t launches = 0;
+  // terrain (variant 2)
+  TerrainDev* terrain_dev = nullptr; std::vector<float*> hf_data; double* box_dev = nullptr;
 };
 static const int MAX_CLIPS = 64;
 
@@ -49,7 +52,7 @@ template <typename real> static Params<real> convert_params(const Params<double>
   q.armature = (real)p.armature; q.damping = (real)p.damping; q.grav = (real)p.grav; q.mu_b = (real)p.mu_b;
   q.kp = (real)p.kp; q.kd = (real)p.kd; q.w_lambda = (real)p.w_lambda; q.force_thr = (real)p.force_thr;
   for (int i = 0; i < 9; i++) q.w[i] = (real)p.w[i];
-  q.use_filter = p.use_filter; q.use_clamp = p.use_clamp; q.use_impulse = p.use_impulse; q.obs_after_inc = p.obs_after_inc;
+  q.use_filter = p.use_filter; q.use_clamp = p.use_clamp; q.use_impulse = p.use_impulse; q.obs_after_inc = p.obs_after_inc; q.use_terrain = p.use_terrain;
   q.impulse_interval = p.impulse_interval; q.impulse_duration = p.impulse_duration; q.impulse_trigger_at_end = p.impulse_trigger_at_end;
   q.max_frame = p.max_frame;
   q.inv_w_lambda = (real)(1.0 / p.w_lambda);
@@ -72,12 +75,14 @@ static void default_params(Params<double>& p, int variant) {
   p.mu_b = 1.2 * (1.2 * 1.0);                           // b = (1.2*mu, 0, 1), mu = 1.2 * floor friction
   p.kp = 120.0; p.kd = 35.0; p.w_lambda = 0.001; p.force_thr = 10000.0;
   p.max_frame = 512;
-  if (variant == SRB_VARIANT_TEST) {
+  p.use_terrain = 0;
+  if (variant == SRB_VARIANT_TEST || variant == SRB_VARIANT_TERRAIN) {
     const double w[9] = {5, 0.1, 0.5, 0, 50, 20, 700, 50, 1};
     memcpy(p.w, w, sizeof(w));
     p.use_filter = 1; p.use_clamp = 1; p.use_impulse = 1; p.obs_after_inc = 0;
     p.impulse_interval = 1000000000; p.impulse_duration = 24; p.impulse_trigger_at_end = 1;
     p.impulse_force[0] = 700; p.impulse_force[1] = 700; p.impulse_force[2] = -350;
+    if (variant == SRB_VARIANT_TERRAIN) { p.use_clamp = 0; p.use_terrain = 1; }     // env/SRBEnv5_mocap_list_terrain_window.py
   } else {
     const double w[9] = {5, 1, 0.5, 0.01, 5, 1.5, 25, 1.5, 0.1};
     memcpy(p.w, w, sizeof(w));
@@ -95,7 +100,7 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   if (cfg->precision != 32 && cfg->precision != 64) return fail(-1, "srb_create: precision must be 32 or 64");
   int G = cfg->lanes_per_env == 0 ? 8 : cfg->lanes_per_env;
   if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(-1, "srb_create: lanes_per_env must be 1,2,4,8,16 or 32");
-  if (cfg->variant != SRB_VARIANT_TEST && cfg->variant != SRB_VARIANT_TRAINING) return fail(-1, "srb_create: unknown variant");
+  if (cfg->variant != SRB_VARIANT_TEST && cfg->variant != SRB_VARIANT_TRAINING && cfg->variant != SRB_VARIANT_TERRAIN) return fail(-1, "srb_create: unknown variant");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(-3, std::string("srb_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
@@ -127,6 +132,8 @@ extern "C" int srb_destroy(srb_env* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->st); cudaFree(h->ist); cudaFree(h->hist); cudaFree(h->clips_dev); cudaFree(h->ep_stats);
   for (auto& c : h->clips) { cudaFree(c.frames); cudaFree(c.feat); }
+  for (auto p : h->hf_data) cudaFree(p);
+  cudaFree(h->box_dev); cudaFree(h->terrain_dev);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_rinfo); cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rinfo); cudaFree(h->d_done);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -185,7 +192,7 @@ template <typename real> static int do_reset(srb_env* h, const int* idx_dev, int
   A.N = h->N; A.Npad = h->Npad; A.count = count; A.idx = idx_dev;
   A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist;
   A.clips = (const ClipDesc<real>*)h->clips_dev; A.nclips = h->nclips;
-  A.plan = plan_dev; A.obs = obs_dev; A.seed = h->cfg.seed; A.p = convert_params<real>(h->p);
+  A.plan = plan_dev; A.obs = obs_dev; A.seed = h->cfg.seed; A.p = convert_params<real>(h->p); A.terrain = h->terrain_dev;
   srb_reset_kernel<real><<<(count + 127) / 128, 128, 0, s>>>(A);
   h->launches++;
   return 0;
@@ -194,6 +201,7 @@ template <typename real> static int do_reset(srb_env* h, const int* idx_dev, int
 extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count, const double* plan_host, float* obs_dev, void* stream) {
   if (!h) return fail(-1, "srb_reset: null handle");
   if (h->nclips == 0) return fail(-1, "srb_reset: no clip uploaded");
+  if (h->p.use_terrain && !h->terrain_dev) return fail(-1, "srb_reset: terrain variant needs srb_upload_terrain first");
   if (count <= 0 || count > h->N) return fail(-1, "srb_reset: bad count");
   for (int c = 0; c < h->nclips; c++) if (h->clips[c].frames == nullptr) return fail(-1, "srb_reset: clip ids must be contiguous from 0");
   CK(cudaSetDevice(h->cfg.device));
@@ -225,7 +233,7 @@ template <typename real, int G> static void launch_step(srb_env* h, const float*
   A.clips = (const ClipDesc<real>*)h->clips_dev; A.nclips = h->nclips;
   A.act = act; A.obs = obs; A.rew = rew; A.done = done; A.rinfo = rinfo; A.term_obs = h->term_obs;
   A.contact_prob = h->contact_prob; A.reset_plan = h->reset_plan; A.dbg = h->dbg; A.ep_stats = h->ep_stats;
-  A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p);
+  A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p); A.terrain = h->terrain_dev;
   constexpr int EPW = 32 / G;
   int blocks = (h->N + EPW - 1) / EPW;
   srb_step_kernel<real, G><<<blocks, 32, 0, s>>>(A);
@@ -249,6 +257,7 @@ extern "C" int srb_step(srb_env* h, const float* act_dev, float* obs_dev, float*
   if (!h) return fail(-1, "srb_step: null handle");
   if (!act_dev || !obs_dev || !rew_dev || !done_dev) return fail(-1, "srb_step: null buffer");
   if (h->nclips == 0) return fail(-1, "srb_step: no clip uploaded");
+  if (h->p.use_terrain && !h->terrain_dev) return fail(-1, "srb_step: terrain variant needs srb_upload_terrain first");
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int rc = h->cfg.precision == 64 ? dispatch_step<double>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s)
@@ -406,15 +415,100 @@ extern "C" int srb_episode_stats(srb_env* h, double out[3], int32_t clear) {
   return 0;
 }
 
+extern "C" int srb_upload_terrain(srb_env* h, const double plane_size[2], int32_t plane_geom, int32_t n_hf, const srb_hfield* hfs,
+                                  int32_t n_box, const srb_box* boxes, int32_t n_body, const srb_terrain_body* bodies) {
+  if (!h || !plane_size) return fail(-1, "srb_upload_terrain: null argument");
+  if (n_hf < 0 || n_hf > MAX_HF || n_body < 0 || n_body > MAX_TBODY || n_box < 0) return fail(-1, "srb_upload_terrain: too many height fields / bodies");
+  if ((n_hf && !hfs) || (n_box && !boxes) || (n_body && !bodies)) return fail(-1, "srb_upload_terrain: null table");
+  CK(cudaSetDevice(h->cfg.device));
+  TerrainDev T;
+  memset(&T, 0, sizeof(T));
+  T.enabled = 1; T.n_hf = n_hf; T.n_body = n_body; T.n_box = n_box;
+  T.plane_geom = plane_geom; T.plane_hx = plane_size[0]; T.plane_hy = plane_size[1];
+  for (auto p : h->hf_data) cudaFree(p);
+  h->hf_data.clear();
+  for (int i = 0; i < n_hf; i++) {
+    const srb_hfield& s = hfs[i];
+    if (!s.data_host || s.nrow < 2 || s.ncol < 2) return fail(-1, "srb_upload_terrain: bad height field");
+    float* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * (size_t)s.nrow * s.ncol));
+    CK(cudaMemcpy(d, s.data_host, sizeof(float) * (size_t)s.nrow * s.ncol, cudaMemcpyHostToDevice));
+    h->hf_data.push_back(d);
+    HFieldDev& o = T.hf[i];
+    o.data = d; o.nrow = s.nrow; o.ncol = s.ncol; o.sx = s.size[0]; o.sy = s.size[1]; o.sz = s.size[2];
+    o.px = s.pos[0]; o.py = s.pos[1]; o.pz = s.pos[2]; o.geom_id = s.geom_id;
+  }
+  std::vector<double> bx((size_t)n_box * 5);
+  for (int k = 0; k < n_box; k++) {
+    if (k > 0 && boxes[k].geom_id != boxes[k - 1].geom_id + 1) return fail(-1, "srb_upload_terrain: boxes must be consecutive geoms in model order");
+    bx[5 * k] = boxes[k].pos[0]; bx[5 * k + 1] = boxes[k].pos[1]; bx[5 * k + 2] = boxes[k].size[0]; bx[5 * k + 3] = boxes[k].size[1];
+    bx[5 * k + 4] = boxes[k].pos[2] + boxes[k].size[2];
+  }
+  T.box_geom0 = n_box ? boxes[0].geom_id : 0;
+  for (int b = 0; b < n_body; b++) {
+    TerrainBodyDev& o = T.body[b];
+    o.cx = bodies[b].xpos[0]; o.cy = bodies[b].xpos[1]; o.snap = bodies[b].snap; o.body_id = bodies[b].body_id;
+    o.first = -1; o.count = 0; o.x0 = o.y0 = 1e300; o.x1 = o.y1 = -1e300;
+    for (int k = 0; k < n_box; k++) {
+      if (boxes[k].body_id != bodies[b].body_id) continue;
+      if (o.first < 0) o.first = k;
+      if (k != o.first + o.count) return fail(-1, "srb_upload_terrain: the boxes of a body must be contiguous");
+      if (o.count > 0 && bx[5 * k + 4] < bx[5 * (k - 1) + 4]) return fail(-1, "srb_upload_terrain: box tops must ascend inside a body");
+      o.count++;
+      o.x0 = std::min(o.x0, boxes[k].pos[0] - boxes[k].size[0]); o.x1 = std::max(o.x1, boxes[k].pos[0] + boxes[k].size[0]);
+      o.y0 = std::min(o.y0, boxes[k].pos[1] - boxes[k].size[1]); o.y1 = std::max(o.y1, boxes[k].pos[1] + boxes[k].size[1]);
+    }
+    if (o.first < 0) o.first = 0;
+  }
+  cudaFree(h->box_dev); h->box_dev = nullptr;
+  if (n_box) {
+    CK(cudaMalloc(&h->box_dev, sizeof(double) * bx.size()));
+    CK(cudaMemcpy(h->box_dev, bx.data(), sizeof(double) * bx.size(), cudaMemcpyHostToDevice));
+  }
+  T.box = h->box_dev;
+  if (!h->terrain_dev) CK(cudaMalloc(&h->terrain_dev, sizeof(TerrainDev)));
+  CK(cudaMemcpy(h->terrain_dev, &T, sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int srb_set_planar_offsets(srb_env* h, const double* xy_host) {
+  if (!h || !xy_host) return fail(-1, "srb_set_planar_offsets: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < 2; c++) {
+    if (h->cfg.precision == 64) {
+      std::vector<double> col(h->N);
+      for (int i = 0; i < h->N; i++) col[i] = xy_host[2 * i + c];
+      CK(cudaMemcpy((double*)h->st + (size_t)(F_PLANAR + c) * h->Npad, col.data(), sizeof(double) * h->N, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<float> col(h->N);
+      for (int i = 0; i < h->N; i++) col[i] = (float)xy_host[2 * i + c];
+      CK(cudaMemcpy((float*)h->st + (size_t)(F_PLANAR + c) * h->Npad, col.data(), sizeof(float) * h->N, cudaMemcpyHostToDevice));
+    }
+  }
+  return 0;
+}
+
+extern "C" int srb_terrain_height(srb_env* h, int32_t n, const double* xy_dev, double* height_dev, int32_t* hit_dev, void* stream) {
+  if (!h || !xy_dev || !height_dev) return fail(-1, "srb_terrain_height: null argument");
+  if (!h->terrain_dev) return fail(-1, "srb_terrain_height: no terrain uploaded");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(h->cfg.device));
+  srb_terrain_height_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->terrain_dev, n, xy_dev, height_dev, hit_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int srb_tracking_action(srb_env* h, float sigma, uint64_t seed, uint32_t step, float* act_dev, void* stream) {
   if (!h || !act_dev) return fail(-1, "srb_tracking_action: null argument");
   if (h->nclips == 0) return fail(-1, "srb_tracking_action: no clip uploaded");
   CK(cudaSetDevice(h->cfg.device));
   int blocks = (h->N + 127) / 128;
   if (h->cfg.precision == 64)
-    srb_tracking_action_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const double*)h->st, h->ist, (const ClipDesc<double>*)h->clips_dev, sigma, seed, step, act_dev);
+    srb_tracking_action_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const double*)h->st, h->ist, (const ClipDesc<double>*)h->clips_dev, sigma, seed, step, act_dev, h->p.use_terrain ? h->terrain_dev : nullptr);
   else
-    srb_tracking_action_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const float*)h->st, h->ist, (const ClipDesc<float>*)h->clips_dev, sigma, seed, step, act_dev);
+    srb_tracking_action_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->N, h->Npad, (const float*)h->st, h->ist, (const ClipDesc<float>*)h->clips_dev, sigma, seed, step, act_dev, h->p.use_terrain ? h->terrain_dev : nullptr);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -23,6 +23,7 @@ template <typename real> struct EnvState {
   real filt_yaw[2]; real ballx[4]; real ballv[4];
   real ep_ret;
   real nu[6];        // QP dual from the last sub-step (warm start only; the optimum is unique)
+  real planar[2];    // initial_pos_planar (terrain variant)
   int flags, frame, rif, clip, fcount, impulse, episode;
 };
 
@@ -43,6 +44,7 @@ template <typename real> __device__ __forceinline__ void load_state(EnvState<rea
   s.ep_ret = LD(F_EPRET);
 #pragma unroll
   for (int i = 0; i < 6; i++) s.nu[i] = LD(F_NU + i);
+  s.planar[0] = LD(F_PLANAR); s.planar[1] = LD(F_PLANAR + 1);
 #undef LD
 #define LDI(f) ist[(size_t)(f) * Npad + e]
   s.flags = LDI(I_FLAGS); s.frame = LDI(I_FRAME); s.rif = LDI(I_RIF); s.clip = LDI(I_CLIP);
@@ -67,11 +69,76 @@ template <typename real> __device__ __forceinline__ void store_state(const EnvSt
   ST(F_EPRET, s.ep_ret);
 #pragma unroll
   for (int i = 0; i < 6; i++) ST(F_NU + i, s.nu[i]);
+  ST(F_PLANAR, s.planar[0]); ST(F_PLANAR + 1, s.planar[1]);
 #undef ST
 #define STI(f, v) ist[(size_t)(f) * Npad + e] = (v)
   STI(I_FLAGS, s.flags); STI(I_FRAME, s.frame); STI(I_RIF, s.rif); STI(I_CLIP, s.clip);
   STI(I_FCOUNT, s.fcount); STI(I_IMPULSE, s.impulse); STI(I_EPISODE, s.episode);
 #undef STI
+}
+
+// ------------------------------------------------------------------------------------------------
+// Terrain query = the vertical mj_ray of terrain_height_ray (env/testSRB_mujoco_original_viewer_terrain.py:741-752)
+// over the group-0 geoms of SRB5_playground.xml: plane, height fields, pyramid boxes.  The highest surface wins,
+// the first geom in model order wins ties (mj_ray keeps the strictly smallest distance).  Integer outputs: geom id,
+// and for height fields the cell (c, r) and the triangle of the (c,r)-(c+1,r+1) split.
+struct TerrainHit { int geom; int cell_c, cell_r, tri; };
+template <typename real>
+__device__ __forceinline__ real terrain_query(const TerrainDev& T, real x, real y, TerrainHit* hit) {
+  real best = real(0);
+  int gid = -1, cc = -1, cr = -1, tri = -1;
+  bool have = false;
+  if (num<real>::abs(x) <= (real)T.plane_hx && num<real>::abs(y) <= (real)T.plane_hy) { best = real(0); gid = T.plane_geom; have = true; }
+  for (int i = 0; i < T.n_hf; i++) {
+    const HFieldDev& h = T.hf[i];
+    real lx = x - (real)h.px, ly = y - (real)h.py;
+    if (num<real>::abs(lx) > (real)h.sx || num<real>::abs(ly) > (real)h.sy) continue;
+    real dx = real(2) * (real)h.sx / (real)(h.ncol - 1), dy = real(2) * (real)h.sy / (real)(h.nrow - 1);
+    real u = (lx + (real)h.sx) / dx, v = (ly + (real)h.sy) / dy;
+    int c = min(max((int)num<real>::floor(u), 0), h.ncol - 2), r = min(max((int)num<real>::floor(v), 0), h.nrow - 2);
+    real fu = u - (real)c, fv = v - (real)r;
+    const float* d0 = h.data + (size_t)r * h.ncol + c;
+    real z00 = (real)__ldg(d0) * (real)h.sz, z10 = (real)__ldg(d0 + 1) * (real)h.sz;
+    real z01 = (real)__ldg(d0 + h.ncol) * (real)h.sz, z11 = (real)__ldg(d0 + h.ncol + 1) * (real)h.sz;
+    int t; real z;
+    if (fu >= fv) { t = 0; z = z00 + fu * (z10 - z00) + fv * (z11 - z10); }
+    else { t = 1; z = z00 + fv * (z01 - z00) + fu * (z11 - z01); }
+    z += (real)h.pz;
+    if (!have || z > best) { best = z; gid = h.geom_id; cc = c; cr = r; tri = t; have = true; }
+  }
+  for (int b = 0; b < T.n_body; b++) {
+    const TerrainBodyDev& B = T.body[b];
+    if ((double)x < B.x0 || (double)x > B.x1 || (double)y < B.y0 || (double)y > B.y1) continue;
+    for (int k = B.first + B.count - 1; k >= B.first; k--) {           // tops ascend in model order: highest first
+      const double* bx = T.box + (size_t)k * 5;
+      if (num<real>::abs(x - (real)bx[0]) <= (real)bx[2] && num<real>::abs(y - (real)bx[1]) <= (real)bx[3]) {
+        real top = (real)bx[4];
+        if (!have || top > best) { best = top; gid = T.box_geom0 + k; cc = cr = tri = -1; have = true; }
+        break;
+      }
+    }
+  }
+  if (hit) { hit->geom = gid; hit->cell_c = cc; hit->cell_r = cr; hit->tri = tri; }
+  return best;
+}
+
+// Reference tables of the terrain variant (viewer_terrain.py:1043-1065 after the planar shift of
+// SRBEnv5_mocap_list_terrain_window.py:636): positions are the flat tables shifted by initial_pos_planar and lifted
+// by the terrain height underneath; "original" foot z (== 0 <=> reference contact) is the flat table's.
+template <typename real> struct LiftedFrame { V3<real> pos; real hc; V3<real> foot[2]; bool contact[2]; };
+template <typename real>
+__device__ __forceinline__ LiftedFrame<real> lifted_frame(const real* __restrict__ fr, const real planar[2], const TerrainDev& T) {
+  LiftedFrame<real> L;
+  real x = fr[0] + planar[0], y = fr[1] + planar[1];
+  L.hc = terrain_query<real>(T, x, y, nullptr);
+  L.pos = {x, y, fr[2] + L.hc};
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    real fx = fr[18 + 3 * i] + planar[0], fy = fr[19 + 3 * i] + planar[1];
+    L.foot[i] = {fx, fy, real(0) + terrain_query<real>(T, fx, fy, nullptr)};
+    L.contact[i] = fr[20 + 3 * i] == real(0);
+  }
+  return L;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -93,7 +160,7 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit unif
 // draws of SRBEnv.reset / set_state (SRBEnv5_mocap_list_window.py:810,823,860-867, viewer.py:719-731):
 // plan = clip, start frame, uniform(-.05,.05)^3 velocity noise, small random quaternion.
 template <typename real>
-__device__ inline void draw_reset_plan(unsigned long long seed, int env, int episode, const ClipDesc<real>* clips, int nclips, double plan[9]) {
+__device__ inline void draw_reset_plan(unsigned long long seed, int env, int episode, const ClipDesc<real>* clips, int nclips, double plan[9], bool terrain = false) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c[4] = {(uint32_t)env, (uint32_t)episode, 0x5EB0u, 0u};
   philox4x32(c, k0, k1);
@@ -104,7 +171,7 @@ __device__ inline void draw_reset_plan(unsigned long long seed, int env, int epi
   const float U32 = 2.3283064365386963e-10f;                         // 2^-32
   int clip = min((int)(__umulhi(c[0], (uint32_t)nclips)), nclips - 1);   // random.randrange(n)
   int cyc = clips[clip].cycle_length;
-  int hi = max(cyc - 2, 512);                                        // random.randint(0, hi) inclusive
+  int hi = terrain ? max(cyc - 2, 0) : max(cyc - 2, 512);            // random.randint(0, hi) inclusive (Q12)
   int frame = min((int)__umulhi(c[1], (uint32_t)(hi + 1)), hi);
   plan[0] = clip; plan[1] = frame;
   plan[2] = (double)((((float)c[2] + 0.5f) * U32 * 2.0f - 1.0f) * 5e-2f);
@@ -132,7 +199,7 @@ __device__ inline void draw_reset_plan(unsigned long long seed, int env, int epi
 // plan[5] (noise quat w) == NaN selects testing_mode (no noise).
 template <typename real>
 __device__ inline void apply_reset(EnvState<real>& s, const ClipDesc<real>* clips, int nclips, const double plan[9],
-                                   real* __restrict__ hist_env) {
+                                   real* __restrict__ hist_env, const TerrainDev* T = nullptr) {
   int clip = min(max((int)plan[0], 0), nclips - 1);
   const ClipDesc<real> cd = clips[clip];
   int f = min(max((int)plan[1], 0), cd.nframes - 1);
@@ -155,6 +222,10 @@ __device__ inline void apply_reset(EnvState<real>& s, const ClipDesc<real>* clip
   bool lc = (fr[20] == real(0)), rc = (fr[23] == real(0));
   s.foot[0] = {fr[18], fr[19], real(0)};
   s.foot[1] = {fr[21], fr[22], real(0)};
+  if (T != nullptr) {                              // terrain variant (..._terrain_window.py:417-443): lifted tables
+    LiftedFrame<real> L = lifted_frame<real>(fr, s.planar, *T);
+    s.pos = L.pos; s.foot[0] = L.foot[0]; s.foot[1] = L.foot[1];
+  }
   s.yc[0] = fr[24]; s.ys[0] = fr[25]; s.yc[1] = fr[26]; s.ys[1] = fr[27];
   // legacy slices [:3] / [3:] of the 10-entry site list (Q2): right = left OR right
   s.flags = (lc ? FLAG_L : 0) | ((lc || rc) ? FLAG_R : 0) | (cd.is_stand ? FLAG_STAND : 0);   // clears FLAG_FILT / FLAG_NU
@@ -176,12 +247,15 @@ __device__ inline void apply_reset(EnvState<real>& s, const ClipDesc<real>* clip
 // Self part (25) from the state; look-ahead part = 5 precomputed 25-float records of the clip table
 // (they depend on the reference frame only).  `lane`/`G`: cooperative copy of the window.
 template <typename real, int G>
-__device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDesc<real>& cd, float* __restrict__ o, int lane, bool active) {
+__device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDesc<real>& cd, float* __restrict__ o, int lane, bool active,
+                                          const TerrainDev* T = nullptr) {
   M3<real> R = quat2mat_normalized(s.qlag);
   real fx, fy;
   yaw_frame(R, &fx, &fy);
   if (active && lane == 0) {
-    o[0] = (float)s.pos.z;
+    real h0 = s.pos.z;
+    if (T != nullptr) h0 -= terrain_query<real>(*T, s.pos.x, s.pos.y, nullptr);     // terrain-relative height (:549-552)
+    o[0] = (float)h0;
     // (proj^T R)[:, :2] flattened column-major
     o[1] = (float)(fx * R.m[0] + fy * R.m[3]); o[2] = (float)(-fy * R.m[0] + fx * R.m[3]); o[3] = (float)R.m[6];
     o[4] = (float)(fx * R.m[1] + fy * R.m[4]); o[5] = (float)(-fy * R.m[1] + fx * R.m[4]); o[6] = (float)R.m[7];
@@ -198,7 +272,38 @@ __device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDes
     int c = s.flags & 3;
     o[21] = c == 0 ? 1.f : 0.f; o[22] = c == 1 ? 1.f : 0.f; o[23] = c == 2 ? 1.f : 0.f; o[24] = c == 3 ? 1.f : 0.f;
   }
-  if (active) {
+  if (active && T != nullptr) {
+    // terrain variant: the look-ahead features depend on the terrain under the shifted reference (:574-623);
+    // one frame per lane
+    const int f0 = s.frame + s.rif + 1;
+    for (int wi = lane; wi < 5; wi += G) {
+      const int f = min(f0 + wi, cd.nframes - 1);
+      const real* fr = cd.frames + (size_t)f * CLIP_W;
+      LiftedFrame<real> L = lifted_frame<real>(fr, s.planar, *T);
+      M3<real> Rr;
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rr.m[i] = fr[3 + i];
+      real rx, ry;
+      yaw_frame(Rr, &rx, &ry);
+      float* w = o + FEAT_W * (1 + wi);
+      w[0] = (float)(L.pos.z - L.hc);
+      w[1] = (float)(rx * Rr.m[0] + ry * Rr.m[3]); w[2] = (float)(-ry * Rr.m[0] + rx * Rr.m[3]); w[3] = (float)Rr.m[6];
+      w[4] = (float)(rx * Rr.m[1] + ry * Rr.m[4]); w[5] = (float)(-ry * Rr.m[1] + rx * Rr.m[4]); w[6] = (float)Rr.m[7];
+      V3<real> vl = yawT(rx, ry, V3<real>{fr[12], fr[13], fr[14]});
+      V3<real> va = yawT(rx, ry, mul(Rr, V3<real>{fr[15], fr[16], fr[17]}));
+      w[7] = (float)vl.x; w[8] = (float)vl.y; w[9] = (float)vl.z; w[10] = (float)va.x; w[11] = (float)va.y; w[12] = (float)va.z;
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        V3<real> l = yawT(rx, ry, L.foot[i] - L.pos);
+        real yc = fr[24 + 2 * i], ys = fr[25 + 2 * i];
+        w[13 + 4 * i] = (float)l.x; w[14 + 4 * i] = (float)l.y; w[15 + 4 * i] = (float)l.z;
+        w[16 + 4 * i] = (float)num<real>::atan2(-ry * yc + rx * ys, rx * yc + ry * ys);
+        if (L.contact[i]) c |= (1 << i);
+      }
+      w[21] = c == 0 ? 1.f : 0.f; w[22] = c == 1 ? 1.f : 0.f; w[23] = c == 2 ? 1.f : 0.f; w[24] = c == 3 ? 1.f : 0.f;
+    }
+  } else if (active) {
     // 5 consecutive frame records are contiguous in the feature table (clamped only at the table end)
     int f0 = min(s.frame + s.rif + 1, max(cd.nframes - 5, 0));
     const float* __restrict__ src = cd.feat + (size_t)f0 * FEAT_W;
@@ -663,9 +768,14 @@ __device__ __forceinline__ real compute_reward(const EnvState<real>& s, const Cl
 }
 
 // SRBEnv._get_done (:916-1003)
-template <typename real> __device__ __forceinline__ bool compute_done(const EnvState<real>& s, const ClipDesc<real>& cd, const Params<real>& p) {
+template <typename real> __device__ __forceinline__ bool compute_done(const EnvState<real>& s, const ClipDesc<real>& cd, const Params<real>& p,
+                                                                      const TerrainDev* T = nullptr) {
   int f1 = min(s.frame + 1 + s.rif, cd.nframes - 1);
   real ref_h = cd.frames[(size_t)f1 * CLIP_W + 2];
+  if (T != nullptr) {
+    const real* fr = cd.frames + (size_t)f1 * CLIP_W;
+    ref_h += terrain_query<real>(*T, fr[0] + s.planar[0], fr[1] + s.planar[1], nullptr);
+  }
   real h = s.pos.z;
   if (ref_h - h > real(0.2) || h - ref_h > real(0.2) || h < real(0.50) || h > real(1.2)) return true;
   M3<real> X = quat2mat_normalized(s.qlag);
@@ -751,7 +861,9 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
       rc = (r0 && (double)p1 < (1.0 - conf)) ? false : ((!r0 && (double)p1 > conf) ? true : r0);
     }
   }
+  const bool last_lc = (s.flags & FLAG_L) != 0, last_rc = (s.flags & FLAG_R) != 0;
   s.flags = (s.flags & ~(FLAG_L | FLAG_R)) | (lc ? FLAG_L : 0) | (rc ? FLAG_R : 0);
+  const TerrainDev* T = P.use_terrain ? A.terrain : nullptr;
 
   // ---- feet (:320-371; training: ..._training.py:231-258)
   if (P.use_filter) {
@@ -777,8 +889,13 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         sds_4steps(s.ballx[2 * i], s.ballv[2 * i], g.x, K0, K1);
         sds_4steps(s.ballx[2 * i + 1], s.ballv[2 * i + 1], g.y, K0, K1);
         s.foot[i] = {s.ballx[2 * i], s.ballx[2 * i + 1], real(0)};
+        real yaw = s.filt_yaw[i];
+        if (T != nullptr) {                             // terrain variant (..._terrain_window.py:340-342,401-403)
+          s.foot[i].z = terrain_query<real>(*T, s.foot[i].x, s.foot[i].y, nullptr);
+          if (i == 1) yaw = a[17];                      // Q9: the right swing foot uses the raw action yaw
+        }
         real sa, ca;
-        num<real>::sincos(s.filt_yaw[i], &sa, &ca);
+        num<real>::sincos(yaw, &sa, &ca);
         s.yc[i] = fx * ca - fy * sa; s.ys[i] = fy * ca + fx * sa;     // ffSRB_ori @ Rz(filter yaw)
       } else {                                          // updateFilter (:1289-1299): rows 0 of both matrices
         real v1x = s.yc[i], v1y = -s.ys[i], v2x = fx, v2y = -fy;
@@ -786,6 +903,33 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         v1x /= n1; v1y /= n1; v2x /= n2; v2y /= n2;
         s.filt_yaw[i] = num<real>::atan2(v1x * v2y - v1y * v2x, v1x * v2x + v1y * v2y);
         s.ballv[2 * i] = real(0); s.ballv[2 * i + 1] = real(0);
+        if (T != nullptr && !(i == 0 ? last_lc : last_rc)) {
+          // touchdown on a pyramid layer: snap the foot to the nearest edge of the mid-size between this layer and
+          // the next geom (..._terrain_window.py:346-380, 407-442); the height sampled while swinging is kept (Q10)
+          TerrainHit hit;
+          terrain_query<real>(*T, s.foot[i].x, s.foot[i].y, &hit);
+          int k = hit.geom - T->box_geom0;
+          if (hit.geom >= 0 && k >= 0 && k + 1 < T->n_box) {
+            int bi = -1;
+            for (int b = 0; b < T->n_body; b++) if (k >= T->body[b].first && k < T->body[b].first + T->body[b].count) bi = b;
+            if (bi >= 0 && T->body[bi].snap) {
+              const double* g0 = T->box + (size_t)k * 5; const double* g1 = g0 + 5;
+              real hx = ((real)g0[2] + (real)g1[2]) / real(2), hy = ((real)g0[3] + (real)g1[3]) / real(2);
+              real x_min = (real)T->body[bi].cx - hx, x_max = (real)T->body[bi].cx + hx;
+              real y_min = (real)T->body[bi].cy - hy, y_max = (real)T->body[bi].cy + hy;
+              real px = s.foot[i].x, py = s.foot[i].y;
+              real dx_min = num<real>::abs(px - x_min), dx_max = num<real>::abs(px - x_max);
+              real dy_min = num<real>::abs(py - y_min), dy_max = num<real>::abs(py - y_max);
+              real cx = px < x_min ? x_min : (px > x_max ? x_max : px), cy = py < y_min ? y_min : (py > y_max ? y_max : py);
+              real md = dx_min; md = dx_max < md ? dx_max : md; md = dy_min < md ? dy_min : md; md = dy_max < md ? dy_max : md;
+              if (md == dx_min) { px = x_min; py = cy; }
+              else if (md == dx_max) { px = x_max; py = cy; }
+              else if (md == dy_min) { px = cx; py = y_min; }
+              else { px = cx; py = y_max; }
+              s.foot[i].x = px; s.foot[i].y = py;
+            }
+          }
+        }
       }
     }
   } else {
@@ -947,12 +1091,18 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 
   // ---- obs / reward / done (:477-494; training variant takes the obs after the frame increment)
   float* obs = A.obs + (size_t)e * OBS_W;
-  if (!P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active);
+  if (!P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T);
   float info[8];
-  real r = compute_reward(s, cd, hist_env, pred_contact, P, info);
-  bool done = compute_done(s, cd, P);
+  real r = real(0);
+  if (T == nullptr) {
+    r = compute_reward(s, cd, hist_env, pred_contact, P, info);
+  } else {                                               // terrain env: _get_reward returns (0, {}) (:525-526)
+#pragma unroll
+    for (int i = 0; i < 8; i++) info[i] = 0.f;
+  }
+  bool done = compute_done(s, cd, P, T);
   s.frame += 1;
-  if (P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active);
+  if (P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T);
   s.ep_ret += r;
   if (active && lane == 0) {
     A.rew[e] = (float)r;
@@ -981,18 +1131,18 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 #pragma unroll
         for (int i = 0; i < 9; i++) plan[i] = A.reset_plan[(size_t)e * 9 + i];
       } else {
-        draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan);
+        draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan, T != nullptr);
       }
       EnvState<real> ns = s;
       real h0[HIST_W];
-      apply_reset(ns, A.clips, A.nclips, plan, h0);
+      apply_reset(ns, A.clips, A.nclips, plan, h0, T);
       s = ns;
       if (active && lane == 0) {
 #pragma unroll
         for (int i = 0; i < HIST_W; i++) hist_env[i] = h0[i];
       }
       const ClipDesc<real> ncd = A.clips[s.clip];
-      write_obs<real, G>(s, ncd, obs, lane, active);
+      write_obs<real, G>(s, ncd, obs, lane, active, T);
     }
   }
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
@@ -1012,14 +1162,15 @@ template <typename real> __global__ void srb_reset_kernel(const ResetArgs<real> 
   if (A.plan != nullptr) {
     for (int k = 0; k < 9; k++) plan[k] = A.plan[(size_t)i * 9 + k];
   } else {
-    draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan);
+    draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan, A.p.use_terrain != 0);
   }
   real* hist_env = A.hist + (size_t)e * HIST_SLOTS * HIST_W;
-  apply_reset(s, A.clips, A.nclips, plan, hist_env);
+  const TerrainDev* T = A.p.use_terrain ? A.terrain : nullptr;
+  apply_reset(s, A.clips, A.nclips, plan, hist_env, T);
   store_state(s, A.st, A.ist, A.Npad, e);
   if (A.obs != nullptr) {
     const ClipDesc<real> cd = A.clips[s.clip];
-    write_obs<real, 1>(s, cd, A.obs + (size_t)e * OBS_W, 0, true);
+    write_obs<real, 1>(s, cd, A.obs + (size_t)e * OBS_W, 0, true, T);
   }
 }
 
@@ -1032,7 +1183,7 @@ template <typename real> __global__ void srb_reset_kernel(const ResetArgs<real> 
 template <typename real>
 __global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restrict__ st, const int* __restrict__ ist,
                                            const ClipDesc<real>* __restrict__ clips, float sigma, unsigned long long seed,
-                                           unsigned int step, float* __restrict__ act) {
+                                           unsigned int step, float* __restrict__ act, const TerrainDev* __restrict__ T) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   EnvState<real> s;
@@ -1047,9 +1198,15 @@ __global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restri
 #pragma unroll
   for (int i = 0; i < ACT_W; i++) a[i] = real(0);
   V3<real> origin = {s.pos.x, s.pos.y, real(0)};
+  V3<real> rpos = {fr[0], fr[1], fr[2]};
+  real px = real(0), py = real(0);
+  if (T != nullptr) {                               // terrain variant: shifted + lifted reference
+    px = s.planar[0]; py = s.planar[1];
+    rpos = lifted_frame<real>(fr, s.planar, *T).pos;
+  }
 #pragma unroll
   for (int i = 0; i < 2; i++) {
-    V3<real> l = yawT(fx, fy, V3<real>{fr[18 + 3 * i], fr[19 + 3 * i], real(0)} - origin);
+    V3<real> l = yawT(fx, fy, V3<real>{fr[18 + 3 * i] + px, fr[19 + 3 * i] + py, real(0)} - origin);
     a[2 * i] = l.x; a[2 * i + 1] = l.y;
     real yc = fr[24 + 2 * i], ys = fr[25 + 2 * i];
     a[16 + i] = num<real>::atan2(-fy * yc + fx * ys, fx * yc + fy * ys);
@@ -1060,7 +1217,7 @@ __global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restri
   V3<real> vl = mulT(R, V3<real>{fr[12], fr[13], fr[14]});
   a[4] = vl.x; a[5] = vl.y; a[6] = vl.z; a[7] = fr[15]; a[8] = fr[16]; a[9] = fr[17];
   V3<real> v_tw, w_tw;
-  V3<real> dp = mulT(R, V3<real>{fr[0], fr[1], fr[2]} - s.pos);
+  V3<real> dp = mulT(R, rpos - s.pos);
   log_se3(matmulTN(R, Rr), dp, &v_tw, &w_tw);
   a[10] = dp.x; a[11] = dp.y; a[12] = dp.z; a[13] = w_tw.x; a[14] = w_tw.y; a[15] = w_tw.z;
   int c = (fr[20] == real(0) ? 1 : 0) + (fr[23] == real(0) ? 2 : 0);
@@ -1076,6 +1233,17 @@ __global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restri
     o[i] = (float)a[i] + sigma * r * cs;
     o[i + 1] = (float)a[i + 1] + sigma * r * sn;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched terrain_height_ray: xy[n][2] -> height[n], hit[n][4] = (geom id, hfield cell c, cell r, triangle)
+__global__ void srb_terrain_height_kernel(const TerrainDev* __restrict__ T, int n, const double* __restrict__ xy, double* __restrict__ height,
+                                          int* __restrict__ hit) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  TerrainHit h;
+  height[i] = terrain_query<double>(*T, xy[2 * i], xy[2 * i + 1], &h);
+  if (hit) { hit[4 * i] = h.geom; hit[4 * i + 1] = h.cell_c; hit[4 * i + 2] = h.cell_r; hit[4 * i + 3] = h.tri; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,7 +19,8 @@ enum RealField {
   F_BALLV = 33,   // 4  SDS velocity state
   F_EPRET = 37,   // 1  running episode return
   F_NU = 38,      // 6  QP dual of the last sub-step (warm start)
-  NF_REAL = 44
+  F_PLANAR = 44,  // 2  initial_pos_planar of this environment's reference (terrain variant)
+  NF_REAL = 46
 };
 enum IntField {
   I_FLAGS = 0,    // bit0 left_foot_in_contact, bit1 right_foot_in_contact, bit2 filter initialised, bit3 is_stand
@@ -51,7 +52,20 @@ template <typename real> struct ClipDesc {
   int pad;
 };
 
-enum Variant { VARIANT_TEST = 0, VARIANT_TRAINING = 1 };
+enum Variant { VARIANT_TEST = 0, VARIANT_TRAINING = 1, VARIANT_TERRAIN = 2 };
+
+// ---- terrain of SRB5_playground.xml: plane + height fields + axis-aligned box stacks (pyramids) -------
+struct HFieldDev { const float* data; int nrow, ncol; double sx, sy, sz, px, py, pz; int geom_id; int pad; };
+struct TerrainBodyDev { double cx, cy; double x0, x1, y0, y1; int first, count, snap, body_id; };
+enum { MAX_HF = 4, MAX_TBODY = 16 };
+struct TerrainDev {
+  int enabled, n_hf, n_body, n_box;
+  int plane_geom, box_geom0;
+  double plane_hx, plane_hy;
+  HFieldDev hf[MAX_HF];
+  TerrainBodyDev body[MAX_TBODY];
+  const double* box;   // [n_box][5] cx cy hx hy top, model order (ascending tops inside a body)
+};
 
 template <typename real> struct Params {
   real h;               // model.opt.timestep
@@ -62,7 +76,7 @@ template <typename real> struct Params {
   real inv_w_lambda, inv_M[6], inv_Mh[6];   // 1/w, 1/(M+armature), 1/(M+armature+h*damping)
   real force_thr;
   real w[9];            // w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c
-  int use_filter, use_clamp, use_impulse, obs_after_inc;
+  int use_filter, use_clamp, use_impulse, obs_after_inc, use_terrain;
   int impulse_interval, impulse_duration, impulse_trigger_at_end;
   real impulse_force[3];
   int max_frame;        // 512
@@ -82,6 +96,7 @@ template <typename real> struct StepArgs {
   double* ep_stats;              // [3] sum of episode returns, sum of episode lengths, episode count (atomicAdd)
   unsigned long long seed;
   int auto_reset;
+  const TerrainDev* terrain;     // device pointer (terrain variant) or null
   Params<real> p;
 };
 
@@ -93,6 +108,7 @@ template <typename real> struct ResetArgs {
   const double* plan;            // [count][9] explicit draws or null (=> device RNG)
   float* obs;                    // [N][OBS_W] rows of the reset envs are written, may be null
   unsigned long long seed;
+  const TerrainDev* terrain;
   Params<real> p;
 };
 

@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM, VARIANT_TEST, VARIANT_TRAINING, SrbConfig, check
+from ._lib import OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM, VARIANT_TEST, VARIANT_TRAINING, VARIANT_TERRAIN, SrbConfig, check
 
 REWARD_INFO_KEYS = ("reward_survive", "reward_contact", "reward_end_effector", "reward_delta_pos",
                     "reward_delta_ori", "reward_pos", "reward_ori", "reward_total")
@@ -49,7 +49,9 @@ class SRBVecEnv:
     """N SRBEnv instances stepped by one CUDA launch."""
 
     def __init__(self, clips, num_envs, variant="test", precision=64, lanes_per_env=0, auto_reset=True,
-                 device=0, seed=0):
+                 device=0, seed=0, terrain=None, initial_pos_planar=None):
+        """variant "terrain" (env/SRBEnv5_mocap_list_terrain_window.py) needs `terrain` (ipcdnnwalk_b200.terrain.TerrainModel);
+        `clips` are the FLAT reference tables, `initial_pos_planar` [N,2] shifts each environment's reference."""
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -57,7 +59,7 @@ class SRBVecEnv:
             raise RuntimeError("SRBVecEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device)
         self.num_envs = int(num_envs)
-        self.variant = {"test": VARIANT_TEST, "training": VARIANT_TRAINING}[variant] if isinstance(variant, str) else int(variant)
+        self.variant = {"test": VARIANT_TEST, "training": VARIANT_TRAINING, "terrain": VARIANT_TERRAIN}[variant] if isinstance(variant, str) else int(variant)
         self.precision = int(precision)
         cfg = SrbConfig(self.num_envs, self.variant, self.precision, int(lanes_per_env), int(bool(auto_reset)), int(device), int(seed))
         self._h = C.c_void_p()
@@ -69,6 +71,15 @@ class SRBVecEnv:
                                            _ptr(pos), _ptr(ori), _ptr(vel), _ptr(quat), _ptr(feet), _ptr(yaw)))
             self.clips.append(clip)
         N = self.num_envs
+        self.terrain = terrain
+        if self.variant == VARIANT_TERRAIN:
+            if terrain is None:
+                raise ValueError("variant 'terrain' needs a TerrainModel")
+            hf, n_hf, bx, n_box, bd, n_body = terrain.c_tables()
+            check(self.lib.srb_upload_terrain(self._h, _ptr(terrain.plane_size), terrain.plane_geom, n_hf, C.cast(hf, C.c_void_p),
+                                              n_box, C.cast(bx, C.c_void_p), n_body, C.cast(bd, C.c_void_p)))
+            if initial_pos_planar is not None:
+                self.set_planar_offsets(initial_pos_planar)
         self.obs = torch.zeros(N, OBS_DIM, dtype=torch.float32, device=self.device)
         self.rew = torch.zeros(N, dtype=torch.float32, device=self.device)
         self.done = torch.zeros(N, dtype=torch.uint8, device=self.device)
@@ -198,7 +209,7 @@ class SRBVecEnv:
                     left_foot_contact_pos_global=r[17:20].copy(), right_foot_contact_pos_global=r[20:23].copy(),
                     left_foot_yaw_cs=r[23:25].copy(), right_foot_yaw_cs=r[25:27].copy(),
                     contactFilter_yaw=r[27:29].copy(), sds_x=r[29:33].copy(), sds_v=r[33:37].copy(),
-                    episode_return=float(r[37]), qp_dual_warm_start=r[38:44].copy(),
+                    episode_return=float(r[37]), qp_dual_warm_start=r[38:44].copy(), initial_pos_planar=r[44:46].copy(),
                     left_foot_in_contact=bool(k[0] & 1), right_foot_in_contact=bool(k[0] & 2),
                     filter_initialised=bool(k[0] & 4), is_stand=bool(k[0] & 8),
                     current_frame=int(k[1]), random_initial_frame=int(k[2]), clip=int(k[3]),
@@ -222,6 +233,20 @@ class SRBVecEnv:
     def set_impulse(self, interval, duration, force):
         f = np.ascontiguousarray(force, dtype=np.float64)
         check(self.lib.srb_set_impulse(self._h, int(interval), int(duration), _ptr(f)))
+
+    def set_planar_offsets(self, xy):
+        """initial_pos_planar per environment ([N,2]); used from each environment's next reset on."""
+        xy = np.ascontiguousarray(np.asarray(xy, dtype=np.float64).reshape(self.num_envs, 2))
+        check(self.lib.srb_set_planar_offsets(self._h, _ptr(xy)))
+
+    def terrain_height(self, xy):
+        """Batched terrain_height_ray: xy float64 [n,2] (device) -> (height [n], hit [n,4] = geom id, hfield cell c, r, triangle)."""
+        t = self.torch
+        xy = xy.to(device=self.device, dtype=t.float64).contiguous()
+        n = xy.shape[0]
+        h = t.empty(n, dtype=t.float64, device=self.device); hit = t.empty(n, 4, dtype=t.int32, device=self.device)
+        check(self.lib.srb_terrain_height(self._h, n, _ptr(xy), _ptr(h), _ptr(hit), self._stream()))
+        return h, hit
 
     def obs_stats(self, acc):
         """acc (float64 [1+2*150], device) += (count, sum, sum of squares) of the current observations."""

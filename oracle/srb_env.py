@@ -213,8 +213,12 @@ class OracleSRBEnv:
     """State-for-state restatement of `SRBEnv` (flat ground).  Clip tables are passed in as a dict
     with the keys loadMocap builds (SRBEnv5_mocap_list_window.py:1187-1197)."""
 
-    def __init__(self, clips, variant="test"):
-        assert variant in ("test", "training")
+    def __init__(self, clips, variant="test", terrain=None):
+        """variant "terrain" = env/SRBEnv5_mocap_list_terrain_window.py: `clips` must be terrain-lifted tables
+        (lift_clip_to_terrain) and `terrain` an oracle.terrain.Terrain."""
+        assert variant in ("test", "training", "terrain")
+        assert (variant == "terrain") == (terrain is not None)
+        self.terrain = terrain
         self.variant = variant
         self.model = mj.FreeBodyModel()
         self.data = mj.FreeBodyData(self.model)
@@ -231,7 +235,7 @@ class OracleSRBEnv:
         self.contact_prob = [None, None]     # Policy_prior_posterior_MoE_window._last_contact_prob side channel
         self.is_stand = False
         self.frame_counter = 0
-        if variant == "test":
+        if variant in ("test", "terrain"):
             self.impulse_interval = 1e9
             self.force = [700, 700, -350]
         else:
@@ -244,7 +248,7 @@ class OracleSRBEnv:
 
     # -- :191-206
     def update_impulse(self):
-        if self.variant == "test":
+        if self.variant in ("test", "terrain"):
             trig = self.frame_counter % self.impulse_interval == self.impulse_interval - 1
         else:
             trig = self.frame_counter % self.impulse_interval == 0
@@ -286,7 +290,9 @@ class OracleSRBEnv:
         next_contact_signal = int(np.argmax(self.next_contact_one_hot))
         if self.variant == "training" and self.is_stand:
             next_contact_signal = 3
-        contact_prob = self.contact_prob if self.variant == "test" else [None, None]
+        contact_prob = self.contact_prob if self.variant in ("test", "terrain") else [None, None]
+        last_left_foot_in_contact = self.left_foot_in_contact
+        last_right_foot_in_contact = self.right_foot_in_contact
         if contact_prob[0] is None:
             left_now = next_contact_signal in (1, 3)
             right_now = next_contact_signal in (2, 3)
@@ -307,7 +313,55 @@ class OracleSRBEnv:
         self.left_foot_in_contact = bool(left_now)
         self.right_foot_in_contact = bool(right_now)
 
-        if self.variant == "test":
+        if self.variant == "terrain":     # ..._terrain_window.py:320-411
+            if self.contactFilter[0] is None:
+                self.initFilter(0, action[16], action[0:2], ffSRB_ori, ffSRB_origin)
+                self.initFilter(1, action[17], action[2:4], ffSRB_ori, ffSRB_origin)
+            for idx in (0, 1):
+                in_contact = self.left_foot_in_contact if idx == 0 else self.right_foot_in_contact
+                last = last_left_foot_in_contact if idx == 0 else last_right_foot_in_contact
+                if not in_contact:
+                    self.filterFoot(idx, action[16 + idx], action[2 * idx:2 * idx + 2], ffSRB_ori, ffSRB_origin)
+                    pos = self.left_foot_contact_pos_global if idx == 0 else self.right_foot_contact_pos_global
+                    h, _ = self.terrain.height_ray(pos[0], pos[1])
+                    pos[2] = h
+                    # Q9: left yaw = EMA filter, right yaw = raw action
+                    yaw = self.contactFilter[0] if idx == 0 else action[17]
+                    ori = ffSRB_ori @ z_axis_rotation_matrix(yaw)
+                    pred = pos.copy(); pred[2] = np.nan
+                else:
+                    ori = self.left_foot_contact_ori if idx == 0 else self.right_foot_contact_ori
+                    self.updateFilter(idx, ori, ffSRB_ori)
+                    pos = self.left_foot_contact_pos_global if idx == 0 else self.right_foot_contact_pos_global
+                    h, geom_id = self.terrain.height_ray(pos[0], pos[1])
+                    box = self.terrain.box_by_geom(geom_id)
+                    body = self.terrain.body(box["body_id"]) if box is not None else None
+                    if body is not None and body["snap"] and not last:      # pyramid edge snap (:346-380, :407-442)
+                        foot_xy = pos[:2]
+                        gs = box["size"]; ngs = self.terrain.box_by_geom(geom_id + 1)["size"]
+                        center = body["xpos"]
+                        half = (gs[:2] + ngs[:2]) / 2
+                        x_min, x_max = center[0] - half[0], center[0] + half[0]
+                        y_min, y_max = center[1] - half[1], center[1] + half[1]
+                        dx_min, dx_max = abs(foot_xy[0] - x_min), abs(foot_xy[0] - x_max)
+                        dy_min, dy_max = abs(foot_xy[1] - y_min), abs(foot_xy[1] - y_max)
+                        cx = np.clip(foot_xy[0], x_min, x_max); cy = np.clip(foot_xy[1], y_min, y_max)
+                        md = min(dx_min, dx_max, dy_min, dy_max)
+                        if md == dx_min:
+                            proj = np.array([x_min, cy])
+                        elif md == dx_max:
+                            proj = np.array([x_max, cy])
+                        elif md == dy_min:
+                            proj = np.array([cx, y_min])
+                        else:
+                            proj = np.array([cx, y_max])
+                        pos[:2] = proj
+                    pred = pos.copy(); pred[2] = 0
+                if idx == 0:
+                    self.left_foot_contact_ori, self.next_predicted_left_foot_pos = ori, pred
+                else:
+                    self.right_foot_contact_ori, self.next_predicted_right_foot_pos = ori, pred
+        elif self.variant == "test":
             if self.contactFilter[0] is None:
                 self.initFilter(0, action[16], action[0:2], ffSRB_ori, ffSRB_origin)
                 self.initFilter(1, action[17], action[2:4], ffSRB_ori, ffSRB_origin)
@@ -360,7 +414,7 @@ class OracleSRBEnv:
             d.qfrc_applied = np.zeros(6)
             mj.mj_step1(m, d)
             self.xquat_lagged = d.qpos[3:7].copy()        # the quaternion data.xmat now corresponds to (Q14)
-            if self.variant == "test":
+            if self.variant in ("test", "terrain"):
                 self.update_impulse()
             set_feet_site_this_step_env(d, next_predicted_feet_pos, curr_feet_ori, des_l, des_r)
             if not self.left_foot_in_contact and not self.right_foot_in_contact:
@@ -407,7 +461,7 @@ class OracleSRBEnv:
         self.simulated_feet_ori_list.append([d.site_xmat[s].copy().reshape(3, 3) for s in self.site_id_list])
         self.contact_signal_list.append(next_contact_signal)
         self.action = action
-        if self.variant == "test":
+        if self.variant in ("test", "terrain"):
             observation = self._get_obs()
             reward, reward_info = self._get_reward()
             done = self._get_done()
@@ -426,6 +480,8 @@ class OracleSRBEnv:
 
     # -- :496-803
     def _get_reward(self):
+        if self.variant == "terrain":       # ..._terrain_window.py:525-526
+            return 0, {}
         d = self.data
         cf, rf = self.current_frame, self.random_initial_frame
         curr_ref_pos = self.mocap_pos_com[cf + rf].copy()
@@ -513,6 +569,9 @@ class OracleSRBEnv:
         self.feet_pos_list = c["feet_pos_list"]
         self.feet_ori_list = c["feet_ori_list"]
         self.is_stand = bool(c.get("is_stand", False))
+        if self.variant == "terrain":
+            self.feet_pos_list_original = c["feet_pos_list_original"]
+            self.mocap_height_com_terrain = c["mocap_height_com_terrain"]
 
     def reset_explicit(self, clip_id, initial_frame, vel_noise=None, noise_quat=None):
         """`vel_noise` (3,), `noise_quat` (4,) are the values np.random would have produced at :860-867;
@@ -528,7 +587,7 @@ class OracleSRBEnv:
         if not self.testing_mode:
             clip = rng_py.randrange(len(self.clips))
             cyc = self.clips[clip]["cycle_length"]
-            frame = rng_py.randint(0, max(cyc - 2, 512))
+            frame = rng_py.randint(0, cyc - 2) if self.variant == "terrain" else rng_py.randint(0, max(cyc - 2, 512))   # Q12
             vel_noise = rng_np.uniform(low=-5e-2, high=5e-2, size=3)
             axis = rng_np.standard_normal(3)
             axis /= np.linalg.norm(axis)
@@ -555,8 +614,12 @@ class OracleSRBEnv:
             d.qvel = self.mocap_vel_com[initial_frame].copy()
         feet_pos = self.feet_pos_list[initial_frame]
         feet_ori = self.feet_ori_list[initial_frame]
-        feet_xy = feet_pos.copy()
-        feet_xy[:, 2] = 0
+        if self.variant == "terrain":       # :429-443: flags from the original (planar) z, positions from the lifted table
+            feet_xy = feet_pos                                   # views into the table, as in the reference
+            feet_pos = self.feet_pos_list_original[initial_frame]
+        else:
+            feet_xy = feet_pos.copy()
+            feet_xy[:, 2] = 0
         self.left_foot_contact_ori = feet_ori[0]        # views into the clip table (mutated by Q11)
         self.right_foot_contact_ori = feet_ori[1]
         self.site_to_apply_force_on = return_site_to_apply_force_on(feet_pos)
@@ -608,6 +671,9 @@ class OracleSRBEnv:
         assert cf + window_size < least_episode_length * 2
         xmat = self._xmat()
         SRB_pos_proj, projSRB_ori = global2projected(xmat, d.qpos[:3].copy(), d.qpos[:3].copy())
+        if self.variant == "terrain":
+            curr_height_terrain, _ = self.terrain.height_ray(d.qpos[0], d.qpos[1])
+            SRB_pos_proj[2] -= curr_height_terrain
         height_proj = np.array([SRB_pos_proj[2]])
         world_mat = xmat.copy()
         projSRB_mat_6D = (projSRB_ori.T @ world_mat)[:, :2].flatten(order='F')
@@ -677,11 +743,14 @@ class OracleSRBEnv:
 def reference_frame_features(env, f):
     """The 25 look-ahead features of reference frame `f` (SRBEnv5_mocap_list_window.py:1096-1161).
     They depend on the clip tables only, never on the simulated state."""
+    terrain = env.variant == "terrain"
     pos = env.mocap_pos_com[f].copy()
     ori = env.mocap_ori_com[f]
     linvel = env.mocap_vel_com[f, :3]
     angvel = env.mocap_vel_com[f, 3:]
     pos_proj, proj = global2projected(ori, pos, pos)
+    if terrain:
+        pos_proj[2] -= env.mocap_height_com_terrain[f]
     h = np.array([pos_proj[2]])
     mat6 = (proj.T @ ori)[:, :2].flatten(order='F')
     vlin = proj.T @ linvel
@@ -692,10 +761,46 @@ def reference_frame_features(env, f):
     for i in range(2):
         fp = env.feet_pos_list[f, i, :]
         fxy = fp.copy()
-        fxy[2] = 0
-        contact.append(bool(fp[2] == 0))
+        if terrain:                         # ..._terrain_window.py:589-606
+            fxy[2], _ = env.terrain.height_ray(fxy[0], fxy[1])
+            contact.append(bool(env.feet_pos_list_original[f, i, 2] == 0))
+        else:
+            fxy[2] = 0
+            contact.append(bool(fp[2] == 0))
         p_ff, ff = global2forward_facing(ori, pos, fxy)
         mat_ff = ff.T @ env.feet_ori_list[f][i]
         out += [p_ff, np.array([np.arctan2(mat_ff[1, 0], mat_ff[0, 0])])]
     out.append(foot_contact_to_one_hot(contact))
     return np.concatenate(out, dtype=np.float32)
+
+
+def lift_clip_to_terrain(clip, terrain, initial_pos_planar=(0.0, 0.0)):
+    """Terrain variant of the reference tables (testSRB_mujoco_original_viewer_terrain.py:1043-1065 applied
+    after `SRBdata.mocap_data[:, :2] += initial_pos_planar`, SRBEnv5_mocap_list_terrain_window.py:636).
+    The planar shift is applied to the finished flat tables: humanoid FK, CoM and the yaw-aligned cycle
+    stitching are translation-equivariant, so this equals re-running humanoid2SRB on the shifted clip up to
+    round-off."""
+    out = dict(clip)
+    sh = np.array([initial_pos_planar[0], initial_pos_planar[1], 0.0])
+    qpos = np.array(clip["mocap_qpos"], dtype=float).copy()
+    qpos[:, :3] += sh
+    feet = np.array(clip["feet_pos_list"], dtype=float).copy()
+    feet += sh
+    original = feet.copy()                       # z == 0 marks reference contact
+    feet[:, :, 2] = 0
+    hts = []
+    for i in range(qpos.shape[0]):
+        hc, _ = terrain.height_ray(qpos[i, 0], qpos[i, 1])
+        hl, _ = terrain.height_ray(feet[i, 0, 0], feet[i, 0, 1])
+        hr, _ = terrain.height_ray(feet[i, 1, 0], feet[i, 1, 1])
+        qpos[i, 2] += hc
+        feet[i, 0, 2] += hl
+        feet[i, 1, 2] += hr
+        hts.append(hc)
+    out["mocap_qpos"] = qpos
+    out["mocap_pos_com"] = qpos[:, :3]
+    out["feet_pos_list"] = feet
+    out["feet_pos_list_original"] = original
+    out["mocap_height_com_terrain"] = np.array(hts)
+    out["initial_pos_planar"] = np.array(initial_pos_planar, dtype=float)
+    return out

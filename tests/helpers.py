@@ -99,7 +99,7 @@ def cuda_state_vector(named):
                            [float(named["left_foot_in_contact"]), float(named["right_foot_in_contact"])], [float(named["current_frame"])]])
 
 
-def oracle_to_cuda_state(env, n_real=44, n_int=7, slots=32, width=8):
+def oracle_to_cuda_state(env, n_real=46, n_int=7, slots=32, width=8):
     """Pack an OracleSRBEnv's full state in the layout of srb_get_state / srb_set_state
     (ipcdnnwalk_b200/csrc/srb_types.h)."""
     d = env.data

@@ -52,7 +52,7 @@ def test_state_dims_and_errors_without_gpu(built_lib):
     import ctypes as C
     d = [C.c_int32() for _ in range(4)]
     assert built_lib.srb_state_dims(*[C.byref(x) for x in d]) == 0
-    assert [x.value for x in d] == [44, 7, 32, 8]
+    assert [x.value for x in d] == [46, 7, 32, 8]
     import torch
     if not torch.cuda.is_available():
         from ipcdnnwalk_b200 import _lib
