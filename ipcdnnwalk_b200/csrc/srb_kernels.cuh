@@ -793,6 +793,8 @@ template <typename real, int G>
 __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   constexpr int EPW = 32 / G;
   const long long tk_entry = clock64();
+  unsigned long long gt_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   const int lane32 = threadIdx.x & 31;
   const int lane = lane32 % G;
   const int e_raw = (blockIdx.x * EPW) + lane32 / G;
@@ -1146,7 +1148,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     }
   }
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
-  if (dbg != nullptr && lane == 0) { dbg[21] = (double)(clock64() - tk0); dbg[22] = (double)(tk_pre - tk_entry); dbg[23] = (double)tk_entry; }
+  if (dbg != nullptr && lane == 0) { dbg[21] = (double)(clock64() - tk0); dbg[22] = (double)(tk_pre - tk_entry); { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[23] = (double)gt; dbg[64 + 23] = (double)gt_entry; } }
 }
 
 // ------------------------------------------------------------------------------------------------

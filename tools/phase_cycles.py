@@ -22,8 +22,8 @@ for k in range(30):
         tot=d[:,0,21]; pre=d[:,0,22]; subs=d[:,0,20]; entry=d[:,0,23]
         qp=d[:,:,19]; its=d[:,:,18]
         w=slice(0,N,4)   # one env per warp
-        end=(entry+pre+tot)
-        t0=entry[entry>0].min()
+        gexit=d[:,0,23]; gentry=d[:,1,23]
+        t0=gentry[w].min()
         print(f"step {k}: event {e0.elapsed_time(e1)*1e3:.1f}us | warp cycles: load+decode {np.median(pre[w]):.0f}  4 substeps med {np.median(subs[w]):.0f} p99 {np.percentile(subs[w],99):.0f} max {subs[w].max():.0f} | total med {np.median(tot[w]):.0f} max {tot[w].max():.0f}"
-              f" | post med {np.median((tot-subs)[w]):.0f} max {(tot-subs)[w].max():.0f} | entry spread {(entry[w].max()-t0):.0f} last end {(end[w].max()-t0):.0f} | qp cyc/substep med {np.median(qp[qp>0]):.0f} iters/step max-in-warp mean {its.reshape(N//4,4,4).max(axis=1).sum(axis=1).mean():.1f}")
+              f" | post med {np.median((tot-subs)[w]):.0f} max {(tot-subs)[w].max():.0f} | globaltimer ns: entry spread {(gentry[w].max()-t0):.0f} exit min {(gexit[w].min()-t0):.0f} med {np.median(gexit[w]-t0):.0f} max {(gexit[w].max()-t0):.0f} | qp cyc/substep med {np.median(qp[qp>0]):.0f} iters/step max-in-warp mean {its.reshape(N//4,4,4).max(axis=1).sum(axis=1).mean():.1f}")
 env.close()
