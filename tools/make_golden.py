@@ -62,9 +62,26 @@ def make_rollout(variant, n_envs=6, n_steps=40, seed=7):
     print(variant, "rollout", {k: np.array(v).shape for k, v in out.items()})
 
 
+def build_builder_case(name="aiming_show", frames=90):
+    """raw mocap rows + contact flags + the oracle's tables for them: pins ipcdnnwalk_b200.clip_builder."""
+    from oracle.srbdata import read_contact_npz
+    md = load_mocap_txt(REF + f"motiondata_mujoco_refined/{name}.txt")[:frames]
+    npz = REF + f"ref_contact/{name}.bvh.constraint.npz"
+    s = SRBdata(md, npz, REF + "Characters/humanoid_deepmimic_withpalm_Tpose.xml")
+    s.humanoid2SRB()
+    left, right = read_contact_npz(npz)
+    fo = np.array(s.feet_ori_list)
+    np.savez_compressed(os.path.join(GOLDEN, "srbdata_case.npz"), mocap_raw=md, left=left[:frames + 5], right=right[:frames + 5],
+                        cycle_length=s.cycle_length, mocap_qpos=s.mocap_com_humanoid, mocap_ori_com=np.array(s.mocap_ori_com),
+                        mocap_vel_com=s.mocap_vel_com, feet_pos_list=s.feet_pos_list,
+                        feet_yaw=np.stack([fo[:, :, 0, 0], fo[:, :, 1, 0]], axis=-1))
+    print("builder case", md.shape, s.mocap_com_humanoid.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     build_clip("stand1", True)
     build_clip("aiming_show", False)
     make_rollout("test")
     make_rollout("training")
+    build_builder_case()
