@@ -86,7 +86,16 @@ __global__ void __launch_bounds__(BLOCK) fk_forward_kernel(const SkelConst* __re
     for (int k = 0; k < 3; k++)
       if (k < sk.nchan[1]) { ang_n[k] = p[7 + k]; if (vel) rate_n[k] = v[6 + k]; }
   }
-  for (int b = 0; b < sk.nb; b++) {
+  // transforms are written 4 bones (28 reals) at a time with 128-bit stores: a thread owns its whole output row, so
+  // one warp-level store touches 32 rows either way -- wide stores cut the L1 sector transactions 4x (fp32) / 2x (fp64)
+  const bool vec_ok = xo != nullptr && ((sk.nb * 7 * (int)sizeof(real)) % 16 == 0);   // row base 16-byte aligned
+  constexpr int GB = sizeof(real) == 4 ? 4 : 2;          // bones per store group: 28 floats = 7 float4, 14 doubles = 7 double2
+  for (int b0 = 0; b0 < sk.nb; b0 += GB) {
+  real outv[7 * GB];
+#pragma unroll
+  for (int jb = 0; jb < GB; jb++) {
+    const int b = b0 + jb;
+    if (b >= sk.nb) break;
     const int d = sk.depth[b];
     real ang[3] = {ang_n[0], ang_n[1], ang_n[2]}, rate[3] = {rate_n[0], rate_n[1], rate_n[2]};
     const int nc = sk.nchan[b];
@@ -149,10 +158,8 @@ __global__ void __launch_bounds__(BLOCK) fk_forward_kernel(const SkelConst* __re
     STK(d, 0) = q.w; STK(d, 1) = q.x; STK(d, 2) = q.y; STK(d, 3) = q.z;
     STK(d, 4) = t.x; STK(d, 5) = t.y; STK(d, 6) = t.z;
     if (vel) { STK(d, 7) = w.x; STK(d, 8) = w.y; STK(d, 9) = w.z; STK(d, 10) = lv.x; STK(d, 11) = lv.y; STK(d, 12) = lv.z; }
-    if (xo) {
-      real* o = xo + b * 7;
-      o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z; o[4] = t.x; o[5] = t.y; o[6] = t.z;
-    }
+    outv[7 * jb] = q.w; outv[7 * jb + 1] = q.x; outv[7 * jb + 2] = q.y; outv[7 * jb + 3] = q.z;
+    outv[7 * jb + 4] = t.x; outv[7 * jb + 5] = t.y; outv[7 * jb + 6] = t.z;
     // CoM and momentum contributions
     const real m = (real)sk.mass[b];
     const V3<real> c = {(real)sk.com[b][0], (real)sk.com[b][1], (real)sk.com[b][2]};
@@ -171,6 +178,23 @@ __global__ void __launch_bounds__(BLOCK) fk_forward_kernel(const SkelConst* __re
       V3<real> Mw = qrot(q, M) + cross(t, Fw);
       HM[0] += Mw.x; HM[1] += Mw.y; HM[2] += Mw.z; HF[0] += Fw.x; HF[1] += Fw.y; HF[2] += Fw.z;
     }
+  }
+  if (xo) {
+    real* o = xo + b0 * 7;
+    if (vec_ok && b0 + GB <= sk.nb) {
+      if constexpr (sizeof(real) == 4) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) reinterpret_cast<float4*>(o)[k] = make_float4(outv[4 * k], outv[4 * k + 1], outv[4 * k + 2], outv[4 * k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 7; k++) reinterpret_cast<double2*>(o)[k] = make_double2(outv[2 * k], outv[2 * k + 1]);
+      }
+    } else {
+      const int cnt = min(GB, sk.nb - b0) * 7;
+#pragma unroll
+      for (int k = 0; k < 7 * GB; k++) if (k < cnt) o[k] = outv[k];
+    }
+  }
   }
   const real itm = (real)sk.inv_total_mass;
   V3<real> com = itm * csum;
