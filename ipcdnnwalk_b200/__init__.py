@@ -5,3 +5,4 @@ from .srb_vec_env import SRBVecEnv, REWARD_INFO_KEYS  # noqa: F401
 from . import vrml_skeleton  # noqa: F401
 from .bone_fk import Skeleton, BoneForwardKinematics, LoaderToTree  # noqa: F401
 from .terrain import TerrainModel  # noqa: F401
+from .srb_env import SRBEnv  # noqa: F401

@@ -276,3 +276,76 @@ def test_obs_stats_kernel(built_lib):
     assert acc[0].item() == n
     assert torch.allclose(acc[1:151], o.sum(0), rtol=1e-12, atol=1e-9) and torch.allclose(acc[151:], (o * o).sum(0), rtol=1e-12, atol=1e-9)
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 33])
+def test_ragged_batch_sizes(built_lib, n):
+    """Batch sizes that do not fill a warp / a 4-environment lane group: every env equals its N=1 evaluation."""
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv
+    clips = helpers.fresh_clips()
+    rng = np.random.default_rng(n)
+    plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
+    acts = rng.normal(0, 0.3, (4, n, 22)).astype(np.float32)
+    env = SRBVecEnv(clips, n, precision=64, auto_reset=False)
+    env.reset(plan=plans)
+    outs = []
+    for k in range(4):
+        o, r, d, _ = env.step(torch.as_tensor(acts[k], device="cuda"))
+        outs.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+    env.close()
+    for i in (0, n - 1):
+        e1 = SRBVecEnv(clips, 1, precision=64, auto_reset=False)
+        e1.reset(plan=plans[i:i + 1])
+        for k in range(4):
+            o, r, d, _ = e1.step(torch.as_tensor(acts[k, i:i + 1], device="cuda"))
+            assert np.array_equal(o.cpu().numpy()[0], outs[k][0][i]) and r.cpu().numpy()[0] == outs[k][1][i] and d.cpu().numpy()[0] == outs[k][2][i]
+        e1.close()
+
+
+def test_nan_action_is_contained_and_terminates(built_lib):
+    """A NaN action poisons only its own environment and the Newton loop still terminates (iteration bounded)."""
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv
+    clips = helpers.fresh_clips()
+    rng = np.random.default_rng(2)
+    n = 8
+    plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
+    a = rng.normal(0, 0.1, (n, 22)).astype(np.float32)
+    a[:, 21] = 2.0                                      # both feet in contact: the QP runs
+    ref = SRBVecEnv(clips, n, precision=32, auto_reset=False); ref.reset(plan=plans)
+    o_ref = ref.step(torch.as_tensor(a, device="cuda"))[0].cpu().numpy().copy()
+    bad = SRBVecEnv(clips, n, precision=32, auto_reset=False); bad.reset(plan=plans)
+    a2 = a.copy(); a2[5, 10:16] = np.nan
+    o_bad = bad.step(torch.as_tensor(a2, device="cuda"))[0].cpu().numpy()
+    torch.cuda.synchronize()
+    ok = [i for i in range(n) if i != 5]
+    assert np.array_equal(o_bad[ok], o_ref[ok]) and np.isnan(o_bad[5, :13]).any()
+    ref.close(); bad.close()
+
+
+def test_single_env_proxy_has_reference_surface(built_lib):
+    """SRBEnv(...) proxy: reset/step signatures, info keys and the attributes the reference drivers read."""
+    from ipcdnnwalk_b200 import SRBEnv, REWARD_INFO_KEYS
+    from oracle.srb_env import OracleSRBEnv
+    env = SRBEnv(helpers.fresh_clips(), variant="test", precision=64)
+    env.testing_mode = True
+    obs, info = env.reset(mocap_id=1)
+    o = OracleSRBEnv(helpers.fresh_clips(), "test"); o.testing_mode = True
+    oo, _ = o.reset_explicit(1, 0, None, None)
+    assert obs.shape == (150,) and obs.dtype == np.float32 and info == {} and np.abs(obs - oo).max() < 2e-6
+    rng = np.random.default_rng(0)
+    for k in range(5):
+        a = helpers.tracking_action(o, rng, 0.05)
+        obs, r, done, trunc, info = env.step(a)
+        oo, rr, dd, _, ii = o.step(a)
+        assert trunc is False and set(info["reward_info"]) == set(REWARD_INFO_KEYS) == set(ii["reward_info"])
+        assert np.abs(obs - oo).max() < 1e-5 and abs(r - rr) < 1e-5 * max(1, abs(rr)) and done == dd
+        assert env.current_frame == o.current_frame and env.left_foot_in_contact == o.left_foot_in_contact
+        assert env.site_to_apply_force_on == o.site_to_apply_force_on
+        assert np.abs(env.data.qpos - o.data.qpos).max() < 1e-6 and np.abs(env.data.site_xpos - o.data.site_xpos).max() < 1e-6
+    st = env.getFullState()
+    env.step(helpers.tracking_action(o, rng, 0.05))
+    env.restoreFullState(st)
+    assert env.current_frame == o.current_frame
+    env.close()
