@@ -6,3 +6,5 @@ from . import vrml_skeleton  # noqa: F401
 from .bone_fk import Skeleton, BoneForwardKinematics, LoaderToTree  # noqa: F401
 from .terrain import TerrainModel  # noqa: F401
 from .srb_env import SRBEnv  # noqa: F401
+from .cdm_vec_env import CDMVecEnv, LuaEnv  # noqa: F401
+from . import cdm_tables  # noqa: F401

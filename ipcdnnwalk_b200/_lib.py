@@ -60,7 +60,36 @@ _FK_SIGNATURES = {          # include/bonefk_b200.h
     "fk_forward_f32": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "fk_forward_f64": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
 }
+class CdmConfig(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("precision", C.c_int32), ("lanes_per_env", C.c_int32), ("auto_reset", C.c_int32),
+                ("device", C.c_int32), ("seed", C.c_uint64)]
+
+
+class CdmSkeleton(C.Structure):
+    _fields_ = [("root_off", C.c_double * 3), ("leg_off", (C.c_double * 3) * 6), ("leg_nchan", C.c_int32 * 6), ("leg_axes", C.c_int32 * 6),
+                ("toe", C.c_double * 3), ("heel", C.c_double * 3)]
+
+
+CDM_OBS_DIM, CDM_ACT_DIM, CDM_TAB_W, CDM_PLAN_DIM, CDM_DBG_DIM = 27, 10, 48, 16, 96
+_CDM_SIGNATURES = {         # include/cdmenv_b200.h
+    "cdm_create": (C.c_int, [C.POINTER(CdmConfig), C.POINTER(_P)]),
+    "cdm_destroy": (C.c_int, [_P]),
+    "cdm_upload_table": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(CdmSkeleton)]),
+    "cdm_set_param": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "cdm_get_param": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "cdm_reset": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
+    "cdm_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "cdm_step_host": (C.c_int, [_P, _P, _P, _P, _P]),
+    "cdm_pinned_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "cdm_set_aux": (C.c_int, [_P, _P, _P, _P]),
+    "cdm_state_dims": (C.c_int, [C.POINTER(C.c_int32)] * 4),
+    "cdm_get_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "cdm_set_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "cdm_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
+    "cdm_launch_count": (C.c_int64, [_P]),
+}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+CDM_EXPORTED_SYMBOLS = tuple(_CDM_SIGNATURES)
 FK_EXPORTED_SYMBOLS = tuple(_FK_SIGNATURES)
 
 _lib = None
@@ -76,7 +105,7 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()):
+    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

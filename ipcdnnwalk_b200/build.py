@@ -1,14 +1,24 @@
-"""In-tree build of the CUDA shared libraries (sm_100a only; nvcc cross-compiles without a GPU)."""
+"""In-tree build of the CUDA shared libraries (sm_100a only; nvcc cross-compiles without a GPU).
+
+Every `.cu` is compiled to its own object (in parallel, only when it or a header changed) and the objects are linked
+into one shared library, so touching one kernel file does not rebuild the others."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+OBJ = os.path.join(CSRC, "_obj")
+INCLUDE = os.path.join(HERE, "..", "include")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 TARGETS = {
-    "libsrbtrack_b200.so": ["srb_api.cu", "fk_api.cu"],
+    "libsrbtrack_b200.so": ["srb_api.cu", "fk_api.cu", "cdm_api.cu"],
+}
+# headers each translation unit depends on (besides itself)
+DEPS = {
+    "srb_api.cu": ["srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/srbtrack_b200.h"],
+    "fk_api.cu": ["fk_kernels.cuh", "srb_math.cuh", "../../include/bonefk_b200.h"],
+    "cdm_api.cu": ["cdm_kernels.cuh", "cdm_types.h", "srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/cdmenv_b200.h"],
 }
 
 
@@ -21,17 +31,31 @@ def _stale(out, deps):
 
 def build(force=False, verbose=True):
     nvcc = os.environ.get("NVCC", "nvcc")
-    deps_all = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "srbtrack_b200.h"), os.path.join(HERE, "..", "include", "bonefk_b200.h")]
+    os.makedirs(OBJ, exist_ok=True)
     built = []
     for lib, srcs in TARGETS.items():
+        procs = []
+        objs = []
+        for s in srcs:
+            src = os.path.join(CSRC, s)
+            obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+            objs.append(obj)
+            deps = [src] + [os.path.normpath(os.path.join(CSRC, d)) for d in DEPS.get(s, [])]
+            if force or _stale(obj, deps):
+                cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src]
+                if verbose:
+                    print("[build]", " ".join(cmd), flush=True)
+                procs.append((cmd, subprocess.Popen(cmd)))
+        failed = [cmd for cmd, p in procs if p.wait() != 0]
+        if failed:
+            raise subprocess.CalledProcessError(1, failed[0])
         out = os.path.join(HERE, lib)
-        if not force and not _stale(out, deps_all):
-            continue
-        cmd = [nvcc] + NVCC_FLAGS + ["-o", out] + [os.path.join(CSRC, s) for s in srcs]
-        if verbose:
-            print("[build]", " ".join(cmd), flush=True)
-        subprocess.check_call(cmd)
-        built.append(lib)
+        if force or procs or _stale(out, objs):
+            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
+            if verbose:
+                print("[build]", " ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+            built.append(lib)
     return built
 
 

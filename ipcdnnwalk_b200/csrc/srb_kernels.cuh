@@ -448,8 +448,8 @@ template <typename real> __device__ __forceinline__ void ldl_solve6(const real* 
 // (I + A_S A_S^T / w) nu = -y.  A full step is accepted when S is reproduced (exact optimum) or phi
 // decreases, otherwise it is halved (globally convergent, finite termination).
 // Columns: c = s*8 + f*4 + d  (site s of 5, foot f, friction direction d), lane owns c = lane + k*G.
-template <typename real, int G> struct QP {
-  static constexpr int NC = (40 + G - 1) / G;
+template <typename real, int G, int NCOLS = 40> struct QP {
+  static constexpr int NC = (NCOLS + G - 1) / G;
   real a[NC][6];
 
   __device__ __forceinline__ void build(int lane, const M3<real>& R, V3<real> p, const V3<real> foot[2], const real yc[2],
@@ -579,6 +579,95 @@ template <typename real, int G> struct QP {
         ph = phn;
         iters++;
         if (same) done = true;
+      }
+    }
+    return iters;
+  }
+  // Same Newton iteration, globalised by an EXACT line search instead of step halving (the finite Newton method of
+  // Mangasarian / Keerthi-DeCoste for this class of piecewise-quadratic problems): along d = nn - nu the derivative
+  //   g(alpha) = d.(nu + y) + alpha |d|^2 + (1/w) sum_j min(0, t_j + alpha s_j) s_j ,   s = A^T d,
+  // is increasing and piecewise linear with one kink per column; its root in (0,1) is found by a bracketed Newton
+  // iteration that stops as soon as a Newton step stays on one linear piece.  phi decreases monotonically, so the
+  // active sets cannot cycle.  Needed when 1/w is huge (gym_cdm2: 2e8), where step halving never reaches the
+  // descent region; typical cost: <3 Newton systems and ~8 evaluations of g per solve.
+  __device__ __forceinline__ int solve_ls(int lane, const real y[6], real inv_w, real nu[6], real t[NC], real* sm) {
+    constexpr int MAX_IT = 32;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_id() / G) * G));
+    const real invw = inv_w;
+    tvals(nu, t);
+    bool done = false;
+    int iters = 0;
+    real rhs[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) rhs[i] = -y[i];
+    for (int it = 0; it < MAX_IT; it++) {
+      if (!__any_sync(0xffffffffu, !done)) break;
+      real H[21];
+      hessian(t, invw, H, sm);
+      real nn[6], tn[NC], s[NC];
+      ldl_solve6(H, rhs, nn);
+      tvals(nn, tn);
+      bool same = true;
+      real a1 = 0;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        same = same && ((tn[k] < 0) == (t[k] < 0));
+        s[k] = tn[k] - t[k];
+        a1 += tn[k] < 0 ? tn[k] * s[k] : real(0);
+      }
+      same = (__ballot_sync(0xffffffffu, same) & gmask) == gmask;
+      real dd = 0, b0 = 0, nmax = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        real d = nn[i] - nu[i];
+        dd += d * d; b0 += d * (nu[i] + y[i]);
+        real av = nn[i] < 0 ? -nn[i] : nn[i];
+        nmax = av > nmax ? av : nmax;
+      }
+      const real g1 = b0 + dd + invw * gsum<G>(a1);
+      real alpha = real(1);
+      bool ls = !done && !same && g1 > 0;
+      if (__any_sync(0xffffffffu, ls)) {
+        real al = 0, lo = 0, hi = 1;
+        real p1 = 0, p2 = 0;
+        unsigned ml = 0;
+#pragma unroll
+        for (int k = 0; k < NC; k++) if (t[k] < 0) { p1 += t[k] * s[k]; p2 += s[k] * s[k]; ml |= 1u << k; }
+        real gl = b0 + invw * gsum<G>(p1), sl = dd + invw * gsum<G>(p2);
+        if (ls && !(gl < 0)) { ls = false; alpha = 0; }                    // no descent left: optimum to rounding
+        for (int k2 = 0; k2 < 48; k2++) {
+          if (!__any_sync(0xffffffffu, ls)) break;
+          real cand = al - gl / sl;
+          const bool newton = cand > lo && cand < hi;
+          if (!newton) cand = real(0.5) * (lo + hi);
+          real q1 = 0, q2 = 0;
+          unsigned mc = 0;
+#pragma unroll
+          for (int k = 0; k < NC; k++) {
+            real r = t[k] + cand * s[k];
+            if (r < 0) { q1 += r * s[k]; q2 += s[k] * s[k]; mc |= 1u << k; }
+          }
+          const real gc = b0 + cand * dd + invw * gsum<G>(q1), sc = dd + invw * gsum<G>(q2);
+          const bool piece = (__ballot_sync(0xffffffffu, mc == ml) & gmask) == gmask;
+          if (ls) {
+            if (newton && piece) { al = cand; ls = false; }
+            else {
+              if (gc < 0) lo = cand; else hi = cand;
+              al = cand; gl = gc; sl = sc; ml = mc;
+              if (hi - lo <= real(4) * num<real>::eps_conv() * hi) ls = false;
+            }
+            alpha = al;
+          }
+        }
+      }
+      if (!done) {
+        real stepn = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { real d = alpha * (nn[i] - nu[i]); nu[i] = same ? nn[i] : nu[i] + d; d = d < 0 ? -d : d; stepn = d > stepn ? d : stepn; }
+#pragma unroll
+        for (int k = 0; k < NC; k++) t[k] = same ? tn[k] : t[k] + alpha * s[k];
+        iters++;
+        if (same || stepn <= num<real>::eps_conv() * (real(1) + nmax)) done = true;
       }
     }
     return iters;
@@ -1239,7 +1328,7 @@ __global__ void srb_tracking_action_kernel(int N, int Npad, const real* __restri
 
 // ------------------------------------------------------------------------------------------------
 // batched terrain_height_ray: xy[n][2] -> height[n], hit[n][4] = (geom id, hfield cell c, cell r, triangle)
-__global__ void srb_terrain_height_kernel(const TerrainDev* __restrict__ T, int n, const double* __restrict__ xy, double* __restrict__ height,
+static __global__ void srb_terrain_height_kernel(const TerrainDev* __restrict__ T, int n, const double* __restrict__ xy, double* __restrict__ height,
                                           int* __restrict__ hit) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1250,7 +1339,7 @@ __global__ void srb_terrain_height_kernel(const TerrainDev* __restrict__ T, int 
 
 // ------------------------------------------------------------------------------------------------
 // look-ahead feature precompute: 25 floats per reference frame (get_obs_window :1096-1161), fp64.
-__global__ void srb_clip_features_kernel(const double* __restrict__ frames, int nframes, float* __restrict__ feat) {
+static __global__ void srb_clip_features_kernel(const double* __restrict__ frames, int nframes, float* __restrict__ feat) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nframes) return;
   const double* fr = frames + (size_t)f * CLIP_W;

@@ -3,6 +3,7 @@ public header declares; the host layer fails loudly without a GPU (no CPU fallba
 import os
 import re
 
+import numpy as np
 import pytest
 
 import helpers
@@ -36,6 +37,48 @@ def test_fk_header_symbols_exported(built_lib):
     assert names == sorted(_lib.FK_EXPORTED_SYMBOLS) and len(names) == 5
     for n in names:
         assert hasattr(built_lib, n)
+
+
+def test_cdm_header_symbols_exported(built_lib):
+    from ipcdnnwalk_b200 import _lib
+    txt = open(os.path.join(helpers.ROOT, "include", "cdmenv_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(cdm_[a-z_0-9]+)\s*\(", txt)))
+    assert names == sorted(_lib.CDM_EXPORTED_SYMBOLS) and len(names) == 15
+    for n in names:
+        assert hasattr(built_lib, n)
+
+
+def test_cdm_errors_without_gpu(built_lib):
+    import ctypes as C
+    from ipcdnnwalk_b200 import _lib
+    d = [C.c_int32() for _ in range(4)]
+    assert built_lib.cdm_state_dims(*[C.byref(x) for x in d]) == 0
+    assert [x.value for x in d] == [61, 4, 8, 8]
+    h = C.c_void_p()
+    for cfg in (_lib.CdmConfig(0, 64, 4, 1, 0, 0), _lib.CdmConfig(4, 16, 4, 1, 0, 0), _lib.CdmConfig(4, 64, 3, 1, 0, 0)):
+        assert built_lib.cdm_create(C.byref(cfg), C.byref(h)) != 0
+    import torch
+    if not torch.cuda.is_available():
+        cfg = _lib.CdmConfig(16, 64, 4, 1, 0, 0)
+        assert built_lib.cdm_create(C.byref(cfg), C.byref(h)) != 0 and b"no CPU fallback" in built_lib.srb_last_error()
+        import helpers_cdm as hc
+        from ipcdnnwalk_b200 import CDMVecEnv
+        tab, skel = hc.load_tables()
+        with pytest.raises(RuntimeError):
+            CDMVecEnv(tab, skel, 4)
+
+
+def test_cdm_skeleton_struct_and_table_packing():
+    import helpers_cdm as hc
+    from ipcdnnwalk_b200 import cdm_tables, cdm_vec_env
+    tab, skel = hc.load_tables()
+    s = cdm_vec_env.skeleton_struct(skel)
+    assert list(s.leg_nchan) == [3, 1, 3, 3, 1, 3]
+    assert list(s.leg_axes) == [1 | (2 << 2) | (0 << 4), 0, 1 | (2 << 2) | (0 << 4)] * 2            # YZX, X, YZX
+    rows = cdm_tables.pack_rows(tab)
+    assert rows.shape == (tab["cdm"].shape[0], 48) and rows[0, 47] in (0, 1, 2, 3)
+    assert (rows[:, 43:47] == np.round(rows[:, 43:47])).all()
 
 
 def test_skeleton_parser_matches_builtin_tables():

@@ -1,0 +1,67 @@
+"""GPU throughput of the batched AdaptiveSRB step (BASELINE config 4: gym_cdm2 deepmimiccdm-v1, walk2-v1 constants,
+16384 environments, actions U(-1,1) (scaled by 0.2 inside the step), seed 3, fused auto-reset).
+One JSON line per (precision, lanes) with env-steps/s, the HBM-roofline fraction (1116 B / env-step) and the
+end-to-end number through cdm_step_host (pinned host buffers, H2D + kernel + D2H per step).
+
+  python tools/bench_cdm.py [--envs 16384] [--steps 200] [--lanes 1,2,4,8] [--precision 32,64]"""
+import argparse, json, os, sys, time
+import numpy as np
+import torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+import helpers_cdm as hc
+from ipcdnnwalk_b200 import CDMVecEnv
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=16384)
+ap.add_argument("--steps", type=int, default=200)
+ap.add_argument("--warmup", type=int, default=16)
+ap.add_argument("--lanes", default="4")
+ap.add_argument("--precision", default="32,64")
+ap.add_argument("--e2e", action="store_true")
+a = ap.parse_args()
+peak = 6547.8
+try:
+    peak = json.load(open(os.path.join(R, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+tab, skel = hc.load_tables()
+BYTES = {32: 108 + 40 + 8 + 2 * (61 * 4 + 16) + 2 * 32, 64: 108 + 40 + 8 + 2 * (61 * 8 + 16) + 2 * 64}   # obs + act + rew/done + state r/w + replay entry r/w
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for prec in [int(x) for x in a.precision.split(",")]:
+    for lanes in [int(x) for x in a.lanes.split(",")]:
+        env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3)
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        acts = [(torch.rand(a.envs, 10, device="cuda", generator=g) * 2 - 1) for _ in range(32)]
+        for i in range(a.warmup):
+            env.step(acts[i % 32])
+        torch.cuda.synchronize()
+        env.episode_stats(clear=True)
+        ts = []
+        for i in range(a.steps):
+            flush.fill_(i & 0xff)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); env.step(acts[i % 32]); e1.record()
+            ts.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = np.array([x.elapsed_time(y) for x, y in ts])
+        st = env.episode_stats()
+        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes,
+               "steps": a.steps, "ms_per_step_mean": float(ms.mean()), "ms_per_step_median": float(np.median(ms)), "env_steps_per_s": a.envs / float(ms.mean()) * 1e3,
+               "algorithmic_bytes_per_env_step": BYTES[prec], "achieved_GBps": BYTES[prec] * a.envs / float(ms.mean()) / 1e6, "peak_GBps": peak,
+               "frac": BYTES[prec] * a.envs / float(ms.mean()) / 1e6 / peak, "episodes_finished": int(st[2]), "mean_episode_len": float(st[1] / max(st[2], 1)),
+               "mean_episode_return": float(st[0] / max(st[2], 1)), "l2": "flushed between steps (256 MiB write)"}
+        if a.e2e:
+            p = env.pinned()
+            hacts = [x.cpu().numpy() for x in acts[:8]]
+            for i in range(4):
+                env.step_host(hacts[i % 8])
+            t0 = time.perf_counter()
+            n = min(a.steps, 100)
+            for i in range(n):
+                env.step_host(hacts[i % 8])
+            dt = time.perf_counter() - t0
+            out["e2e"] = {"value": a.envs * n / dt, "unit": "env-steps/s", "h2d_bytes_per_step": a.envs * 40, "d2h_bytes_per_step": a.envs * (108 + 4 + 1)}
+        print(json.dumps(out), flush=True)
+        env.close()
