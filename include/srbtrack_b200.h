@@ -69,6 +69,9 @@ int srb_step(srb_env* env, const float* act_dev, float* obs_dev, float* rew_dev,
  * pinned staging buffers in place (see srb_pinned_buffers). */
 int srb_step_host(srb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host);
 int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint8_t** done, float** rinfo);
+/* How srb_step_host moves data: 1 (default) = zero copy, the step kernel reads the actions from and writes its results to
+ * the mapped pinned buffers directly (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies. */
+int srb_set_host_mode(srb_env* env, int32_t mode);
 
 /* Optional side channels (any may be NULL = detach):
  *   contact_prob_dev[N][2]  Policy_prior_posterior_MoE_window._last_contact_prob hysteresis input

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrbtrack_b200.so")
+LIB_PATH = os.environ.get("IPCDNNWALK_B200_LIB", os.path.join(_HERE, "libsrbtrack_b200.so"))   # override: A/B runs of two builds
 
 OBS_DIM, ACT_DIM, RINFO_DIM, PLAN_DIM, DBG_DIM = 150, 22, 8, 9, 256
 VARIANT_TEST, VARIANT_TRAINING, VARIANT_TERRAIN = 0, 1, 2
@@ -39,6 +39,7 @@ _SIGNATURES = {
     "srb_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "srb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "srb_pinned_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "srb_set_host_mode": (C.c_int, [_P, C.c_int32]),
     "srb_set_aux": (C.c_int, [_P, _P, _P, _P, _P]),
     "srb_set_reward_weights": (C.c_int, [_P, _P]),
     "srb_set_impulse": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
@@ -106,6 +107,8 @@ def load():
             "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()):
+        if "IPCDNNWALK_B200_LIB" in os.environ and not hasattr(lib, name):
+            continue                       # an older build loaded for an A/B timing run
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

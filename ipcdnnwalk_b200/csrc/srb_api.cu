@@ -40,6 +40,7 @@ struct srb_env {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
   int64_t launches = 0;
+  int host_mode = 1;                    // srb_step_host: 1 = kernel reads / writes the mapped pinned buffers directly, 0 = staged copies
   // terrain (variant 2)
   TerrainDev* terrain_dev = nullptr; std::vector<float*> hf_data; double* box_dev = nullptr;
 };
@@ -226,7 +227,7 @@ extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count,
   return 0;
 }
 
-template <typename real, int G> static void launch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
+template <typename real, int G, bool CIO = false> static void launch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
   StepArgs<real> A;
   A.N = h->N; A.Npad = h->Npad;
   A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist;
@@ -236,11 +237,17 @@ template <typename real, int G> static void launch_step(srb_env* h, const float*
   A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p); A.terrain = h->terrain_dev;
   constexpr int EPW = 32 / G;
   int blocks = (h->N + EPW - 1) / EPW;
-  srb_step_kernel<real, G><<<blocks, 32, 0, s>>>(A);
+  srb_step_kernel<real, G, CIO><<<blocks, 32, 0, s>>>(A);
   h->launches++;
 }
 
-template <typename real> static int dispatch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
+static bool cio_supported(int G) { return G == 4 || G == 8; }
+template <typename real> static int dispatch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s, bool cio = false) {
+  if (cio) {
+    if (h->G == 8) { launch_step<real, 8, true>(h, act, obs, rew, done, rinfo, s); return 0; }
+    if (h->G == 4) { launch_step<real, 4, true>(h, act, obs, rew, done, rinfo, s); return 0; }
+    return fail(-1, "coalesced-I/O step is built for lanes_per_env 4 and 8");
+  }
   switch (h->G) {
     case 1: launch_step<real, 1>(h, act, obs, rew, done, rinfo, s); break;
     case 2: launch_step<real, 2>(h, act, obs, rew, done, rinfo, s); break;
@@ -253,15 +260,19 @@ template <typename real> static int dispatch_step(srb_env* h, const float* act, 
   return 0;
 }
 
+static int step_impl(srb_env* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream, bool cio);
 extern "C" int srb_step(srb_env* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream) {
+  return step_impl(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, stream, false);
+}
+static int step_impl(srb_env* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream, bool cio) {
   if (!h) return fail(-1, "srb_step: null handle");
   if (!act_dev || !obs_dev || !rew_dev || !done_dev) return fail(-1, "srb_step: null buffer");
   if (h->nclips == 0) return fail(-1, "srb_step: no clip uploaded");
   if (h->p.use_terrain && !h->terrain_dev) return fail(-1, "srb_step: terrain variant needs srb_upload_terrain first");
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = h->cfg.precision == 64 ? dispatch_step<double>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s)
-                                  : dispatch_step<float>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s);
+  int rc = h->cfg.precision == 64 ? dispatch_step<double>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s, cio)
+                                  : dispatch_step<float>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s, cio);
   if (rc) return rc;
   CK(cudaGetLastError());
   return 0;
@@ -270,11 +281,11 @@ extern "C" int srb_step(srb_env* h, const float* act_dev, float* obs_dev, float*
 static int ensure_host_buffers(srb_env* h) {
   if (h->h_act) return 0;
   size_t N = h->N;
-  CK(cudaMallocHost(&h->h_act, sizeof(float) * N * ACT_W));
-  CK(cudaMallocHost(&h->h_obs, sizeof(float) * N * OBS_W));
-  CK(cudaMallocHost(&h->h_rew, sizeof(float) * N));
-  CK(cudaMallocHost(&h->h_rinfo, sizeof(float) * N * RINFO_W));
-  CK(cudaMallocHost(&h->h_done, N));
+  CK(cudaHostAlloc(&h->h_act, sizeof(float) * N * ACT_W, cudaHostAllocMapped));
+  CK(cudaHostAlloc(&h->h_obs, sizeof(float) * N * OBS_W, cudaHostAllocMapped));
+  CK(cudaHostAlloc(&h->h_rew, sizeof(float) * N, cudaHostAllocMapped));
+  CK(cudaHostAlloc(&h->h_rinfo, sizeof(float) * N * RINFO_W, cudaHostAllocMapped));
+  CK(cudaHostAlloc(&h->h_done, N, cudaHostAllocMapped));
   CK(cudaMalloc(&h->d_act, sizeof(float) * N * ACT_W));
   CK(cudaMalloc(&h->d_obs, sizeof(float) * N * OBS_W));
   CK(cudaMalloc(&h->d_rew, sizeof(float) * N));
@@ -300,18 +311,38 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   size_t N = h->N;
   if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
   cudaStream_t s = h->stream;
-  CK(cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * N * ACT_W, cudaMemcpyHostToDevice, s));
-  rc = srb_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_rinfo, s);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * OBS_W, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_rinfo, h->d_rinfo, sizeof(float) * N * RINFO_W, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  if (h->host_mode == 1 && cio_supported(h->G)) {
+    // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
+    // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions
+    // that overlap the computation of the other warps instead of four copies serialised after it
+    float *a = nullptr, *o = nullptr, *r = nullptr, *ri = nullptr; uint8_t* d = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&a, h->h_act, 0)); CK(cudaHostGetDevicePointer((void**)&o, h->h_obs, 0));
+    CK(cudaHostGetDevicePointer((void**)&r, h->h_rew, 0)); CK(cudaHostGetDevicePointer((void**)&d, h->h_done, 0));
+    CK(cudaHostGetDevicePointer((void**)&ri, h->h_rinfo, 0));
+    rc = step_impl(h, a, o, r, d, ri, s, true);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+  } else {
+    CK(cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * N * ACT_W, cudaMemcpyHostToDevice, s));
+    rc = srb_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_rinfo, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * OBS_W, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_rinfo, h->d_rinfo, sizeof(float) * N * RINFO_W, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   if (obs_host && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, sizeof(float) * N * OBS_W);
   if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, sizeof(float) * N);
   if (done_host && done_host != h->h_done) memcpy(done_host, h->h_done, N);
   if (rinfo_host && rinfo_host != h->h_rinfo) memcpy(rinfo_host, h->h_rinfo, sizeof(float) * N * RINFO_W);
+  return 0;
+}
+
+extern "C" int srb_set_host_mode(srb_env* h, int32_t mode) {
+  if (!h) return fail(-1, "srb_set_host_mode: null handle");
+  if (mode != 0 && mode != 1) return fail(-1, "srb_set_host_mode: mode must be 0 (staged copies) or 1 (zero copy)");
+  h->host_mode = mode;
   return 0;
 }
 

@@ -145,6 +145,10 @@ class SRBVecEnv:
         p = self.pinned()
         return p["obs"], p["rew"], p["done"], p["rinfo"]
 
+    def set_host_mode(self, mode):
+        """step_host data movement: 1 = zero copy through mapped pinned memory (default), 0 = staged copies."""
+        check(self.lib.srb_set_host_mode(self._h, int(mode)))
+
     def pinned(self):
         if getattr(self, "_pinned", None) is None:
             ptrs = [C.c_void_p() for _ in range(5)]

@@ -241,25 +241,32 @@ def test_tracking_action_kernel_matches_host_formula(built_lib):
     env.close()
 
 
-def test_host_buffer_step_equals_device_step(built_lib):
-    """srb_step_host (pinned H2D/D2H path used for the e2e number) returns what srb_step returns."""
+@pytest.mark.parametrize("mode,n,lanes", [(1, 64, 8), (0, 64, 8), (1, 61, 8), (1, 37, 4), (1, 16, 2)])
+def test_host_buffer_step_equals_device_step(built_lib, mode, n, lanes):
+    """srb_step_host (host-buffer path used for the e2e number) returns what srb_step returns: zero-copy mode (the
+    coalesced-I/O kernel writing mapped pinned memory, incl. ragged last warps and auto-resets), staged copies, and the
+    fallback to staged copies for lane counts the coalesced kernel is not built for."""
     import torch
     from ipcdnnwalk_b200 import SRBVecEnv
-    n = 64
     clips = helpers.fresh_clips()
     rng = np.random.default_rng(8)
     plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
-    e1 = SRBVecEnv(clips, n, precision=64, auto_reset=True, seed=1)
-    e2 = SRBVecEnv(clips, n, precision=64, auto_reset=True, seed=1)
+    plans[::5, 4] = -8.0                                 # some environments start falling and terminate inside the loop
+    e1 = SRBVecEnv(clips, n, precision=64, lanes_per_env=lanes, auto_reset=True, seed=1)
+    e2 = SRBVecEnv(clips, n, precision=64, lanes_per_env=lanes, auto_reset=True, seed=1)
+    e2.set_host_mode(mode)
     e1.reset(plan=plans); e2.reset(plan=plans)
     act = torch.zeros(n, 22, device="cuda")
-    for k in range(5):
+    ndone = 0
+    for k in range(8):
         e1.tracking_action(act, sigma=0.1, seed=2, step=k)
         o1, r1, d1, i1 = e1.step(act)
         o2, r2, d2, i2 = e2.step_host(act.cpu().numpy())
         torch.cuda.synchronize()
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2) and np.array_equal(i1.cpu().numpy(), i2)
+        ndone += int(d2.sum())
+    assert ndone > 0
     e1.close(); e2.close()
 
 
