@@ -61,7 +61,8 @@ int cdm_upload_table(cdm_env* env, int32_t nframes, int32_t nf_cycle, const doub
 /* model / QPparam overrides of a spec file (gym_cdm2/spec/walk2-v1.lua, defaultRLsetting.lua:13-45).  Names:
  * k_p k_d acc_clamp max_leg_len max_foot_vel stride_thr max_contact_len min_swing_phase max_contact_y healthy_min
  * healthy_max fall_angle timing_mod_coef facing_weight ef_scale limit_length max_turning filter_end_phase logQ
- * w_ddq w_lam inv_fric mass inertia_x inertia_y inertia_z grav noise_q noise_pos noise_dq noise_vx noise_vy noise_vz */
+ * w_ddq w_lam inv_fric mass inertia_x inertia_y inertia_z grav noise_q noise_pos noise_dq noise_vx noise_vy noise_vz
+ * use_lqr_cache filter_K0 filter_K1 (contact-filter LQR gain; default = the gain the shipped reference build always uses, Q15) */
 int cdm_set_param(cdm_env* env, const char* name, double value);
 int cdm_get_param(cdm_env* env, const char* name, double* value);
 

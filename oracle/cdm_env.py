@@ -24,9 +24,25 @@ a-16 ... a-20.  Paths relative to the reference root:
   work/taesooLib/Resource/scripts/control/SDRE.lua:37-146,470-620 (SDS, MassParticle3D), PhysicsLib/SDRE.cpp:100-245
       (continuous ARE -> LQR gain; closed form for the 2x2 spring-damper, see `lqr_gain`)
 
-taesooLib / Lua cannot run here and the reference ships no expected outputs: PARITY UNPINNED.  The
-restatement is pinned by analytic checks in tests/test_oracle_cdm_cpu.py (KKT of the un-eliminated QP, ARE residual,
-free fall, marker FK vs the full-body FK oracle) and by the committed golden roll-out.
+taesooLib / Lua cannot run here.  PARITY PARTLY PINNED against the reference's own recorded outputs:
+  * gym_cdm2/spec/refTraj_walk2-v1.dat / refTraj_run2-v1.dat are roll-outs RECORDED BY THE REFERENCE SIMULATOR
+    (deepmimiccdm-v1.lua:1095-1146: root pose, filtered feet, dq, foot yaws, raw contact targets, swing flags / phases
+    at every RL step).  tests/test_oracle_cdm_refpins_cpu.py replays them through this file's own methods: the swing-foot
+    contact filter + yaw filter + getFilteredFootPos (1572 swing rows, < 4e-6 m, 1e-8 rad), the swing / touch-down
+    state machine against the restated rtt tables (3596 rows), and the contact-free sub-steps of the running clip
+    (505 flight rows: gravity, Euler equations, quaternion integration, < 1e-7).
+  * work/_LQR_CACHE_2.DAT holds one LQR gain computed by the reference (A, B, Q, R, K): a known-answer vector for
+    `lqr_gain`.
+  NOT pinned by reference outputs (no recorded intermediate exists): the contact QP and the reward; they are checked
+  analytically in tests/test_oracle_cdm_cpu.py (KKT of the un-eliminated QP as _QPsolve states it, second solver) and
+  by the committed golden roll-out.
+
+Q15 (found through the recorded roll-outs): the shipped build sets NoLapack (src/CMakeLists.txt:41,
+work/taesooLib/Samples/Common.cmake:3) => EXCLUDE_CLAPACK, and Physics.LQR then returns the gain cached in
+work/_LQR_CACHE_2.DAT -- K = (9999.00005, 1095.39024412), computed for M=60, b=1e-3, k=1, Q=1e8 -- for EVERY 2x2
+system (work/taesooLib/PhysicsLib/SDRE.cpp:136-154).  The contact filter (M=30, Q=10^7) therefore runs with that gain;
+the recorded roll-outs reproduce only with it.  `filter_K` below; `lqr_gain` is the real ARE solution kept for the
+known-answer test.
 
 Stated simplifications (all below 1e-12 relative, i.e. far inside the 1e-5 gate): the JOINT_VALUE/JOINT_VELOCITY
 round trips of QPsim:frameMove through an identity reference frame (refCoord, flat ground) are skipped; randomised
@@ -50,7 +66,8 @@ HEEL_LOCAL = np.array([0.0, -0.01, -0.14])
 PARAMS = dict(k_p=120.0, k_d=35.0, w_ddq=10000.0, w_tau=0.0001, w_lam=0.0001, acc_clamp=400.0, max_leg_len=1.10,
               max_foot_vel=3.0, logQ=7.0, stride_thr=0.45, max_contact_len=0.9, min_swing_phase=0.25, max_contact_y=1.1,
               healthy_min=0.8, healthy_max=2.0, fall_angle=math.radians(20), timing_mod_coef=0.4, facing_weight=1.5,
-              ef_scale=1.0, limit_length=300.0, max_turning=0.5, filter_end_phase=0.4, inv_fric=1.0)
+              ef_scale=1.0, limit_length=300.0, max_turning=0.5, filter_end_phase=0.4, inv_fric=1.0,
+              filter_K=(9999.00005, 1095.39024412))
 
 
 def lqr_gain(M, b, k, q, qd=0.0):
@@ -126,7 +143,7 @@ class OracleCDMEnv:
         self.nf = int(tab["nf"])
         names = skel["names"]
         self.iRA, self.iLA = names.index("RightAnkle"), names.index("LeftAnkle")
-        self.K_filter = lqr_gain(30.0, 0.001, 1.0, 10.0 ** self.P["logQ"])
+        self.K_filter = tuple(self.P["filter_K"])                # Q15: the cached gain, not lqr_gain(30, 1e-3, 1, 10^logQ)
         self.debug = {}
 
     # ---------------------------------------------------------------- model (defaultRLsetting.lua)

@@ -8,6 +8,8 @@ Writes:
                                      hanyang_lowdof_T.wrl) + the parsed skeleton as JSON
   tests/golden/cdm_rollout.npz       seeded oracle roll-outs: reset draws, float32 actions, per-step observation /
                                      reward / done / state vectors / QP accelerations and multipliers
+  tests/golden/cdm_reference_recordings.npz   the first 700 rows of gym_cdm2/spec/refTraj_{walk2,run2}-v1.dat (roll-outs
+                                     recorded by the reference simulator) + the LQR known answer of work/_LQR_CACHE_2.DAT
 """
 import json
 import os
@@ -82,6 +84,26 @@ def make_rollout(n_envs=6, n_steps=90, seed=11):
     print("rollout: episodes finished", int(done.sum()), "mean reward", rew.mean(), "swing steps", int((ints[:, :, 0] != 0).sum()))
 
 
+
+
+def make_reference_recordings(rows=700):
+    """Slices of the roll-outs the reference simulator itself recorded (gym_cdm2/spec/refTraj_*.dat, written by
+    deepmimiccdm-v1.lua:1095-1146) and the reference's cached LQR solution (work/_LQR_CACHE_2.DAT)."""
+    from ipcdnnwalk_b200 import tl_binary as tb
+    out = {}
+    for name in ("walk2", "run2"):
+        t = tb.load_table(f"/root/reference/gym_cdm2/spec/refTraj_{name}-v1.dat")
+        out[name + "_globalTraj"] = t["globalTraj"][:rows]
+        out[name + "_rawFootInfo"] = t["rawFootInfo"][:rows]
+        out[name + "_refFrames"] = t["refFrames"][:rows]
+    r = tb.BinaryReader(open("/root/reference/work/_LQR_CACHE_2.DAT", "rb").read())
+    for k in ("lqr_K", "lqr_A", "lqr_B", "lqr_Q", "lqr_R"):
+        out[k] = r.unpack_any()
+    np.savez_compressed(os.path.join(GOLDEN, "cdm_reference_recordings.npz"), **out)
+    print("reference recordings:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     make_tables()
     make_rollout()
+    make_reference_recordings()
