@@ -91,6 +91,17 @@ int cdm_set_state(cdm_env* env, int32_t env_index, const double* reals, const in
 int cdm_episode_stats(cdm_env* env, double out[3], int32_t clear);
 int64_t cdm_launch_count(cdm_env* env);
 
+/* ---- OBJloader::Terrain (work/taesooLib/BaseLib/motion/Terrain.cpp:305-470), the height field of the gym_cdm2 terrain spec
+ * (gym_cdm2/deepmimiccdm-v1.lua:368-423, spec/walkterrain-v1.lua).  heights_host[rows][cols] = mHeight (already scaled,
+ * same unit as the query coordinates); size_x / size_z = mSize.x / mSize.z; tile_along_z as the constructor flag.
+ * tlterrain_height: xz_dev[n][2] (terrain-local) -> height_dev[n]; hit_dev[n][3] (may be NULL) = cell row i, cell column j,
+ * triangle (0 upper, 1 lower), all -1 outside the field (height 0). */
+typedef struct tl_terrain tl_terrain;
+int tlterrain_create(int32_t device, int32_t rows, int32_t cols, double size_x, double size_z, int32_t tile_along_z,
+                     const double* heights_host, tl_terrain** out);
+int tlterrain_destroy(tl_terrain* t);
+int tlterrain_height(tl_terrain* t, int64_t n, const double* xz_dev, double* height_dev, int32_t* hit_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

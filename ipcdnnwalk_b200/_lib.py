@@ -89,8 +89,14 @@ _CDM_SIGNATURES = {         # include/cdmenv_b200.h
     "cdm_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
     "cdm_launch_count": (C.c_int64, [_P]),
 }
+_TLT_SIGNATURES = {
+    "tlterrain_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P, C.POINTER(_P)]),
+    "tlterrain_destroy": (C.c_int, [_P]),
+    "tlterrain_height": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 CDM_EXPORTED_SYMBOLS = tuple(_CDM_SIGNATURES)
+TLT_EXPORTED_SYMBOLS = tuple(_TLT_SIGNATURES)
 FK_EXPORTED_SYMBOLS = tuple(_FK_SIGNATURES)
 
 _lib = None
@@ -106,7 +112,7 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()):
+    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()) + list(_TLT_SIGNATURES.items()):
         if "IPCDNNWALK_B200_LIB" in os.environ and not hasattr(lib, name):
             continue                       # an older build loaded for an A/B timing run
         fn = getattr(lib, name)

@@ -389,3 +389,38 @@ extern "C" int cdm_episode_stats(cdm_env* h, double out[3], int32_t clear) {
   return 0;
 }
 extern "C" int64_t cdm_launch_count(cdm_env* h) { return h ? h->launches : 0; }
+
+// ---- OBJloader::Terrain (gym_cdm2 terrain spec) -------------------------------------------------------
+struct tl_terrain { int device; double* h = nullptr; TLTerrainDev T; };
+extern "C" int tlterrain_create(int32_t device, int32_t rows, int32_t cols, double size_x, double size_z, int32_t tile_along_z,
+                                const double* heights_host, tl_terrain** out) {
+  if (!heights_host || !out) return srb_set_error(-1, "tlterrain_create: null argument");
+  if (rows < 2 || cols < 2 || !(size_x > 0) || !(size_z > 0)) return srb_set_error(-1, "tlterrain_create: bad dimensions");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return srb_set_error(-3, std::string("tlterrain_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (device < 0 || device >= ndev) return srb_set_error(-1, "tlterrain_create: bad device ordinal");
+  CK(cudaSetDevice(device));
+  tl_terrain* t = new tl_terrain();
+  t->device = device;
+  CK(cudaMalloc(&t->h, sizeof(double) * (size_t)rows * cols));
+  CK(cudaMemcpy(t->h, heights_host, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice));
+  t->T.h = t->h; t->T.rows = rows; t->T.cols = cols; t->T.size_x = size_x; t->T.size_z = size_z; t->T.tile = tile_along_z ? 1 : 0;
+  *out = t;
+  return 0;
+}
+extern "C" int tlterrain_destroy(tl_terrain* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->device);
+  cudaFree(t->h);
+  delete t;
+  return 0;
+}
+extern "C" int tlterrain_height(tl_terrain* t, int64_t n, const double* xz_dev, double* height_dev, int32_t* hit_dev, void* stream) {
+  if (!t || !xz_dev || !height_dev) return srb_set_error(-1, "tlterrain_height: null argument");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(t->device));
+  tl_terrain_height_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t->T, n, xz_dev, height_dev, hit_dev);
+  CK(cudaGetLastError());
+  return 0;
+}

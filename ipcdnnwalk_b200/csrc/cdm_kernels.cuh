@@ -854,6 +854,55 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// OBJloader::Terrain::height (work/taesooLib/BaseLib/motion/Terrain.cpp:305-393): cell by floor, triangle by dx > dz,
+// plane through the triangle (Plane::setPlane, intersectionTest.cpp:96-104) intersected with the vertical ray from y = 1000
+// (Ray::intersects :243-260), tiling along Z.  hit = (cell row i, cell column j, triangle 0 upper / 1 lower), -1 outside.
+struct TLTerrainDev { const double* h; int rows, cols; double size_x, size_z; int tile; };
+__device__ __forceinline__ double tl_terrain_height(const TLTerrainDev& T, double x0, double x1, int* hit) {
+  const int nsx = T.cols - 1, nsz = T.rows - 1;
+  const double nx = (x0 / T.size_x) * (double)nsx;
+  double nz = (x1 / T.size_z) * (double)nsz;
+  int j = (int)::floor(nx), i = (int)::floor(nz);
+  const double dx = nx - ::floor(nx), dz = nz - ::floor(nz);
+  if (hit) { hit[0] = -1; hit[1] = -1; hit[2] = -1; }
+  if (j < 0 || j >= nsx || !(nx == nx) || !(nz == nz)) return 0.0;
+  if (T.tile) {
+    i %= nsz;
+    if (i < 0) i += nsz;
+    nz = (double)i + dz;
+    x1 = nz / (double)nsz * T.size_z;
+  } else if (i < 0 || i >= nsz) {
+    return 0.0;
+  }
+  const double* h = T.h;
+  V3<double> v0, v1, v2;
+  const bool upper = dx > dz;
+  v0 = {(double)j * T.size_x / (double)nsx, __ldg(h + (size_t)i * T.cols + j), (double)i * T.size_z / (double)nsz};
+  if (upper) {
+    v1 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
+    v2 = {v1.x, __ldg(h + (size_t)i * T.cols + j + 1), v0.z};
+  } else {
+    v2 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
+    v1 = {v0.x, __ldg(h + (size_t)(i + 1) * T.cols + j), v2.z};
+  }
+  V3<double> n = cross(v1 - v0, v2 - v0);
+  n = (1.0 / ::sqrt(dot(n, n))) * n;
+  const double d = -dot(n, v0);
+  const V3<double> org = {x0, 1000.0, x1};
+  const double denom = dot(n, V3<double>{0.0, -1.0, 0.0});
+  const double t = -((dot(n, org) + d) / denom);
+  if (hit) { hit[0] = i; hit[1] = j; hit[2] = upper ? 0 : 1; }
+  return org.y + t * -1.0;
+}
+static __global__ void tl_terrain_height_kernel(TLTerrainDev T, long long n, const double* __restrict__ xz, double* __restrict__ out, int* __restrict__ hit) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int hh[3];
+  out[k] = tl_terrain_height(T, xz[2 * k], xz[2 * k + 1], hh);
+  if (hit) { hit[3 * k] = hh[0]; hit[3 * k + 1] = hh[1]; hit[3 * k + 2] = hh[2]; }
+}
+
 // explicit / random reset: one thread per environment
 template <typename real> __global__ void cdm_reset_kernel(const ResetArgs<real> A) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -49,6 +49,16 @@ def test_cdm_header_symbols_exported(built_lib):
         assert hasattr(built_lib, n)
 
 
+def test_terrain_header_symbols_exported(built_lib):
+    from ipcdnnwalk_b200 import _lib
+    txt = open(os.path.join(helpers.ROOT, "include", "cdmenv_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(tlterrain_[a-z_0-9]+)\s*\(", txt)))
+    assert names == sorted(_lib.TLT_EXPORTED_SYMBOLS) and len(names) == 3
+    for n in names:
+        assert hasattr(built_lib, n)
+
+
 def test_cdm_errors_without_gpu(built_lib):
     import ctypes as C
     from ipcdnnwalk_b200 import _lib

@@ -10,6 +10,7 @@ Writes:
                                      reward / done / state vectors / QP accelerations and multipliers
   tests/golden/cdm_reference_recordings.npz   the first 700 rows of gym_cdm2/spec/refTraj_{walk2,run2}-v1.dat (roll-outs
                                      recorded by the reference simulator) + the LQR known answer of work/_LQR_CACHE_2.DAT
+  tests/golden/cdm_terrain_heights.npz   mHeight of the gym_cdm2 terrain (heightmap1_256_256_2bytes.raw through the loader)
 """
 import json
 import os
@@ -103,7 +104,17 @@ def make_reference_recordings(rows=700):
     print("reference recordings:", {k: v.shape for k, v in out.items()})
 
 
+def make_terrain():
+    """Height table of the gym_cdm2 terrain spec (deepmimiccdm-v1.lua:368-382): 64 x 64 after the loader's decimation, in cm."""
+    from oracle import tl_terrain as tt
+    img = tt.load_raw("/root/reference/work/taesooLib/Resource/motion/crowdEditingScripts/terrain/heightmap1_256_256_2bytes.raw", 256, 256)
+    np.savez_compressed(os.path.join(GOLDEN, "cdm_terrain_heights.npz"), heights=tt.load_heights(img, 100.0), size_x=4800.0, size_z=4800.0,
+                        terrain_pos=np.array([-24.0, 0.1, -24.0]))
+    print("terrain heights written")
+
+
 if __name__ == "__main__":
     make_tables()
     make_rollout()
     make_reference_recordings()
+    make_terrain()
