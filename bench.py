@@ -323,7 +323,7 @@ def run_ours(args, rank, local_rank, world):
         if e2e_ms is not None:
             line["e2e"] = {"value": world * N * Ke / (e2e_ms_max * 1e-3), "unit": "env-steps/s",
                            "h2d_bytes_per_step": N * ACT_DIM * 4, "d2h_bytes_per_step": N * (OBS_DIM * 4 + 4 + 1 + RINFO_DIM * 4),
-                           "steps": Ke, "api": "srb_step_host (pinned host buffers, H2D + kernel + D2H + sync per step)"}
+                           "steps": Ke, "api": "srb_step_host, host buffers: the coalesced-I/O step kernel reads the actions from and writes obs/reward/done/info to mapped pinned host memory over PCIe inside the timed region (zero copy), then stream sync"}
         if not args.no_cpu_baseline:
             cores = usable_cores()
             v, total, tmax = cpu_oracle_throughput(cores, 1, 1, None, args.variant, budget_s=15.0)

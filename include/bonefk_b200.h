@@ -24,6 +24,15 @@ typedef struct fk_skeleton fk_skeleton;   /* opaque: one skeleton (VRMLloader) r
 int fk_create(int32_t device, int32_t nbones, const int32_t* parent, const double* offset, const int32_t* nchan,
               const int32_t* axes, const double* mass, const double* local_com, const double* inertia, fk_skeleton** out);
 int fk_destroy(fk_skeleton* sk);
+/* Skeletons whose tree structure equals hanyang_lowdof_T(_sh).wrl (20 bones, 53 channels: the skeleton of the SRBTrack
+ * full-body mapping) run a skeleton-specialised kernel; fk_set_generic(sk, 1) forces the structure-agnostic kernel (A/B runs,
+ * tests).  fk_is_specialised reports which one fk_forward_* will launch. */
+int fk_set_generic(fk_skeleton* sk, int32_t force_generic);
+int fk_is_specialised(fk_skeleton* sk);
+/* The specialised path moves full 64-pose tiles with TMA bulk copies through shared memory.  mode -1 (default) = measured
+ * best variant per precision / outputs; 0 = rows accessed directly by the owning thread; 1 = rolled bone loop on TMA tiles;
+ * 3 = unrolled sweep on TMA tiles (A/B runs, tests). */
+int fk_set_tma(fk_skeleton* sk, int32_t use_tma);
 /* pose / dq row lengths: 7 + #angles (root xyz, root quaternion wxyz, angles) and 6 + #angles
  * (root angular velocity world, root linear velocity world, joint rates). */
 int fk_dims(fk_skeleton* sk, int32_t* nbones, int32_t* n_pose, int32_t* n_dq);

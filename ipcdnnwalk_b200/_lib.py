@@ -57,6 +57,9 @@ _SIGNATURES = {
 _FK_SIGNATURES = {          # include/bonefk_b200.h
     "fk_create": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "fk_destroy": (C.c_int, [_P]),
+    "fk_set_generic": (C.c_int, [_P, C.c_int32]),
+    "fk_is_specialised": (C.c_int, [_P]),
+    "fk_set_tma": (C.c_int, [_P, C.c_int32]),
     "fk_dims": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fk_forward_f32": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "fk_forward_f64": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),

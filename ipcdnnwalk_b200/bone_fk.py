@@ -58,6 +58,20 @@ class Skeleton:
     def numBone(self):
         return self.num_bones
 
+    def set_generic(self, force=True):
+        """Force the structure-agnostic kernel even when the skeleton-specialised one applies (A/B runs, tests)."""
+        check(self.lib.fk_set_generic(self._h, int(bool(force))))
+
+    def set_tma(self, use=True):
+        """Specialised path: -1 / True = automatic choice, 0 / False = rows accessed directly, 1 = rolled loop on TMA tiles,
+        3 = unrolled sweep on TMA tiles (A/B runs, tests)."""
+        if use is True:
+            use = -1
+        check(self.lib.fk_set_tma(self._h, int(use)))
+
+    def is_specialised(self):
+        return bool(self.lib.fk_is_specialised(self._h))
+
     def forward(self, pose, dq=None, want_xform=True, want_com=True, want_momentum=True, out=None):
         t = self.torch
         assert pose.is_cuda and pose.dim() == 2 and pose.shape[1] == self.n_pose and pose.is_contiguous()

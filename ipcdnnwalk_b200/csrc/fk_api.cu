@@ -4,6 +4,7 @@
 #include <vector>
 #include <cmath>
 #include <string.h>
+#include <stdint.h>
 #include "../../include/bonefk_b200.h"
 #include "fk_kernels.cuh"
 
@@ -19,6 +20,9 @@ struct fk_skeleton {
   int device = 0;
   fk::SkelConst host;
   fk::SkelConst* dev = nullptr;
+  bool hanyang = false;        // tree structure equals the compile-time table of fk::Hanyang -> specialised kernel
+  bool force_generic = false;
+  int tma_mode = -1;           // see fk_launch
 };
 
 extern "C" int fk_create(int32_t device, int32_t nb, const int32_t* parent, const double* offset, const int32_t* nchan,
@@ -69,9 +73,22 @@ extern "C" int fk_create(int32_t device, int32_t nb, const int32_t* parent, cons
   FCK(cudaSetDevice(device));
   FCK(cudaMalloc(&s->dev, sizeof(fk::SkelConst)));
   FCK(cudaMemcpy(s->dev, &k, sizeof(k), cudaMemcpyHostToDevice));
+  s->hanyang = fk::Hanyang::matches(k);
   *out = s;
   return 0;
 }
+
+extern "C" int fk_set_generic(fk_skeleton* s, int32_t force_generic) {
+  if (!s) return srb_set_error(-1, "fk_set_generic: null handle");
+  s->force_generic = force_generic != 0;
+  return 0;
+}
+extern "C" int fk_set_tma(fk_skeleton* s, int32_t use_tma) {
+  if (!s) return srb_set_error(-1, "fk_set_tma: null handle");
+  s->tma_mode = use_tma;
+  return 0;
+}
+extern "C" int fk_is_specialised(fk_skeleton* s) { return (s && s->hanyang && !s->force_generic) ? 1 : 0; }
 
 extern "C" int fk_destroy(fk_skeleton* s) {
   if (!s) return 0;
@@ -94,6 +111,51 @@ static int fk_launch(fk_skeleton* s, int64_t n, const real* pose, const real* dq
   if (!pose) return srb_set_error(-1, "fk_forward: null pose buffer");
   if (n > 2000000000LL) return srb_set_error(-1, "fk_forward: n too large for one call");
   FCK(cudaSetDevice(s->device));
+  if (s->hanyang && !s->force_generic) {               // skeleton-specialised instantiations
+    const bool al = ((uintptr_t)pose % 16 == 0) && (!xform || (uintptr_t)xform % 16 == 0) && (!dq || (uintptr_t)dq % 16 == 0) &&
+                    (!com || (uintptr_t)com % 16 == 0) && (!mom || (uintptr_t)mom % 16 == 0);
+    const bool momentum = dq && mom;
+    // fp64 + momentum: 119 doubles of inputs next to the sweep exceed the register file; the structure-agnostic kernel wins
+    if (al && !(s->tma_mode < 0 && momentum && sizeof(real) == 8)) {
+      cudaStream_t st = (cudaStream_t)stream;
+      // tma_mode: -1 auto (measured best per precision / outputs, tools/bench_fk.py), 0 direct rows, 1 rolled loop on TMA tiles,
+      //           3 unrolled sweep on TMA tiles.  (A per-bone CTA barrier to share instruction-cache lines was tried with
+      //           128- and 256-pose tiles: 10-20 % slower than the plain unrolled tile kernel, removed.)
+      int mode = s->tma_mode;
+      if (mode < 0) mode = sizeof(real) == 4 ? (momentum ? 1 : 3) : 0;
+      if (mode != 0 && mode != 1) mode = 3;
+      const int TB = mode == 0 ? 1 : 64;
+      const int64_t full = mode == 0 ? 0 : n / TB;
+      if (full > 0) {
+#define FK_LAUNCH_TILE(KERN, TBV, EXTRA)                                                                                     \
+        do {                                                                                                                  \
+          const size_t tile = (size_t)(TBV) * (140 + 3 + 6 + (EXTRA)) * sizeof(real);                                        \
+          auto k = KERN;                                                                                                      \
+          FCK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile));                               \
+          k<<<(unsigned)full, (TBV), tile, st>>>(s->dev, pose, momentum ? dq : nullptr, xform, com, momentum ? mom : nullptr); \
+        } while (0)
+        if (mode == 1) {
+          if (momentum) FK_LAUNCH_TILE((fk::fk_hanyang_tma_rolled_kernel<real, true, 64>), 64, 59);
+          else FK_LAUNCH_TILE((fk::fk_hanyang_tma_rolled_kernel<real, false, 64>), 64, 0);
+        } else {
+          if (momentum) FK_LAUNCH_TILE((fk::fk_hanyang_tma_unrolled_kernel<real, true, false, 64>), 64, 0);
+          else FK_LAUNCH_TILE((fk::fk_hanyang_tma_unrolled_kernel<real, false, false, 64>), 64, 0);
+        }
+#undef FK_LAUNCH_TILE
+      }
+      const int64_t done = full * TB, rest = n - done;
+      if (rest > 0) {                                    // ragged tail (or everything when the TMA path is switched off)
+        constexpr int HB = 128;
+        const int blocks = (int)((rest + HB - 1) / HB);
+        const real* p2 = pose + done * 60; const real* d2 = dq ? dq + done * 59 : nullptr;
+        real* x2 = xform ? xform + done * 140 : nullptr; real* c2 = com ? com + done * 3 : nullptr; real* m2 = mom ? mom + done * 6 : nullptr;
+        if (momentum) fk::fk_hanyang_kernel<real, true, HB><<<blocks, HB, 0, st>>>(s->dev, (int)rest, p2, d2, x2, c2, m2);
+        else fk::fk_hanyang_kernel<real, false, HB><<<blocks, HB, 0, st>>>(s->dev, (int)rest, p2, nullptr, x2, c2, nullptr);
+      }
+      FCK(cudaGetLastError());
+      return 0;
+    }
+  }
   size_t smem = (size_t)(s->host.maxdepth + 1) * 13 * BLOCK * sizeof(real);
   auto kern = fk::fk_forward_kernel<real, BLOCK>;
   FCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

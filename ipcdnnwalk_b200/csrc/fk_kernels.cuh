@@ -208,4 +208,413 @@ __global__ void __launch_bounds__(BLOCK) fk_forward_kernel(const SkelConst* __re
 #undef STK
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Skeleton-specialised instantiation for the skeleton the SRBTrack full-body mapping uses
+// (gym_trackSRB/taesooLib/hanyang_lowdof_T_sh.wrl and work/taesooLib/Resource/motion/MOB1/hanyang_lowdof_T.wrl: 20 bones,
+// 53 Euler channels).  The tree structure (depth, channel count, axes, first pose column of every bone) is a compile-time
+// table, the bone loop is fully unrolled, so the pose row (60 reals, loaded up front with 128-bit loads -- every byte of
+// the row is requested before the first use, which is what hides the DRAM latency of the thread-per-row layout), the
+// root-to-bone stack and the 140 output reals all live in registers: no shared-memory stack (the occupancy limiter of
+// the generic kernel), no structure look-ups, no branches.  Numeric constants (offsets, masses, inertias) stay run-time.
+struct Hanyang {
+  static constexpr int NB = 20, NPOSE = 60, NDQ = 59, MAXDEPTH = 8;
+  __host__ __device__ static constexpr int depth(int b) { constexpr int t[NB] = {0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7, 4, 5}; return t[b]; }
+  __host__ __device__ static constexpr int nchan(int b) { constexpr int t[NB] = {0, 3, 1, 3, 3, 1, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3}; return t[b]; }
+  __host__ __device__ static constexpr int axes(int b) { constexpr int t[NB] = {0, 9, 0, 9, 9, 0, 9, 9, 9, 9, 9, 36, 18, 18, 9, 36, 18, 18, 9, 9}; return t[b]; }
+  __host__ __device__ static constexpr int start(int b) { constexpr int t[NB] = {0, 7, 10, 11, 14, 17, 18, 21, 24, 27, 30, 33, 36, 39, 42, 45, 48, 51, 54, 57}; return t[b]; }
+  // parent of bone b: 0 = the previous bone, 1 = Hips, 2 = Chest2 (the two branch points of this tree)
+  __host__ __device__ static constexpr int psel(int b) { constexpr int t[NB] = {0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 2, 0}; return t[b]; }
+  static constexpr int CHEST2 = 9;
+  // the same tables packed into immediates for the rolled loop (a table indexed at run time would live in local memory)
+  template <typename F> __host__ __device__ static constexpr unsigned long long pack(F f, int bits, int first, int count) {
+    unsigned long long r = 0;
+    for (int i = 0; i < count; i++) r |= (unsigned long long)f(first + i) << (bits * i);
+    return r;
+  }
+  __device__ static __forceinline__ int nchan_rt(int b) { constexpr unsigned long long m = pack(nchan, 2, 0, NB); return (int)((m >> (2 * b)) & 3); }
+  __device__ static __forceinline__ int psel_rt(int b) { constexpr unsigned long long m = pack(psel, 2, 0, NB); return (int)((m >> (2 * b)) & 3); }
+  __device__ static __forceinline__ int axes_rt(int b) {
+    constexpr unsigned long long lo = pack(axes, 6, 0, 10), hi = pack(axes, 6, 10, 10);
+    return (int)(((b < 10 ? lo >> (6 * b) : hi >> (6 * (b - 10)))) & 63);
+  }
+  __device__ static __forceinline__ int start_rt(int b) {
+    constexpr unsigned long long lo = pack(start, 6, 0, 10), hi = pack(start, 6, 10, 10);
+    return (int)(((b < 10 ? lo >> (6 * b) : hi >> (6 * (b - 10)))) & 63);
+  }
+  static bool matches(const SkelConst& k) {
+    if (k.nb != NB || k.n_pose != NPOSE || k.n_dq != NDQ) return false;
+    for (int b = 0; b < NB; b++)
+      if (k.depth[b] != depth(b) || k.nchan[b] != nchan(b) || (b > 0 && k.axes[b] != axes(b))) return false;
+    return true;
+  }
+};
+
+template <typename real> struct BoneNum { real off[Hanyang::NB][3], mass[Hanyang::NB], com[Hanyang::NB][3], inr[Hanyang::NB][6], itm; };
+
+// The unrolled sweep over the 20 bones.  p / v: the pose and dq rows in registers; StoreX(k, a, b, c, d): sink of the k-th
+// group of output reals (128 bits: 4 floats or 2 doubles), called as soon as its words are final.
+// SYNC: a CTA-wide barrier in front of every bone keeps the warps of a CTA inside the same ~5-7 kB of this 100-150 kB
+// straight-line code, so an instruction-cache line fetched for one warp serves all of them.
+template <typename real, bool MOM, bool SYNC, typename StoreX>
+__device__ __forceinline__ void hanyang_sweep(const BoneNum<real>& bn, const real (&p)[Hanyang::NPOSE], const real* v, bool want_x, StoreX&& store_x,
+                                              V3<real>* com_o, real mom_o[6]) {
+  using H = Hanyang;
+  real S[H::MAXDEPTH][MOM ? 13 : 7];
+  real out[H::NB * 7];
+  V3<real> csum = {0, 0, 0};
+  real HM[3] = {0, 0, 0}, HF[3] = {0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < H::NB; b++) {
+    if constexpr (SYNC) __syncthreads();
+    const int d = H::depth(b), nc = H::nchan(b), ax = H::axes(b), st = H::start(b);
+    Q4<real> q; V3<real> t, w = {0, 0, 0}, lv = {0, 0, 0};
+    const V3<real> off = {bn.off[b][0], bn.off[b][1], bn.off[b][2]};
+    if (b == 0) {
+      q = {p[3], p[4], p[5], p[6]};
+      t = {p[0] + off.x, p[1] + off.y, p[2] + off.z};
+      if constexpr (MOM) {
+        Q4<real> qi = qconj_unit(q);
+        w = qrot(qi, V3<real>{v[0], v[1], v[2]});
+        lv = qrot(qi, V3<real>{v[3], v[4], v[5]});
+      }
+    } else {
+      const int pd = d > 0 ? d - 1 : 0;
+      const Q4<real> pq = {S[pd][0], S[pd][1], S[pd][2], S[pd][3]};
+      const V3<real> pt = {S[pd][4], S[pd][5], S[pd][6]};
+      Q4<real> lq = {real(1), real(0), real(0), real(0)};
+      if constexpr (MOM) {
+        V3<real> pw = {S[pd][7], S[pd][8], S[pd][9]};
+        V3<real> pv = {S[pd][10], S[pd][11], S[pd][12]};
+        w = pw;
+        lv = pv + cross(pw, off);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k < nc) {
+          const int a = (ax >> (2 * k)) & 3;
+          real s, c;
+          num<real>::sincos(real(0.5) * p[st + k], &s, &c);
+          Q4<real> r;
+          if (a == 0) r = {lq.w * c - lq.x * s, lq.x * c + lq.w * s, lq.y * c + lq.z * s, lq.z * c - lq.y * s};
+          else if (a == 1) r = {lq.w * c - lq.y * s, lq.x * c - lq.z * s, lq.y * c + lq.w * s, lq.z * c + lq.x * s};
+          else r = {lq.w * c - lq.z * s, lq.x * c + lq.y * s, lq.y * c - lq.x * s, lq.z * c + lq.w * s};
+          lq = r;
+          if constexpr (MOM) {
+            const real C = c * c - s * s, Sn = real(2) * s * c;
+            const real rate = v[6 + (st - 7) + k];
+            if (a == 0) { w = {w.x, C * w.y + Sn * w.z, C * w.z - Sn * w.y}; lv = {lv.x, C * lv.y + Sn * lv.z, C * lv.z - Sn * lv.y}; w.x += rate; }
+            else if (a == 1) { w = {C * w.x - Sn * w.z, w.y, C * w.z + Sn * w.x}; lv = {C * lv.x - Sn * lv.z, lv.y, C * lv.z + Sn * lv.x}; w.y += rate; }
+            else { w = {C * w.x + Sn * w.y, C * w.y - Sn * w.x, w.z}; lv = {C * lv.x + Sn * lv.y, C * lv.y - Sn * lv.x, lv.z}; w.z += rate; }
+          }
+        }
+      }
+      q = quat_mul(pq, lq);
+      t = qrot(pq, off) + pt;
+    }
+    S[d][0] = q.w; S[d][1] = q.x; S[d][2] = q.y; S[d][3] = q.z; S[d][4] = t.x; S[d][5] = t.y; S[d][6] = t.z;
+    if constexpr (MOM) { S[d][7] = w.x; S[d][8] = w.y; S[d][9] = w.z; S[d][10] = lv.x; S[d][11] = lv.y; S[d][12] = lv.z; }
+    out[7 * b] = q.w; out[7 * b + 1] = q.x; out[7 * b + 2] = q.y; out[7 * b + 3] = q.z; out[7 * b + 4] = t.x; out[7 * b + 5] = t.y; out[7 * b + 6] = t.z;
+    const real m = bn.mass[b];
+    const V3<real> c = {bn.com[b][0], bn.com[b][1], bn.com[b][2]};
+    csum = csum + m * (qrot(q, c) + t);
+    if constexpr (MOM) {
+      const real Ixx = bn.inr[b][0], Iyy = bn.inr[b][1], Izz = bn.inr[b][2], Ixy = bn.inr[b][3], Ixz = bn.inr[b][4], Iyz = bn.inr[b][5];
+      const V3<real> r = m * c;
+      V3<real> M = {Ixx * w.x + Ixy * w.y + Ixz * w.z + r.y * lv.z - r.z * lv.y,
+                    Ixy * w.x + Iyy * w.y + Iyz * w.z + r.z * lv.x - r.x * lv.z,
+                    Ixz * w.x + Iyz * w.y + Izz * w.z + r.x * lv.y - r.y * lv.x};
+      V3<real> F = {w.y * r.z - w.z * r.y + m * lv.x, w.z * r.x - w.x * r.z + m * lv.y, w.x * r.y - w.y * r.x + m * lv.z};
+      V3<real> Fw = qrot(q, F);
+      V3<real> Mw = qrot(q, M) + cross(t, Fw);
+      HM[0] += Mw.x; HM[1] += Mw.y; HM[2] += Mw.z; HF[0] += Fw.x; HF[1] += Fw.y; HF[2] += Fw.z;
+    }
+    if (want_x) {
+      constexpr int W = sizeof(real) == 4 ? 4 : 2;
+      const int done_words = 7 * (b + 1), prev_words = 7 * b;
+#pragma unroll
+      for (int k = prev_words / W; k < done_words / W; k++) {
+        if constexpr (sizeof(real) == 4) store_x(k, out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+        else store_x(k, out[2 * k], out[2 * k + 1], real(0), real(0));
+      }
+    }
+  }
+  const V3<real> com = bn.itm * csum;
+  *com_o = com;
+  if constexpr (MOM) {
+    V3<real> Fv = {HF[0], HF[1], HF[2]};
+    V3<real> sh = cross(com, Fv);
+    mom_o[0] = HM[0] - sh.x; mom_o[1] = HM[1] - sh.y; mom_o[2] = HM[2] - sh.z; mom_o[3] = HF[0]; mom_o[4] = HF[1]; mom_o[5] = HF[2];
+  }
+}
+
+template <typename real, int BLOCK> __device__ __forceinline__ void load_bone_numbers(BoneNum<real>& bn, const SkelConst* __restrict__ skp) {
+  for (int k = threadIdx.x; k < Hanyang::NB; k += BLOCK) {
+    for (int c = 0; c < 3; c++) { bn.off[k][c] = (real)skp->offset[k][c]; bn.com[k][c] = (real)skp->com[k][c]; }
+    for (int c = 0; c < 6; c++) bn.inr[k][c] = (real)skp->inertia[k][c];
+    bn.mass[k] = (real)skp->mass[k];
+  }
+  if (threadIdx.x == 0) bn.itm = (real)skp->inv_total_mass;
+}
+
+// Variant A: rows read / written directly by the owning thread (used for the ragged tail and unaligned buffers).
+template <typename real, bool MOM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fk_hanyang_kernel(const SkelConst* __restrict__ skp, int n, const real* __restrict__ pose,
+                                                           const real* __restrict__ dq, real* __restrict__ xform,
+                                                           real* __restrict__ com_out, real* __restrict__ mom_out) {
+  using H = Hanyang;
+  __shared__ BoneNum<real> bn;
+  load_bone_numbers<real, BLOCK>(bn, skp);
+  __syncthreads();
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  real p[H::NPOSE];
+  if constexpr (sizeof(real) == 4) {
+    const float4* r = reinterpret_cast<const float4*>(pose + (size_t)i * H::NPOSE);
+#pragma unroll
+    for (int k = 0; k < H::NPOSE / 4; k++) { float4 t = __ldg(r + k); p[4 * k] = t.x; p[4 * k + 1] = t.y; p[4 * k + 2] = t.z; p[4 * k + 3] = t.w; }
+  } else {
+    const double2* r = reinterpret_cast<const double2*>(pose + (size_t)i * H::NPOSE);
+#pragma unroll
+    for (int k = 0; k < H::NPOSE / 2; k++) { double2 t = __ldg(r + k); p[2 * k] = t.x; p[2 * k + 1] = t.y; }
+  }
+  real v[MOM ? H::NDQ : 1];
+  if constexpr (MOM) {
+    const real* r = dq + (size_t)i * H::NDQ;
+#pragma unroll
+    for (int k = 0; k < H::NDQ; k++) v[k] = __ldg(r + k);
+  }
+  real* xrow = xform ? xform + (size_t)i * (H::NB * 7) : nullptr;
+  V3<real> com; real mom[6];
+  hanyang_sweep<real, MOM, false>(bn, p, v, xrow != nullptr, [&](int k, real a, real b, real c, real d) {
+    if constexpr (sizeof(real) == 4) reinterpret_cast<float4*>(xrow)[k] = make_float4(a, b, c, d);
+    else reinterpret_cast<double2*>(xrow)[k] = make_double2(a, b);
+  }, &com, mom);
+  if (com_out) { real* o = com_out + (size_t)i * 3; o[0] = com.x; o[1] = com.y; o[2] = com.z; }
+  if constexpr (MOM) {
+    real* o = mom_out + (size_t)i * 6;
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = mom[k];
+  }
+}
+
+// Variant B (full tiles of BLOCK poses): TMA-staged rows and a ROLLED bone loop.
+//  * I/O.  With rows accessed straight from global memory every warp-level LDG / STG touches 32 different 128-byte lines
+//    and the L1TEX wavefront queue (one FIFO per SM, ~2 cycles per line) is the bound: (15 + 35) requests x 32 lines x 2
+//    cycles per 32 poses = 0.36 ms per 1M poses against 0.13 ms of HBM time.  Here every thread owns a 140-real slot of
+//    shared memory.  Its pose row is dropped into the LAST 60 reals of the slot by a TMA bulk copy (cp.async.bulk, one per
+//    row, all completing on one mbarrier); the dq tile is one more bulk copy.  The 140 output reals are written into the
+//    slot from its start -- bone b's seven reals end at word 7(b+1) <= 80 + (first pose column of bone b+1), i.e. they
+//    never reach an angle that is still unread -- and the whole tile of transforms, then CoM and momentum, leaves by
+//    bulk stores.  No LSU traffic to global memory at all.
+//  * Code size.  The unrolled sweep is 104 kB (FK) / 146 kB (momentum) of SASS, the instruction caches hold 6 kB (L0) and
+//    32 kB (L1.5): ncu showed 26 % / 61 % of the stall samples on instruction fetch.  The tree of this skeleton has two
+//    branch points only (Hips, Chest2), so the root-to-bone stack collapses to "previous bone, Hips, Chest2" in registers
+//    and the bone loop can stay rolled: one bone body (~10 kB), angles and rates read from shared memory by index.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <typename real> struct BoneState { Q4<real> q; V3<real> t, w, lv; };
+template <typename real, bool MOM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fk_hanyang_tma_rolled_kernel(const SkelConst* __restrict__ skp, const real* __restrict__ pose,
+                                                               const real* __restrict__ dq, real* __restrict__ xform,
+                                                               real* __restrict__ com_out, real* __restrict__ mom_out) {
+  using H = Hanyang;
+  constexpr int XW = H::NB * 7;                               // 140 reals per slot
+  constexpr int PIN = XW - H::NPOSE;                          // the pose row sits at words [80, 140) of the slot
+  extern __shared__ __align__(128) unsigned char fk_tile[];
+  real* sx = reinterpret_cast<real*>(fk_tile);                // [BLOCK][140]
+  real* sc = sx + BLOCK * XW;                                  // [BLOCK][3]
+  real* sm = sc + BLOCK * 3;                                   // [BLOCK][6]
+  real* sdq = sm + BLOCK * 6;                                  // [BLOCK][59]  (momentum only)
+  __shared__ BoneNum<real> bn;
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * BLOCK;
+  constexpr unsigned row_bytes = H::NPOSE * sizeof(real), dq_bytes = BLOCK * H::NDQ * sizeof(real);
+  static_assert(row_bytes % 16 == 0 && dq_bytes % 16 == 0 && (XW * sizeof(real)) % 16 == 0 && (PIN * sizeof(real)) % 16 == 0 &&
+                (BLOCK * 3 * sizeof(real)) % 16 == 0, "bulk copies need 16-byte multiples");
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(BLOCK * row_bytes + (MOM ? dq_bytes : 0u)) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sdq)), "l"(dq + row0 * H::NDQ), "r"(dq_bytes), "r"(smem_u32(&mbar)) : "memory");
+  }
+  load_bone_numbers<real, BLOCK>(bn, skp);
+  __syncthreads();                                             // barrier armed, bone numbers in place
+  real* slot = sx + tid * XW;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(slot + PIN)), "l"(pose + (row0 + tid) * H::NPOSE), "r"(row_bytes), "r"(smem_u32(&mbar)) : "memory");
+  {
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred P; mbarrier.try_wait.parity.shared::cta.b64 P, [%1], 0; selp.u32 %0, 1, 0, P; }" : "=r"(ok) : "r"(smem_u32(&mbar)) : "memory");
+  }
+  const real* p = slot + PIN;
+  const real* v = sdq + tid * H::NDQ;
+  const bool want_x = xform != nullptr;
+  BoneState<real> cur, hips, chest2;
+  V3<real> csum = {0, 0, 0};
+  real HM[3] = {0, 0, 0}, HF[3] = {0, 0, 0};
+#pragma unroll 1
+  for (int b = 0; b < H::NB; b++) {
+    const int nc = H::nchan_rt(b), ax = H::axes_rt(b), st = H::start_rt(b), sel = H::psel_rt(b);
+    const V3<real> off = {bn.off[b][0], bn.off[b][1], bn.off[b][2]};
+    Q4<real> q; V3<real> t, w = {0, 0, 0}, lv = {0, 0, 0};
+    if (b == 0) {
+      q = {p[3], p[4], p[5], p[6]};
+      t = {p[0] + off.x, p[1] + off.y, p[2] + off.z};
+      if constexpr (MOM) {
+        Q4<real> qi = qconj_unit(q);
+        w = qrot(qi, V3<real>{v[0], v[1], v[2]});
+        lv = qrot(qi, V3<real>{v[3], v[4], v[5]});
+      }
+    } else {
+      BoneState<real> par = cur;
+      if (sel == 1) par = hips; else if (sel == 2) par = chest2;
+      Q4<real> lq = {real(1), real(0), real(0), real(0)};
+      if constexpr (MOM) { w = par.w; lv = par.lv + cross(par.w, off); }
+#pragma unroll 1
+      for (int k = 0; k < nc; k++) {
+        const int a = (ax >> (2 * k)) & 3;
+        real s, c;
+        num<real>::sincos(real(0.5) * p[st + k], &s, &c);
+        // lq * (c, s e_a) written once for all axes: e_a picks the component pair that mixes
+        const real e0 = a == 0 ? s : real(0), e1 = a == 1 ? s : real(0), e2 = a == 2 ? s : real(0);
+        lq = {lq.w * c - lq.x * e0 - lq.y * e1 - lq.z * e2, lq.x * c + lq.w * e0 + lq.y * e2 - lq.z * e1,
+              lq.y * c + lq.w * e1 + lq.z * e0 - lq.x * e2, lq.z * c + lq.w * e2 + lq.x * e1 - lq.y * e0};
+        if constexpr (MOM) {
+          const real C = c * c - s * s, Sn = real(2) * s * c;
+          const real rate = v[6 + (st - 7) + k];
+          if (a == 0) { w = {w.x, C * w.y + Sn * w.z, C * w.z - Sn * w.y}; lv = {lv.x, C * lv.y + Sn * lv.z, C * lv.z - Sn * lv.y}; w.x += rate; }
+          else if (a == 1) { w = {C * w.x - Sn * w.z, w.y, C * w.z + Sn * w.x}; lv = {C * lv.x - Sn * lv.z, lv.y, C * lv.z + Sn * lv.x}; w.y += rate; }
+          else { w = {C * w.x + Sn * w.y, C * w.y - Sn * w.x, w.z}; lv = {C * lv.x + Sn * lv.y, C * lv.y - Sn * lv.x, lv.z}; w.z += rate; }
+        }
+      }
+      q = quat_mul(par.q, lq);
+      t = qrot(par.q, off) + par.t;
+    }
+    cur.q = q; cur.t = t; cur.w = w; cur.lv = lv;
+    if (b == 0) hips = cur;
+    if (b == H::CHEST2) chest2 = cur;
+    if (want_x) {                                             // the angles of this bone have been consumed: overwrite from the slot start
+      real* o = slot + 7 * b;
+      o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z; o[4] = t.x; o[5] = t.y; o[6] = t.z;
+    }
+    const real m = bn.mass[b];
+    const V3<real> c = {bn.com[b][0], bn.com[b][1], bn.com[b][2]};
+    csum = csum + m * (qrot(q, c) + t);
+    if constexpr (MOM) {
+      const real Ixx = bn.inr[b][0], Iyy = bn.inr[b][1], Izz = bn.inr[b][2], Ixy = bn.inr[b][3], Ixz = bn.inr[b][4], Iyz = bn.inr[b][5];
+      const V3<real> r = m * c;
+      V3<real> M = {Ixx * w.x + Ixy * w.y + Ixz * w.z + r.y * lv.z - r.z * lv.y,
+                    Ixy * w.x + Iyy * w.y + Iyz * w.z + r.z * lv.x - r.x * lv.z,
+                    Ixz * w.x + Iyz * w.y + Izz * w.z + r.x * lv.y - r.y * lv.x};
+      V3<real> F = {w.y * r.z - w.z * r.y + m * lv.x, w.z * r.x - w.x * r.z + m * lv.y, w.x * r.y - w.y * r.x + m * lv.z};
+      V3<real> Fw = qrot(q, F);
+      V3<real> Mw = qrot(q, M) + cross(t, Fw);
+      HM[0] += Mw.x; HM[1] += Mw.y; HM[2] += Mw.z; HF[0] += Fw.x; HF[1] += Fw.y; HF[2] += Fw.z;
+    }
+  }
+  const V3<real> com = bn.itm * csum;
+  sc[tid * 3] = com.x; sc[tid * 3 + 1] = com.y; sc[tid * 3 + 2] = com.z;
+  if constexpr (MOM) {
+    V3<real> Fv = {HF[0], HF[1], HF[2]};
+    V3<real> sh = cross(com, Fv);
+    real* o = sm + tid * 6;
+    o[0] = HM[0] - sh.x; o[1] = HM[1] - sh.y; o[2] = HM[2] - sh.z; o[3] = HF[0]; o[4] = HF[1]; o[5] = HF[2];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk-copy engine
+  __syncthreads();
+  if (tid == 0) {
+    if (want_x)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xform + row0 * XW), "r"(smem_u32(sx)), "r"((unsigned)(BLOCK * XW * sizeof(real))) : "memory");
+    if (com_out != nullptr)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(com_out + row0 * 3), "r"(smem_u32(sc)), "r"((unsigned)(BLOCK * 3 * sizeof(real))) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mom_out + row0 * 6), "r"(smem_u32(sm)), "r"((unsigned)(BLOCK * 6 * sizeof(real))) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must stay alive until the engine has read it
+  }
+}
+
+// Variant C (full tiles): TMA-staged rows with the UNROLLED sweep.  Pose / dq tiles arrive by two bulk copies, every thread
+// pulls its row into registers with conflict-free 128-bit shared loads (pitch 240 / 560 bytes: the eight 16-byte spans of
+// a quarter-warp fall in distinct bank groups), the region is then reused for the output tile, which leaves by bulk stores.
+// SYNC (see hanyang_sweep) is what makes the 100-150 kB of straight-line code affordable.
+template <typename real, bool MOM, bool SYNC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fk_hanyang_tma_unrolled_kernel(const SkelConst* __restrict__ skp, const real* __restrict__ pose,
+                                                                        const real* __restrict__ dq, real* __restrict__ xform,
+                                                                        real* __restrict__ com_out, real* __restrict__ mom_out) {
+  using H = Hanyang;
+  constexpr int XW = H::NB * 7;
+  extern __shared__ __align__(128) unsigned char fk_tile[];
+  real* sx = reinterpret_cast<real*>(fk_tile);                // [BLOCK][140]   (first: pose rows [BLOCK][60], dq rows [BLOCK][59])
+  real* sc = sx + BLOCK * XW;
+  real* sm = sc + BLOCK * 3;
+  __shared__ BoneNum<real> bn;
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * BLOCK;
+  constexpr unsigned in_bytes = BLOCK * H::NPOSE * sizeof(real), dq_bytes = BLOCK * H::NDQ * sizeof(real);
+  static_assert(in_bytes % 16 == 0 && dq_bytes % 16 == 0 && (BLOCK * 3 * sizeof(real)) % 16 == 0, "tile sizes must be multiples of 16 bytes");
+  real* sdq = sx + BLOCK * H::NPOSE;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(in_bytes + (MOM ? dq_bytes : 0u)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sx)), "l"(pose + row0 * H::NPOSE), "r"(in_bytes), "r"(smem_u32(&mbar)) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sdq)), "l"(dq + row0 * H::NDQ), "r"(dq_bytes), "r"(smem_u32(&mbar)) : "memory");
+  }
+  load_bone_numbers<real, BLOCK>(bn, skp);
+  __syncthreads();
+  {
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred P; mbarrier.try_wait.parity.shared::cta.b64 P, [%1], 0; selp.u32 %0, 1, 0, P; }" : "=r"(ok) : "r"(smem_u32(&mbar)) : "memory");
+  }
+  real p[H::NPOSE];
+  if constexpr (sizeof(real) == 4) {
+    const float4* r = reinterpret_cast<const float4*>(sx + tid * H::NPOSE);
+#pragma unroll
+    for (int k = 0; k < H::NPOSE / 4; k++) { float4 t = r[k]; p[4 * k] = t.x; p[4 * k + 1] = t.y; p[4 * k + 2] = t.z; p[4 * k + 3] = t.w; }
+  } else {
+    const double2* r = reinterpret_cast<const double2*>(sx + tid * H::NPOSE);
+#pragma unroll
+    for (int k = 0; k < H::NPOSE / 2; k++) { double2 t = r[k]; p[2 * k] = t.x; p[2 * k + 1] = t.y; }
+  }
+  real v[MOM ? H::NDQ : 1];
+  if constexpr (MOM) {
+#pragma unroll
+    for (int k = 0; k < H::NDQ; k++) v[k] = sdq[tid * H::NDQ + k];
+  }
+  __syncthreads();                                             // all inputs are in registers: the region becomes the output tile
+  real* xrow = sx + tid * XW;
+  V3<real> com; real mom[6];
+  hanyang_sweep<real, MOM, SYNC>(bn, p, v, xform != nullptr, [&](int k, real a, real b, real c, real d) {
+    if constexpr (sizeof(real) == 4) reinterpret_cast<float4*>(xrow)[k] = make_float4(a, b, c, d);
+    else reinterpret_cast<double2*>(xrow)[k] = make_double2(a, b);
+  }, &com, mom);
+  sc[tid * 3] = com.x; sc[tid * 3 + 1] = com.y; sc[tid * 3 + 2] = com.z;
+  if constexpr (MOM) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) sm[tid * 6 + k] = mom[k];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    if (xform != nullptr)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xform + row0 * XW), "r"(smem_u32(sx)), "r"((unsigned)(BLOCK * XW * sizeof(real))) : "memory");
+    if (com_out != nullptr)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(com_out + row0 * 3), "r"(smem_u32(sc)), "r"((unsigned)(BLOCK * 3 * sizeof(real))) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mom_out + row0 * 6), "r"(smem_u32(sm)), "r"((unsigned)(BLOCK * 6 * sizeof(real))) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
 }  // namespace fk
