@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--variant", default="test", choices=["test", "training"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flush", default="write", choices=["write", "read", "none"],
+                    help="L2 flush between steps: write a 256 MiB buffer (default, the timing rule), read it, or nothing (diagnostic)")
     return ap.parse_args()
 
 
@@ -205,12 +207,16 @@ def run_ours(args, rank, local_rank, world):
     env.reset()
     act = torch.zeros(N, ACT_DIM, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
     acc = torch.zeros(1 + 2 * OBS_DIM, dtype=torch.float64, device=dev)
     K, W = args.steps, args.warmup
 
     def one_step(k, timed):
         env.tracking_action(act, sigma=SIGMA, seed=99 + rank, step=k)      # the "policy": outside the timed events
-        flush.fill_(k & 0xFF)                                               # L2 flush between steps
+        if args.flush == "write":
+            flush.fill_(k & 0xFF)                                           # L2 flush between steps
+        elif args.flush == "read":
+            flush_sink.add_(flush.view(torch.int64).sum())                  # diagnostic: evict with clean lines
         ev = None
         if timed:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -310,7 +316,7 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), {N} envs per GPU x {world} GPU",
                        "envs_per_gpu": N, "clips": "stand1 + aiming_show (shipped clips; walk/run clips are absent from the reference mount)",
                        "actions": f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done",
-                       "l2": "flushed between steps (256 MiB write); per-step CUDA events on the launching stream",
+                       "l2": {"write": "flushed between steps (256 MiB write)", "read": "DIAGNOSTIC: evicted between steps by reading 256 MiB", "none": "DIAGNOSTIC: not flushed"}[args.flush] + "; per-step CUDA events on the launching stream",
                        "collective": f"obs-normaliser statistics kernel + NCCL all-reduce every {ROLLOUT} steps, inside the timed total",
                        "lanes_per_env": env_lanes(args), "median_step_ms": med_ms_max, "wall_s_timed_loop": t_wall,
                        "episodes_finished": int(ep[2]), "mean_episode_len": float(ep[1] / max(ep[2], 1))},

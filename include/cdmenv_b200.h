@@ -29,7 +29,7 @@ typedef struct cdm_env cdm_env;
 typedef struct cdm_config {
   int32_t num_envs;
   int32_t precision;      /* 64: fp64 state + arithmetic (reference precision); 32: fp32 state, QP still fp64 (ridge 1e-8) */
-  int32_t lanes_per_env;  /* 0 = default (2); 1,2,4,8 lanes of a warp cooperate on one environment */
+  int32_t lanes_per_env;  /* 0 = default (1: one thread per environment, structured QP); 2,4,8 lanes of a warp cooperate on one environment */
   int32_t auto_reset;     /* 1: a terminated env is reset inside the step */
   int32_t device;
   uint64_t seed;          /* stream of the device-side reset draws (CT.randomUniform / math.random in RagdollSim:reset) */

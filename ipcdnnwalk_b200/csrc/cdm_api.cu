@@ -136,7 +136,7 @@ extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   if (!cfg || !out) return srb_set_error(-1, "cdm_create: null argument");
   if (cfg->num_envs <= 0) return srb_set_error(-1, "cdm_create: num_envs must be positive");
   if (cfg->precision != 32 && cfg->precision != 64) return srb_set_error(-1, "cdm_create: precision must be 32 or 64");
-  int G = cfg->lanes_per_env == 0 ? 2 : cfg->lanes_per_env;   // measured best at 16384 envs (tools/bench_cdm.py)
+  int G = cfg->lanes_per_env == 0 ? 1 : cfg->lanes_per_env;   // thread per environment + structured QP: measured best at 16384 envs (tools/bench_cdm.py)
   if (G != 1 && G != 2 && G != 4 && G != 8) return srb_set_error(-1, "cdm_create: lanes_per_env must be 1,2,4 or 8");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -468,6 +468,167 @@ __device__ inline void apply_reset(CdmState<real>& s, const Params<real>& P, con
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Structured contact QP for ONE thread (lanes_per_env = 1).  The 20 columns are never stored: with the contact arms
+// r_c = R^T (c - p) and the friction directions n_d = R^T basis_d in the body frame,
+//     a_{c,d} = D [r_c x n_d ; n_d],  D = diag(1/I, 1/m),     t_{c,d} = a_{c,d} . nu = n_d . (V + W x r_c),  W = D_w nu_w, V = D_v nu_v,
+//     sum_{d in S_c} a a^T = D [[ [r]x N [r]x^T, [r]x N ], [ N [r]x^T, N ]] D,   N = sum_{d in S_c} n_d n_d^T,
+// so a Newton system costs ~460 flops and the line search evaluates t on the fly (the active set travels as a 20-bit
+// mask).  Same algorithm as srb::QP::solve_ls (exact line search on the dual), fp64.
+struct SQP {
+  double r[4][3], n[5][3], Di[6];
+  unsigned valid;                                              // bit c: contact c present
+
+  // t(nu) for all columns; returns the mask of t < 0 (invalid contacts contribute no bits); optionally sum_{t<0} t * t2 etc.
+  __device__ __forceinline__ unsigned tmask(const double nu[6]) const {
+    const double W[3] = {nu[0] * Di[0], nu[1] * Di[1], nu[2] * Di[2]}, V[3] = {nu[3] * Di[3], nu[4] * Di[4], nu[5] * Di[5]};
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double u0 = V[0] + W[1] * r[c][2] - W[2] * r[c][1], u1 = V[1] + W[2] * r[c][0] - W[0] * r[c][2], u2 = V[2] + W[0] * r[c][1] - W[1] * r[c][0];
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const double t = n[d][0] * u0 + n[d][1] * u1 + n[d][2] * u2;
+        if (t < 0 && ((valid >> c) & 1)) m |= 1u << (5 * c + d);
+      }
+    }
+    return m;
+  }
+  // along nu + alpha * dir: g-sum = sum_{r_j<0} r_j s_j, slope-sum = sum_{r_j<0} s_j^2, mask of r_j < 0   (r = t(nu + alpha dir), s = t(dir))
+  __device__ __forceinline__ unsigned line(const double nu[6], const double dir[6], double alpha, double* gsum, double* ssum) const {
+    double W[3], V[3], Wd[3], Vd[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Wd[i] = dir[i] * Di[i]; Vd[i] = dir[3 + i] * Di[3 + i];
+      W[i] = (nu[i] + alpha * dir[i]) * Di[i]; V[i] = (nu[3 + i] + alpha * dir[3 + i]) * Di[3 + i];
+    }
+    unsigned m = 0;
+    double g = 0, sl = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double u0 = V[0] + W[1] * r[c][2] - W[2] * r[c][1], u1 = V[1] + W[2] * r[c][0] - W[0] * r[c][2], u2 = V[2] + W[0] * r[c][1] - W[1] * r[c][0];
+      const double e0 = Vd[0] + Wd[1] * r[c][2] - Wd[2] * r[c][1], e1 = Vd[1] + Wd[2] * r[c][0] - Wd[0] * r[c][2], e2 = Vd[2] + Wd[0] * r[c][1] - Wd[1] * r[c][0];
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const double t = n[d][0] * u0 + n[d][1] * u1 + n[d][2] * u2;
+        const double sd = n[d][0] * e0 + n[d][1] * e1 + n[d][2] * e2;
+        if (t < 0 && ((valid >> c) & 1)) { m |= 1u << (5 * c + d); g += t * sd; sl += sd * sd; }
+      }
+    }
+    *gsum = g; *ssum = sl;
+    return m;
+  }
+  // H (lower triangle, 21) = I + invw * sum_{j in mask} a_j a_j^T
+  __device__ __forceinline__ void hessian(unsigned mask, double invw, double H[21]) const {
+    double TT[6] = {0, 0, 0, 0, 0, 0};      // xx yy zz xy xz yz of the torque block
+    double TF[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // torque row i, force column j
+    double FF[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      double N[6] = {0, 0, 0, 0, 0, 0};     // xx yy zz xy xz yz
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const double m = ((mask >> (5 * c + d)) & 1) ? 1.0 : 0.0;
+        const double a0 = m * n[d][0], a1 = m * n[d][1], a2 = m * n[d][2];
+        N[0] += a0 * n[d][0]; N[1] += a1 * n[d][1]; N[2] += a2 * n[d][2]; N[3] += a0 * n[d][1]; N[4] += a0 * n[d][2]; N[5] += a1 * n[d][2];
+      }
+      const double rx = r[c][0], ry = r[c][1], rz = r[c][2];
+      // X = [r]x N : column j of X = r x (column j of N)
+      const double Nc[3][3] = {{N[0], N[3], N[4]}, {N[3], N[1], N[5]}, {N[4], N[5], N[2]}};   // Nc[j] = column j (symmetric)
+      double X[3][3];                       // X[i][j]
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        X[0][j] = ry * Nc[j][2] - rz * Nc[j][1];
+        X[1][j] = rz * Nc[j][0] - rx * Nc[j][2];
+        X[2][j] = rx * Nc[j][1] - ry * Nc[j][0];
+      }
+      // Y = X [r]x^T : row i of Y = r x (row i of X)
+      double Y[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        Y[i][0] = ry * X[i][2] - rz * X[i][1];
+        Y[i][1] = rz * X[i][0] - rx * X[i][2];
+        Y[i][2] = rx * X[i][1] - ry * X[i][0];
+      }
+      TT[0] += Y[0][0]; TT[1] += Y[1][1]; TT[2] += Y[2][2]; TT[3] += Y[1][0]; TT[4] += Y[2][0]; TT[5] += Y[2][1];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) TF[3 * i + j] += X[i][j];
+#pragma unroll
+      for (int k = 0; k < 6; k++) FF[k] += N[k];
+    }
+    // lower triangle, index i*(i+1)/2+j, rows 0..2 torque, 3..5 force; scaled by D on both sides
+    const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d3 = Di[3], d4 = Di[4], d5 = Di[5];
+    H[0] = 1.0 + invw * d0 * d0 * TT[0];
+    H[1] = invw * d1 * d0 * TT[3]; H[2] = 1.0 + invw * d1 * d1 * TT[1];
+    H[3] = invw * d2 * d0 * TT[4]; H[4] = invw * d2 * d1 * TT[5]; H[5] = 1.0 + invw * d2 * d2 * TT[2];
+    // force rows: H[3+i][j] = (TF^T)[i][j] = TF[j][i]  (torque column j)
+    H[6] = invw * d3 * d0 * TF[0]; H[7] = invw * d3 * d1 * TF[3]; H[8] = invw * d3 * d2 * TF[6]; H[9] = 1.0 + invw * d3 * d3 * FF[0];
+    H[10] = invw * d4 * d0 * TF[1]; H[11] = invw * d4 * d1 * TF[4]; H[12] = invw * d4 * d2 * TF[7]; H[13] = invw * d4 * d3 * FF[3]; H[14] = 1.0 + invw * d4 * d4 * FF[1];
+    H[15] = invw * d5 * d0 * TF[2]; H[16] = invw * d5 * d1 * TF[5]; H[17] = invw * d5 * d2 * TF[8]; H[18] = invw * d5 * d3 * FF[4]; H[19] = invw * d5 * d4 * FF[5];
+    H[20] = 1.0 + invw * d5 * d5 * FF[2];
+  }
+  // returns the number of Newton systems; nu in: initial guess, out: solution
+  __device__ __forceinline__ int solve_ls(const double y[6], double invw, double nu[6]) const {
+    unsigned S = tmask(nu);
+    int iters = 0;
+    double rhs[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) rhs[i] = -y[i];
+#pragma unroll 1
+    for (int it = 0; it < 32; it++) {
+      double H[21], nn[6];
+      hessian(S, invw, H);
+      srb::ldl_solve6<double>(H, rhs, nn);
+      iters++;
+      const unsigned Sn = tmask(nn);
+      if (Sn == S) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = nn[i];
+        break;
+      }
+      double dir[6], dd = 0, b0 = 0, nmax = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        dir[i] = nn[i] - nu[i];
+        dd += dir[i] * dir[i]; b0 += dir[i] * (nu[i] + y[i]);
+        nmax = fmax(nmax, fabs(nn[i]));
+      }
+      double gs, ss;
+      line(nu, dir, 1.0, &gs, &ss);
+      double alpha = 1.0;
+      if (b0 + dd + invw * gs > 0) {                           // the full step overshoots: exact line search in (0, 1)
+        unsigned ml = line(nu, dir, 0.0, &gs, &ss);
+        double gl = b0 + invw * gs, sl = dd + invw * ss, al = 0.0, lo = 0.0, hi = 1.0;
+        if (!(gl < 0)) alpha = 0.0;
+        else {
+#pragma unroll 1
+          for (int k2 = 0; k2 < 48; k2++) {
+            double cand = al - gl / sl;
+            const bool newton = cand > lo && cand < hi;
+            if (!newton) cand = 0.5 * (lo + hi);
+            const unsigned mc = line(nu, dir, cand, &gs, &ss);
+            const double gc = b0 + cand * dd + invw * gs, sc = dd + invw * ss;
+            al = cand;
+            if (newton && mc == ml) break;
+            if (gc < 0) lo = cand; else hi = cand;
+            gl = gc; sl = sc; ml = mc;
+            if (hi - lo <= 4e-13 * hi) break;
+          }
+          alpha = al;
+        }
+      }
+      double stepn = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) { const double dlt = alpha * dir[i]; nu[i] += dlt; stepn = fmax(stepn, fabs(dlt)); }
+      if (stepn <= 1e-13 * (1.0 + nmax)) break;
+      S = tmask(nu);
+    }
+    return iters;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // the step kernel (RagdollSim:step :1014-1574)
 template <typename real, int G>
 __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
@@ -673,6 +834,44 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
 #pragma unroll
       for (int i = 0; i < 6; i++) { y[i] = (double)ades[i] + (double)bias[i] / Md[i]; nu[i] = -y[i]; }
       int iters = 0;
+      if constexpr (G == 1) {
+        // one thread per environment: structured QP, nothing stored per column
+        unsigned lam_mask = 0;
+        SQP sq;
+        if (use != 0) {
+          const Q4<double> Qid = {(double)Qi.w, (double)Qi.x, (double)Qi.y, (double)Qi.z};
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const V3<real> cp = cpt[c >> 1][c & 1];
+            V3<double> rb = qrot(Qid, V3<double>{(double)cp.x - (double)s.p.x, (double)cp.y - (double)s.p.y, (double)cp.z - (double)s.p.z});
+            sq.r[c][0] = rb.x; sq.r[c][1] = rb.y; sq.r[c][2] = rb.z;
+          }
+#pragma unroll
+          for (int d = 0; d < 5; d++) {
+            V3<double> nb = qrot(Qid, V3<double>{(double)P.basis[d][0], (double)P.basis[d][1], (double)P.basis[d][2]});
+            sq.n[d][0] = nb.x; sq.n[d][1] = nb.y; sq.n[d][2] = nb.z;
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) sq.Di[i] = 1.0 / Md[i];
+          sq.valid = (unsigned)use;
+          iters = sq.solve_ls(y, P.inv_ridge2, nu);
+          lam_mask = sq.tmask(nu);
+        }
+        if (A.dbg != nullptr && active) {
+          double* dl = A.dbg + (size_t)e * DBG_W + 24 + 20 * it;
+          for (int c = 0; c < NQCOL; c++) dl[c] = 0.0;
+          if (use != 0) {
+            const double W[3] = {nu[0] * sq.Di[0], nu[1] * sq.Di[1], nu[2] * sq.Di[2]}, V[3] = {nu[3] * sq.Di[3], nu[4] * sq.Di[4], nu[5] * sq.Di[5]};
+            for (int c = 0; c < 4; c++) {
+              const double u0 = V[0] + W[1] * sq.r[c][2] - W[2] * sq.r[c][1], u1 = V[1] + W[2] * sq.r[c][0] - W[0] * sq.r[c][2], u2 = V[2] + W[0] * sq.r[c][1] - W[1] * sq.r[c][0];
+              for (int d = 0; d < 5; d++) {
+                const double t = sq.n[d][0] * u0 + sq.n[d][1] * u1 + sq.n[d][2] * u2;
+                if ((lam_mask >> (5 * c + d)) & 1) dl[5 * c + d] = -t * P.inv_ridge2 * 0.5;
+              }
+            }
+          }
+        }
+      } else {
       double t[QPT::NC];
       QPT qp;
       if (__any_sync(0xffffffffu, use != 0)) {
@@ -695,14 +894,6 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
         }
         iters = qp.solve_ls(lane, y, P.inv_ridge2, nu, t, hsm);
       }
-      real qdd[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) qdd[i] = (real)(nu[i] + (double)ades[i]);
-      if (dbg != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) { dbg[6 * it + i] = (double)qdd[i]; dbg[12 + 6 * it + i] = (double)ades[i]; }
-        dbg[75 + it] = (double)iters;
-      }
       if (A.dbg != nullptr && active) {
         double* dl = A.dbg + (size_t)e * DBG_W + 24 + 20 * it;
 #pragma unroll
@@ -710,6 +901,15 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
           const int c = lane + k * G;
           if (c < NQCOL) dl[c] = (use != 0 && ((use >> (c / 5)) & 1) && t[k] < 0) ? -t[k] * P.inv_ridge2 * 0.5 : 0.0;
         }
+      }
+      }
+      real qdd[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) qdd[i] = (real)(nu[i] + (double)ades[i]);
+      if (dbg != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { dbg[6 * it + i] = (double)qdd[i]; dbg[12 + 6 * it + i] = (double)ades[i]; }
+        dbg[75 + it] = (double)iters;
       }
       // stepKinematic (QPservo_v3.lua:305-321 -> Trbdl integrate :758-763, integrateQuater :211-250)
       V3<real> lin_acc = qrot(s.Q, V3<real>{qdd[3], qdd[4], qdd[5]} + cross(s.wb, vb));
