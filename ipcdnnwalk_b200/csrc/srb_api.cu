@@ -227,7 +227,7 @@ extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count,
   return 0;
 }
 
-template <typename real, int G, bool CIO = false> static void launch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
+template <typename real, int G, bool CIO = false, bool TERRAIN = false> static void launch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s) {
   StepArgs<real> A;
   A.N = h->N; A.Npad = h->Npad;
   A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist;
@@ -237,12 +237,17 @@ template <typename real, int G, bool CIO = false> static void launch_step(srb_en
   A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p); A.terrain = h->terrain_dev;
   constexpr int EPW = 32 / G;
   int blocks = (h->N + EPW - 1) / EPW;
-  srb_step_kernel<real, G, CIO><<<blocks, 32, 0, s>>>(A);
+  srb_step_kernel<real, G, CIO, TERRAIN><<<blocks, 32, 0, s>>>(A);
   h->launches++;
 }
 
 static bool cio_supported(int G) { return G == 4 || G == 8; }
 template <typename real> static int dispatch_step(srb_env* h, const float* act, float* obs, float* rew, uint8_t* done, float* rinfo, cudaStream_t s, bool cio = false) {
+  if (h->p.use_terrain) {                                // terrain variant: separate instantiations
+    if (h->G == 8) { launch_step<real, 8, false, true>(h, act, obs, rew, done, rinfo, s); return 0; }
+    if (h->G == 4) { launch_step<real, 4, false, true>(h, act, obs, rew, done, rinfo, s); return 0; }
+    return fail(-1, "the terrain variant is built for lanes_per_env 4 and 8");
+  }
   if (cio) {
     if (h->G == 8) { launch_step<real, 8, true>(h, act, obs, rew, done, rinfo, s); return 0; }
     if (h->G == 4) { launch_step<real, 4, true>(h, act, obs, rew, done, rinfo, s); return 0; }
@@ -311,7 +316,7 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   size_t N = h->N;
   if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
   cudaStream_t s = h->stream;
-  if (h->host_mode == 1 && cio_supported(h->G)) {
+  if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
     // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
     // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions
     // that overlap the computation of the other warps instead of four copies serialised after it
