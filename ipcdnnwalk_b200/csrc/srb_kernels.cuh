@@ -1266,6 +1266,8 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   }
   // ---- fused auto-reset (what SB3's VecEnv does after a terminal step)
   const bool any_reset = A.auto_reset && __any_sync(0xffffffffu, done);
+  long long tk_r0 = 0;
+  if (A.dbg != nullptr) tk_r0 = clock64();                // reset-path clocks land in the pad slots of sub-step 1
   if (any_reset) {
     __syncwarp();                                        // obs row of this env was written by sibling lanes
     if (done && active && A.term_obs != nullptr) {
@@ -1286,19 +1288,23 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
       } else {
         draw_reset_plan(A.seed, e, s.episode, A.clips, A.nclips, plan, T != nullptr);
       }
+      if (dbg != nullptr && lane == 0) dbg[DBG_SUB + 19] = (double)(clock64() - tk_r0);
       EnvState<real> ns = s;
       real h0[HIST_W];
       apply_reset(ns, A.clips, A.nclips, plan, h0, T);
       s = ns;
+      if (dbg != nullptr && lane == 0) dbg[DBG_SUB + 20] = (double)(clock64() - tk_r0);
       if (active && lane == 0) {
 #pragma unroll
         for (int i = 0; i < HIST_W; i++) hist_env[i] = h0[i];
       }
       const ClipDesc<real> ncd = A.clips[s.clip];
       write_obs<real, G>(s, ncd, obs, lane, active, T);
+      if (dbg != nullptr && lane == 0) dbg[DBG_SUB + 21] = (double)(clock64() - tk_r0);
     }
   }
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
+  if (dbg != nullptr && lane == 0) dbg[DBG_SUB + 22] = (double)(clock64() - tk_r0);
   if (CIO) {                                             // the warp's observation rows: one contiguous block
     __syncwarp();
     float* dst = A.obs + (size_t)env0 * OBS_W;

@@ -26,4 +26,8 @@ for k in range(30):
         t0=gentry[w].min()
         print(f"step {k}: event {e0.elapsed_time(e1)*1e3:.1f}us | warp cycles: load+decode {np.median(pre[w]):.0f}  4 substeps med {np.median(subs[w]):.0f} p99 {np.percentile(subs[w],99):.0f} max {subs[w].max():.0f} | total med {np.median(tot[w]):.0f} max {tot[w].max():.0f}"
               f" | post med {np.median((tot-subs)[w]):.0f} max {(tot-subs)[w].max():.0f} | globaltimer ns: entry spread {(gentry[w].max()-t0):.0f} exit min {(gexit[w].min()-t0):.0f} med {np.median(gexit[w]-t0):.0f} max {(gexit[w].max()-t0):.0f} | qp cyc/substep med {np.median(qp[qp>0]):.0f} iters/step max-in-warp mean {its.reshape(N//4,4,4).max(axis=1).sum(axis=1).mean():.1f}")
+        rs = d[:, 1, 19:23]
+        m = rs[:, 2] > 0                                   # environments that were reset in this step
+        if m.any():
+            print(f"   reset path (cycles after done is known, {int(m.sum())} envs): plan drawn {np.median(rs[m,0]):.0f}  state reset {np.median(rs[m,1]):.0f}  obs rewritten {np.median(rs[m,2]):.0f}  state stored {np.median(rs[m,3]):.0f} | no-reset envs: state stored {np.median(rs[~m,3]):.0f}")
 env.close()
