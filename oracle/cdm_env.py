@@ -33,6 +33,8 @@ taesooLib / Lua cannot run here.  PARITY PARTLY PINNED against the r
     (505 flight rows: gravity, Euler equations, quaternion integration, < 1e-7).
   * work/_LQR_CACHE_2.DAT holds one LQR gain computed by the reference (A, B, Q, R, K): a known-answer vector for
     `lqr_gain`.
+  * trained_models/ppo/walk2-v1.pt, the policy the reference trained on this environment, walks in this restatement
+    at the speed of the reference's own recorded roll-out (tests/test_cdm_policy.py).
   NOT pinned by reference outputs (no recorded intermediate exists): the contact QP and the reward; they are checked
   analytically in tests/test_oracle_cdm_cpu.py (KKT of the un-eliminated QP as _QPsolve states it, second solver) and
   by the committed golden roll-out.

@@ -11,6 +11,8 @@ Writes:
   tests/golden/cdm_reference_recordings.npz   the first 700 rows of gym_cdm2/spec/refTraj_{walk2,run2}-v1.dat (roll-outs
                                      recorded by the reference simulator) + the LQR known answer of work/_LQR_CACHE_2.DAT
   tests/golden/cdm_terrain_heights.npz   mHeight of the gym_cdm2 terrain (heightmap1_256_256_2bytes.raw through the loader)
+  tests/golden/cdm_policy_walk2.npz  the reference's trained walk2-v1 policy (actor weights + observation normaliser) and gait
+                                     statistics of the roll-out the reference recorded with it
 """
 import json
 import os
@@ -113,8 +115,68 @@ def make_terrain():
     print("terrain heights written")
 
 
+def _gait_stats(p, sup):
+    """forward speed (m/s), mean height, lateral drift per metre, mean swing duration (RL steps) from root positions / support flags."""
+    n = len(p)
+    dist = float(np.linalg.norm(p[-1, [0, 2]] - p[0, [0, 2]]))
+    d = (p[-1, [0, 2]] - p[0, [0, 2]]) / dist
+    lat = float(np.abs((p[:, [0, 2]] - p[0, [0, 2]]) @ np.array([-d[1], d[0]])).max())
+    durs = []
+    for leg in range(2):
+        s = sup[:, leg]
+        i = 0
+        while i < n:
+            if s[i] == 0:
+                j = i
+                while j < n and s[j] == 0:
+                    j += 1
+                if i > 0 and j < n:
+                    durs.append(j - i)
+                i = j
+            else:
+                i += 1
+    return np.array([dist / (n / 60.0), float(p[:, 1].mean()), lat / dist, float(np.mean(durs)), float((sup.sum(1) == 2).mean())])
+
+
+def make_policy_fixture():
+    """The policy the reference trained on walk2-v1 (trained_models/ppo/walk2-v1.pt = [gym_gang.model.Policy, obs_rms],
+    gym_cdm2/train_gym.py:230-233), imported here from /root/reference and flattened to plain arrays, plus gait statistics
+    of the roll-out the reference recorded with it (gym_cdm2/spec/refTraj_walk2-v1.dat)."""
+    import types
+    import torch
+    sys.path.insert(0, "/root/reference")
+    for name in ("stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.running_mean_std",
+                 "stable_baselines3.common.vec_env", "stable_baselines3.common.vec_env.vec_normalize"):      # not installed: stubs for unpickling
+        m = types.ModuleType(name); m.__path__ = []
+        sys.modules.setdefault(name, m)
+    sys.modules["stable_baselines3.common.running_mean_std"].RunningMeanStd = type("RunningMeanStd", (), {})
+    sys.modules["stable_baselines3.common.vec_env.vec_normalize"].VecNormalize = type("VecNormalize", (), {})
+    sys.modules["stable_baselines3.common.vec_env"].VecNormalize = sys.modules["stable_baselines3.common.vec_env.vec_normalize"].VecNormalize
+    ac, rms = torch.load("/root/reference/trained_models/ppo/walk2-v1.pt", weights_only=False, map_location="cpu")
+    layers = [m for m in list(ac.base.actor) + list(ac.dist.fc_mean) if isinstance(m, torch.nn.Linear)]
+    acts = [type(m).__name__ for m in list(ac.base.actor) + list(ac.dist.fc_mean) if not isinstance(m, torch.nn.Linear)]
+    assert all(a == "Tanh" for a in acts) and len(acts) == len(layers), "expected Linear/Tanh pairs"
+    out = {f"W{i}": l.weight.detach().numpy().astype(np.float64) for i, l in enumerate(layers)}
+    out.update({f"b{i}": l.bias.detach().numpy().astype(np.float64) for i, l in enumerate(layers)})
+    out["obs_mean"] = np.asarray(rms.mean, np.float64); out["obs_var"] = np.asarray(rms.var, np.float64)
+    # the flattened network reproduces Policy.act(deterministic=True)
+    x = np.random.default_rng(0).normal(size=(16, 27)).astype(np.float32)
+    with torch.no_grad():
+        _, a, _, _ = ac.act(torch.from_numpy(x), torch.zeros(16, ac.recurrent_hidden_state_size), torch.ones(16, 1), deterministic=True)
+    h = x.astype(np.float64)
+    for i in range(len(layers)):
+        h = np.tanh(h @ out[f"W{i}"].T + out[f"b{i}"])
+    assert np.abs(h - a.numpy()).max() < 1e-5
+    from ipcdnnwalk_b200 import tl_binary as tb
+    t = tb.load_table("/root/reference/gym_cdm2/spec/refTraj_walk2-v1.dat")
+    out["recorded_gait"] = _gait_stats(t["globalTraj"][:, 0:3], t["rawFootInfo"][:, 0:2])
+    np.savez_compressed(os.path.join(GOLDEN, "cdm_policy_walk2.npz"), n_layers=len(layers), **out)
+    print("policy:", [out[f"W{i}"].shape for i in range(len(layers))], "recorded gait [speed, height, lateral/m, swing steps, double support]:", out["recorded_gait"])
+
+
 if __name__ == "__main__":
     make_tables()
     make_rollout()
     make_reference_recordings()
     make_terrain()
+    make_policy_fixture()
