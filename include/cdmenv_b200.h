@@ -97,10 +97,18 @@ int64_t cdm_launch_count(cdm_env* env);
  * tlterrain_height: xz_dev[n][2] (terrain-local) -> height_dev[n]; hit_dev[n][3] (may be NULL) = cell row i, cell column j,
  * triangle (0 upper, 1 lower), all -1 outside the field (height 0). */
 typedef struct tl_terrain tl_terrain;
+#define CDM_OBS_DIM_TERRAIN 31   /* + 4 terrain height samples ahead of the body (gym_cdm2/deepmimiccdmterrain-v1.lua:3-16) */
 int tlterrain_create(int32_t device, int32_t rows, int32_t cols, double size_x, double size_z, int32_t tile_along_z,
                      const double* heights_host, tl_terrain** out);
 int tlterrain_destroy(tl_terrain* t);
 int tlterrain_height(tl_terrain* t, int64_t n, const double* xz_dev, double* height_dev, int32_t* hit_dev, void* stream);
+/* The terrain variant of the environment (gym_cdm2/spec/walkterrain-v1.lua -> deepmimiccdmterrain-v1.lua): every
+ * RagdollSim:projectToGround goes to this height field (terrain_pos = g_terrainPos in metres, heights / sizes in cm,
+ * deepmimiccdm-v1.lua:368-424), the targets follow the terrain (:1205-1238), the observation grows to CDM_OBS_DIM_TERRAIN.
+ * t == NULL returns to flat ground.  The terrain must outlive the environment.  Spec values that differ from walk2-v1
+ * (healthy_min 0.7) are set with cdm_set_param.  Call before cdm_reset. */
+int cdm_set_terrain(cdm_env* env, tl_terrain* t, const double terrain_pos[3]);
+int cdm_obs_dim(cdm_env* env);   /* CDM_OBS_DIM or CDM_OBS_DIM_TERRAIN: row length of obs_dev / term_obs_dev */
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,8 @@ _CDM_SIGNATURES = {         # include/cdmenv_b200.h
     "cdm_set_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "cdm_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
     "cdm_launch_count": (C.c_int64, [_P]),
+    "cdm_set_terrain": (C.c_int, [_P, _P, _P]),
+    "cdm_obs_dim": (C.c_int, [_P]),
 }
 _TLT_SIGNATURES = {
     "tlterrain_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P, C.POINTER(_P)]),

@@ -56,8 +56,10 @@ def skeleton_struct(skel):
 class CDMVecEnv:
     """N `deepmimiccdm-v1` environments stepped by one CUDA launch."""
 
-    def __init__(self, tables, skel, num_envs, precision=64, lanes_per_env=0, auto_reset=True, device=0, seed=0, params=None):
-        """`tables`: dict from cdm_tables.build_tables (or any table with the same keys); `skel`: parsed .wrl skeleton."""
+    def __init__(self, tables, skel, num_envs, precision=64, lanes_per_env=0, auto_reset=True, device=0, seed=0, params=None, terrain=None):
+        """`tables`: dict from cdm_tables.build_tables (or any table with the same keys); `skel`: parsed .wrl skeleton;
+        `terrain`: dict(heights [rows, cols] in cm, size_x, size_z in cm, terrain_pos [3] in metres) selects the
+        `walkterrain-v1` variant (deepmimiccdmterrain-v1.lua: 31-float observation)."""
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -69,6 +71,15 @@ class CDMVecEnv:
         cfg = CdmConfig(self.num_envs, self.precision, int(lanes_per_env), int(bool(auto_reset)), int(device), int(seed))
         self._h = C.c_void_p()
         check(self.lib.cdm_create(C.byref(cfg), C.byref(self._h)))
+        self.terrain = None
+        self.obs_dim = CDM_OBS_DIM
+        if terrain is not None:
+            from .tl_terrain import Terrain
+            self.terrain = Terrain(terrain["heights"], float(terrain["size_x"]), float(terrain["size_z"]), True, device=device)
+            tp = np.ascontiguousarray(terrain["terrain_pos"], dtype=np.float64)
+            check(self.lib.cdm_set_terrain(self._h, self.terrain._h, _ptr(tp)))
+            self.set_param("healthy_min", 0.7)              # spec/walkterrain-v1.lua: healthy_y_range = {0.7, 2.0}
+            self.obs_dim = int(self.lib.cdm_obs_dim(self._h))
         for k, v in (params or {}).items():
             self.set_param(k, v)
         rows = np.ascontiguousarray(cdm_tables.pack_rows(tables), dtype=np.float64)
@@ -76,7 +87,7 @@ class CDMVecEnv:
         self._skel = skeleton_struct(skel)
         check(self.lib.cdm_upload_table(self._h, rows.shape[0], int(tables["nf"]), _ptr(rows), C.byref(self._skel)))
         N = self.num_envs
-        self.obs = torch.zeros(N, CDM_OBS_DIM, dtype=torch.float32, device=self.device)
+        self.obs = torch.zeros(N, self.obs_dim, dtype=torch.float32, device=self.device)
         self.rew = torch.zeros(N, dtype=torch.float32, device=self.device)
         self.done = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self.term_obs = None
@@ -97,7 +108,7 @@ class CDMVecEnv:
     def attach(self, term_obs=False, reset_plan=False, dbg=False):
         t, N = self.torch, self.num_envs
         if term_obs and self.term_obs is None:
-            self.term_obs = t.zeros(N, CDM_OBS_DIM, dtype=t.float32, device=self.device)
+            self.term_obs = t.zeros(N, self.obs_dim, dtype=t.float32, device=self.device)
         if reset_plan and self.reset_plan is None:
             self.reset_plan = t.zeros(N, CDM_PLAN_DIM, dtype=t.float64, device=self.device)
         if dbg and self.dbg is None:
@@ -154,7 +165,7 @@ class CDMVecEnv:
             def view(p, ctype, shape):
                 n = int(np.prod(shape))
                 return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).reshape(shape)
-            self._pinned = dict(act=view(ptrs[0], C.c_float, (N, CDM_ACT_DIM)), obs=view(ptrs[1], C.c_float, (N, CDM_OBS_DIM)),
+            self._pinned = dict(act=view(ptrs[0], C.c_float, (N, CDM_ACT_DIM)), obs=view(ptrs[1], C.c_float, (N, self.obs_dim)),
                                 rew=view(ptrs[2], C.c_float, (N,)), done=view(ptrs[3], C.c_uint8, (N,)))
         return self._pinned
 

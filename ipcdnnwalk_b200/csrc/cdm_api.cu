@@ -34,7 +34,10 @@ struct cdm_env {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t* d_done = nullptr;
   int64_t launches = 0;
+  Ground ground;                             // T.h == nullptr: flat ground (walk2-v1); else the walkterrain-v1 height field
+  int obs_w = OBS_W;
 };
+struct tl_terrain { int device; double* h = nullptr; TLTerrainDev T; };
 
 static void default_params(std::map<std::string, double>& p) {
   // gym_cdm2/spec/walk2-v1.lua over defaultRLsetting.lua('walk4') in training mode (no GUI)
@@ -149,6 +152,7 @@ extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   h->rsz = cfg->precision == 64 ? 8 : 4;
   default_params(h->hp);
   memset(&h->skel, 0, sizeof(h->skel));
+  memset(&h->ground, 0, sizeof(h->ground));
   CK(cudaMalloc(&h->st, h->rsz * NF_REAL * h->Npad));
   CK(cudaMemset(h->st, 0, h->rsz * NF_REAL * h->Npad));
   CK(cudaMalloc(&h->ist, sizeof(int) * NF_INT * h->Npad));
@@ -223,6 +227,7 @@ extern "C" int cdm_upload_table(cdm_env* h, int32_t nframes, int32_t nf_cycle, c
 template <typename real> static void do_reset(cdm_env* h, const int* idx_dev, int count, const double* plan_dev, float* obs_dev, cudaStream_t s) {
   ResetArgs<real> A;
   A.N = h->N; A.Npad = h->Npad; A.count = count; A.nframes = h->nframes; A.nf_cycle = h->nf_cycle; A.idx = idx_dev;
+  A.obs_w = h->obs_w; A.ground = h->ground;
   A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist; A.tab = (const real*)h->tab;
   A.plan = plan_dev; A.seed = h->cfg.seed; A.obs = obs_dev; A.p = make_params<real>(h); A.rc = make_rc<real>(h);
   cdm_reset_kernel<real><<<(count + 127) / 128, 128, 0, s>>>(A);
@@ -258,6 +263,7 @@ extern "C" int cdm_reset(cdm_env* h, const int32_t* env_idx_host, int32_t count,
 template <typename real, int G> static void launch_step(cdm_env* h, const float* act, float* obs, float* rew, uint8_t* done, cudaStream_t s) {
   StepArgs<real> A;
   A.N = h->N; A.Npad = h->Npad; A.nframes = h->nframes; A.nf_cycle = h->nf_cycle;
+  A.obs_w = h->obs_w; A.ground = h->ground;
   A.st = (real*)h->st; A.ist = h->ist; A.hist = (real*)h->hist; A.tab = (const real*)h->tab;
   A.act = act; A.obs = obs; A.rew = rew; A.done = done;
   A.term_obs = h->term_obs; A.ep_stats = h->ep_stats; A.reset_plan = h->reset_plan; A.dbg = h->dbg;
@@ -293,11 +299,11 @@ static int ensure_host_buffers(cdm_env* h) {
   if (h->h_act) return 0;
   size_t N = h->N;
   CK(cudaMallocHost(&h->h_act, sizeof(float) * N * ACT_W));
-  CK(cudaMallocHost(&h->h_obs, sizeof(float) * N * OBS_W));
+  CK(cudaMallocHost(&h->h_obs, sizeof(float) * N * OBS_W_TERRAIN));
   CK(cudaMallocHost(&h->h_rew, sizeof(float) * N));
   CK(cudaMallocHost(&h->h_done, N));
   CK(cudaMalloc(&h->d_act, sizeof(float) * N * ACT_W));
-  CK(cudaMalloc(&h->d_obs, sizeof(float) * N * OBS_W));
+  CK(cudaMalloc(&h->d_obs, sizeof(float) * N * OBS_W_TERRAIN));
   CK(cudaMalloc(&h->d_rew, sizeof(float) * N));
   CK(cudaMalloc(&h->d_done, N));
   return 0;
@@ -321,11 +327,11 @@ extern "C" int cdm_step_host(cdm_env* h, const float* act_host, float* obs_host,
   CK(cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * N * ACT_W, cudaMemcpyHostToDevice, s));
   rc = cdm_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, s);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * OBS_W, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * h->obs_w, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  if (obs_host && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, sizeof(float) * N * OBS_W);
+  if (obs_host && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, sizeof(float) * N * h->obs_w);
   if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, sizeof(float) * N);
   if (done_host && done_host != h->h_done) memcpy(done_host, h->h_done, N);
   return 0;
@@ -336,6 +342,17 @@ extern "C" int cdm_set_aux(cdm_env* h, float* term_obs_dev, const double* reset_
   h->term_obs = term_obs_dev; h->reset_plan = reset_plan_dev; h->dbg = dbg_dev;
   return 0;
 }
+
+extern "C" int cdm_set_terrain(cdm_env* h, tl_terrain* t, const double terrain_pos[3]) {
+  if (!h) return srb_set_error(-1, "cdm_set_terrain: null handle");
+  if (t == nullptr) { memset(&h->ground, 0, sizeof(h->ground)); h->obs_w = OBS_W; return 0; }
+  if (!terrain_pos) return srb_set_error(-1, "cdm_set_terrain: null terrain_pos");
+  if (t->device != h->cfg.device) return srb_set_error(-1, "cdm_set_terrain: terrain lives on another device");
+  h->ground.T = t->T; h->ground.px = terrain_pos[0]; h->ground.py = terrain_pos[1]; h->ground.pz = terrain_pos[2];
+  h->obs_w = OBS_W_TERRAIN;
+  return 0;
+}
+extern "C" int cdm_obs_dim(cdm_env* h) { return h ? h->obs_w : 0; }
 
 extern "C" int cdm_state_dims(int32_t* n_real, int32_t* n_int, int32_t* hist_slots, int32_t* hist_width) {
   if (n_real) *n_real = NF_REAL; if (n_int) *n_int = NF_INT; if (hist_slots) *hist_slots = HIST_SLOTS; if (hist_width) *hist_width = HIST_W;
@@ -391,7 +408,6 @@ extern "C" int cdm_episode_stats(cdm_env* h, double out[3], int32_t clear) {
 extern "C" int64_t cdm_launch_count(cdm_env* h) { return h ? h->launches : 0; }
 
 // ---- OBJloader::Terrain (gym_cdm2 terrain spec) -------------------------------------------------------
-struct tl_terrain { int device; double* h = nullptr; TLTerrainDev T; };
 extern "C" int tlterrain_create(int32_t device, int32_t rows, int32_t cols, double size_x, double size_z, int32_t tile_along_z,
                                 const double* heights_host, tl_terrain** out) {
   if (!heights_host || !out) return srb_set_error(-1, "tlterrain_create: null argument");

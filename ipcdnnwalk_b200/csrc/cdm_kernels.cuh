@@ -167,6 +167,54 @@ template <typename T, int NCOL> __device__ __forceinline__ void tab_mix(const T*
   for (int k = 0; k < NCOL; k++) out[k] = __ldg(r0 + k) * m.w0 + __ldg(r1 + k) * m.w1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// OBJloader::Terrain::height (work/taesooLib/BaseLib/motion/Terrain.cpp:305-393): cell by floor, triangle by dx > dz,
+// plane through the triangle (Plane::setPlane, intersectionTest.cpp:96-104) intersected with the vertical ray from y = 1000
+// (Ray::intersects :243-260), tiling along Z.  hit = (cell row i, cell column j, triangle 0 upper / 1 lower), -1 outside.
+__device__ __forceinline__ double tl_terrain_height(const TLTerrainDev& T, double x0, double x1, int* hit) {
+  const int nsx = T.cols - 1, nsz = T.rows - 1;
+  const double nx = (x0 / T.size_x) * (double)nsx;
+  double nz = (x1 / T.size_z) * (double)nsz;
+  int j = (int)::floor(nx), i = (int)::floor(nz);
+  const double dx = nx - ::floor(nx), dz = nz - ::floor(nz);
+  if (hit) { hit[0] = -1; hit[1] = -1; hit[2] = -1; }
+  if (j < 0 || j >= nsx || !(nx == nx) || !(nz == nz)) return 0.0;
+  if (T.tile) {
+    i %= nsz;
+    if (i < 0) i += nsz;
+    nz = (double)i + dz;
+    x1 = nz / (double)nsz * T.size_z;
+  } else if (i < 0 || i >= nsz) {
+    return 0.0;
+  }
+  const double* h = T.h;
+  V3<double> v0, v1, v2;
+  const bool upper = dx > dz;
+  v0 = {(double)j * T.size_x / (double)nsx, __ldg(h + (size_t)i * T.cols + j), (double)i * T.size_z / (double)nsz};
+  if (upper) {
+    v1 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
+    v2 = {v1.x, __ldg(h + (size_t)i * T.cols + j + 1), v0.z};
+  } else {
+    v2 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
+    v1 = {v0.x, __ldg(h + (size_t)(i + 1) * T.cols + j), v2.z};
+  }
+  V3<double> n = cross(v1 - v0, v2 - v0);
+  n = (1.0 / ::sqrt(dot(n, n))) * n;
+  const double d = -dot(n, v0);
+  const V3<double> org = {x0, 1000.0, x1};
+  const double denom = dot(n, V3<double>{0.0, -1.0, 0.0});
+  const double t = -((dot(n, org) + d) / denom);
+  if (hit) { hit[0] = i; hit[1] = j; hit[2] = upper ? 0 : 1; }
+  return org.y + t * -1.0;
+}
+
+// Ground under a world point: RagdollSim:projectToGround / OBJloader.Terrain:getTerrainPos (deepmimiccdm-v1.lua:415-424,2171-2177).
+// `Ground` with T.h == nullptr is flat ground (walk2-v1); otherwise the gym_cdm2 terrain (walkterrain-v1), metres <-> cm.
+template <typename real> __device__ __forceinline__ real ground_y(const Ground* g, real x, real z) {
+  if (g == nullptr || g->T.h == nullptr) return real(0);
+  return (real)(tl_terrain_height(g->T, ((double)x - g->px) * 100.0, ((double)z - g->pz) * 100.0, nullptr) / 100.0 + g->py);
+}
+
 // ---- state in registers ------------------------------------------------------------------------------------------
 template <typename real> struct Leg {
   V3<real> cpos, pre, bx, bv; real fq_x, fq_v; Q4<real> org; real swph;
@@ -286,7 +334,7 @@ template <typename real> __device__ __forceinline__ real tab_at(const real* __re
 
 // getFilteredFootPos (:1865-1903)
 template <typename real>
-__device__ __noinline__ void filtered_foot_pos(const CdmState<real>& s, Q4<real> rotY, int l, const real* __restrict__ tab, int F, V3<real>* pos_out, Q4<real>* ori_out) {
+__device__ __noinline__ void filtered_foot_pos(const CdmState<real>& s, Q4<real> rotY, int l, const real* __restrict__ tab, int F, const Ground* gr, V3<real>* pos_out, Q4<real>* ori_out) {
   const Leg<real>& li = s.leg[l];
   const Leg<real>& oli = s.leg[1 - l];
   V3<real> pos = li.bx;
@@ -307,7 +355,7 @@ __device__ __noinline__ void filtered_foot_pos(const CdmState<real>& s, Q4<real>
       }
     }
   }
-  pos.y = real(0);
+  pos.y = ground_y<real>(gr, pos.x, pos.z);
   *pos_out = pos; *ori_out = ori;
 }
 
@@ -330,23 +378,28 @@ template <typename real> __device__ __forceinline__ real get_phase(CdmState<real
 
 // _get_obs (:1779-1859), flat ground
 template <typename real, int G>
-__device__ __noinline__ void write_obs(CdmState<real>& s, const real* __restrict__ tab, int F, int nf, float* __restrict__ o, int lane, bool active, bool force_zero) {
+__device__ __noinline__ void write_obs(CdmState<real>& s, const real* __restrict__ tab, int F, int nf, float* __restrict__ o, int lane, bool active, bool force_zero,
+                                       const Ground* gr) {
   const Q4<real> QI = {real(1), real(0), real(0), real(0)};
   Q4<real> rotY = rotation_y(s.Q);
   Q4<real> iry = qinv(rotY);
   V3<real> ww = qrot(s.Q, s.wb);
-  real ob[OBS_W];
-  ob[0] = s.p.y - real(0);
+  real ob[OBS_W_TERRAIN];
+  const bool terr = gr != nullptr && gr->T.h != nullptr;
+  const real gy = ground_y<real>(gr, s.p.x, s.p.z);            // getRefCoord: the root projected to the ground
+  ob[0] = s.p.y - gy;
   Q4<real> offq = qalign(quat_mul(iry, s.Q), QI);
   ob[1] = offq.w; ob[2] = offq.x; ob[3] = offq.y; ob[4] = offq.z;
   V3<real> a = qrot(iry, ww), b = qrot(iry, s.v);
   ob[5] = a.x; ob[6] = a.y; ob[7] = a.z; ob[8] = b.x; ob[9] = b.y; ob[10] = b.z;
-  V3<real> ref_t = {s.p.x, real(0), s.p.z};
+  V3<real> ref_t = {s.p.x, gy, s.p.z};
 #pragma unroll
   for (int l = 0; l < 2; l++) {
     const Leg<real>& li = s.leg[l];
     int c = 11 + 6 * l;
-    V3<real> lp = qrot(iry, li.bx - ref_t);
+    V3<real> cpos = li.bx;
+    if (terr) cpos.y = ground_y<real>(gr, cpos.x, cpos.z);     // deepmimiccdmterrain-v1.lua:58-60
+    V3<real> lp = qrot(iry, cpos - ref_t);
     ob[c] = lp.x; ob[c + 1] = lp.y; ob[c + 2] = lp.z;
     V3<real> dv = li.swing ? li.bv : V3<real>{real(0), real(0), real(0)};
     V3<real> vv = qrot(iry, dv);
@@ -358,10 +411,20 @@ __device__ __noinline__ void write_obs(CdmState<real>& s, const real* __restrict
   ob[24] = map_sin(phase, real(0), real(0.25), real(0), real(1));
   V3<real> tv = qrot(quat_mul(iry, s.tgt), V3<real>{real(0), real(0), real(1)});
   ob[25] = tv.x; ob[26] = tv.z;
+#pragma unroll
+  for (int k = 0; k < 4; k++) ob[OBS_W + k] = real(0);
+  if (terr) {                                                  // terrain_sample_loc (deepmimiccdmterrain-v1.lua:3-8,95-99)
+    const real sx[4] = {real(0), real(0.5), real(-0.5), real(1)};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      V3<real> pos = qrot(rotY, V3<real>{sx[k], real(0), real(0.5)}) + ref_t;
+      ob[OBS_W + k] = ground_y<real>(gr, pos.x, pos.z) - ref_t.y;
+    }
+  }
   if (active) {
 #pragma unroll
-    for (int i = 0; i < OBS_W; i++)
-      if ((i % G) == lane) o[i] = force_zero ? 0.f : (float)ob[i];
+    for (int i = 0; i < OBS_W_TERRAIN; i++)
+      if ((i % G) == lane && (i < OBS_W || terr)) o[i] = force_zero ? 0.f : (float)ob[i];
   }
 }
 template <typename real> __device__ __forceinline__ bool obs_has_nan(const CdmState<real>& s) {
@@ -373,7 +436,8 @@ template <typename real> __device__ __forceinline__ bool obs_has_nan(const CdmSt
 
 // ---- reference markers: FK of the two leg chains (getJointStateFromRefTree :996-1012, BoneForwardKinematics) -------
 template <typename real>
-__device__ __noinline__ void ref_markers(const real* __restrict__ tab, int F, real f, const Params<real>& P, V3<real> mk[4], V3<real>* cdm_pos, Q4<real>* cdm_q) {
+__device__ __noinline__ void ref_markers(const real* __restrict__ tab, int F, real f, const Params<real>& P, V3<real> mk[4], V3<real>* cdm_pos, Q4<real>* cdm_q,
+                                         const Ground* gr = nullptr) {
   RowMix<real> m = row_mix(f, F, true);
   real c[7];
   tab_mix<real, 7>(tab, m, T_CDM, c);
@@ -406,7 +470,7 @@ __device__ __noinline__ void ref_markers(const real* __restrict__ tab, int F, re
     }
     V3<real> toe = qrot(q, V3<real>{P.toe[0], P.toe[1], P.toe[2]}) + t;
     V3<real> heel = qrot(q, V3<real>{P.heel[0], P.heel[1], P.heel[2]}) + t;
-    toe.y = real(0); heel.y = real(0);                  // projectToGround (flat)
+    toe.y = ground_y<real>(gr, toe.x, toe.z); heel.y = ground_y<real>(gr, heel.x, heel.z);       // projectToGround
     const int o = side == 0 ? 2 : 0;                    // marker order: R toe, R heel, L toe, L heel
     mk[o] = toe; mk[o + 1] = heel;
   }
@@ -429,14 +493,15 @@ template <typename real> __device__ inline void draw_reset_plan(unsigned long lo
   for (int i = 0; i < 3; i++) plan[13 + i] = (u[13 + i] - 0.5) * (double)P.noise_v[i];       // (math.random()-0.5)*scale
 }
 template <typename real>
-__device__ inline void apply_reset(CdmState<real>& s, const Params<real>& P, const ResetConst<real>& rc, const double plan[PLAN_W], real hist0[HIST_W]) {
+__device__ inline void apply_reset(CdmState<real>& s, const Params<real>& P, const ResetConst<real>& rc, const double plan[PLAN_W], real hist0[HIST_W],
+                                   const Ground* gr = nullptr) {
   s.tgt = {real(1), real(0), real(0), real(0)};
   s.gtime = real(0);
   s.iframe = real(0);
   s.ep_ret = real(0);
   s.steps = 0;
   s.episode += 1;
-  V3<real> pos = {real(0) + (real)plan[4], rc.cdm0[1] + (real)plan[5], real(0) + (real)plan[6]};
+  V3<real> pos = {real(0) + (real)plan[4], rc.cdm0[1] + ground_y<real>(gr, real(0), real(0)) + (real)plan[5], real(0) + (real)plan[6]};   // :1595-1596
   Q4<real> q = {rc.cdm0[3] + (real)plan[0], rc.cdm0[4] + (real)plan[1], rc.cdm0[5] + (real)plan[2], rc.cdm0[6] + (real)plan[3]};
   q = qnormalize(q);
   s.p = pos; s.Q = q;
@@ -666,7 +731,8 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
     }
   }
   double* dbg = (A.dbg != nullptr && active && lane == 0) ? A.dbg + (size_t)e * DBG_W : nullptr;
-  float* obs = A.obs + (size_t)e * OBS_W;
+  float* obs = A.obs + (size_t)e * A.obs_w;
+  const Ground* gr = A.ground.T.h != nullptr ? &A.ground : nullptr;
   const real RL_STEP = real(1.0 / 60.0), FRAME_RATE = real(30);
   const Q4<real> QI = {real(1), real(0), real(0), real(0)};
   const V3<real> Zv = {real(0), real(0), real(1)};
@@ -675,7 +741,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
   bool done = false;
   if (s.iframe >= real(F)) {                                   // :1017-1025 ran past the reference table
     done = true;
-    write_obs<real, G>(s, tab, F, nf, obs, lane, active, false);
+    write_obs<real, G>(s, tab, F, nf, obs, lane, active, false, gr);
   } else {
     const Q4<real> Q0 = s.Q;
     const V3<real> p0 = s.p;
@@ -719,14 +785,19 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
         const int oc = l == 0 ? T_OFFR : T_OFFL;
         V3<real> off = {tab_at(tab, F, s.iframe, oc), tab_at(tab, F, s.iframe, oc + 1), tab_at(tab, F, s.iframe, oc + 2)};
         V3<real> desired = p0 + qrot(rotY, V3<real>{act[2 * l], real(0), act[2 * l + 1] + real(0)} + off);
-        desired.y = real(0);
+        desired.y = ground_y<real>(gr, desired.x, desired.z);     // projectToGround
         li.swph += RL_STEP;
         update_swing_foot(li, desired, Q0, p0, rotY, gv, P);
         const int rt = (int)tab_at(tab, F, s.iframe, T_RTTD + l);
+        real com_height = p0.y;
+        if (gr != nullptr) {                             // :686-692 height relative to the terrain between body and landing spot
+          const real ph = clamp_map(tab_at(tab, F, s.iframe, T_RTTD + l), real(0), tab_at(tab, F, s.iframe, T_SWDUR + l), real(0), real(1));
+          com_height -= map_cos(ph, real(0), real(1), ground_y<real>(gr, p0.x, p0.z), ground_y<real>(gr, li.cpos.x, li.cpos.z));
+        }
         if (rt <= 0) {
-          li.cpos.y = real(0);                           // unlimitedLeglen (training)
+          li.cpos.y = ground_y<real>(gr, li.cpos.x, li.cpos.z);       // unlimitedLeglen (training): projectToGround
           start_spprt(li, rotY);
-        } else if (p0.y < real(0) && li.swph > P.min_swing_phase) {     // touchDownHeight = 0 (training)
+        } else if (com_height < real(0) && li.swph > P.min_swing_phase) {     // touchDownHeight = 0 (training)
           has_early[l] = true; early[l] = real(rt);
         } else {
           const Leg<real>& oli = s.leg[1 - l];
@@ -737,7 +808,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
         }
       }
       V3<real> pos; Q4<real> ori;
-      filtered_foot_pos(s, rotY, l, tab, F, &pos, &ori);
+      filtered_foot_pos(s, rotY, l, tab, F, gr, &pos, &ori);
       cpt[l][0] = pos + qrot(ori, V3<real>{real(0), real(0), real(0.12)});
       cpt[l][1] = pos + qrot(ori, V3<real>{real(0), real(0), real(-0.12)});
     }
@@ -751,7 +822,11 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       for (int l = 0; l < 2; l++) {
         if (!have && has_early[l]) {
           real ev = early[l];
-          if (ev > mspc) ev = mspc; else start_spprt(s.leg[l], rotY);     // enforceTouchDown
+          if (ev > mspc) ev = mspc;
+          else {                                                           // enforceTouchDown (:767-774)
+            start_spprt(s.leg[l], rotY);
+            s.leg[l].cpos.y = ground_y<real>(gr, s.leg[l].cpos.x, s.leg[l].cpos.z);
+          }
           etd = ev; have = true;
         }
       }
@@ -790,6 +865,18 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       thp = qrot(iq, thp - dp_);
       thq = quat_mul(iq, thq);
     }
+    real terrain_y = real(0);
+    if (gr != nullptr) {                                       // :1205-1238 targets follow the terrain
+      terrain_y = ground_y<real>(gr, thp.x, thp.z);
+      thp.y += terrain_y;
+      const real nxt = ground_y<real>(gr, p0.x + gv.x * real(0.5), p0.z + gv.z * real(0.5));
+      real dy = (nxt - ground_y<real>(gr, p0.x, p0.z)) / real(0.5);
+      if (dy < real(0)) {
+        V3<real> v_d = qrot(Q0, dth_v);
+        v_d.y += num<real>::fmax(dy, real(-5));
+        dth_v = qrot(qinv(Q0), v_d);
+      }
+    }
     // ---- contact list (:1242-1261)
     int cmask = 0;
 #pragma unroll
@@ -797,7 +884,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       if (!s.leg[l].swing) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          cpt[l][j].y = real(0);
+          cpt[l][j].y = ground_y<real>(gr, cpt[l][j].x, cpt[l][j].z);
           if (norm(cpt[l][j] - p0) < P.max_contact_len) cmask |= 1 << (2 * l + j);
         }
       }
@@ -829,7 +916,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       V3<real> bw = cross(s.wb, Iw);
       V3<real> bl = qrot(Qi, V3<real>{real(0), P.mass * P.grav, real(0)}) + P.mass * cross(s.wb, vb);
       real bias[6] = {bw.x, bw.y, bw.z, bl.x, bl.y, bl.z};
-      const int use = (s.p.y > real(0) && s.p.y < P.max_contact_y) ? cmask : 0;
+      const int use = (s.p.y - terrain_y > real(0) && s.p.y - terrain_y < P.max_contact_y) ? cmask : 0;   // refCoord = vertical shift by terrain_y
       double y[6], nu[6];
 #pragma unroll
       for (int i = 0; i < 6; i++) { y[i] = (double)ades[i] + (double)bias[i] / Md[i]; nu[i] = -y[i]; }
@@ -939,17 +1026,17 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       V3<real> c0p, c1p; Q4<real> c0q, c1q;
       V3<real> mk[4];
       ref_markers<real>(tab, F, num<real>::fmin(s.iframe + real(0), real(F - 1)), P, nullptr, &c0p, &c0q);
-      ref_markers<real>(tab, F, num<real>::fmin(s.iframe + delta_frame, real(F - 1)), P, mk, &c1p, &c1q);
+      ref_markers<real>(tab, F, num<real>::fmin(s.iframe + delta_frame, real(F - 1)), P, mk, &c1p, &c1q, gr);
       ref_y = c1p.y;
       const Q4<real> sim_rotY = rotation_y(s.Q);
       V3<real> smk[4];
 #pragma unroll
       for (int l = 0; l < 2; l++) {
         V3<real> pos; Q4<real> ori;
-        filtered_foot_pos(s, sim_rotY, l, tab, F, &pos, &ori);
+        filtered_foot_pos(s, sim_rotY, l, tab, F, gr, &pos, &ori);
         smk[2 * l] = pos + qrot(ori, V3<real>{real(0), real(0), real(0.12)});
         smk[2 * l + 1] = pos + qrot(ori, V3<real>{real(0), real(0), real(-0.12)});
-        smk[2 * l].y = real(0); smk[2 * l + 1].y = real(0);
+        smk[2 * l].y = ground_y<real>(gr, smk[2 * l].x, smk[2 * l].z); smk[2 * l + 1].y = ground_y<real>(gr, smk[2 * l + 1].x, smk[2 * l + 1].z);
       }
       RowMix<real> ms = row_mix(num<real>::fmax(s.iframe + prev_delta, real(0)), F, true);
       real sr[7];
@@ -961,7 +1048,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       pose_dif = rotation_angle(quat_mul(qinv(d_sim), d_ref)) * real(5);
       V3<real> v_sim = qrot(ips, s.p - sp), v_ref = qrot(ipr, c1p - srp);
       pose_dif += norm(v_sim - v_ref);
-      const V3<real> rcm_t = {srp.x, real(0), srp.z}, rcs_t = {sp.x, real(0), sp.z};
+      const V3<real> rcm_t = {srp.x, real(0), srp.z}, rcs_t = {sp.x, ground_y<real>(gr, sp.x, sp.z), sp.z};
       real ef = real(0);
       const real com_d = norm(qrot(ipr, c1p - rcm_t) - qrot(ips, s.p - rcs_t));
 #pragma unroll
@@ -1004,14 +1091,15 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
     const real timing_mod = P.timing_mod_coef * (num<real>::fmax(com_lvdif, real(0.7)) / num<real>::fmax(ref_comvel, real(0.7)));
     // ---- is_healthy / reward (:1350-1461)
     const real min_y = num<real>::fmin(P.healthy_min, ref_y * real(0.7));
-    bool healthy = (min_y < s.p.y) && (s.p.y < P.healthy_max);
+    const real curr_y = s.p.y - ground_y<real>(gr, s.p.x, s.p.z);          // :1361-1365 height above the terrain
+    bool healthy = (min_y < curr_y) && (curr_y < P.healthy_max);
     if (rotation_angle(quat_mul(qinv(rotation_y(s.Q)), s.Q)) > P.fall_angle) healthy = false;
     const real delta_y = rotation_angle_about_y(quat_mul(qinv(rotY), s.tgt));
     const real facing = cos1(delta_y) - real(1);
     reward = exp((double)(-pose_dif * real(2))) * exp((double)(-com_lvdif * real(2))) * exp((double)(facing * P.facing_weight));
     done = !healthy;
     const bool bad = obs_has_nan(s) || !(reward == reward);
-    write_obs<real, G>(s, tab, F, nf, obs, lane, active, bad);
+    write_obs<real, G>(s, tab, F, nf, obs, lane, active, bad, gr);
     if (s.gtime * FRAME_RATE > P.limit_length) done = true;
     if (bad) { reward = real(0); done = true; s.iframe = real(0); }
     s.iframe += FRAME_RATE * RL_STEP * (real(1) + timing_mod);
@@ -1025,8 +1113,8 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
   if (A.auto_reset && __any_sync(0xffffffffu, done)) {
     __syncwarp();
     if (done && active && A.term_obs != nullptr) {
-      float* to = A.term_obs + (size_t)e * OBS_W;
-      for (int i = lane; i < OBS_W; i += G) to[i] = obs[i];
+      float* to = A.term_obs + (size_t)e * A.obs_w;
+      for (int i = lane; i < A.obs_w; i += G) to[i] = obs[i];
     }
     __syncwarp();
     if (done) {
@@ -1043,58 +1131,17 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
         draw_reset_plan(A.seed, e, s.episode, P, plan);
       }
       real h0[HIST_W];
-      apply_reset(s, P, A.rc, plan, h0);
+      apply_reset(s, P, A.rc, plan, h0, gr);
       if (active && lane == 0) {
 #pragma unroll
         for (int i = 0; i < HIST_W; i++) hist_env[i] = h0[i];
       }
-      write_obs<real, G>(s, tab, F, nf, obs, lane, active, false);
+      write_obs<real, G>(s, tab, F, nf, obs, lane, active, false, gr);
     }
   }
   if (active && lane == 0) store_state(s, A.st, A.ist, A.Npad, e);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// OBJloader::Terrain::height (work/taesooLib/BaseLib/motion/Terrain.cpp:305-393): cell by floor, triangle by dx > dz,
-// plane through the triangle (Plane::setPlane, intersectionTest.cpp:96-104) intersected with the vertical ray from y = 1000
-// (Ray::intersects :243-260), tiling along Z.  hit = (cell row i, cell column j, triangle 0 upper / 1 lower), -1 outside.
-struct TLTerrainDev { const double* h; int rows, cols; double size_x, size_z; int tile; };
-__device__ __forceinline__ double tl_terrain_height(const TLTerrainDev& T, double x0, double x1, int* hit) {
-  const int nsx = T.cols - 1, nsz = T.rows - 1;
-  const double nx = (x0 / T.size_x) * (double)nsx;
-  double nz = (x1 / T.size_z) * (double)nsz;
-  int j = (int)::floor(nx), i = (int)::floor(nz);
-  const double dx = nx - ::floor(nx), dz = nz - ::floor(nz);
-  if (hit) { hit[0] = -1; hit[1] = -1; hit[2] = -1; }
-  if (j < 0 || j >= nsx || !(nx == nx) || !(nz == nz)) return 0.0;
-  if (T.tile) {
-    i %= nsz;
-    if (i < 0) i += nsz;
-    nz = (double)i + dz;
-    x1 = nz / (double)nsz * T.size_z;
-  } else if (i < 0 || i >= nsz) {
-    return 0.0;
-  }
-  const double* h = T.h;
-  V3<double> v0, v1, v2;
-  const bool upper = dx > dz;
-  v0 = {(double)j * T.size_x / (double)nsx, __ldg(h + (size_t)i * T.cols + j), (double)i * T.size_z / (double)nsz};
-  if (upper) {
-    v1 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
-    v2 = {v1.x, __ldg(h + (size_t)i * T.cols + j + 1), v0.z};
-  } else {
-    v2 = {(double)(j + 1) * T.size_x / (double)nsx, __ldg(h + (size_t)(i + 1) * T.cols + j + 1), (double)(i + 1) * T.size_z / (double)nsz};
-    v1 = {v0.x, __ldg(h + (size_t)(i + 1) * T.cols + j), v2.z};
-  }
-  V3<double> n = cross(v1 - v0, v2 - v0);
-  n = (1.0 / ::sqrt(dot(n, n))) * n;
-  const double d = -dot(n, v0);
-  const V3<double> org = {x0, 1000.0, x1};
-  const double denom = dot(n, V3<double>{0.0, -1.0, 0.0});
-  const double t = -((dot(n, org) + d) / denom);
-  if (hit) { hit[0] = i; hit[1] = j; hit[2] = upper ? 0 : 1; }
-  return org.y + t * -1.0;
-}
 static __global__ void tl_terrain_height_kernel(TLTerrainDev T, long long n, const double* __restrict__ xz, double* __restrict__ out, int* __restrict__ hit) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -1118,10 +1165,11 @@ template <typename real> __global__ void cdm_reset_kernel(const ResetArgs<real> 
     draw_reset_plan(A.seed, e, s.episode, A.p, plan);
   }
   real h0[HIST_W];
-  apply_reset(s, A.p, A.rc, plan, h0);
+  const Ground* gr = A.ground.T.h != nullptr ? &A.ground : nullptr;
+  apply_reset(s, A.p, A.rc, plan, h0, gr);
   real* hist_env = A.hist + (size_t)e * HIST_SLOTS * HIST_W;
   for (int k = 0; k < HIST_W; k++) hist_env[k] = h0[k];
-  if (A.obs != nullptr) write_obs<real, 1>(s, A.tab, A.nframes, A.nf_cycle, A.obs + (size_t)e * OBS_W, 0, true, false);
+  if (A.obs != nullptr) write_obs<real, 1>(s, A.tab, A.nframes, A.nf_cycle, A.obs + (size_t)e * A.obs_w, 0, true, false, gr);
   store_state(s, A.st, A.ist, A.Npad, e);
 }
 

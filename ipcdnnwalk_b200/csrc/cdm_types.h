@@ -7,6 +7,7 @@ namespace cdm {
 enum {
   ACT_W = 10,          // [R foot xz, L foot xz, d(lin vel) 3, d(ang vel) 3]          (deepmimiccdm-v1.lua:434)
   OBS_W = 27,          // 11 + 6*numLegs + 2 + 2                                        (:435)
+  OBS_W_TERRAIN = 31,  // + 4 terrain height samples                                    (deepmimiccdmterrain-v1.lua:14-16)
   TAB_W = 48,          // reference-table row, see ipcdnnwalk_b200/cdm_tables.py: pack_rows
   HIST_SLOTS = 8, HIST_W = 8,   // replay buffer ring (RagdollSim.lua:128-143): root pose of the last steps
   DBG_W = 96,          // qdd 2x6 | a_des 2x6 | lambda 2x20 | pose_dif com_lvdif ref_comvel timing_mod | theta_d 7 | iters 2 | ncontacts
@@ -49,8 +50,13 @@ template <typename real> struct ResetConst {
   int start_swing[2];
 };
 
+// height field of the gym_cdm2 terrain spec (OBJloader::Terrain); h == nullptr: flat ground
+struct TLTerrainDev { const double* h; int rows, cols; double size_x, size_z; int tile; };
+struct Ground { TLTerrainDev T; double px, py, pz; };
+
 template <typename real> struct StepArgs {
-  int N, Npad, nframes, nf_cycle;
+  int N, Npad, nframes, nf_cycle, obs_w;
+  Ground ground;
   real* st; int* ist; real* hist;
   const real* tab;
   const float* act; float* obs; float* rew; uint8_t* done;
@@ -62,7 +68,8 @@ template <typename real> struct StepArgs {
 };
 
 template <typename real> struct ResetArgs {
-  int N, Npad, count, nframes, nf_cycle;
+  int N, Npad, count, nframes, nf_cycle, obs_w;
+  Ground ground;
   const int* idx;
   real* st; int* ist; real* hist;
   const real* tab;

@@ -135,10 +135,18 @@ def solve_contact_qp(Q, p, a_des, bias, contacts, P):
     return qdd, lam.reshape(-1, 5)
 
 
+TERRAIN_SAMPLES = ((0.0, 0.0, 0.5), (0.5, 0.0, 0.5), (-0.5, 0.0, 0.5), (1.0, 0.0, 0.5))     # deepmimiccdmterrain-v1.lua:3-8
+
+
 class OracleCDMEnv:
-    def __init__(self, tab, skel, params=None):
+    def __init__(self, tab, skel, params=None, terrain=None, terrain_pos=None):
+        """terrain: oracle.tl_terrain.OracleTerrain (gym_cdm2 `walkterrain-v1`, deepmimiccdmterrain-v1.lua: 31-float observation,
+        terrain-shifted targets, projectToGround everywhere); None = flat ground (`walk2-v1`)."""
         self.tab, self.skel = tab, skel
         self.P = dict(PARAMS)
+        self.terrain, self.terrain_pos = terrain, (np.asarray(terrain_pos, float) if terrain is not None else None)
+        if terrain is not None:
+            self.P["healthy_min"] = 0.7                              # spec/walkterrain-v1.lua: healthy_y_range = {0.7, 2.0}
         if params:
             self.P.update(params)
         self.F = tab["cdm"].shape[0]
@@ -147,6 +155,12 @@ class OracleCDMEnv:
         self.iRA, self.iLA = names.index("RightAnkle"), names.index("LeftAnkle")
         self.K_filter = tuple(self.P["filter_K"])                # Q15: the cached gain, not lqr_gain(30, 1e-3, 1, 10^logQ)
         self.debug = {}
+
+    def G(self, v):
+        """RagdollSim:projectToGround / OBJloader.Terrain:getTerrainPos (deepmimiccdm-v1.lua:415-424,2171-2177): ground height under v."""
+        if self.terrain is None:
+            return 0.0
+        return self.terrain.height((v[0] - self.terrain_pos[0]) * 100.0, (v[2] - self.terrain_pos[2]) * 100.0)[0] / 100.0 + self.terrain_pos[1]
 
     # ---------------------------------------------------------------- model (defaultRLsetting.lua)
     def _ti(self, arr, ileg):
@@ -189,7 +203,7 @@ class OracleCDMEnv:
         for b in (self.iRA, self.iLA):
             for lp in (TOE_LOCAL, HEEL_LOCAL):
                 g = tl.qrot(rot[b], lp) + tr[b]
-                g[1] = 0.0                                     # projectToGround (flat)
+                g[1] = self.G(g)                               # projectToGround
                 mk.append(g)
         return cdm, mk
 
@@ -265,15 +279,18 @@ class OracleCDMEnv:
         if is_swing:
             off = self.feet_offset(ileg)
             desired = p + tl.qrot(rotY, np.array([act2[0], 0.0, act2[1] + 0.0]) + off)
-            desired[1] = 0.0
+            desired[1] = self.G(desired)
             li.swingPhase += RL_STEP
             li.contactPos = desired.copy()
             self.update_swing_foot(li, li.contactPos, Q, p, rotY, gv)
             rt = self.rtt_down(ileg)
+            com_height = p[1]
+            if self.terrain is not None:                        # :686-692 height relative to the terrain between body and landing spot
+                com_height -= tl.map_cos(self.swing_phase(ileg), 0.0, 1.0, self.G(p), self.G(li.contactPos))
             if rt <= 0:
-                li.contactPos[1] = 0.0                          # unlimitedLeglen (training)
+                li.contactPos[1] = self.G(li.contactPos)        # unlimitedLeglen (training): projectToGround
                 self.start_spprt(li, rotY)
-            elif p[1] < 0.0 and li.swingPhase > self.P["min_swing_phase"]:     # touchDownHeight = 0 (training)
+            elif com_height < 0.0 and li.swingPhase > self.P["min_swing_phase"]:     # touchDownHeight = 0 (training)
                 li.earlyTouchDown = rt
             else:
                 oli = self.leg[ileg % 2 + 1]
@@ -301,7 +318,7 @@ class OracleCDMEnv:
                         pos = pos - side * ((depth - thr) * weight)
                 elif -depth < thr:
                     pos = pos + side * ((-depth - thr) * weight)
-        pos[1] = 0.0
+        pos[1] = self.G(pos)
         return pos, ori
 
     def sim_markers(self, rotY):
@@ -310,7 +327,7 @@ class OracleCDMEnv:
             pos, ori = self.filtered_foot_pos(rotY, ileg)
             for s in (1.0, -1.0):
                 g = pos + tl.qrot(ori, np.array([0.0, 0.0, s * 0.12]))
-                g[1] = 0.0
+                g[1] = self.G(g)
                 mk.append(g)
         return self.p.copy(), mk
 
@@ -330,6 +347,7 @@ class OracleCDMEnv:
         _, ref_mk = self.ref_tree()
         delta_root = np.array([st[0], 0.0, st[2]])
         st[0] = 0.0; st[2] = 0.0
+        st[1] += self.G(np.zeros(3))                              # :1595-1596
         st[3:7] += z["q"]
         st[0:3] += z["pos"]
         st[3:7] = tl.qnormalize(st[3:7])
@@ -376,21 +394,25 @@ class OracleCDMEnv:
 
     # ---------------------------------------------------------------- observation
     def get_obs(self):
+        """_get_obs (:1779-1859); with a terrain the version of deepmimiccdmterrain-v1.lua:25-103 (4 height samples appended)."""
         P = self.P
         rotY = tl.rotation_y(self.Q)
         dq = self.get_dq()
-        ref_t = np.array([self.p[0], 0.0, self.p[2]])
+        ref_t = np.array([self.p[0], self.G(self.p), self.p[2]])       # getRefCoord: root projected to the ground
         offq = tl.qalign(tl.qmult(tl.qinv(rotY), self.Q), QI)
         iry = tl.qinv(rotY)
-        o = np.zeros(27)
-        o[0] = self.p[1] - 0.0
+        o = np.zeros(27 if self.terrain is None else 27 + len(TERRAIN_SAMPLES))
+        o[0] = self.p[1] - ref_t[1]
         o[1:5] = offq
         o[5:8] = tl.qrot(iry, dq[0:3])
         o[8:11] = tl.qrot(iry, dq[3:6])
         c = 11
         for i in (1, 2):
             li = self.leg[i]
-            o[c:c + 3] = tl.qrot(iry, li.contactFilter - ref_t)
+            cpos = li.contactFilter.copy()
+            if self.terrain is not None:
+                cpos[1] = self.G(cpos)                            # terrain version: the filtered contact point is projected first
+            o[c:c + 3] = tl.qrot(iry, cpos - ref_t)
             vv = tl.qrot(iry, li.dotContactFilter)
             o[c + 3], o[c + 4] = vv[0], vv[2]
             if li.isSwing:
@@ -404,6 +426,10 @@ class OracleCDMEnv:
         o[c + 1] = tl.map_sin(phase, 0.0, 0.25, 0.0, 1.0)
         tv = tl.qrot(tl.qmult(iry, self.target_Y), np.array([0.0, 0.0, 1.0]))
         o[c + 2], o[c + 3] = tv[0], tv[2]
+        if self.terrain is not None:
+            for k, v in enumerate(TERRAIN_SAMPLES):
+                pos = tl.qrot(rotY, np.array(v)) + ref_t
+                o[c + 4 + k] = self.G(pos) - ref_t[1]
         return o
 
     # ---------------------------------------------------------------- step
@@ -430,8 +456,9 @@ class OracleCDMEnv:
         ang = min(max(ang, -mx), mx)
         return tl.qmult(rotY, tl.qaxis(Y, ang))
 
-    def frame_move(self, contacts, theta_d, dtheta_d, daction):
-        """QPsim:frameMove with niter = 2 (flat ground: refCoord = identity)."""
+    def frame_move(self, contacts, theta_d, dtheta_d, daction, terrain_y=0.0):
+        """QPsim:frameMove with niter = 2.  refCoord is a pure vertical translation by `terrain_y` (:1229); the QP and the
+        integrator are translation invariant, so the only place the reference frame shows is the contact gate on the body height."""
         P = self.P
         dtheta_d = dtheta_d.copy()
         self.debug["qdd"] = []; self.debug["lam"] = []; self.debug["ades"] = []
@@ -448,7 +475,7 @@ class OracleCDMEnv:
             # mass matrix / bias in the body frame (calcMassMatrix3): b = [w x I w, R^T(m g) + m w x v_b]
             bias = np.concatenate([np.cross(self.wb, INERTIA * self.wb),
                                    tl.qrot(tl.qinv(self.Q), np.array([0.0, MASS * GRAV, 0.0])) + MASS * np.cross(self.wb, vb)])
-            use = contacts if (self.p[1] > 0 and self.p[1] < P["max_contact_y"]) else []
+            use = contacts if (self.p[1] - terrain_y > 0 and self.p[1] - terrain_y < P["max_contact_y"]) else []
             qdd, lam = solve_contact_qp(self.Q, self.p, a_des, bias, use, P)
             self.debug["qdd"].append(qdd.copy()); self.debug["lam"].append(lam.copy()); self.debug["ades"].append(a_des.copy())
             # stepKinematic: QDDot = [R dV + R (w x v_b), dW]; semi-implicit Euler
@@ -492,7 +519,7 @@ class OracleCDMEnv:
         dd = v_sim - v_ref
         pose_dif += math.sqrt(dd.dot(dd))
         rc_m = (prev_ref_ori, np.array([sample_ref[0], 0.0, sample_ref[2]]))
-        rc_s = (prev_sim_ori, np.array([sample[0], 0.0, sample[2]]))
+        rc_s = (prev_sim_ori, np.array([sample[0], self.G(sample), sample[2]]))
 
         def loc(rc, x): return tl.qrot(tl.qinv(rc[0]), x - rc[1])
         def locd(rc, x): return tl.qrot(tl.qinv(rc[0]), x)
@@ -553,7 +580,8 @@ class OracleCDMEnv:
                     if e > mspc:
                         e = mspc
                     else:
-                        self.start_spprt(self.leg[ileg], rotY)          # enforceTouchDown
+                        self.start_spprt(self.leg[ileg], rotY)          # enforceTouchDown (:767-774)
+                        self.leg[ileg].contactPos[1] = self.G(self.leg[ileg].contactPos)
                     etd = e
                     break
             self.leg[1].earlyTouchDown = None; self.leg[2].earlyTouchDown = None
@@ -575,13 +603,23 @@ class OracleCDMEnv:
         iq = tl.qinv(dq_)
         theta_d[0:3] = tl.qrot(iq, theta_d[0:3] - dp_)
         theta_d[3:7] = tl.qmult(iq, theta_d[3:7])
+        terrain_y = 0.0
+        if self.terrain is not None:                              # :1205-1238
+            terrain_y = self.G(theta_d[0:3])
+            theta_d[1] += terrain_y
+            nxt = self.G(p + gv * 0.5)
+            dy = (nxt - self.G(p)) / 0.5
+            if dy < 0:
+                v_d = tl.qrot(Q, dtheta_d[0:3])
+                v_d[1] += max(dy, -5.0)
+                dtheta_d[0:3] = tl.qrot(tl.qinv(Q), v_d)
         contacts = []
         cmask = 0
         for i in (1, 2):
             if not self.leg[i].isSwing:
                 for j in range(2):
                     c = contact_pos[i][j]
-                    c[1] = 0.0
+                    c[1] = self.G(c)
                     dd = c - p
                     if math.sqrt(dd.dot(dd)) < P["max_contact_len"]:
                         contacts.append(c.copy()); contacts.append(c.copy())       # pushed twice (Q7)
@@ -589,12 +627,13 @@ class OracleCDMEnv:
         self.debug["cmask"] = cmask
         self.debug["contacts"] = [c.copy() for c in contacts]
         self.debug["theta_d"] = theta_d.copy()
-        self.frame_move(contacts, theta_d, dtheta_d, cdm_action)
+        self.frame_move(contacts, theta_d, dtheta_d, cdm_action, terrain_y)
         pose_dif, com_lvdif, ref_comvel = self.calc_ref_dif(rotY)
         timing_mod = P["timing_mod_coef"] * (max(com_lvdif, 0.7) / max(ref_comvel, 0.7))
         # is_healthy (:1350-1398)
         min_y = min(P["healthy_min"], self.ref_y * 0.7)
-        healthy = (min_y < self.p[1]) and (self.p[1] < P["healthy_max"])
+        curr_y = self.p[1] - self.G(self.p)                       # :1361-1365 height above the terrain
+        healthy = (min_y < curr_y) and (curr_y < P["healthy_max"])
         if tl.rotation_angle(tl.offset_q(self.Q)) > P["fall_angle"]:
             healthy = False
         target_delta = tl.qmult(tl.qinv(rotY), self.target_Y)

@@ -73,3 +73,15 @@ def compare_state(dev, env, rtol, atol, what=""):
             sel[b + 9:b + 12] = True                  # particle velocity is carried through support by both
     err = np.abs(dr[sel] - r[sel]) - (atol + rtol * np.abs(r[sel]))
     assert (err <= 0).all(), f"{what}: state mismatch at fields {np.nonzero(sel)[0][err > 0]} dev {dr[sel][err > 0]} oracle {r[sel][err > 0]}"
+
+
+def load_terrain():
+    """tests/golden/cdm_terrain_heights.npz -> dict(heights [cm], size_x, size_z [cm], terrain_pos [m]) as CDMVecEnv(terrain=...) takes it."""
+    d = np.load(os.path.join(helpers.GOLDEN, "cdm_terrain_heights.npz"))
+    return dict(heights=d["heights"].copy(), size_x=float(d["size_x"]), size_z=float(d["size_z"]), terrain_pos=d["terrain_pos"].copy())
+
+
+def load_terrain_oracle():
+    from oracle import tl_terrain as tt
+    t = load_terrain()
+    return tt.OracleTerrain(t["heights"], t["size_x"], t["size_z"], True), t["terrain_pos"]

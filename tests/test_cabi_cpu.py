@@ -44,7 +44,7 @@ def test_cdm_header_symbols_exported(built_lib):
     txt = open(os.path.join(helpers.ROOT, "include", "cdmenv_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     names = sorted(set(re.findall(r"\b(cdm_[a-z_0-9]+)\s*\(", txt)))
-    assert names == sorted(_lib.CDM_EXPORTED_SYMBOLS) and len(names) == 15
+    assert names == sorted(_lib.CDM_EXPORTED_SYMBOLS) and len(names) == 17
     for n in names:
         assert hasattr(built_lib, n)
 

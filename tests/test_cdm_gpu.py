@@ -30,12 +30,12 @@ def _assert_close(a, b, rtol, atol, what):
         raise AssertionError(f"{what}: {(~ok).sum()} mismatches, first at {idx.tolist()} got {[float(a[tuple(i)]) for i in idx]} want {[float(b[tuple(i)]) for i in idx]}")
 
 
-def _run_golden(tab, skel, roll, lanes, precision=64, rtol=1e-5, atol=1e-7, steps=None):
+def _run_golden(tab, skel, roll, lanes, precision=64, rtol=1e-5, atol=1e-7, steps=None, terrain=None):
     import torch
     from ipcdnnwalk_b200 import CDMVecEnv
     n = roll["plans0"].shape[0]
     T = roll["acts"].shape[0] if steps is None else steps
-    env = CDMVecEnv(tab, skel, n, precision=precision, lanes_per_env=lanes, auto_reset=False)
+    env = CDMVecEnv(tab, skel, n, precision=precision, lanes_per_env=lanes, auto_reset=False, terrain=terrain)
     env.attach(dbg=True)
     obs = env.reset(plan=roll["plans0"])
     torch.cuda.synchronize()
@@ -73,6 +73,16 @@ def _run_golden(tab, skel, roll, lanes, precision=64, rtol=1e-5, atol=1e-7, step
 def test_golden_rollout_fp64(data, lanes):
     tab, skel, roll = data
     _run_golden(tab, skel, roll, lanes)
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_golden_rollout_terrain_fp64(data, lanes):
+    """walkterrain-v1 variant (deepmimiccdmterrain-v1.lua): 31-float observation, projectToGround on the height field,
+    terrain-following targets -- golden roll-out of the terrain oracle incl. resets."""
+    tab, skel, _ = data
+    roll = dict(np.load(hc.ROLLOUT.replace("cdm_rollout", "cdm_rollout_terrain")))
+    assert roll["obs"].shape[2] == 31
+    _run_golden(tab, skel, roll, lanes, terrain=hc.load_terrain())
 
 
 def test_fp32_single_step(data):

@@ -20,11 +20,19 @@ def policy():
     return d
 
 
+@pytest.fixture(scope="module")
+def policy_terrain():
+    return dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_walkterrain.npz")))
+
+
 def act_numpy(pol, obs):
     """gym_gang.model.Policy.act(deterministic=True) behind SB3 VecNormalize(norm_obs=True) (gym_cdm2/test_gym.py:89-145)."""
     h = np.clip((obs - pol["obs_mean"]) / np.sqrt(pol["obs_var"] + 1e-8), -10.0, 10.0).astype(np.float32).astype(np.float64)
-    for i in range(int(pol["n_layers"])):
-        h = np.tanh(h @ pol[f"W{i}"].T + pol[f"b{i}"])
+    n = int(pol["n_layers"])
+    for i in range(n):
+        h = h @ pol[f"W{i}"].T + pol[f"b{i}"]
+        if i < n - 1 or int(pol["final_tanh"]):
+            h = np.tanh(h)
     return h.astype(np.float32)
 
 
@@ -69,6 +77,72 @@ def test_reference_policy_walks_in_the_oracle(policy):
     assert np.mean(R) > 0.2 and min(np.array(P)[:, 1]) > 0.78
 
 
+def test_reference_terrain_policy_walks_over_the_terrain_in_the_oracle(policy_terrain):
+    """walkterrain-v1 (deepmimiccdmterrain-v1.lua): the reference's terrain policy (31-float observation with 4 height
+    samples) crosses the height field in the terrain oracle -- 8 s, ground under the path between 0.1 and 0.6 m."""
+    from oracle.cdm_env import OracleCDMEnv
+    tab, skel = hc.load_tables()
+    T, tpos = hc.load_terrain_oracle()
+    env = OracleCDMEnv(tab, skel, terrain=T, terrain_pos=tpos)
+    obs = env.reset()
+    assert obs.shape == (31,)
+    P, S, H = [], [], []
+    for t in range(480):
+        obs, r, d = env.step(act_numpy(policy_terrain, obs))
+        assert not d, f"the reference's terrain policy fell at step {t}"
+        P.append(env.p.copy()); S.append([env.leg[1].isSwing, env.leg[2].isSwing]); H.append(env.G(env.p))
+    P, H = np.array(P), np.array(H)
+    speed, _, lat, swing_steps, _ = gait_stats(P, np.array(S))
+    rs, rh, rl, rsw, rds = policy_terrain["recorded_gait"]         # recorded on flat ground (collectRefTraj sets terrainHeight = 0)
+    assert abs(speed - rs) < 0.15 * rs and abs(swing_steps - rsw) < 0.2 * rsw and lat < 0.05
+    assert H.max() - H.min() > 0.25                                 # the path really climbs and descends
+    above = P[:, 1] - H
+    assert above.min() > 0.75 and above.max() < 0.95               # body height above the terrain stays in the walking band
+
+
+@pytest.mark.gpu
+def test_reference_terrain_policy_on_the_gpu(policy_terrain):
+    import torch
+    from ipcdnnwalk_b200 import CDMVecEnv
+    from oracle.cdm_env import OracleCDMEnv
+    tab, skel = hc.load_tables()
+    n, T = 128, 300
+    rng = np.random.default_rng(6)
+    plans = np.stack([hc.random_plan(rng, 0.2) for _ in range(n)])
+    plans[0] = 0.0
+    env = CDMVecEnv(tab, skel, n, precision=64, auto_reset=False, terrain=hc.load_terrain())
+    obs = env.reset(plan=plans)
+    assert obs.shape == (n, 31)
+    pol = policy_terrain
+    nl = int(pol["n_layers"])
+    W = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device="cuda") for i in range(nl)]
+    B = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device="cuda") for i in range(nl)]
+    mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device="cuda")
+    istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device="cuda")
+    Tt, tpos = hc.load_terrain_oracle()
+    oracle = OracleCDMEnv(tab, skel, terrain=Tt, terrain_pos=tpos)
+    o_obs = hc.oracle_reset(oracle, plans[0])
+    alive = torch.ones(n, dtype=torch.bool, device="cuda")
+    worst = 0.0
+    for t in range(T):
+        h = torch.clamp((obs - mean) * istd, -10.0, 10.0)
+        for i, (w, b) in enumerate(zip(W, B)):
+            h = h @ w.T + b
+            if i < nl - 1 or int(pol["final_tanh"]):
+                h = torch.tanh(h)
+        obs, rew, done, _ = env.step(h)
+        alive &= done == 0
+        if t < 100:
+            o_obs, o_r, o_d = oracle.step(act_numpy(pol, o_obs))
+            worst = max(worst, float(np.abs(obs[0].cpu().numpy() - o_obs).max()))
+    torch.cuda.synchronize()
+    assert worst < 2e-3, worst
+    assert float(alive.float().mean()) > 0.9
+    z = np.array([env.get_state(i)["reals"][2] for i in range(0, n, 8)])
+    assert abs(z[alive.cpu().numpy()[::8]].mean() / (T / 60.0) - pol["recorded_gait"][0]) < 0.2 * pol["recorded_gait"][0]
+    env.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", [64, 32])
 def test_reference_policy_walks_on_the_gpu(policy, precision):
@@ -98,7 +172,7 @@ def test_reference_policy_walks_on_the_gpu(policy, precision):
     for t in range(T):
         h = torch.clamp((obs - mean) * istd, -10.0, 10.0)
         for w, b in zip(W, B):
-            h = torch.tanh(h @ w.T + b)
+            h = torch.tanh(h @ w.T + b)                   # walk2-v1 head ends in Tanh (final_tanh = 1)
         obs, rew, done, _ = env.step(h)
         alive &= done == 0
         rsum += rew * alive

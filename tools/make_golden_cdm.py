@@ -50,21 +50,26 @@ def unique_lambda(lam, cmask):
     return out
 
 
-def make_rollout(n_envs=6, n_steps=90, seed=11):
+def make_rollout(n_envs=6, n_steps=90, seed=11, terrain=False):
     import helpers_cdm as hc
     tab, skel = hc.load_tables()
     rng = np.random.default_rng(seed)
     scales = [0.0, 0.05, 0.1, 0.1, 0.3, 1.0][:n_envs]
-    envs = [OracleCDMEnv(tab, skel) for _ in range(n_envs)]
+    kw = {}
+    if terrain:
+        T, tpos = hc.load_terrain_oracle()
+        kw = dict(terrain=T, terrain_pos=tpos)
+    envs = [OracleCDMEnv(tab, skel, **kw) for _ in range(n_envs)]
+    OW = 31 if terrain else 27
     plans0 = np.stack([hc.random_plan(rng, scales[i]) for i in range(n_envs)])
     obs0 = np.stack([hc.oracle_reset(e, plans0[i]) for i, e in enumerate(envs)])
     reals0 = np.stack([hc.oracle_state_vectors(e)[0] for e in envs])
     T = n_steps
     acts = np.zeros((T, n_envs, 10), np.float32); plans = np.zeros((T, n_envs, 16))
-    obs = np.zeros((T, n_envs, 27)); rew = np.zeros((T, n_envs)); done = np.zeros((T, n_envs), bool)
+    obs = np.zeros((T, n_envs, OW)); rew = np.zeros((T, n_envs)); done = np.zeros((T, n_envs), bool)
     reals = np.zeros((T, n_envs, 61)); ints = np.zeros((T, n_envs, 4), np.int32)
     qdd = np.zeros((T, n_envs, 2, 6)); lam = np.zeros((T, n_envs, 2, 20)); cm = np.zeros((T, n_envs), np.int32)
-    scal = np.zeros((T, n_envs, 4)); reset_obs = np.zeros((T, n_envs, 27))
+    scal = np.zeros((T, n_envs, 4)); reset_obs = np.zeros((T, n_envs, OW))
     for t in range(T):
         for i, e in enumerate(envs):
             amp = [0.0, 0.2, 0.5, 1.0, 0.5, 0.5][i]
@@ -82,7 +87,7 @@ def make_rollout(n_envs=6, n_steps=90, seed=11):
             plans[t, i] = hc.random_plan(rng, scales[i])
             if d:
                 reset_obs[t, i] = hc.oracle_reset(e, plans[t, i])
-    np.savez_compressed(os.path.join(GOLDEN, "cdm_rollout.npz"), plans0=plans0, obs0=obs0, reals0=reals0, acts=acts, plans=plans,
+    np.savez_compressed(os.path.join(GOLDEN, "cdm_rollout_terrain.npz" if terrain else "cdm_rollout.npz"), plans0=plans0, obs0=obs0, reals0=reals0, acts=acts, plans=plans,
                         obs=obs, rew=rew, done=done, reals=reals, ints=ints, qdd=qdd, lam=lam, cmask=cm, scal=scal, reset_obs=reset_obs)
     print("rollout: episodes finished", int(done.sum()), "mean reward", rew.mean(), "swing steps", int((ints[:, :, 0] != 0).sum()))
 
@@ -138,39 +143,48 @@ def _gait_stats(p, sup):
     return np.array([dist / (n / 60.0), float(p[:, 1].mean()), lat / dist, float(np.mean(durs)), float((sup.sum(1) == 2).mean())])
 
 
-def make_policy_fixture():
-    """The policy the reference trained on walk2-v1 (trained_models/ppo/walk2-v1.pt = [gym_gang.model.Policy, obs_rms],
+def make_policy_fixture(name="walk2"):
+    """The policy the reference trained on walk2-v1 / walkterrain-v1 (trained_models/ppo/walk2-v1.pt = [gym_gang.model.Policy, obs_rms],
     gym_cdm2/train_gym.py:230-233), imported here from /root/reference and flattened to plain arrays, plus gait statistics
     of the roll-out the reference recorded with it (gym_cdm2/spec/refTraj_walk2-v1.dat)."""
     import types
     import torch
     sys.path.insert(0, "/root/reference")
-    for name in ("stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.running_mean_std",
-                 "stable_baselines3.common.vec_env", "stable_baselines3.common.vec_env.vec_normalize"):      # not installed: stubs for unpickling
-        m = types.ModuleType(name); m.__path__ = []
-        sys.modules.setdefault(name, m)
+    for mod in ("stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.running_mean_std",
+                 "stable_baselines3.common.vec_env", "stable_baselines3.common.vec_env.vec_normalize",
+                 "baselines", "baselines.common", "baselines.common.running_mean_std"):      # not installed: stubs for unpickling
+        m = types.ModuleType(mod); m.__path__ = []
+        sys.modules.setdefault(mod, m)
     sys.modules["stable_baselines3.common.running_mean_std"].RunningMeanStd = type("RunningMeanStd", (), {})
+    sys.modules["baselines.common.running_mean_std"].RunningMeanStd = type("RunningMeanStd", (), {})
     sys.modules["stable_baselines3.common.vec_env.vec_normalize"].VecNormalize = type("VecNormalize", (), {})
     sys.modules["stable_baselines3.common.vec_env"].VecNormalize = sys.modules["stable_baselines3.common.vec_env.vec_normalize"].VecNormalize
-    ac, rms = torch.load("/root/reference/trained_models/ppo/walk2-v1.pt", weights_only=False, map_location="cpu")
-    layers = [m for m in list(ac.base.actor) + list(ac.dist.fc_mean) if isinstance(m, torch.nn.Linear)]
-    acts = [type(m).__name__ for m in list(ac.base.actor) + list(ac.dist.fc_mean) if not isinstance(m, torch.nn.Linear)]
-    assert all(a == "Tanh" for a in acts) and len(acts) == len(layers), "expected Linear/Tanh pairs"
+    ac, rms = torch.load(f"/root/reference/trained_models/ppo/{name}-v1.pt", weights_only=False, map_location="cpu")
+    nobs = int(np.asarray(rms.mean).shape[0])
+    head = list(ac.dist.fc_mean) if isinstance(ac.dist.fc_mean, torch.nn.Sequential) else [ac.dist.fc_mean]   # older checkpoints: plain Linear
+    mods = list(ac.base.actor) + head
+    layers = [m for m in mods if isinstance(m, torch.nn.Linear)]
+    acts = [type(m).__name__ for m in mods if not isinstance(m, torch.nn.Linear)]
+    final_tanh = len(acts) == len(layers)
+    assert all(a == "Tanh" for a in acts) and len(acts) in (len(layers), len(layers) - 1), "expected Linear/Tanh pairs"
     out = {f"W{i}": l.weight.detach().numpy().astype(np.float64) for i, l in enumerate(layers)}
     out.update({f"b{i}": l.bias.detach().numpy().astype(np.float64) for i, l in enumerate(layers)})
     out["obs_mean"] = np.asarray(rms.mean, np.float64); out["obs_var"] = np.asarray(rms.var, np.float64)
     # the flattened network reproduces Policy.act(deterministic=True)
-    x = np.random.default_rng(0).normal(size=(16, 27)).astype(np.float32)
+    x = np.random.default_rng(0).normal(size=(16, nobs)).astype(np.float32)
     with torch.no_grad():
         _, a, _, _ = ac.act(torch.from_numpy(x), torch.zeros(16, ac.recurrent_hidden_state_size), torch.ones(16, 1), deterministic=True)
     h = x.astype(np.float64)
     for i in range(len(layers)):
-        h = np.tanh(h @ out[f"W{i}"].T + out[f"b{i}"])
+        h = h @ out[f"W{i}"].T + out[f"b{i}"]
+        if i < len(layers) - 1 or final_tanh:
+            h = np.tanh(h)
     assert np.abs(h - a.numpy()).max() < 1e-5
+    out["final_tanh"] = np.array(int(final_tanh))
     from ipcdnnwalk_b200 import tl_binary as tb
-    t = tb.load_table("/root/reference/gym_cdm2/spec/refTraj_walk2-v1.dat")
+    t = tb.load_table(f"/root/reference/gym_cdm2/spec/refTraj_{name}-v1.dat")
     out["recorded_gait"] = _gait_stats(t["globalTraj"][:, 0:3], t["rawFootInfo"][:, 0:2])
-    np.savez_compressed(os.path.join(GOLDEN, "cdm_policy_walk2.npz"), n_layers=len(layers), **out)
+    np.savez_compressed(os.path.join(GOLDEN, f"cdm_policy_{name}.npz"), n_layers=len(layers), **out)
     print("policy:", [out[f"W{i}"].shape for i in range(len(layers))], "recorded gait [speed, height, lateral/m, swing steps, double support]:", out["recorded_gait"])
 
 
@@ -179,4 +193,6 @@ if __name__ == "__main__":
     make_rollout()
     make_reference_recordings()
     make_terrain()
-    make_policy_fixture()
+    make_rollout(n_envs=6, n_steps=60, seed=12, terrain=True)
+    make_policy_fixture("walk2")
+    make_policy_fixture("walkterrain")
