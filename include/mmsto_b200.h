@@ -1,0 +1,60 @@
+/* C-ABI of the batched momentum-mapped space-time optimiser (MMSTO): SURVEY 8f rank 1.
+ *
+ * Replaces, for a batch of independent characters, one call each of
+ *   gym_cdm2/shortTermOptimizer.lua:349-367,368-860   ShortTrajOpt:solveEndEffectors / solveEndEffectors_euler
+ * in the online configuration of walk_SRBTrack2025.py:529-587 (onlineOpt = true, frames 0 and 1 constant, no collision
+ * half-spaces, weightEEvel = 0), including the L-BFGS loop it drives:
+ *   BaseLib/math/optimize.h:426-470 (LBFGS_METHOD, backtracking line search), BaseLib/motion/IK_lbfgs/lbfgs.cpp:246-738.
+ * The kinematic tree is LoaderToTree in the Euler-root mode (BaseLib/motion/IK_sdls/NodeWrap.cpp:496-573,1262-1560):
+ *   q = [root xyz, root Euler angles YZX, joint angles in tree order], ndof = 6 + #joint angles.
+ * All arrays are DEVICE pointers to double unless stated otherwise; one launch solves all problems.  fp64 only (the
+ * reference solves in double; weights of 1e5 on squared metres leave no room for fp32). */
+#pragma once
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmsto_solver mmsto_solver;   /* opaque: skeleton + weights + workspace on one device */
+
+enum { MMSTO_MAX_FRAMES = 8, MMSTO_MARKERS = 4, MMSTO_MAX_VELCON = 4, MMSTO_VELCON_W = 10, MMSTO_INFO_W = 4 };
+
+/* Skeleton tables (HOST) exactly as fk_create takes them (include/bonefk_b200.h); the root bone gets the translational
+ * channels XYZ and the rotational channels YZX (VRMLloader.cpp:16,1887).  Limits: nb <= 24, ndof <= 64.
+ * markers (shortTermOptimizer.lua `markers`, walk_SRBTrack2025.py:336-347): bone index, local position, weight.
+ * nf = number of frames of the window (planningHorizon, <= 8). */
+int mmsto_create(int32_t device, int32_t nbones, const int32_t* parent, const double* offset, const int32_t* nchan,
+                 const int32_t* axes, const double* mass, const double* local_com, const double* inertia,
+                 int32_t nf, const int32_t* marker_bone, const double* marker_lpos, const double* marker_weight,
+                 mmsto_solver** out);
+int mmsto_destroy(mmsto_solver* s);
+int mmsto_ndof(mmsto_solver* s);
+/* named scalars: weightDDX weightDX weightAngleOriginal weightEE weightEEcon weightVelHalfSpace weightMomentum weightCOM
+ * clampThr (degrees) epsilon max_iterations (0 = unlimited as in libLBFGS; capped by iteration_cap) iteration_cap */
+int mmsto_set_param(mmsto_solver* s, const char* name, double value);
+int mmsto_get_param(mmsto_solver* s, const char* name, double* value);
+/* dof_weights[ndof] (HOST), ShortTrajOpt.dof_weights */
+int mmsto_set_dof_weights(mmsto_solver* s, const double* w);
+
+/* One solveEndEffectors_euler per problem.
+ *   x_original [n][nf][ndof], dx [n][nf-1][ndof], ddx [n][nf-2][ndof]   desired Euler motion and its derivatives
+ *   euler_mot  [n][nf][ndof]    the input motion (only frames 0, 1 are read: the constants)
+ *   gpos_target[n][nf][3*4]     marker targets; com [n][nf][3]; momentum [n][nf-1][6] ([M, F] about the CoM)
+ *   con        [n] int32        contact bits, bit (marker*8 + frame); used when weightEEcon > 0
+ *   velcon     [n][4][10]       velocity half-space constraints: frame (or -1), bone, min speed, normal 3, local pos 3, pad
+ *   x_out      [n][nf][ndof]    solution; info [n][4] = final objective, libLBFGS return code, iterations, evaluations
+ * stream = cudaStream_t as void*.  Returns 0, or a negative error code (mmsto_last_error has the text). */
+int mmsto_solve(mmsto_solver* s, int32_t n, const double* x_original, const double* dx, const double* ddx,
+                const double* euler_mot, const double* gpos_target, const double* com, const double* momentum,
+                const int32_t* con, const double* velcon, double* x_out, double* info, void* stream);
+/* objective and gradient at x [n][nf][ndof] (one evaluation of LBFGS_opta's function, all variables): obj [n],
+ * grad [n][nf][ndof]; the momentum Jacobian cache is rebuilt at x as on the first evaluation of a solve. */
+int mmsto_evaluate(mmsto_solver* s, int32_t n, const double* x, const double* x_original, const double* dx, const double* ddx,
+                   const double* gpos_target, const double* com, const double* momentum, const int32_t* con,
+                   const double* velcon, double* obj, double* grad, void* stream);
+long long mmsto_launch_count(mmsto_solver* s);
+const char* mmsto_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif

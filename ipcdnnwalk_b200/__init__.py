@@ -8,3 +8,4 @@ from .terrain import TerrainModel  # noqa: F401
 from .srb_env import SRBEnv  # noqa: F401
 from .cdm_vec_env import CDMVecEnv, LuaEnv  # noqa: F401
 from . import cdm_tables  # noqa: F401
+from .short_traj_opt import ShortTrajOpt  # noqa: F401

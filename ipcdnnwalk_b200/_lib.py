@@ -99,6 +99,19 @@ _TLT_SIGNATURES = {
     "tlterrain_destroy": (C.c_int, [_P]),
     "tlterrain_height": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
 }
+_MMSTO_SIGNATURES = {       # include/mmsto_b200.h
+    "mmsto_create": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
+    "mmsto_destroy": (C.c_int, [_P]),
+    "mmsto_ndof": (C.c_int, [_P]),
+    "mmsto_set_param": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "mmsto_get_param": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "mmsto_set_dof_weights": (C.c_int, [_P, _P]),
+    "mmsto_solve": (C.c_int, [_P, C.c_int32] + [_P] * 11 + [_P]),
+    "mmsto_evaluate": (C.c_int, [_P, C.c_int32] + [_P] * 11 + [_P]),
+    "mmsto_launch_count": (C.c_int64, [_P]),
+    "mmsto_last_error": (C.c_char_p, []),
+}
+MMSTO_EXPORTED_SYMBOLS = tuple(_MMSTO_SIGNATURES)
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 CDM_EXPORTED_SYMBOLS = tuple(_CDM_SIGNATURES)
 TLT_EXPORTED_SYMBOLS = tuple(_TLT_SIGNATURES)
@@ -117,7 +130,7 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  ipcdnnwalk_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()) + list(_TLT_SIGNATURES.items()):
+    for name, (res, args) in list(_SIGNATURES.items()) + list(_FK_SIGNATURES.items()) + list(_CDM_SIGNATURES.items()) + list(_TLT_SIGNATURES.items()) + list(_MMSTO_SIGNATURES.items()):
         if "IPCDNNWALK_B200_LIB" in os.environ and not hasattr(lib, name):
             continue                       # an older build loaded for an A/B timing run
         fn = getattr(lib, name)

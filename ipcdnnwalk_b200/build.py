@@ -12,12 +12,13 @@ INCLUDE = os.path.join(HERE, "..", "include")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 TARGETS = {
-    "libsrbtrack_b200.so": ["srb_api.cu", "fk_api.cu", "cdm_api.cu"],
+    "libsrbtrack_b200.so": ["srb_api.cu", "fk_api.cu", "cdm_api.cu", "mmsto_api.cu"],
 }
 # headers each translation unit depends on (besides itself)
 DEPS = {
     "srb_api.cu": ["srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/srbtrack_b200.h"],
     "fk_api.cu": ["fk_kernels.cuh", "srb_math.cuh", "../../include/bonefk_b200.h"],
+    "mmsto_api.cu": ["mmsto_kernels.cuh", "../../include/mmsto_b200.h"],
     "cdm_api.cu": ["cdm_kernels.cuh", "cdm_types.h", "srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/cdmenv_b200.h"],
 }
 

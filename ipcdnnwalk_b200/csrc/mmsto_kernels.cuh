@@ -1,0 +1,635 @@
+// Batched momentum-mapped space-time optimiser (MMSTO): gym_cdm2/shortTermOptimizer.lua:349-860 in the
+// online configuration of walk_SRBTrack2025.py:529-587, with the L-BFGS loop of BaseLib/motion/IK_lbfgs/lbfgs.cpp:246-738
+// inside the kernel.
+//
+// Mapping: 8 lanes per problem, lane = frame of the window (nf <= 8), 4 problems per warp, one warp per CTA.  A lane owns
+// the kinematic tree of its frame (LoaderToTree in the Euler-root mode: one slide / hinge node per dof); everything that
+// couples frames -- finite-difference velocities, the Gaussian-filtered marker / CoM residuals, the momentum Jacobian
+// averaged over the window, the L-BFGS dot products -- is an 8-lane shuffle.  The L-BFGS vectors (x, g, d, xp, gp, 6 s,
+// 6 y, the targets) live in a per-warp workspace laid out [vector][dof][32 lanes]: every access of the warp is one
+// contiguous 256-byte row.  Per-bone frames (R, t), the velocity / force accumulators and the middle hinge axes live in
+// shared memory as [bone][21][32 lanes] (105 kB per warp, bank-conflict free).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+namespace mmsto {
+
+enum { MAXB = 24, MAXD = 64, NFMAX = 8, NMARK = 4, MAXHS = 4, HS_W = 10, LB_M = 6, GRP = 8, PPW = 4,
+       V_X = 0, V_G, V_D, V_XP, V_GP, V_XO, V_DX, V_DDX, V_SUMO, V_S, V_Y = V_S + LB_M, NV = V_Y + LB_M,
+       SM_W = 21, SM_R = 0, SM_T = 9, SM_A = 12, SM_WM = 18 };
+
+enum { LBFGS_SUCCESS = 0, LBFGS_ALREADY_MINIMIZED = 2, LBFGSERR_MINIMUMSTEP = -1000, LBFGSERR_MAXIMUMSTEP = -999,
+       LBFGSERR_MAXIMUMLINESEARCH = -998, LBFGSERR_MAXIMUMITERATION = -997, LBFGSERR_INCREASEGRADIENT = -994 };
+
+struct Skel {
+  int nb, ndof;
+  int parent[MAXB], nchan[MAXB], axis[MAXB][3], dof0[MAXB], sub_end[MAXB];
+  double off[MAXB][3], mass[MAXB], com[MAXB][3], inertia[MAXB][6];   // inertia: xx yy zz xy xz yz
+  double total_mass;
+};
+
+struct Prm {
+  int nf, max_iter, iter_cap, max_ls;
+  double w_ddx, w_dx, w_ao, w_ee, w_eecon, w_velhs, w_mom, w_com;
+  double s_ddx[MAXD], s_dx[MAXD], s_ao[MAXD];      // sqrt(weight * dof_weight)  (OperatorStitch.cpp:286)
+  int mbone[NMARK];
+  double mlpos[NMARK][3], mweight[NMARK];
+  double filt[NFMAX];                              // Filter::GetGaussFilter(nf)
+  double clamp, eps, ftol, wolfe, min_step, max_step;
+};
+
+struct Args {
+  int n;
+  const double *x_original, *dx, *ddx, *euler_mot, *gpos_target, *com, *momentum, *velcon, *x_in;
+  const int* con;
+  double *x_out, *info, *obj, *grad;
+  double *ws, *mc;
+  const Skel* sk;
+  const Prm* prm;
+};
+
+__device__ __forceinline__ double grp_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void mat_vec(const double* R, const double* v, double* o) {
+  o[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2]; o[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2]; o[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+}
+__device__ __forceinline__ void matT_vec(const double* R, const double* v, double* o) {
+  o[0] = R[0] * v[0] + R[3] * v[1] + R[6] * v[2]; o[1] = R[1] * v[0] + R[4] * v[1] + R[7] * v[2]; o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+}
+// R <- R * Rot(axis a, angle): columns u = a+1, v = a+2 (cyclic) mix
+__device__ __forceinline__ void rot_axis(double* R, int a, double s, double c) {
+  const int u = a == 2 ? 0 : a + 1, v = u == 2 ? 0 : u + 1;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double cu = R[r * 3 + u], cv = R[r * 3 + v];
+    R[r * 3 + u] = cu * c + cv * s;
+    R[r * 3 + v] = cv * c - cu * s;
+  }
+}
+
+struct Ctx {
+  const Skel* sk; const Prm* P;
+  double* V;       // this warp's vector workspace
+  double* MC;      // this warp's momentum-Jacobian cache [dof][6][PPW]
+  double* sm;      // shared memory
+  int lane, f, pg; bool valid;
+  double tgt[3 * NMARK], comt[3], momt[6];
+  int con;
+  const double* velcon;   // this problem's [MAXHS][HS_W]
+};
+
+#define VEC(ctx, v, j) (ctx).V[((size_t)(v) * MAXD + (j)) * 32 + (ctx).lane]
+#define SMB(ctx, b, k) (ctx).sm[((b) * SM_W + (k)) * 32 + (ctx).lane]
+
+__device__ __forceinline__ void load_frame(const Ctx& c, int b, double* R, double* t) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = SMB(c, b, SM_R + k);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = SMB(c, b, SM_T + k);
+}
+// world axis of channel ch of bone b (HingeJoint::ComputeW): first channel = column of the parent frame, last = column of
+// the bone frame, middle = stored in the forward sweep
+__device__ __forceinline__ void hinge_axis(const Ctx& c, int b, int ch, double* W) {
+  const Skel& sk = *c.sk;
+  const int a = sk.axis[b][ch], nc = sk.nchan[b];
+  if (ch == nc - 1) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) W[r] = SMB(c, b, SM_R + r * 3 + a);
+  } else if (ch == 0) {
+    const int p = sk.parent[b];
+    if (p < 0) { W[0] = a == 0; W[1] = a == 1; W[2] = a == 2; }
+    else {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) W[r] = SMB(c, p, SM_R + r * 3 + a);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) W[r] = SMB(c, b, SM_WM + r);
+  }
+}
+
+// momentum about `C` of bone b moving with world angular velocity w and origin velocity v (Liegroup.cpp:66-74 Inertia * se3,
+// then dAd to the world frame): adds to Hm (about the WORLD origin) and Hf
+__device__ __forceinline__ void bone_momentum(const Skel& sk, int b, const double* R, const double* t, const double* w, const double* v,
+                                               double* Hm, double* Hf) {
+  double wb[3], vb[3], r[3], M[3], F[3], tmp[3];
+  matT_vec(R, w, wb); matT_vec(R, v, vb);
+  const double m = sk.mass[b];
+  r[0] = m * sk.com[b][0]; r[1] = m * sk.com[b][1]; r[2] = m * sk.com[b][2];
+  const double* I = sk.inertia[b];
+  cross3(r, vb, tmp);
+  M[0] = I[0] * wb[0] + I[3] * wb[1] + I[4] * wb[2] + tmp[0];
+  M[1] = I[3] * wb[0] + I[1] * wb[1] + I[5] * wb[2] + tmp[1];
+  M[2] = I[4] * wb[0] + I[5] * wb[1] + I[2] * wb[2] + tmp[2];
+  cross3(wb, r, tmp);
+  F[0] = tmp[0] + m * vb[0]; F[1] = tmp[1] + m * vb[1]; F[2] = tmp[2] + m * vb[2];
+  double Fw[3], Mw[3];
+  mat_vec(R, F, Fw); mat_vec(R, M, Mw);
+  cross3(t, Fw, tmp);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { Hm[k] += Mw[k] + tmp[k]; Hf[k] += Fw[k]; }
+}
+
+__device__ __forceinline__ void add_force(const Ctx& c, int b, const double* p, const double* F) {
+  double N[3];
+  cross3(p, F, N);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { SMB(c, b, SM_A + k) += F[k]; SMB(c, b, SM_A + 3 + k) += N[k]; }
+}
+
+// One evaluation of LBFGS_opta's function at V_X: objective (same value on the 8 lanes of a problem) and, in V_G, the
+// gradient of this lane's frame.  `first`: rebuild the momentum-Jacobian cache (shortTermOptimizer.lua:669-684).
+__device__ double evaluate(Ctx& c, bool first) {
+  const Skel& sk = *c.sk; const Prm& P = *c.P;
+  const int nf = P.nf, nd = sk.ndof, f = c.f;
+  const bool valid = c.valid, has_next = valid && f + 1 < nf;
+  const double INV = 30.0, INVS = 900.0;
+  double o = 0.0;
+
+  // ---------------- forward sweep: Tree::Compute + ComputeDS + calcCOM + calcMomentumCOM of this frame
+  double comacc[3] = {0, 0, 0}, Hm[3] = {0, 0, 0}, Hf[3] = {0, 0, 0};
+  for (int b = 0; b < sk.nb; ++b) {
+    double R[9], t[3], w[3], v[3];
+    const int p = sk.parent[b];
+    if (p < 0) {
+      R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double q = valid ? VEC(c, V_X, k) : 0.0;
+        t[k] = sk.off[b][k] + q;
+        v[k] = has_next ? (c.V[((size_t)V_X * MAXD + k) * 32 + c.lane + 1] - q) * INV : 0.0;
+        w[k] = 0.0;
+      }
+    } else {
+      double tp[3], wp[3], vp[3], d[3], x[3];
+      load_frame(c, p, R, tp);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { wp[k] = SMB(c, p, SM_A + k); vp[k] = SMB(c, p, SM_A + 3 + k); }
+      mat_vec(R, sk.off[b], d);
+      cross3(wp, d, x);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { t[k] = tp[k] + d[k]; w[k] = wp[k]; v[k] = vp[k] + x[k]; }
+    }
+    const int j0 = sk.dof0[b], nc = sk.nchan[b];
+    for (int ch = 0; ch < nc; ++ch) {
+      const int a = sk.axis[b][ch], j = j0 + ch;
+      const double W0 = R[a], W1 = R[3 + a], W2 = R[6 + a];
+      if (ch == 1 && nc == 3) { SMB(c, b, SM_WM) = W0; SMB(c, b, SM_WM + 1) = W1; SMB(c, b, SM_WM + 2) = W2; }
+      const double q = valid ? VEC(c, V_X, j) : 0.0;
+      const double dq = has_next ? (c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] - q) * INV : 0.0;
+      double s, cs;
+      sincos(q, &s, &cs);
+      rot_axis(R, a, s, cs);
+      w[0] += W0 * dq; w[1] += W1 * dq; w[2] += W2 * dq;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) SMB(c, b, SM_R + k) = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { SMB(c, b, SM_T + k) = t[k]; SMB(c, b, SM_A + k) = w[k]; SMB(c, b, SM_A + 3 + k) = v[k]; }
+    double cb[3];
+    mat_vec(R, sk.com[b], cb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) comacc[k] += (cb[k] + t[k]) * sk.mass[b];
+    bone_momentum(sk, b, R, t, w, v, Hm, Hf);
+  }
+  double C[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) C[k] = comacc[k] * (1.0 / sk.total_mass);
+
+  // ---------------- momentum Jacobian cache: mean over frames 0 .. nf-2 of calcMomentumJacobianTranspose
+  if (first && P.w_mom > 0) {
+    const bool use = valid && f < nf - 1;
+    for (int j = 0; j < nd; ++j) {
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      int b0 = 0, ch = 0;
+      bool slide = j < 3;
+      if (!slide) {
+        for (b0 = 0; b0 < sk.nb; ++b0) if (j >= sk.dof0[b0] && j < sk.dof0[b0] + sk.nchan[b0]) break;
+        ch = j - sk.dof0[b0];
+      }
+      double W[3], sj[3];
+      if (slide) { W[0] = j == 0; W[1] = j == 1; W[2] = j == 2; sj[0] = sj[1] = sj[2] = 0; }
+      else {
+        hinge_axis(c, b0, ch, W);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sj[k] = SMB(c, b0, SM_T + k);
+      }
+      for (int b = b0; b < sk.sub_end[b0]; ++b) {
+        double R[9], t[3], w[3], v[3], d[3], hm[3] = {0, 0, 0}, hf[3] = {0, 0, 0};
+        load_frame(c, b, R, t);
+        if (slide) { w[0] = w[1] = w[2] = 0; v[0] = W[0]; v[1] = W[1]; v[2] = W[2]; }
+        else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { w[k] = W[k]; d[k] = t[k] - sj[k]; }
+          cross3(W, d, v);
+        }
+        bone_momentum(sk, b, R, t, w, v, hm, hf);
+        double x[3];
+        cross3(C, hf, x);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { acc[k] += hm[k] - x[k]; acc[3 + k] += hf[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double s = grp_sum(use ? acc[k] : 0.0) * (1.0 / (nf - 1));
+        if (f == 0) c.MC[((size_t)j * 6 + k) * PPW + c.pg] = s;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---------------- residuals that couple the frames
+  double mom_c[6] = {0, 0, 0, 0, 0, 0};      // (-2 w filt[f] invDT) (desired - actual momentum) of interval f
+  if (P.w_mom > 0) {
+    double x[3];
+    cross3(C, Hf, x);
+    const bool use = valid && f < nf - 1;
+    const double fl = use ? P.filt[f] : 0.0;
+    double ss = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double dm = c.momt[k] - (Hm[k] - x[k]), df = c.momt[3 + k] - Hf[k];
+      ss += dm * dm + df * df;
+      mom_c[k] = (-2.0 * P.w_mom * fl * INV) * dm; mom_c[3 + k] = (-2.0 * P.w_mom * fl * INV) * df;
+    }
+    if (use) o += ss * P.w_mom * fl;
+  }
+  // zero the force accumulators (they alias the velocity slots, which are not needed any more)
+  for (int b = 0; b < sk.nb; ++b)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) SMB(c, b, SM_A + k) = 0.0;
+
+  // marker terms (:713-784)
+  for (int m = 0; m < NMARK; ++m) {
+    const int b = P.mbone[m];
+    double R[9], t[3], pm[3], F[3] = {0, 0, 0};
+    load_frame(c, b, R, t);
+    mat_vec(R, P.mlpos[m], pm);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pm[k] += t[k];
+    const double fl = valid ? P.filt[f] : 0.0;
+    const bool cn = valid && ((c.con >> (m * 8 + f)) & 1);
+    double dS[3], dC[3];
+    const double cnt = grp_sum(cn ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double e = c.tgt[3 * m + k] - pm[k];
+      dS[k] = grp_sum(valid ? e * fl : 0.0);
+      dC[k] = grp_sum(cn ? e : 0.0);
+    }
+    if (P.w_ee > 0) {
+      const double w = P.w_ee * P.mweight[m];
+      if (f == 0) o += dot3(dS, dS) * w;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F[k] += -(2.0 * w * fl) * dS[k];
+    }
+    if (P.w_eecon > 0 && cnt > 0) {
+      const double w = P.w_eecon * P.mweight[m];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dC[k] *= 1.0 / cnt;
+      if (f == 0) o += dot3(dC, dC) * w;
+      if (cn) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) F[k] += -(2.0 * w / cnt) * dC[k];
+      }
+    }
+    if (valid) add_force(c, b, pm, F);
+  }
+  // velocity half-space terms (:466-503): frame fc against frame fc - 1, fc >= 2
+  if (P.w_velhs != 0) {
+    for (int h = 0; h < MAXHS; ++h) {
+      const double* hc = c.velcon + h * HS_W;
+      const int fc = (int)hc[0];
+      const bool act = fc >= 2 && fc < nf;               // uniform over the problem's lanes, not over the warp
+      const int b = min(max((int)hc[1], 0), sk.nb - 1);
+      double R[9], t[3], pm[3];
+      load_frame(c, b, R, t);
+      mat_vec(R, hc + 6, pm);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pm[k] += t[k];
+      double gv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double prev = __shfl_up_sync(0xffffffffu, pm[k], 1, GRP), next = __shfl_down_sync(0xffffffffu, pm[k], 1, GRP);
+        gv[k] = f == fc ? (pm[k] - prev) * INV : (next - pm[k]) * INV;
+      }
+      const double* nrm = hc + 3;
+      const double d = (nrm[0] * hc[2] - gv[0]) * nrm[0] + (nrm[1] * hc[2] - gv[1]) * nrm[1] + (nrm[2] * hc[2] - gv[2]) * nrm[2];
+      if (act && valid && d > 0 && (f == fc || f == fc - 1)) {
+        const double sgn = f == fc ? -1.0 : 1.0;
+        double F[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) F[k] = sgn * (2.0 * P.w_velhs * INV * d) * nrm[k];
+        if (f == fc) o += d * d * P.w_velhs;
+        add_force(c, b, pm, F);
+      }
+    }
+  }
+  // CoM term (:786-809)
+  if (P.w_com > 0) {
+    const int fs = max(nf / 2, 2);
+    const bool use = valid && f < fs;
+    double dS[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dS[k] = grp_sum(use ? c.comt[k] - C[k] : 0.0) * (1.0 / fs);
+    if (f == 0) o += dot3(dS, dS) * P.w_com;
+    if (use) {
+      for (int b = 0; b < sk.nb; ++b) {
+        double R[9], t[3], cb[3], F[3];
+        load_frame(c, b, R, t);
+        mat_vec(R, sk.com[b], cb);
+        const double s = (-2.0 * P.w_com / fs) * (sk.mass[b] / sk.total_mass);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { cb[k] += t[k]; F[k] = s * dS[k]; }
+        add_force(c, b, cb, F);
+      }
+    }
+  }
+
+  // ---------------- reverse sweep: g_j = W_j . (N - s_j x F) for hinges, W_j . F for slides (Node.cpp:386-400,466-469)
+  for (int b = sk.nb - 1; b >= 0; --b) {
+    double F[3], N[3], t[3], x[3], tau[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { F[k] = SMB(c, b, SM_A + k); N[k] = SMB(c, b, SM_A + 3 + k); t[k] = SMB(c, b, SM_T + k); }
+    cross3(t, F, x);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tau[k] = N[k] - x[k];
+    for (int ch = sk.nchan[b] - 1; ch >= 0; --ch) {
+      double W[3];
+      hinge_axis(c, b, ch, W);
+      if (valid) VEC(c, V_G, sk.dof0[b] + ch) = dot3(W, tau);
+    }
+    const int p = sk.parent[b];
+    if (p >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { SMB(c, p, SM_A + k) += F[k]; SMB(c, p, SM_A + 3 + k) += N[k]; }
+    } else if (valid) {
+      VEC(c, V_G, 0) = F[0]; VEC(c, V_G, 1) = F[1]; VEC(c, V_G, 2) = F[2];
+    }
+  }
+
+  // ---------------- quadratic default terms (:164-265) and the momentum gradient through the cached Jacobian
+  {
+    double mom_p[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double pv = __shfl_up_sync(0xffffffffu, mom_c[k], 1, GRP);
+      mom_p[k] = (f == 0 ? 0.0 : pv) - mom_c[k];           // G[f] += mcache (c_{f-1} - c_f)
+    }
+    const bool ctr = valid && f >= 1 && f <= nf - 2;       // this frame is the centre i of a ddx / dx term
+    const bool ctr_n = valid && f + 1 >= 1 && f + 1 <= nf - 2, ctr_p = valid && f - 1 >= 1 && f - 1 <= nf - 2;
+    const double* X = c.V + (size_t)V_X * MAXD * 32;
+    const int base = c.lane - f;                           // lane of frame 0 of this problem
+    double oq = 0.0;
+    for (int j = 0; j < nd; ++j) {
+      const double* Xj = X + (size_t)j * 32 + base;
+      double xs[NFMAX + 4];
+#pragma unroll
+      for (int k = 0; k < NFMAX; ++k) xs[k + 2] = k < nf ? Xj[k] : 0.0;
+      xs[0] = xs[1] = xs[NFMAX + 2] = xs[NFMAX + 3] = 0.0;
+      // dynamic frame index -> select with a small unrolled scan (keeps xs in registers)
+      double xm2 = 0, xm1 = 0, x0 = 0, xp1 = 0, xp2 = 0, sum = 0;
+#pragma unroll
+      for (int k = 0; k < NFMAX; ++k) {
+        const double xv = xs[k + 2];
+        sum += xv;
+        xm2 = (k == f - 2) ? xv : xm2; xm1 = (k == f - 1) ? xv : xm1; x0 = (k == f) ? xv : x0;
+        xp1 = (k == f + 1) ? xv : xp1; xp2 = (k == f + 2) ? xv : xp2;
+      }
+      double g = 0.0;
+      if (P.w_ddx != 0) {
+        const double s = P.s_ddx[j], a = s * INVS, bq = s * (-2.0 * INVS);
+        const double dd0 = VEC(c, V_DDX, j);               // ddx[f-1] is stored at row f (see load_problem)
+        const double ddn = has_next ? c.V[((size_t)V_DDX * MAXD + j) * 32 + c.lane + 1] : 0.0;
+        const double ddp = f > 0 ? c.V[((size_t)V_DDX * MAXD + j) * 32 + c.lane - 1] : 0.0;
+        if (ctr) { const double e = a * xm1 + bq * x0 + a * xp1 + s * (-dd0); oq += e * e; g += 2.0 * e * bq; }
+        if (ctr_n) { const double e = a * x0 + bq * xp1 + a * xp2 + s * (-ddn); g += 2.0 * e * a; }
+        if (ctr_p) { const double e = a * xm2 + bq * xm1 + a * x0 + s * (-ddp); g += 2.0 * e * a; }
+      }
+      if (P.w_dx != 0) {
+        const double s = P.s_dx[j], a = s * INV;
+        const double d0 = VEC(c, V_DX, j);                 // dx[f-1] at row f
+        const double dn = has_next ? c.V[((size_t)V_DX * MAXD + j) * 32 + c.lane + 1] : 0.0;
+        if (ctr) { const double e = (-a) * xm1 + a * x0 + s * (-d0); oq += e * e; g += 2.0 * e * a; }
+        if (ctr_n) { const double e = (-a) * x0 + a * xp1 + s * (-dn); g += 2.0 * e * (-a); }
+      }
+      if (P.w_ao != 0) {
+        const double s = P.s_ao[j];
+        const double e = s * sum + s * (-VEC(c, V_SUMO, j));
+        if (f == 0) oq += e * e;
+        g += 2.0 * e * s;
+      }
+      if (P.w_mom > 0) {
+        const double* mc = c.MC + (size_t)j * 6 * PPW + c.pg;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g += mc[k * PPW] * mom_p[k];
+      }
+      if (valid) VEC(c, V_G, j) += g;
+    }
+    if (valid) o += oq;
+  }
+  __syncwarp();
+  return grp_sum(valid ? o : 0.0);
+}
+
+// three dot products over the free variables (frames >= 2) of this problem
+__device__ __forceinline__ void dots3(const Ctx& c, bool fr, int nd, int a0, int b0, int a1, int b1, int a2, int b2, double* r0, double* r1, double* r2) {
+  double s0 = 0, s1 = 0, s2 = 0;
+  if (fr)
+    for (int j = 0; j < nd; ++j) {
+      s0 += VEC(c, a0, j) * VEC(c, b0, j); s1 += VEC(c, a1, j) * VEC(c, b1, j); s2 += VEC(c, a2, j) * VEC(c, b2, j);
+    }
+  *r0 = grp_sum(s0); *r1 = grp_sum(s1); *r2 = grp_sum(s2);
+}
+__device__ __forceinline__ double dot1(const Ctx& c, bool fr, int nd, int a, int b) {
+  double s = 0;
+  if (fr) for (int j = 0; j < nd; ++j) s += VEC(c, a, j) * VEC(c, b, j);
+  return grp_sum(s);
+}
+
+template <bool EVAL_ONLY>
+__global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
+  extern __shared__ double smem[];
+  const Skel& sk = *A.sk; const Prm& P = *A.prm;
+  const int lane = threadIdx.x, f = lane & 7, pg = lane >> 3, nf = P.nf, nd = sk.ndof;
+  const int prob = blockIdx.x * PPW + pg;
+  const bool pvalid = prob < A.n, valid = pvalid && f < nf;
+  Ctx c;
+  c.sk = &sk; c.P = &P; c.sm = smem; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
+  c.V = A.ws + (size_t)blockIdx.x * NV * MAXD * 32;
+  c.MC = A.mc + (size_t)blockIdx.x * MAXD * 6 * PPW;
+  const size_t p64 = pvalid ? prob : 0;
+  c.velcon = A.velcon + p64 * MAXHS * HS_W;
+  c.con = A.con ? A.con[p64] : 0;
+#pragma unroll
+  for (int k = 0; k < 3 * NMARK; ++k) c.tgt[k] = valid ? A.gpos_target[(p64 * nf + f) * 3 * NMARK + k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.comt[k] = valid ? A.com[(p64 * nf + f) * 3 + k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) c.momt[k] = (valid && f < nf - 1) ? A.momentum[(p64 * (nf - 1) + f) * 6 + k] : 0.0;
+
+  // ---- problem -> workspace.  Row f of V_DX holds dx[f-1], row f of V_DDX holds ddx[f-1] (the rows the terms centred at f use).
+  const double thr = P.clamp * (3.14159265358979323846 / 180.0);
+  for (int j = 0; j < MAXD; ++j) {
+    double xo = 0, dxv = 0, ddxv = 0, x = 0;
+    if (valid && j < nd) {
+      xo = A.x_original[(p64 * nf + f) * nd + j];
+      if (f >= 1 && f - 1 < nf - 1) dxv = A.dx[(p64 * (nf - 1) + f - 1) * nd + j];
+      if (f >= 1 && f - 1 < nf - 2) ddxv = A.ddx[(p64 * (nf - 2) + f - 1) * nd + j];
+      if (EVAL_ONLY) x = A.x_in[(p64 * nf + f) * nd + j];
+      else if (f < 2) x = fmin(fmax(A.euler_mot[(p64 * nf + f) * nd + j], xo - thr), xo + thr);     // :829-838
+      else x = xo;
+    }
+    VEC(c, V_XO, j) = xo; VEC(c, V_DX, j) = dxv; VEC(c, V_DDX, j) = ddxv; VEC(c, V_X, j) = x; VEC(c, V_G, j) = 0.0;
+    const double s = grp_sum(xo);                          // sum over the frames (:231-235); fixed order inside the shuffle tree
+    VEC(c, V_SUMO, j) = s;
+  }
+  __syncwarp();
+
+  if (EVAL_ONLY) {
+    const double fx = evaluate(c, true);
+    if (valid) {
+      for (int j = 0; j < nd; ++j) A.grad[(p64 * nf + f) * nd + j] = VEC(c, V_G, j);
+      if (f == 0) A.obj[p64] = fx;
+    }
+    return;
+  }
+
+  // ---- lbfgs() (lbfgs.cpp:246-640) as a per-problem state machine; one evaluation per trip of the loop
+  const bool fr = valid && f >= 2;                         // the free variables (W2 of oracle/mmsto.py)
+  int phase = pvalid ? 0 : 2, k = 1, end = 0, count = 0, ret = 0, n_eval = 0, iters = 0;
+  double step = 0, finit = 0, dginit = 0, dgtest = 0, fx = 0;
+  double alpha[LB_M], ys_h[LB_M];
+#pragma unroll
+  for (int i = 0; i < LB_M; ++i) { alpha[i] = 0; ys_h[i] = 1; }
+  bool firstev = true;
+  for (int trip = 0; trip < 1000000; ++trip) {
+    if (__all_sync(0xffffffffu, phase == 2)) break;
+    const double fv = evaluate(c, firstev);
+    firstev = false;
+    if (phase != 2) ++n_eval;
+    double dg, gg, xx;
+    dots3(c, fr, nd, V_G, V_D, V_G, V_G, V_X, V_X, &dg, &gg, &xx);
+    bool begin_ls = false, accepted = false;
+    if (phase == 0) {
+      fx = fv;
+      const double xnorm = fmax(sqrt(xx), 1.0), gnorm = sqrt(gg);
+      if (gnorm / xnorm <= P.eps) { ret = LBFGS_ALREADY_MINIMIZED; phase = 2; }
+      else { step = 1.0 / sqrt(gg); begin_ls = true; }
+    } else if (phase == 1) {
+      ++count;
+      fx = fv;
+      double width = 0;
+      if (fv > finit + step * dgtest) width = 0.5;
+      else if (dg < P.wolfe * dginit) width = 2.1;
+      else accepted = true;
+      if (!accepted) {
+        int err = 0;
+        if (step < P.min_step) err = LBFGSERR_MINIMUMSTEP;
+        else if (step > P.max_step) err = LBFGSERR_MAXIMUMSTEP;
+        else if (P.max_ls <= count) err = LBFGSERR_MAXIMUMLINESEARCH;
+        if (err) {                                         // revert to the previous point (:437-443)
+          if (fr) for (int j = 0; j < nd; ++j) { VEC(c, V_X, j) = VEC(c, V_XP, j); VEC(c, V_G, j) = VEC(c, V_GP, j); }
+          ret = err; phase = 2; iters = k;
+        } else {
+          step *= width;
+          if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_X, j) = VEC(c, V_XP, j) + VEC(c, V_D, j) * step;
+        }
+      }
+    }
+    if (phase == 0 && begin_ls) {                          // d = -g
+      if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) = -VEC(c, V_G, j);
+    }
+    bool upd = false;
+    if (accepted) {
+      const double xnorm = fmax(sqrt(xx), 1.0), gnorm = sqrt(gg);
+      iters = k;
+      if (gnorm / xnorm <= P.eps) { ret = LBFGS_SUCCESS; phase = 2; }
+      else if ((P.max_iter != 0 && P.max_iter < k + 1) || P.iter_cap < k + 1) { ret = LBFGSERR_MAXIMUMITERATION; phase = 2; }
+      else upd = true;
+    }
+    if (__any_sync(0xffffffffu, upd)) {
+      // s = x - xp, y = g - gp, two-loop recursion (:470-530); groups that do not update run it on dummy predicates
+      const int vs = V_S + end, vy = V_Y + end;
+      double ys = 0, yy = 0;
+      {
+        double s0 = 0, s1 = 0;
+        if (fr && upd)
+          for (int j = 0; j < nd; ++j) {
+            const double sv = VEC(c, V_X, j) - VEC(c, V_XP, j), yv = VEC(c, V_G, j) - VEC(c, V_GP, j);
+            VEC(c, vs, j) = sv; VEC(c, vy, j) = yv;
+            s0 += yv * sv; s1 += yv * yv;
+          }
+        ys = grp_sum(s0); yy = grp_sum(s1);
+      }
+      int bound = 0, jn = end;
+      if (upd) {
+#pragma unroll
+        for (int i = 0; i < LB_M; ++i) ys_h[i] = (i == end) ? ys : ys_h[i];
+        bound = LB_M <= k ? LB_M : k;
+        ++k;
+        end = (end + 1) % LB_M;
+        jn = end;
+        if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) = -VEC(c, V_G, j);
+      }
+      for (int i = 0; i < LB_M; ++i) {
+        const bool on = upd && i < bound;
+        if (on) jn = (jn + LB_M - 1) % LB_M;
+        double ysj = 1;
+#pragma unroll
+        for (int q = 0; q < LB_M; ++q) ysj = (q == jn) ? ys_h[q] : ysj;
+        const double a = dot1(c, fr && on, nd, V_S + jn, V_D) / ysj;
+        if (on) {
+#pragma unroll
+          for (int q = 0; q < LB_M; ++q) alpha[q] = (q == jn) ? a : alpha[q];
+          if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) += VEC(c, V_Y + jn, j) * (-a);
+        }
+      }
+      if (upd && fr) { const double sc = ys / yy; for (int j = 0; j < nd; ++j) VEC(c, V_D, j) *= sc; }
+      for (int i = 0; i < LB_M; ++i) {
+        const bool on = upd && i < bound;
+        double ysj = 1, aj = 0;
+#pragma unroll
+        for (int q = 0; q < LB_M; ++q) { ysj = (q == jn) ? ys_h[q] : ysj; aj = (q == jn) ? alpha[q] : aj; }
+        const double beta = dot1(c, fr && on, nd, V_Y + jn, V_D) / ysj;
+        if (on) {
+          if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) += VEC(c, V_S + jn, j) * (aj - beta);
+          jn = (jn + 1) % LB_M;
+        }
+      }
+      if (upd) { step = 1.0; begin_ls = true; }
+    }
+    if (__any_sync(0xffffffffu, begin_ls)) {
+      const double d0 = dot1(c, fr && begin_ls, nd, V_G, V_D);
+      if (begin_ls) {
+        if (0 < d0) { ret = LBFGSERR_INCREASEGRADIENT; phase = 2; iters = k; }
+        else {
+          dginit = d0; finit = fx; dgtest = P.ftol * dginit; count = 0; phase = 1;
+          if (fr) for (int j = 0; j < nd; ++j) {
+            const double xv = VEC(c, V_X, j);
+            VEC(c, V_XP, j) = xv; VEC(c, V_GP, j) = VEC(c, V_G, j);
+            VEC(c, V_X, j) = xv + VEC(c, V_D, j) * step;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (valid) {
+    for (int j = 0; j < nd; ++j) A.x_out[(p64 * nf + f) * nd + j] = VEC(c, V_X, j);
+    if (f == 0) {
+      A.info[p64 * 4 + 0] = fx; A.info[p64 * 4 + 1] = ret; A.info[p64 * 4 + 2] = iters; A.info[p64 * 4 + 3] = n_eval;
+    }
+  }
+}
+
+}  // namespace mmsto

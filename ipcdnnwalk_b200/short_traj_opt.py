@@ -1,0 +1,221 @@
+"""Batched look-alike of gym_cdm2's `ShortTrajOpt` (shortTermOptimizer.lua) over the CUDA MMSTO kernel.
+
+Reference interface mirrored (the calls walk_SRBTrack2025.py:293,370-376,529-587 makes on one optimiser):
+  ShortTrajOpt(loader, motion)                     -> ShortTrajOpt(skel, nf, markers, device)
+  trajOpt.set('weightMomentum', w) ...             -> set(name, value)
+  trajOpt.get('dof_weights').range(s, s+3).setAllValue(0.1)   -> dof_weights[s:s+3] = 0.1; set_dof_weights()
+  trajOpt:calculateOriginalEulerPoses(mot, {poseOnly=true})   -> calculateOriginalEulerPoses(pose)  (host side, numpy)
+  trajOpt:solveEndEffectors(mot, markers, gpos_target, nil, nil, hsVelConInfo)   -> solveEndEffectors_euler(...)
+Every array carries a leading batch dimension: one independent window per character.  The online configuration only
+(onlineOpt = true, no collision half-spaces, weightEEvel = 0): anything else raises.  torch is used for device memory."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+
+AX = {"X": 0, "Y": 1, "Z": 2}
+ROOT_ROT_CHANNELS = "YZX"          # VRMLloader.cpp:16 DEFAULT_ROT_CHANNELS
+INFO_KEYS = ("fx", "ret", "iterations", "evaluations")
+
+
+class MmstoError(RuntimeError):
+    pass
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise MmstoError(f"libsrbtrack_b200 mmsto error {rc}: {lib.mmsto_last_error().decode()}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(t.data_ptr())
+
+
+def _quat_to_yzx(q):
+    """Euler angles (ry, rz, rx) with R = Ry Rz Rx from quaternions [.., 4] (w x y z); rz in [-pi/2, pi/2]."""
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    r00 = 1 - 2 * (y * y + z * z); r10 = 2 * (x * y + w * z); r20 = 2 * (x * z - w * y)
+    r11 = 1 - 2 * (x * x + z * z); r12 = 2 * (y * z - w * x)
+    rz = np.arcsin(np.clip(r10, -1.0, 1.0))
+    ry = np.arctan2(-r20, r00)
+    rx = np.arctan2(-r12, r11)
+    return np.stack([ry, rz, rx], axis=-1)
+
+
+def _yzx_to_quat(e):
+    def ax(axis, a):
+        q = np.zeros(a.shape + (4,)); q[..., 0] = np.cos(a / 2); q[..., 1 + axis] = np.sin(a / 2)
+        return q
+
+    def mul(a, b):
+        w1, x1, y1, z1 = np.moveaxis(a, -1, 0); w2, x2, y2, z2 = np.moveaxis(b, -1, 0)
+        return np.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                         w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2, w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2], axis=-1)
+    return mul(mul(ax(1, e[..., 0]), ax(2, e[..., 1])), ax(0, e[..., 2]))
+
+
+def align_euler_angles(a):
+    """vectorn::alignEulerAngles along the last axis: remove 2 pi jumps between consecutive frames."""
+    a = np.array(a, dtype=np.float64)
+    for i in range(1, a.shape[-1]):
+        d = a[..., i] - a[..., i - 1]
+        a[..., i] -= np.round(d / (2 * math.pi)) * (2 * math.pi)
+    return a
+
+
+class ShortTrajOpt:
+    def __init__(self, skel, nf, markers, device=0):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("ipcdnnwalk_b200.short_traj_opt needs a CUDA device (sm_100a); there is no CPU fallback")
+        if len(markers) != 4:
+            raise ValueError("four markers (l toe, l heel, r toe, r heel) as in walk_SRBTrack2025.py:336-347")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.nf = int(nf)
+        nb = len(skel["parent"])
+        parent = np.ascontiguousarray(skel["parent"], dtype=np.int32)
+        offset = np.ascontiguousarray(skel["offset"], dtype=np.float64)
+        nchan = np.ascontiguousarray([len(c) for c in skel["channels"]], dtype=np.int32)
+        axes = np.zeros((nb, 3), dtype=np.int32)
+        for b, ch in enumerate(skel["channels"]):
+            for k, c in enumerate(ch):
+                axes[b, k] = AX[c]
+        mass = np.ascontiguousarray(skel["mass"], dtype=np.float64)
+        com = np.ascontiguousarray(skel["com"], dtype=np.float64)
+        inertia = np.ascontiguousarray(skel["inertia"], dtype=np.float64)
+        mb = np.ascontiguousarray([m["bone"] for m in markers], dtype=np.int32)
+        ml = np.ascontiguousarray([m["lpos"] for m in markers], dtype=np.float64)
+        mw = np.ascontiguousarray([m["weight"] for m in markers], dtype=np.float64)
+        self._h = C.c_void_p()
+        _check(self.lib, self.lib.mmsto_create(int(device), nb, _ptr(parent), _ptr(offset), _ptr(nchan), _ptr(axes), _ptr(mass), _ptr(com),
+                                               _ptr(inertia), self.nf, _ptr(mb), _ptr(ml), _ptr(mw), C.byref(self._h)))
+        self.ndof = self.lib.mmsto_ndof(self._h)
+        self.dof_weights = np.ones(self.ndof)
+
+    # ---- parameters
+    def set(self, name, value):
+        if name in ("weightEEvel", "weightHalfSpace", "weightRelativeHalfSpace", "weightAngleInput"):
+            if name == "weightEEvel" and float(value) != 0.0 or name == "weightAngleInput" and float(value) != 0.0:
+                raise NotImplementedError(f"{name} != 0 is outside the online configuration (walk_SRBTrack2025.py:529-537)")
+            return                         # collision half-space weights have no effect without constraints
+        _check(self.lib, self.lib.mmsto_set_param(self._h, name.encode(), float(value)))
+
+    def get(self, name):
+        v = C.c_double()
+        _check(self.lib, self.lib.mmsto_get_param(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def set_dof_weights(self, w=None):
+        if w is not None:
+            self.dof_weights = np.ascontiguousarray(w, dtype=np.float64)
+        _check(self.lib, self.lib.mmsto_set_dof_weights(self._h, _ptr(np.ascontiguousarray(self.dof_weights, dtype=np.float64))))
+
+    # ---- host-side conversions (shortTermOptimizer.lua:4-49; LoaderToTree::setPoseDOF / getPoseDOF with an Euler root)
+    def calculateOriginalEulerPoses(self, pose, prev_ry=None):
+        """pose [.., nframes, 7 + #angles] (root xyz, quaternion wxyz, angles) -> q [.., nframes, ndof]; ry aligned along the frames."""
+        pose = np.asarray(pose, dtype=np.float64)
+        q = np.concatenate([pose[..., 0:3], _quat_to_yzx(pose[..., 3:7]), pose[..., 7:]], axis=-1)
+        ry = q[..., 3]
+        if prev_ry is not None:
+            ry = np.concatenate([np.asarray(prev_ry, dtype=np.float64)[..., None], ry], axis=-1)
+        ry = align_euler_angles(ry)
+        q[..., 3] = ry[..., 1:] if prev_ry is not None else ry
+        return q
+
+    def eulerToPoseDOF(self, q):
+        q = np.asarray(q, dtype=np.float64)
+        return np.concatenate([q[..., 0:3], _yzx_to_quat(q[..., 3:6]), q[..., 6:]], axis=-1)
+
+    # ---- the solve
+    def _dev(self, a, shape, dtype=None):
+        torch = self.torch
+        t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+        t = t.to(self.device, dtype or torch.float64).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def pack_velcon(self, n, hsVelConInfo):
+        """hsVelConInfo: per problem a dict {lua frame index (1-based): (min_speed[k], normals[k,3], tree_indices[k], local_positions[k,3])}
+        (walk_SRBTrack2025.py:561-577; tree index = bone index + 1) -> [n, 4, 10]."""
+        v = np.zeros((n, 4, 10)); v[:, :, 0] = -1
+        for i, info in enumerate(hsVelConInfo or []):
+            k = 0
+            for lua_frame, (speed, normals, tis, lps) in (info or {}).items():
+                for s, nr, ti, lp in zip(speed, normals, tis, lps):
+                    if k >= 4:
+                        raise ValueError("at most 4 velocity constraints per window")
+                    v[i, k, 0] = lua_frame - 1; v[i, k, 1] = ti - 1; v[i, k, 2] = s; v[i, k, 3:6] = nr; v[i, k, 6:9] = lp
+                    k += 1
+        return v
+
+    def solveEndEffectors_euler(self, euler_mot, gpos_target, x_original, dx, ddx, com, momentum, con=None, velcon=None, stream=None):
+        """All arrays [n, ...] as in include/mmsto_b200.h -> (x [n, nf, ndof] torch.float64 on the device, info [n, 4])."""
+        torch = self.torch
+        nf, nd = self.nf, self.ndof
+        n = int(x_original.shape[0])
+        xo = self._dev(x_original, (n, nf, nd)); dxd = self._dev(dx, (n, nf - 1, nd)); ddxd = self._dev(ddx, (n, nf - 2, nd))
+        em = self._dev(euler_mot, (n, nf, nd)); gt = self._dev(gpos_target, (n, nf, 12)); cm = self._dev(com, (n, nf, 3))
+        mo = self._dev(momentum, (n, nf - 1, 6))
+        cn = None
+        if con is not None:
+            c = np.asarray(con.cpu() if torch.is_tensor(con) else con).astype(bool)          # [n, 4, nf]
+            bits = np.zeros(n, dtype=np.int32)
+            for m in range(4):
+                for f in range(nf):
+                    bits |= (c[:, m, f].astype(np.int32) << (m * 8 + f))
+            cn = torch.as_tensor(bits, device=self.device)
+        vc = self._dev(velcon, (n, 4, 10)) if velcon is not None else None
+        x = torch.empty(n, nf, nd, dtype=torch.float64, device=self.device)
+        info = torch.empty(n, 4, dtype=torch.float64, device=self.device)
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        _check(self.lib, self.lib.mmsto_solve(self._h, n, _ptr(xo), _ptr(dxd), _ptr(ddxd), _ptr(em), _ptr(gt), _ptr(cm), _ptr(mo), _ptr(cn), _ptr(vc),
+                                              _ptr(x), _ptr(info), st))
+        return x, info
+
+    def evaluate(self, x, gpos_target, x_original, dx, ddx, com, momentum, con=None, velcon=None):
+        """Objective [n] and gradient [n, nf, ndof] of LBFGS_opta's function at x (test / diagnostic entry)."""
+        torch = self.torch
+        nf, nd = self.nf, self.ndof
+        n = int(x_original.shape[0])
+        xd = self._dev(x, (n, nf, nd))
+        xo = self._dev(x_original, (n, nf, nd)); dxd = self._dev(dx, (n, nf - 1, nd)); ddxd = self._dev(ddx, (n, nf - 2, nd))
+        gt = self._dev(gpos_target, (n, nf, 12)); cm = self._dev(com, (n, nf, 3)); mo = self._dev(momentum, (n, nf - 1, 6))
+        cn = None
+        if con is not None:
+            c = np.asarray(con).astype(bool)
+            bits = np.zeros(n, dtype=np.int32)
+            for m in range(4):
+                for f in range(nf):
+                    bits |= (c[:, m, f].astype(np.int32) << (m * 8 + f))
+            cn = torch.as_tensor(bits, device=self.device)
+        vc = self._dev(velcon, (n, 4, 10)) if velcon is not None else None
+        obj = torch.empty(n, dtype=torch.float64, device=self.device)
+        grad = torch.empty(n, nf, nd, dtype=torch.float64, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _check(self.lib, self.lib.mmsto_evaluate(self._h, n, _ptr(xd), _ptr(xo), _ptr(dxd), _ptr(ddxd), _ptr(gt), _ptr(cm), _ptr(mo), _ptr(cn), _ptr(vc),
+                                                 _ptr(obj), _ptr(grad), st))
+        return obj, grad
+
+    def launch_count(self):
+        return int(self.lib.mmsto_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.mmsto_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

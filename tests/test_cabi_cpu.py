@@ -59,6 +59,22 @@ def test_terrain_header_symbols_exported(built_lib):
         assert hasattr(built_lib, n)
 
 
+def test_mmsto_header_symbols_exported(built_lib):
+    from ipcdnnwalk_b200 import _lib
+    txt = open(os.path.join(helpers.ROOT, "include", "mmsto_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(mmsto_[a-z_0-9]+)\s*\(", txt)))
+    assert names == sorted(_lib.MMSTO_EXPORTED_SYMBOLS) and len(names) == 10
+    for n in names:
+        assert hasattr(built_lib, n)
+    import torch
+    if not torch.cuda.is_available():
+        import helpers_mmsto as hm
+        from ipcdnnwalk_b200 import ShortTrajOpt
+        with pytest.raises(RuntimeError):
+            ShortTrajOpt(hm.skeleton(), hm.NF, hm.MARKERS)
+
+
 def test_cdm_errors_without_gpu(built_lib):
     import ctypes as C
     from ipcdnnwalk_b200 import _lib
