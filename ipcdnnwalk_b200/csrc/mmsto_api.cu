@@ -79,7 +79,7 @@ static int prepare(mmsto_solver* s, int n) {
 }
 
 template <bool EVAL_ONLY> static int launch(mmsto_solver* s, mmsto::Args& A, void* stream) {
-  const size_t smem = (size_t)s->sk.nb * mmsto::SM_W * 32 * sizeof(double);
+  const size_t smem = ((size_t)s->sk.nb * mmsto::SM_W * 32 + mmsto::PPW * mmsto::GM_W) * sizeof(double);
   auto kern = mmsto::mmsto_kernel<EVAL_ONLY>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int warps = (A.n + mmsto::PPW - 1) / mmsto::PPW;

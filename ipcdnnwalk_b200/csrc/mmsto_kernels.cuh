@@ -17,7 +17,8 @@ namespace mmsto {
 
 enum { MAXB = 24, MAXD = 64, NFMAX = 8, NMARK = 4, MAXHS = 4, HS_W = 10, LB_M = 6, GRP = 8, PPW = 4,
        V_X = 0, V_G, V_D, V_XP, V_GP, V_XO, V_DX, V_DDX, V_SUMO, V_S, V_Y = V_S + LB_M, NV = V_Y + LB_M,
-       SM_W = 21, SM_R = 0, SM_T = 9, SM_A = 12, SM_WM = 18 };
+       SM_W = 21, SM_R = 0, SM_T = 9, SM_A = 12, SM_WM = 18,
+       GM_CG = 144, GM_W = 152 };   // per-problem L-BFGS scalars in shared memory: Gram matrices 3 x 36, g.S, g.Y, coefficients, alpha, ys
 
 enum { LBFGS_SUCCESS = 0, LBFGS_ALREADY_MINIMIZED = 2, LBFGSERR_MINIMUMSTEP = -1000, LBFGSERR_MAXIMUMSTEP = -999,
        LBFGSERR_MAXIMUMLINESEARCH = -998, LBFGSERR_MAXIMUMITERATION = -997, LBFGSERR_INCREASEGRADIENT = -994 };
@@ -80,7 +81,8 @@ struct Ctx {
   const Skel* sk; const Prm* P;
   double* V;       // this warp's vector workspace
   double* MC;      // this warp's momentum-Jacobian cache [dof][6][PPW]
-  double* sm;      // shared memory
+  double* sm;      // shared memory: bone frames
+  double* gm;      // shared memory: this problem's L-BFGS scalars
   int lane, f, pg; bool valid;
   double tgt[3 * NMARK], comt[3], momt[6];
   int con;
@@ -180,16 +182,26 @@ __device__ double evaluate(Ctx& c, bool first) {
       for (int k = 0; k < 3; ++k) { t[k] = tp[k] + d[k]; w[k] = wp[k]; v[k] = vp[k] + x[k]; }
     }
     const int j0 = sk.dof0[b], nc = sk.nchan[b];
-    for (int ch = 0; ch < nc; ++ch) {
-      const int a = sk.axis[b][ch], j = j0 + ch;
-      const double W0 = R[a], W1 = R[3 + a], W2 = R[6 + a];
-      if (ch == 1 && nc == 3) { SMB(c, b, SM_WM) = W0; SMB(c, b, SM_WM + 1) = W1; SMB(c, b, SM_WM + 2) = W2; }
-      const double q = valid ? VEC(c, V_X, j) : 0.0;
-      const double dq = has_next ? (c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] - q) * INV : 0.0;
-      double s, cs;
-      sincos(q, &s, &cs);
-      rot_axis(R, a, s, cs);
-      w[0] += W0 * dq; w[1] += W1 * dq; w[2] += W2 * dq;
+    double qv[3], dqv[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {                       // all loads of the bone first (they are independent)
+      const int j = j0 + (ch < nc ? ch : 0);
+      qv[ch] = valid ? VEC(c, V_X, j) : 0.0;
+      dqv[ch] = has_next ? c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] : 0.0;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (ch < nc) {
+        const int a = sk.axis[b][ch];
+        const double W0 = R[a], W1 = R[3 + a], W2 = R[6 + a];
+        if (ch == 1 && nc == 3) { SMB(c, b, SM_WM) = W0; SMB(c, b, SM_WM + 1) = W1; SMB(c, b, SM_WM + 2) = W2; }
+        const double q = qv[ch];
+        const double dq = has_next ? (dqv[ch] - q) * INV : 0.0;
+        double s, cs;
+        sincos(q, &s, &cs);
+        rot_axis(R, a, s, cs);
+        w[0] += W0 * dq; w[1] += W1 * dq; w[2] += W2 * dq;
+      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) SMB(c, b, SM_R + k) = R[k];
@@ -387,44 +399,35 @@ __device__ double evaluate(Ctx& c, bool first) {
     }
     const bool ctr = valid && f >= 1 && f <= nf - 2;       // this frame is the centre i of a ddx / dx term
     const bool ctr_n = valid && f + 1 >= 1 && f + 1 <= nf - 2, ctr_p = valid && f - 1 >= 1 && f - 1 <= nf - 2;
-    const double* X = c.V + (size_t)V_X * MAXD * 32;
-    const int base = c.lane - f;                           // lane of frame 0 of this problem
     double oq = 0.0;
+#pragma unroll 2
     for (int j = 0; j < nd; ++j) {
-      const double* Xj = X + (size_t)j * 32 + base;
-      double xs[NFMAX + 4];
-#pragma unroll
-      for (int k = 0; k < NFMAX; ++k) xs[k + 2] = k < nf ? Xj[k] : 0.0;
-      xs[0] = xs[1] = xs[NFMAX + 2] = xs[NFMAX + 3] = 0.0;
-      // dynamic frame index -> select with a small unrolled scan (keeps xs in registers)
-      double xm2 = 0, xm1 = 0, x0 = 0, xp1 = 0, xp2 = 0, sum = 0;
-#pragma unroll
-      for (int k = 0; k < NFMAX; ++k) {
-        const double xv = xs[k + 2];
-        sum += xv;
-        xm2 = (k == f - 2) ? xv : xm2; xm1 = (k == f - 1) ? xv : xm1; x0 = (k == f) ? xv : x0;
-        xp1 = (k == f + 1) ? xv : xp1; xp2 = (k == f + 2) ? xv : xp2;
-      }
+      // the frames of a problem sit in neighbouring lanes: neighbours' values by shuffle instead of reloading them
+      const double gold = VEC(c, V_G, j);
+      const double x0 = valid ? VEC(c, V_X, j) : 0.0;
+      const double dd0 = VEC(c, V_DDX, j), d0 = VEC(c, V_DX, j);            // rows f hold ddx[f-1] / dx[f-1] (see the prologue)
+      const double sumo = VEC(c, V_SUMO, j);
+      const double xm1 = __shfl_up_sync(0xffffffffu, x0, 1, GRP), xm2 = __shfl_up_sync(0xffffffffu, x0, 2, GRP);
+      const double xp1 = __shfl_down_sync(0xffffffffu, x0, 1, GRP), xp2 = __shfl_down_sync(0xffffffffu, x0, 2, GRP);
+      const double ddn = __shfl_down_sync(0xffffffffu, dd0, 1, GRP), ddp = __shfl_up_sync(0xffffffffu, dd0, 1, GRP);
+      const double dn = __shfl_down_sync(0xffffffffu, d0, 1, GRP);
+      double sum = x0;                                                       // frames in order 0..7 regardless of the lane
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
       double g = 0.0;
       if (P.w_ddx != 0) {
         const double s = P.s_ddx[j], a = s * INVS, bq = s * (-2.0 * INVS);
-        const double dd0 = VEC(c, V_DDX, j);               // ddx[f-1] is stored at row f (see load_problem)
-        const double ddn = has_next ? c.V[((size_t)V_DDX * MAXD + j) * 32 + c.lane + 1] : 0.0;
-        const double ddp = f > 0 ? c.V[((size_t)V_DDX * MAXD + j) * 32 + c.lane - 1] : 0.0;
         if (ctr) { const double e = a * xm1 + bq * x0 + a * xp1 + s * (-dd0); oq += e * e; g += 2.0 * e * bq; }
         if (ctr_n) { const double e = a * x0 + bq * xp1 + a * xp2 + s * (-ddn); g += 2.0 * e * a; }
         if (ctr_p) { const double e = a * xm2 + bq * xm1 + a * x0 + s * (-ddp); g += 2.0 * e * a; }
       }
       if (P.w_dx != 0) {
         const double s = P.s_dx[j], a = s * INV;
-        const double d0 = VEC(c, V_DX, j);                 // dx[f-1] at row f
-        const double dn = has_next ? c.V[((size_t)V_DX * MAXD + j) * 32 + c.lane + 1] : 0.0;
         if (ctr) { const double e = (-a) * xm1 + a * x0 + s * (-d0); oq += e * e; g += 2.0 * e * a; }
         if (ctr_n) { const double e = (-a) * x0 + a * xp1 + s * (-dn); g += 2.0 * e * (-a); }
       }
       if (P.w_ao != 0) {
         const double s = P.s_ao[j];
-        const double e = s * sum + s * (-VEC(c, V_SUMO, j));
+        const double e = s * sum + s * (-sumo);
         if (f == 0) oq += e * e;
         g += 2.0 * e * s;
       }
@@ -433,7 +436,7 @@ __device__ double evaluate(Ctx& c, bool first) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) g += mc[k * PPW] * mom_p[k];
       }
-      if (valid) VEC(c, V_G, j) += g;
+      if (valid) VEC(c, V_G, j) = gold + g;
     }
     if (valid) o += oq;
   }
@@ -445,6 +448,7 @@ __device__ double evaluate(Ctx& c, bool first) {
 __device__ __forceinline__ void dots3(const Ctx& c, bool fr, int nd, int a0, int b0, int a1, int b1, int a2, int b2, double* r0, double* r1, double* r2) {
   double s0 = 0, s1 = 0, s2 = 0;
   if (fr)
+#pragma unroll 4
     for (int j = 0; j < nd; ++j) {
       s0 += VEC(c, a0, j) * VEC(c, b0, j); s1 += VEC(c, a1, j) * VEC(c, b1, j); s2 += VEC(c, a2, j) * VEC(c, b2, j);
     }
@@ -452,7 +456,10 @@ __device__ __forceinline__ void dots3(const Ctx& c, bool fr, int nd, int a0, int
 }
 __device__ __forceinline__ double dot1(const Ctx& c, bool fr, int nd, int a, int b) {
   double s = 0;
-  if (fr) for (int j = 0; j < nd; ++j) s += VEC(c, a, j) * VEC(c, b, j);
+  if (fr) {
+#pragma unroll 4
+    for (int j = 0; j < nd; ++j) s += VEC(c, a, j) * VEC(c, b, j);
+  }
   return grp_sum(s);
 }
 
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
   const int prob = blockIdx.x * PPW + pg;
   const bool pvalid = prob < A.n, valid = pvalid && f < nf;
   Ctx c;
-  c.sk = &sk; c.P = &P; c.sm = smem; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
+  c.sk = &sk; c.P = &P; c.sm = smem; c.gm = smem + (size_t)sk.nb * SM_W * 32 + pg * GM_W; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
   c.V = A.ws + (size_t)blockIdx.x * NV * MAXD * 32;
   c.MC = A.mc + (size_t)blockIdx.x * MAXD * 6 * PPW;
   const size_t p64 = pvalid ? prob : 0;
@@ -489,6 +496,10 @@ __global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
       else if (f < 2) x = fmin(fmax(A.euler_mot[(p64 * nf + f) * nd + j], xo - thr), xo + thr);     // :829-838
       else x = xo;
     }
+    if (!EVAL_ONLY) {
+#pragma unroll
+      for (int q = 0; q < 2 * LB_M; ++q) VEC(c, V_S + q, j) = 0.0;                 // stale history of an earlier solve
+    }
     VEC(c, V_XO, j) = xo; VEC(c, V_DX, j) = dxv; VEC(c, V_DDX, j) = ddxv; VEC(c, V_X, j) = x; VEC(c, V_G, j) = 0.0;
     const double s = grp_sum(xo);                          // sum over the frames (:231-235); fixed order inside the shuffle tree
     VEC(c, V_SUMO, j) = s;
@@ -508,9 +519,6 @@ __global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
   const bool fr = valid && f >= 2;                         // the free variables (W2 of oracle/mmsto.py)
   int phase = pvalid ? 0 : 2, k = 1, end = 0, count = 0, ret = 0, n_eval = 0, iters = 0;
   double step = 0, finit = 0, dginit = 0, dgtest = 0, fx = 0;
-  double alpha[LB_M], ys_h[LB_M];
-#pragma unroll
-  for (int i = 0; i < LB_M; ++i) { alpha[i] = 0; ys_h[i] = 1; }
   bool firstev = true;
   for (int trip = 0; trip < 1000000; ++trip) {
     if (__all_sync(0xffffffffu, phase == 2)) break;
@@ -558,52 +566,77 @@ __global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
       else upd = true;
     }
     if (__any_sync(0xffffffffu, upd)) {
-      // s = x - xp, y = g - gp, two-loop recursion (:470-530); groups that do not update run it on dummy predicates
-      const int vs = V_S + end, vy = V_Y + end;
-      double ys = 0, yy = 0;
-      {
-        double s0 = 0, s1 = 0;
-        if (fr && upd)
-          for (int j = 0; j < nd; ++j) {
-            const double sv = VEC(c, V_X, j) - VEC(c, V_XP, j), yv = VEC(c, V_G, j) - VEC(c, V_GP, j);
-            VEC(c, vs, j) = sv; VEC(c, vy, j) = yv;
-            s0 += yv * sv; s1 += yv * yv;
-          }
-        ys = grp_sum(s0); yy = grp_sum(s1);
-      }
-      int bound = 0, jn = end;
-      if (upd) {
-#pragma unroll
-        for (int i = 0; i < LB_M; ++i) ys_h[i] = (i == end) ? ys : ys_h[i];
-        bound = LB_M <= k ? LB_M : k;
-        ++k;
-        end = (end + 1) % LB_M;
-        jn = end;
-        if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) = -VEC(c, V_G, j);
-      }
-      for (int i = 0; i < LB_M; ++i) {
-        const bool on = upd && i < bound;
-        if (on) jn = (jn + LB_M - 1) % LB_M;
-        double ysj = 1;
-#pragma unroll
-        for (int q = 0; q < LB_M; ++q) ysj = (q == jn) ? ys_h[q] : ysj;
-        const double a = dot1(c, fr && on, nd, V_S + jn, V_D) / ysj;
-        if (on) {
-#pragma unroll
-          for (int q = 0; q < LB_M; ++q) alpha[q] = (q == jn) ? a : alpha[q];
-          if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) += VEC(c, V_Y + jn, j) * (-a);
+      // s = x - xp, y = g - gp and the two-loop recursion (:470-530).  The recursion runs on COEFFICIENTS: the direction is
+      // d = cg g + sum_i cs_i s_i + cy_i y_i, and every inner product the recursion needs is an entry of the Gram matrix of
+      // {s_i, y_i, g}, of which only the rows of the new pair and of g change per iteration.  That replaces 2 m dependent
+      // dot-product / axpy passes over the workspace by m independent passes of inner products and one pass that forms d.
+      double *SS = c.gm, *SY = c.gm + 36, *YY = c.gm + 72, *gS = c.gm + 108, *gY = c.gm + 114, *cs = c.gm + 120, *cy = c.gm + 126,
+             *al = c.gm + 132, *ysv = c.gm + 138;
+      const int e = end;
+      if (fr && upd) {
+#pragma unroll 4
+        for (int j = 0; j < nd; ++j) {
+          const double sv = VEC(c, V_X, j) - VEC(c, V_XP, j), yv = VEC(c, V_G, j) - VEC(c, V_GP, j);
+          VEC(c, V_S + e, j) = sv; VEC(c, V_Y + e, j) = yv;
         }
       }
-      if (upd && fr) { const double sc = ys / yy; for (int j = 0; j < nd; ++j) VEC(c, V_D, j) *= sc; }
       for (int i = 0; i < LB_M; ++i) {
-        const bool on = upd && i < bound;
-        double ysj = 1, aj = 0;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+        if (fr && upd) {
+#pragma unroll 4
+          for (int j = 0; j < nd; ++j) {
+            const double Si = VEC(c, V_S + i, j), Yi = VEC(c, V_Y + i, j), sj = VEC(c, V_S + e, j), yj = VEC(c, V_Y + e, j), gj = VEC(c, V_G, j);
+            a0 += sj * Si; a1 += sj * Yi; a2 += yj * Si; a3 += yj * Yi; a4 += gj * Si; a5 += gj * Yi;
+          }
+        }
+        a0 = grp_sum(a0); a1 = grp_sum(a1); a2 = grp_sum(a2); a3 = grp_sum(a3); a4 = grp_sum(a4); a5 = grp_sum(a5);
+        if (upd && f == 0) {
+          SS[e * 6 + i] = a0; SS[i * 6 + e] = a0; SY[e * 6 + i] = a1; SY[i * 6 + e] = a2; YY[e * 6 + i] = a3; YY[i * 6 + e] = a3;
+          gS[i] = a4; gY[i] = a5;
+        }
+      }
+      __syncwarp();
+      if (upd) {
+        const int bound = LB_M <= k ? LB_M : k;
+        ++k;
+        end = (end + 1) % LB_M;
+        if (f == 0) {                                      // one lane per problem runs the recursion on the coefficients
+          const double ys = SY[e * 6 + e], yy = YY[e * 6 + e];
+          ysv[e] = ys;
+          for (int q = 0; q < LB_M; ++q) { cs[q] = 0; cy[q] = 0; }
+          double cg = -1.0;
+          int jn = end;
+          for (int i = 0; i < bound; ++i) {
+            jn = (jn + LB_M - 1) % LB_M;
+            double sq = cg * gS[jn];
+            for (int q = 0; q < LB_M; ++q) sq += cs[q] * SS[jn * 6 + q] + cy[q] * SY[jn * 6 + q];
+            const double a = sq / ysv[jn];
+            al[jn] = a; cy[jn] -= a;
+          }
+          const double sc = ys / yy;
+          cg *= sc;
+          for (int q = 0; q < LB_M; ++q) { cs[q] *= sc; cy[q] *= sc; }
+          for (int i = 0; i < bound; ++i) {
+            double yq = cg * gY[jn];
+            for (int q = 0; q < LB_M; ++q) yq += cs[q] * SY[q * 6 + jn] + cy[q] * YY[jn * 6 + q];
+            cs[jn] += al[jn] - yq / ysv[jn];
+            jn = (jn + 1) % LB_M;
+          }
+          c.gm[GM_CG] = cg;
+        }
+      }
+      __syncwarp();
+      if (fr && upd) {
+        double rs[LB_M], ry[LB_M];
 #pragma unroll
-        for (int q = 0; q < LB_M; ++q) { ysj = (q == jn) ? ys_h[q] : ysj; aj = (q == jn) ? alpha[q] : aj; }
-        const double beta = dot1(c, fr && on, nd, V_Y + jn, V_D) / ysj;
-        if (on) {
-          if (fr) for (int j = 0; j < nd; ++j) VEC(c, V_D, j) += VEC(c, V_S + jn, j) * (aj - beta);
-          jn = (jn + 1) % LB_M;
+        for (int q = 0; q < LB_M; ++q) { rs[q] = cs[q]; ry[q] = cy[q]; }
+        const double cg = c.gm[GM_CG];
+#pragma unroll 2
+        for (int j = 0; j < nd; ++j) {
+          double d = cg * VEC(c, V_G, j);
+#pragma unroll
+          for (int q = 0; q < LB_M; ++q) d += rs[q] * VEC(c, V_S + q, j) + ry[q] * VEC(c, V_Y + q, j);
+          VEC(c, V_D, j) = d;
         }
       }
       if (upd) { step = 1.0; begin_ls = true; }

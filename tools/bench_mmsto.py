@@ -1,0 +1,39 @@
+"""GPU throughput of the batched MMSTO solve: windows per second and objective evaluations per second at a
+fixed iteration budget, plus the numpy oracle on one host core for scale.  Usage: python tools/bench_mmsto.py [n] [max_iterations]"""
+import json, os, sys, time
+import numpy as np
+import torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+import helpers_mmsto as hm
+from ipcdnnwalk_b200 import ShortTrajOpt
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+skel = hm.skeleton()
+base = [hm.make_problem(s, skel=skel) for s in range(16)]
+ps = [base[i % 16] for i in range(n)]
+keys = ("gpos_target", "x_original", "dx", "ddx", "com", "momentum")
+dev = [torch.as_tensor(hm.stack(ps, k), device="cuda") for k in keys]
+em = torch.as_tensor(hm.stack(ps, "euler_mot"), device="cuda"); vc = torch.as_tensor(hm.stack(ps, "velcon"), device="cuda")
+opt = ShortTrajOpt(skel, hm.NF, hm.MARKERS)
+opt.set_dof_weights(hm.ankle_dof_weights(skel))
+opt.set("max_iterations", iters)
+for _ in range(2):
+    x, info = opt.solveEndEffectors_euler(em, *dev, velcon=vc)
+torch.cuda.synchronize()
+ts = []
+for _ in range(5):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); x, info = opt.solveEndEffectors_euler(em, *dev, velcon=vc); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ms = sorted(ts)[len(ts) // 2]
+ev = float(info[:, 3].sum().item())
+out = {"kernel": "mmsto_kernel<false>", "windows": n, "max_iterations": iters, "ms": ms, "windows_per_s": n / ms * 1e3,
+       "evaluations": ev, "evaluations_per_s": ev / ms * 1e3, "evals_per_window": ev / n, "dtype": "f64"}
+if "--cpu" in sys.argv:
+    o = hm.oracle_opt(base[0], skel, dof_weights=hm.ankle_dof_weights(skel))
+    t = time.perf_counter(); X, inf = o.solve(base[0]["euler_mot"], max_iterations=iters); dt = time.perf_counter() - t
+    out["oracle_numpy_1core"] = {"s_per_window": dt, "evaluations": inf["evaluations"], "evaluations_per_s": inf["evaluations"] / dt}
+print(json.dumps(out))
+opt.close()
