@@ -159,6 +159,13 @@ __device__ double evaluate(Ctx& c, bool first) {
 
   // ---------------- forward sweep: Tree::Compute + ComputeDS + calcCOM + calcMomentumCOM of this frame
   double comacc[3] = {0, 0, 0}, Hm[3] = {0, 0, 0}, Hf[3] = {0, 0, 0};
+  double qn[3], dqn[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const int j = sk.dof0[0] + ch;
+    qn[ch] = valid ? VEC(c, V_X, j) : 0.0;
+    dqn[ch] = has_next ? c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] : 0.0;
+  }
   for (int b = 0; b < sk.nb; ++b) {
     double R[9], t[3], w[3], v[3];
     const int p = sk.parent[b];
@@ -181,13 +188,18 @@ __device__ double evaluate(Ctx& c, bool first) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { t[k] = tp[k] + d[k]; w[k] = wp[k]; v[k] = vp[k] + x[k]; }
     }
-    const int j0 = sk.dof0[b], nc = sk.nchan[b];
+    const int nc = sk.nchan[b];
     double qv[3], dqv[3];
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {                       // all loads of the bone first (they are independent)
-      const int j = j0 + (ch < nc ? ch : 0);
-      qv[ch] = valid ? VEC(c, V_X, j) : 0.0;
-      dqv[ch] = has_next ? c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] : 0.0;
+    for (int ch = 0; ch < 3; ++ch) { qv[ch] = qn[ch]; dqv[ch] = dqn[ch]; }
+    if (b + 1 < sk.nb) {                                   // the angles of the next bone are fetched while this one is computed
+      const int jb = sk.dof0[b + 1], ncn = sk.nchan[b + 1];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const int j = jb + (ch < ncn ? ch : 0);
+        qn[ch] = valid ? VEC(c, V_X, j) : 0.0;
+        dqn[ch] = has_next ? c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] : 0.0;
+      }
     }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -400,7 +412,7 @@ __device__ double evaluate(Ctx& c, bool first) {
     const bool ctr = valid && f >= 1 && f <= nf - 2;       // this frame is the centre i of a ddx / dx term
     const bool ctr_n = valid && f + 1 >= 1 && f + 1 <= nf - 2, ctr_p = valid && f - 1 >= 1 && f - 1 <= nf - 2;
     double oq = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < nd; ++j) {
       // the frames of a problem sit in neighbouring lanes: neighbours' values by shuffle instead of reloading them
       const double gold = VEC(c, V_G, j);
@@ -583,7 +595,7 @@ __global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
       for (int i = 0; i < LB_M; ++i) {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
         if (fr && upd) {
-#pragma unroll 4
+#pragma unroll 8
           for (int j = 0; j < nd; ++j) {
             const double Si = VEC(c, V_S + i, j), Yi = VEC(c, V_Y + i, j), sj = VEC(c, V_S + e, j), yj = VEC(c, V_Y + e, j), gj = VEC(c, V_G, j);
             a0 += sj * Si; a1 += sj * Yi; a2 += yj * Si; a3 += yj * Yi; a4 += gj * Si; a5 += gj * Yi;
