@@ -79,7 +79,7 @@ static int prepare(mmsto_solver* s, int n) {
 }
 
 template <bool EVAL_ONLY> static int launch(mmsto_solver* s, mmsto::Args& A, void* stream) {
-  const size_t smem = ((size_t)s->sk.nb * mmsto::SM_W * 32 + mmsto::PPW * mmsto::GM_W) * sizeof(double);
+  const size_t smem = (((size_t)s->sk.nb * mmsto::SM_W + mmsto::STK_LEVELS * mmsto::STK_W) * 32 + mmsto::PPW * mmsto::GM_W) * sizeof(double);
   auto kern = mmsto::mmsto_kernel<EVAL_ONLY>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int warps = (A.n + mmsto::PPW - 1) / mmsto::PPW;
@@ -119,6 +119,8 @@ int mmsto_create(int32_t device, int32_t nb, const int32_t* parent, const double
       for (int k = 0; k < 3; ++k) sk.axis[b][k] = k < nchan[b] ? axes[b * 3 + k] : 0;
     }
     sk.dof0[b] = d; d += sk.nchan[b];
+    sk.depth[b] = b == 0 ? 0 : sk.depth[parent[b]] + 1;
+    if (sk.depth[b] >= mmsto::STK_LEVELS) { delete s; return fail(-1, "mmsto_create: tree depth <= 8 bones required"); }
     for (int k = 0; k < 3; ++k) { sk.off[b][k] = offset[b * 3 + k]; sk.com[b][k] = local_com[b * 3 + k]; }
     sk.mass[b] = mass[b]; sk.total_mass += mass[b];
     const double* I = inertia + b * 9;

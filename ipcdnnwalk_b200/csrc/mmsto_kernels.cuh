@@ -17,7 +17,7 @@ namespace mmsto {
 
 enum { MAXB = 24, MAXD = 64, NFMAX = 8, NMARK = 4, MAXHS = 4, HS_W = 10, LB_M = 6, GRP = 8, PPW = 4,
        V_X = 0, V_G, V_D, V_XP, V_GP, V_XO, V_DX, V_DDX, V_SUMO, V_S, V_Y = V_S + LB_M, NV = V_Y + LB_M,
-       SM_W = 21, SM_R = 0, SM_T = 9, SM_A = 12, SM_WM = 18,
+       SM_W = 7, SM_Q = 0, SM_T = 4, STK_LEVELS = 8, STK_W = 6,
        GM_CG = 144, GM_W = 152 };   // per-problem L-BFGS scalars in shared memory: Gram matrices 3 x 36, g.S, g.Y, coefficients, alpha, ys
 
 enum { LBFGS_SUCCESS = 0, LBFGS_ALREADY_MINIMIZED = 2, LBFGSERR_MINIMUMSTEP = -1000, LBFGSERR_MAXIMUMSTEP = -999,
@@ -25,7 +25,7 @@ enum { LBFGS_SUCCESS = 0, LBFGS_ALREADY_MINIMIZED = 2, LBFGSERR_MINIMUMSTEP = -1
 
 struct Skel {
   int nb, ndof;
-  int parent[MAXB], nchan[MAXB], axis[MAXB][3], dof0[MAXB], sub_end[MAXB];
+  int parent[MAXB], nchan[MAXB], axis[MAXB][3], dof0[MAXB], sub_end[MAXB], depth[MAXB];
   double off[MAXB][3], mass[MAXB], com[MAXB][3], inertia[MAXB][6];   // inertia: xx yy zz xy xz yz
   double total_mass;
 };
@@ -91,32 +91,57 @@ struct Ctx {
 
 #define VEC(ctx, v, j) (ctx).V[((size_t)(v) * MAXD + (j)) * 32 + (ctx).lane]
 #define SMB(ctx, b, k) (ctx).sm[((b) * SM_W + (k)) * 32 + (ctx).lane]
+#define STK(ctx, d, k) (ctx).sm[(((ctx).sk->nb * SM_W) + (d) * STK_W + (k)) * 32 + (ctx).lane]
 
-__device__ __forceinline__ void load_frame(const Ctx& c, int b, double* R, double* t) {
+// unit quaternion (w x y z) -> rotation matrix, row major
+__device__ __forceinline__ void quat_to_mat(const double* q, double* R) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  R[0] = 1.0 - 2.0 * (yy + zz); R[1] = 2.0 * (xy - wz); R[2] = 2.0 * (xz + wy);
+  R[3] = 2.0 * (xy + wz); R[4] = 1.0 - 2.0 * (xx + zz); R[5] = 2.0 * (yz - wx);
+  R[6] = 2.0 * (xz - wy); R[7] = 2.0 * (yz + wx); R[8] = 1.0 - 2.0 * (xx + yy);
+}
+// column a of the rotation matrix of q: the world direction of the local axis a
+__device__ __forceinline__ void quat_col(const double* q, int a, double* W) {
+  const int u = a == 2 ? 0 : a + 1, v = u == 2 ? 0 : u + 1;
+  const double w = q[0], qa = q[1 + a], qu = q[1 + u], qv = q[1 + v];
+  W[a] = 1.0 - 2.0 * (qu * qu + qv * qv); W[u] = 2.0 * (qa * qu + w * qv); W[v] = 2.0 * (qa * qv - w * qu);
+}
+// q <- q * (cos, sin e_a): right-multiplied rotation about the local axis a by the angle whose HALF has sine s, cosine c
+__device__ __forceinline__ void quat_rot_axis(double* q, int a, double s, double c) {
+  const int u = a == 2 ? 0 : a + 1, v = u == 2 ? 0 : u + 1;
+  const double w = q[0], qa = q[1 + a], qu = q[1 + u], qv = q[1 + v];
+  q[0] = w * c - qa * s; q[1 + a] = qa * c + w * s; q[1 + u] = qu * c + qv * s; q[1 + v] = qv * c - qu * s;
+}
+__device__ __forceinline__ void load_quat(const Ctx& c, int b, double* q) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = SMB(c, b, SM_R + k);
+  for (int k = 0; k < 4; ++k) q[k] = SMB(c, b, SM_Q + k);
+}
+__device__ __forceinline__ void load_frame(const Ctx& c, int b, double* R, double* t) {
+  double q[4];
+  load_quat(c, b, q);
+  quat_to_mat(q, R);
 #pragma unroll
   for (int k = 0; k < 3; ++k) t[k] = SMB(c, b, SM_T + k);
 }
-// world axis of channel ch of bone b (HingeJoint::ComputeW): first channel = column of the parent frame, last = column of
-// the bone frame, middle = stored in the forward sweep
+// world axis of channel ch of bone b (HingeJoint::ComputeW).  Only the bone frames are kept (as quaternions): the last
+// channel's axis is a column of the bone frame, the first one a column of the parent frame, and a middle one is rebuilt
+// from the parent frame and the preceding angle(s)
 __device__ __forceinline__ void hinge_axis(const Ctx& c, int b, int ch, double* W) {
   const Skel& sk = *c.sk;
   const int a = sk.axis[b][ch], nc = sk.nchan[b];
-  if (ch == nc - 1) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) W[r] = SMB(c, b, SM_R + r * 3 + a);
-  } else if (ch == 0) {
+  double q[4];
+  if (ch == nc - 1) load_quat(c, b, q);
+  else {
     const int p = sk.parent[b];
-    if (p < 0) { W[0] = a == 0; W[1] = a == 1; W[2] = a == 2; }
-    else {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) W[r] = SMB(c, p, SM_R + r * 3 + a);
+    if (p < 0) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else load_quat(c, p, q);
+    for (int k = 0; k < ch; ++k) {
+      double sn, cs;
+      sincos(0.5 * (c.valid ? VEC(c, V_X, sk.dof0[b] + k) : 0.0), &sn, &cs);
+      quat_rot_axis(q, sk.axis[b][k], sn, cs);
     }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) W[r] = SMB(c, b, SM_WM + r);
   }
+  quat_col(q, a, W);
 }
 
 // momentum about `C` of bone b moving with world angular velocity w and origin velocity v (Liegroup.cpp:66-74 Inertia * se3,
@@ -141,13 +166,6 @@ __device__ __forceinline__ void bone_momentum(const Skel& sk, int b, const doubl
   for (int k = 0; k < 3; ++k) { Hm[k] += Mw[k] + tmp[k]; Hf[k] += Fw[k]; }
 }
 
-__device__ __forceinline__ void add_force(const Ctx& c, int b, const double* p, const double* F) {
-  double N[3];
-  cross3(p, F, N);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { SMB(c, b, SM_A + k) += F[k]; SMB(c, b, SM_A + 3 + k) += N[k]; }
-}
-
 // One evaluation of LBFGS_opta's function at V_X: objective (same value on the 8 lanes of a problem) and, in V_G, the
 // gradient of this lane's frame.  `first`: rebuild the momentum-Jacobian cache (shortTermOptimizer.lua:669-684).
 __device__ double evaluate(Ctx& c, bool first) {
@@ -167,22 +185,23 @@ __device__ double evaluate(Ctx& c, bool first) {
     dqn[ch] = has_next ? c.V[((size_t)V_X * MAXD + j) * 32 + c.lane + 1] : 0.0;
   }
   for (int b = 0; b < sk.nb; ++b) {
-    double R[9], t[3], w[3], v[3];
-    const int p = sk.parent[b];
+    double q[4], R[9], t[3], w[3], v[3];
+    const int p = sk.parent[b], dep = sk.depth[b];
     if (p < 0) {
-      R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+      q[0] = 1; q[1] = q[2] = q[3] = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double q = valid ? VEC(c, V_X, k) : 0.0;
-        t[k] = sk.off[b][k] + q;
-        v[k] = has_next ? (c.V[((size_t)V_X * MAXD + k) * 32 + c.lane + 1] - q) * INV : 0.0;
+        const double x0 = valid ? VEC(c, V_X, k) : 0.0;
+        t[k] = sk.off[b][k] + x0;
+        v[k] = has_next ? (c.V[((size_t)V_X * MAXD + k) * 32 + c.lane + 1] - x0) * INV : 0.0;
         w[k] = 0.0;
       }
     } else {
       double tp[3], wp[3], vp[3], d[3], x[3];
-      load_frame(c, p, R, tp);
+      load_quat(c, p, q);
+      quat_to_mat(q, R);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { wp[k] = SMB(c, p, SM_A + k); vp[k] = SMB(c, p, SM_A + 3 + k); }
+      for (int k = 0; k < 3; ++k) { tp[k] = SMB(c, p, SM_T + k); wp[k] = STK(c, dep - 1, k); vp[k] = STK(c, dep - 1, 3 + k); }
       mat_vec(R, sk.off[b], d);
       cross3(wp, d, x);
 #pragma unroll
@@ -205,20 +224,21 @@ __device__ double evaluate(Ctx& c, bool first) {
     for (int ch = 0; ch < 3; ++ch) {
       if (ch < nc) {
         const int a = sk.axis[b][ch];
-        const double W0 = R[a], W1 = R[3 + a], W2 = R[6 + a];
-        if (ch == 1 && nc == 3) { SMB(c, b, SM_WM) = W0; SMB(c, b, SM_WM + 1) = W1; SMB(c, b, SM_WM + 2) = W2; }
-        const double q = qv[ch];
-        const double dq = has_next ? (dqv[ch] - q) * INV : 0.0;
-        double s, cs;
-        sincos(q, &s, &cs);
-        rot_axis(R, a, s, cs);
-        w[0] += W0 * dq; w[1] += W1 * dq; w[2] += W2 * dq;
+        double W[3];
+        quat_col(q, a, W);
+        const double th = qv[ch];
+        const double dq = has_next ? (dqv[ch] - th) * INV : 0.0;
+        double sn, cs;
+        sincos(0.5 * th, &sn, &cs);
+        quat_rot_axis(q, a, sn, cs);
+        w[0] += W[0] * dq; w[1] += W[1] * dq; w[2] += W[2] * dq;
       }
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) SMB(c, b, SM_R + k) = R[k];
+    for (int k = 0; k < 4; ++k) SMB(c, b, SM_Q + k) = q[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { SMB(c, b, SM_T + k) = t[k]; SMB(c, b, SM_A + k) = w[k]; SMB(c, b, SM_A + 3 + k) = v[k]; }
+    for (int k = 0; k < 3; ++k) { SMB(c, b, SM_T + k) = t[k]; STK(c, dep, k) = w[k]; STK(c, dep, 3 + k) = v[k]; }
+    quat_to_mat(q, R);
     double cb[3];
     mat_vec(R, sk.com[b], cb);
 #pragma unroll
@@ -287,12 +307,14 @@ __device__ double evaluate(Ctx& c, bool first) {
     }
     if (use) o += ss * P.w_mom * fl;
   }
-  // zero the force accumulators (they alias the velocity slots, which are not needed any more)
-  for (int b = 0; b < sk.nb; ++b)
+  // point forces of this frame, applied when the reverse sweep visits their bone
+  double Fm[NMARK][3], cfh[MAXHS], Fcom[3] = {0, 0, 0};
+  bool com_on = false;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) SMB(c, b, SM_A + k) = 0.0;
+  for (int h = 0; h < MAXHS; ++h) cfh[h] = 0.0;
 
   // marker terms (:713-784)
+#pragma unroll
   for (int m = 0; m < NMARK; ++m) {
     const int b = P.mbone[m];
     double R[9], t[3], pm[3], F[3] = {0, 0, 0};
@@ -326,10 +348,12 @@ __device__ double evaluate(Ctx& c, bool first) {
         for (int k = 0; k < 3; ++k) F[k] += -(2.0 * w / cnt) * dC[k];
       }
     }
-    if (valid) add_force(c, b, pm, F);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Fm[m][k] = valid ? F[k] : 0.0;
   }
   // velocity half-space terms (:466-503): frame fc against frame fc - 1, fc >= 2
   if (P.w_velhs != 0) {
+#pragma unroll
     for (int h = 0; h < MAXHS; ++h) {
       const double* hc = c.velcon + h * HS_W;
       const int fc = (int)hc[0];
@@ -349,12 +373,8 @@ __device__ double evaluate(Ctx& c, bool first) {
       const double* nrm = hc + 3;
       const double d = (nrm[0] * hc[2] - gv[0]) * nrm[0] + (nrm[1] * hc[2] - gv[1]) * nrm[1] + (nrm[2] * hc[2] - gv[2]) * nrm[2];
       if (act && valid && d > 0 && (f == fc || f == fc - 1)) {
-        const double sgn = f == fc ? -1.0 : 1.0;
-        double F[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) F[k] = sgn * (2.0 * P.w_velhs * INV * d) * nrm[k];
+        cfh[h] = (f == fc ? -1.0 : 1.0) * (2.0 * P.w_velhs * INV * d);      // force = cfh * normal at the constrained point
         if (f == fc) o += d * d * P.w_velhs;
-        add_force(c, b, pm, F);
       }
     }
   }
@@ -367,23 +387,48 @@ __device__ double evaluate(Ctx& c, bool first) {
     for (int k = 0; k < 3; ++k) dS[k] = grp_sum(use ? c.comt[k] - C[k] : 0.0) * (1.0 / fs);
     if (f == 0) o += dot3(dS, dS) * P.w_com;
     if (use) {
-      for (int b = 0; b < sk.nb; ++b) {
-        double R[9], t[3], cb[3], F[3];
-        load_frame(c, b, R, t);
-        mat_vec(R, sk.com[b], cb);
-        const double s = (-2.0 * P.w_com / fs) * (sk.mass[b] / sk.total_mass);
+      com_on = true;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { cb[k] += t[k]; F[k] = s * dS[k]; }
-        add_force(c, b, cb, F);
-      }
+      for (int k = 0; k < 3; ++k) Fcom[k] = (-2.0 * P.w_com / fs) * dS[k] * (1.0 / sk.total_mass);      // times the bone mass, at the bone CoM
     }
   }
 
-  // ---------------- reverse sweep: g_j = W_j . (N - s_j x F) for hinges, W_j . F for slides (Node.cpp:386-400,466-469)
-  for (int b = sk.nb - 1; b >= 0; --b) {
-    double F[3], N[3], t[3], x[3], tau[3];
+  // ---------------- reverse sweep: g_j = W_j . (N - s_j x F) for hinges, W_j . F for slides (Node.cpp:386-400,466-469).
+  // Bones are stored depth first, so when bone b is reached level depth[b] of the stack holds exactly the sum over its children.
+  for (int d = 0; d < STK_LEVELS; ++d)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { F[k] = SMB(c, b, SM_A + k); N[k] = SMB(c, b, SM_A + 3 + k); t[k] = SMB(c, b, SM_T + k); }
+    for (int k = 0; k < STK_W; ++k) STK(c, d, k) = 0.0;
+  for (int b = sk.nb - 1; b >= 0; --b) {
+    const int dep = sk.depth[b];
+    double F[3], N[3], R[9], t[3], x[3], tau[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { F[k] = STK(c, dep, k); N[k] = STK(c, dep, 3 + k); STK(c, dep, k) = 0.0; STK(c, dep, 3 + k) = 0.0; }
+    load_frame(c, b, R, t);
+    auto push = [&](const double* lp, const double* Fp) {
+      double pw[3], n[3];
+      mat_vec(R, lp, pw);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pw[k] += t[k];
+      cross3(pw, Fp, n);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { F[k] += Fp[k]; N[k] += n[k]; }
+    };
+#pragma unroll
+    for (int m = 0; m < NMARK; ++m) if (P.mbone[m] == b) push(P.mlpos[m], Fm[m]);
+    if (P.w_velhs != 0) {
+#pragma unroll
+      for (int h = 0; h < MAXHS; ++h) {
+        const double* hc = c.velcon + h * HS_W;
+        if (cfh[h] != 0.0 && (int)hc[1] == b) {
+          const double Fp[3] = {cfh[h] * hc[3], cfh[h] * hc[4], cfh[h] * hc[5]};
+          push(hc + 6, Fp);
+        }
+      }
+    }
+    if (com_on) {
+      const double Fp[3] = {Fcom[0] * sk.mass[b], Fcom[1] * sk.mass[b], Fcom[2] * sk.mass[b]};
+      push(sk.com[b], Fp);
+    }
     cross3(t, F, x);
 #pragma unroll
     for (int k = 0; k < 3; ++k) tau[k] = N[k] - x[k];
@@ -392,10 +437,9 @@ __device__ double evaluate(Ctx& c, bool first) {
       hinge_axis(c, b, ch, W);
       if (valid) VEC(c, V_G, sk.dof0[b] + ch) = dot3(W, tau);
     }
-    const int p = sk.parent[b];
-    if (p >= 0) {
+    if (sk.parent[b] >= 0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { SMB(c, p, SM_A + k) += F[k]; SMB(c, p, SM_A + 3 + k) += N[k]; }
+      for (int k = 0; k < 3; ++k) { STK(c, dep - 1, k) += F[k]; STK(c, dep - 1, 3 + k) += N[k]; }
     } else if (valid) {
       VEC(c, V_G, 0) = F[0]; VEC(c, V_G, 1) = F[1]; VEC(c, V_G, 2) = F[2];
     }
@@ -476,14 +520,14 @@ __device__ __forceinline__ double dot1(const Ctx& c, bool fr, int nd, int a, int
 }
 
 template <bool EVAL_ONLY>
-__global__ void __launch_bounds__(32, 1) mmsto_kernel(const Args A) {
+__global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
   extern __shared__ double smem[];
   const Skel& sk = *A.sk; const Prm& P = *A.prm;
   const int lane = threadIdx.x, f = lane & 7, pg = lane >> 3, nf = P.nf, nd = sk.ndof;
   const int prob = blockIdx.x * PPW + pg;
   const bool pvalid = prob < A.n, valid = pvalid && f < nf;
   Ctx c;
-  c.sk = &sk; c.P = &P; c.sm = smem; c.gm = smem + (size_t)sk.nb * SM_W * 32 + pg * GM_W; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
+  c.sk = &sk; c.P = &P; c.sm = smem; c.gm = smem + ((size_t)sk.nb * SM_W + STK_LEVELS * STK_W) * 32 + pg * GM_W; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
   c.V = A.ws + (size_t)blockIdx.x * NV * MAXD * 32;
   c.MC = A.mc + (size_t)blockIdx.x * MAXD * 6 * PPW;
   const size_t p64 = pvalid ? prob : 0;
