@@ -52,6 +52,16 @@ int mmsto_solve(mmsto_solver* s, int32_t n, const double* x_original, const doub
 int mmsto_evaluate(mmsto_solver* s, int32_t n, const double* x, const double* x_original, const double* dx, const double* ddx,
                    const double* gpos_target, const double* com, const double* momentum, const int32_t* con,
                    const double* velcon, double* obj, double* grad, void* stream);
+/* removeCOMsliding_online (gym_trackSRB/taesooLib/DeltaExtractor.py:421-512; called right after the solve,
+ * walk_SRBTrack2025.py:617, walk_SRBTrack2025_terrain_singlethreaded.py:610): for every window of nvar (<= 8) poses
+ *   poses [n][nvar][ndof + 1]  MotionDOF rows (root xyz, root quaternion w x y z, joint angles), updated IN PLACE
+ *   com_srb, desired_com [n][nvar][3]; fix_y_also as in the reference; ground_h [n][nvar] = terrain height under each
+ *   current CoM (what projectToGround returns there; get the CoMs with mmsto_window_com) or NULL for no projection
+ *   curr_com_out / opt_com_out [n][nvar][3]: optional outputs (currCOM, optCOM). */
+int mmsto_remove_com_sliding(mmsto_solver* s, int32_t n, int32_t nvar, double* poses, const double* com_srb, const double* desired_com,
+                             int32_t fix_y_also, const double* ground_h, double* curr_com_out, double* opt_com_out, void* stream);
+/* CoM of every pose of every window (mLoader_full.setPoseDOF + calcCOM, DeltaExtractor.py:428-430): com_out [n][nvar][3] */
+int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* poses, double* com_out, void* stream);
 long long mmsto_launch_count(mmsto_solver* s);
 const char* mmsto_last_error(void);
 

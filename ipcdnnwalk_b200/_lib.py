@@ -108,6 +108,8 @@ _MMSTO_SIGNATURES = {       # include/mmsto_b200.h
     "mmsto_set_dof_weights": (C.c_int, [_P, _P]),
     "mmsto_solve": (C.c_int, [_P, C.c_int32] + [_P] * 11 + [_P]),
     "mmsto_evaluate": (C.c_int, [_P, C.c_int32] + [_P] * 11 + [_P]),
+    "mmsto_remove_com_sliding": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "mmsto_window_com": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmsto_launch_count": (C.c_int64, [_P]),
     "mmsto_last_error": (C.c_char_p, []),
 }

@@ -212,6 +212,36 @@ int mmsto_evaluate(mmsto_solver* s, int32_t n, const double* x, const double* x_
   return launch<true>(s, A, stream);
 }
 
+int mmsto_remove_com_sliding(mmsto_solver* s, int32_t n, int32_t nvar, double* poses, const double* com_srb, const double* desired_com,
+                             int32_t fix_y_also, const double* ground_h, double* curr_com_out, double* opt_com_out, void* stream) {
+  if (!s) return fail(-1, "mmsto_remove_com_sliding: null solver");
+  if (n <= 0) return 0;
+  if (nvar < 4 || nvar > mmsto::NFMAX) return fail(-1, "mmsto_remove_com_sliding: 4 <= nvar <= 8 required");
+  if (!poses || !com_srb || !desired_com) return fail(-1, "mmsto_remove_com_sliding: null array");
+  CK(cudaSetDevice(s->device));
+  mmsto::ComSlideArgs A{};
+  A.n = n; A.nvar = nvar; A.npose = s->sk.ndof + 1; A.fix_y = fix_y_also; A.com_only = 0; A.poses = poses; A.com_srb = com_srb;
+  A.desired_com = desired_com; A.ground_h = ground_h; A.curr_out = curr_com_out; A.opt_out = opt_com_out; A.sk = s->d_sk;
+  mmsto::comslide_kernel<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(A);
+  CK(cudaGetLastError());
+  ++s->launches;
+  return 0;
+}
+
+int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* poses, double* com_out, void* stream) {
+  if (!s) return fail(-1, "mmsto_window_com: null solver");
+  if (n <= 0) return 0;
+  if (nvar < 1 || nvar > mmsto::NFMAX) return fail(-1, "mmsto_window_com: 1 <= nvar <= 8 required");
+  if (!poses || !com_out) return fail(-1, "mmsto_window_com: null array");
+  CK(cudaSetDevice(s->device));
+  mmsto::ComSlideArgs A{};
+  A.n = n; A.nvar = nvar; A.npose = s->sk.ndof + 1; A.com_only = 1; A.poses = const_cast<double*>(poses); A.curr_out = com_out; A.sk = s->d_sk;
+  mmsto::comslide_kernel<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(A);
+  CK(cudaGetLastError());
+  ++s->launches;
+  return 0;
+}
+
 long long mmsto_launch_count(mmsto_solver* s) { return s ? s->launches : 0; }
 
 }  // extern "C"

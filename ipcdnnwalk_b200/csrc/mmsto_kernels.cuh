@@ -722,3 +722,164 @@ __global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
 }
 
 }  // namespace mmsto
+
+// ---------------------------------------------------------------------------------------------------------------------
+// removeCOMsliding_online (gym_trackSRB/taesooLib/DeltaExtractor.py:421-512), SURVEY 8f rank 2: the step after the MMSTO
+// solve in the online loop.  8 lanes per window (lane = frame of the nvar <= 8 poses), 16 windows per 128-thread CTA.
+// Per lane: CoM of its pose (quaternion-root FK, parent frames on a depth-indexed stack); lanes 0..2 of a window then
+// solve the three 1-D hard-constrained smoothing problems (QuadraticFunctionHardCon: KKT system of nvar + 3 unknowns,
+// Gaussian elimination with partial pivoting as math.LUsolve); every lane finally moves its root so that the CoM lands
+// on the optimised one, leaning about the ground point (plusCOM * R * minusCOM).
+namespace mmsto {
+
+struct ComSlideArgs {
+  int n, nvar, npose, fix_y, com_only;
+  double* poses;                 // [n][nvar][npose] in/out
+  const double *com_srb, *desired_com, *ground_h;
+  double *curr_out, *opt_out;
+  const Skel* sk;
+};
+
+__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* o) {
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+  o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+
+__global__ void __launch_bounds__(128) comslide_kernel(const ComSlideArgs A) {
+  __shared__ double xs[16][3][NFMAX];
+  const Skel& sk = *A.sk;
+  const int lane = threadIdx.x & 31, f = lane & 7, wl = threadIdx.x >> 3;           // wl: window within the CTA
+  const int win = blockIdx.x * 16 + wl, nvar = A.nvar;
+  const bool pvalid = win < A.n, valid = pvalid && f < nvar;
+  const size_t w64 = pvalid ? win : 0;
+  double* pose = A.poses + (w64 * nvar + (valid ? f : 0)) * A.npose;
+
+  // ---- CoM of this pose (BoneForwardKinematics::setPoseDOF + calcCOM; root quaternion normalised as quater::normalize)
+  double sq[STK_LEVELS][4], st[STK_LEVELS][3];
+  double com[3] = {0, 0, 0}, rootq[4], roott[3];
+  {
+    double q0[4] = {pose[3], pose[4], pose[5], pose[6]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rootq[k] = q0[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) roott[k] = pose[k];
+    int ja = 7;
+    for (int b = 0; b < sk.nb; ++b) {
+      const int dep = sk.depth[b];
+      double q[4], t[3], R[9];
+      if (b == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = q0[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = pose[k] + sk.off[0][k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = sq[dep - 1][k];
+        quat_to_mat(q, R);
+        double d[3];
+        mat_vec(R, sk.off[b], d);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = st[dep - 1][k] + d[k];
+        for (int ch = 0; ch < sk.nchan[b]; ++ch) {
+          double sn, cs;
+          sincos(0.5 * pose[ja + ch], &sn, &cs);
+          quat_rot_axis(q, sk.axis[b][ch], sn, cs);
+        }
+        ja += sk.nchan[b];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sq[dep][k] = q[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) st[dep][k] = t[k];
+      quat_to_mat(q, R);
+      double cb[3];
+      mat_vec(R, sk.com[b], cb);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) com[k] += (cb[k] + t[k]) * sk.mass[b];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) com[k] *= 1.0 / sk.total_mass;
+  }
+  if (valid && A.curr_out) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) A.curr_out[(w64 * nvar + f) * 3 + k] = com[k];
+  }
+  if (A.com_only) return;
+
+  // ---- three hard-constrained 1-D problems per window: lane `dim` of the window solves dimension dim
+  double c0[3], c1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { c0[k] = __shfl_sync(0xffffffffu, com[k], (lane & ~7) + 0); c1[k] = __shfl_sync(0xffffffffu, com[k], (lane & ~7) + 1); }
+  if (pvalid && f < 3) {
+    const int dim = f, N = nvar + 3;
+    double K[11][12];
+    for (int r = 0; r < N; ++r) for (int cc = 0; cc <= N; ++cc) K[r][cc] = 0.0;
+    const double* cs = A.com_srb + w64 * nvar * 3;
+    const double s = sqrt(1.5);
+    for (int v = 1; v < nvar - 1; ++v) {
+      const double cf[3] = {s * -1.0, s * 2.0, s * -1.0};
+      const double cst = s * (-1 * (-1 * cs[(v - 1) * 3 + dim] + 2 * cs[v * 3 + dim] - cs[(v + 1) * 3 + dim]));
+      for (int a = 0; a < 3; ++a) {
+        K[v - 1 + a][v - 1 + a] += 2.0 * cf[a] * cf[a];
+        for (int b2 = a + 1; b2 < 3; ++b2) { K[v - 1 + a][v - 1 + b2] += 2.0 * cf[a] * cf[b2]; K[v - 1 + b2][v - 1 + a] = K[v - 1 + a][v - 1 + b2]; }
+        K[v - 1 + a][N] -= 2.0 * cst * cf[a];
+      }
+    }
+    K[nvar][0] = 1.0; K[0][nvar] = 1.0; K[nvar][N] = dim == 0 ? c0[0] : dim == 1 ? c0[1] : c0[2];
+    K[nvar + 1][1] = 1.0; K[1][nvar + 1] = 1.0; K[nvar + 1][N] = dim == 0 ? c1[0] : dim == 1 ? c1[1] : c1[2];
+    double sum = 0.0;
+    for (int v = 0; v < nvar - 1; ++v) sum += A.desired_com[(w64 * nvar + v) * 3 + dim];
+    for (int v = 1; v < nvar; ++v) { K[nvar + 2][v] = 1.0; K[v][nvar + 2] = 1.0; }
+    K[nvar + 2][N] = sum;
+    for (int col = 0; col < N; ++col) {                    // Gaussian elimination, partial pivoting
+      int piv = col; double best = fabs(K[col][col]);
+      for (int r = col + 1; r < N; ++r) if (fabs(K[r][col]) > best) { best = fabs(K[r][col]); piv = r; }
+      if (piv != col) for (int cc = col; cc <= N; ++cc) { const double tmp = K[col][cc]; K[col][cc] = K[piv][cc]; K[piv][cc] = tmp; }
+      const double inv = 1.0 / K[col][col];
+      for (int r = col + 1; r < N; ++r) {
+        const double m = K[r][col] * inv;
+        if (m != 0.0) for (int cc = col; cc <= N; ++cc) K[r][cc] -= m * K[col][cc];
+      }
+    }
+    for (int r = N - 1; r >= 0; --r) {
+      double acc = K[r][N];
+      for (int cc = r + 1; cc < N; ++cc) acc -= K[r][cc] * K[cc][N];
+      K[r][N] = acc / K[r][r];
+    }
+    for (int v = 0; v < nvar; ++v) xs[wl][dim][v] = K[v][N];
+  }
+  __syncthreads();
+  if (!valid) return;
+  double opt[3] = {xs[wl][0][f], xs[wl][1][f], xs[wl][2][f]};
+  if (!A.fix_y) opt[1] = com[1];
+  if (A.opt_out) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) A.opt_out[(w64 * nvar + f) * 3 + k] = opt[k];
+  }
+  // ---- root <- T(opt) * R * T(-curr) * root, R = rotation by -|delta| * height * 0.5 about delta x up
+  const double dx = opt[0] - com[0], dz = opt[2] - com[2];
+  double axis[3] = {-dz, 0.0, dx};                          // (dx, 0, dz) x (0, 1, 0)
+  const double ln = sqrt(axis[0] * axis[0] + axis[2] * axis[2]);
+  const double il = ln == 0 ? 0.0 : 1.0 / ln;
+  axis[0] *= il; axis[2] *= il;
+  double cy = com[1];
+  if (A.ground_h) cy -= A.ground_h[w64 * nvar + f];
+  const double ang = -sqrt(dx * dx + dz * dz) * cy * 0.5;
+  double sn, cs;
+  sincos(0.5 * ang, &sn, &cs);
+  const double Rq[4] = {cs, sn * axis[0], sn * axis[1], sn * axis[2]};
+  double nq[4], R[9], d[3], nt[3];
+  quat_mul(Rq, rootq, nq);
+  quat_to_mat(Rq, R);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d[k] = roott[k] - com[k];
+  mat_vec(R, d, nt);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pose[k] = nt[k] + opt[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pose[3 + k] = nq[k];
+}
+
+}  // namespace mmsto

@@ -206,6 +206,32 @@ class ShortTrajOpt:
                                                  _ptr(obj), _ptr(grad), st))
         return obj, grad
 
+    # ---- the step after the solve (DeltaExtractor.py:421-512)
+    def removeCOMsliding_online(self, com_srb, desired_com, output, fix_y_also=True, ground_h=None):
+        """output [n, nvar, ndof + 1] poses (torch.float64 on the device, updated in place); com_srb, desired_com [n, nvar, 3];
+        ground_h [n, nvar] terrain height under the current CoMs or None -> (currCOM, optCOM) [n, nvar, 3]."""
+        torch = self.torch
+        assert torch.is_tensor(output) and output.is_cuda and output.dtype == torch.float64 and output.is_contiguous()
+        n, nvar, npose = output.shape
+        if npose != self.ndof + 1:
+            raise ValueError(f"poses have {npose} columns, expected {self.ndof + 1}")
+        cs = self._dev(com_srb, (n, nvar, 3)); dc = self._dev(desired_com, (n, nvar, 3))
+        gh = self._dev(ground_h, (n, nvar)) if ground_h is not None else None
+        curr = torch.empty(n, nvar, 3, dtype=torch.float64, device=self.device); opt = torch.empty_like(curr)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _check(self.lib, self.lib.mmsto_remove_com_sliding(self._h, n, nvar, _ptr(output), _ptr(cs), _ptr(dc), int(bool(fix_y_also)), _ptr(gh),
+                                                           _ptr(curr), _ptr(opt), st))
+        return curr, opt
+
+    def windowCOM(self, poses):
+        torch = self.torch
+        p = self._dev(poses, tuple(poses.shape))
+        n, nvar, _ = p.shape
+        com = torch.empty(n, nvar, 3, dtype=torch.float64, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _check(self.lib, self.lib.mmsto_window_com(self._h, n, nvar, _ptr(p), _ptr(com), st))
+        return com
+
     def launch_count(self):
         return int(self.lib.mmsto_launch_count(self._h))
 

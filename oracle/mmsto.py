@@ -411,3 +411,64 @@ def lbfgs(x, evaluate, epsilon=1e-5, m=6, max_iterations=0):
             d = d + S[j] * (alpha[j] - beta)
             j = (j + 1) % m
         step = 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# removeCOMsliding_online (gym_trackSRB/taesooLib/DeltaExtractor.py:421-512): the step right after the MMSTO solve in the
+# online loop (walk_SRBTrack2025.py:617, walk_SRBTrack2025_terrain_singlethreaded.py:610).  SURVEY 8f rank 2.
+#   QuadraticFunctionHardCon: BaseLib/math/OperatorStitch.cpp:531-620 (H = 2 sum c c^T, R = -2 sum v c, KKT matrix),
+#   Resource/scripts/module.lua:2108-2124,2165-2207 (addWeighted, con, solve = math.LUsolve of the KKT system).
+# PARITY UNPINNED (no recorded outputs); pinned by the KKT conditions and constraint residuals in tests/test_oracle_mmsto_cpu.py.
+
+def hardcon_solve(nvar, sq_terms, con_terms):
+    """sq_terms: (weight, [(coef, index)...], const); con_terms: ([(coef, index)...], const) -> x[nvar]."""
+    ncon = len(con_terms)
+    K = np.zeros((nvar + ncon, nvar + ncon)); d = np.zeros(nvar + ncon)
+    for w, ci, const in sq_terms:
+        s = math.sqrt(w)
+        for a, (ca, ia) in enumerate(ci):
+            K[ia, ia] += 2.0 * (s * ca) ** 2
+            for cb, ib in ci[a + 1:]:
+                K[ia, ib] += 2.0 * (s * ca) * (s * cb); K[ib, ia] = K[ia, ib]
+            d[ia] -= 2.0 * (s * const) * (s * ca)
+    for r, (ci, const) in enumerate(con_terms):
+        for ca, ia in ci:
+            K[nvar + r, ia] = ca; K[ia, nvar + r] = ca
+        d[nvar + r] = -const
+    return np.linalg.solve(K, d)[:nvar]
+
+
+def remove_com_sliding_online(skel, com_srb, desired_com, output, fix_y_also=True, ground_h=None):
+    """output: poses [nvar, 7 + #angles] (root xyz, quaternion wxyz, angles), modified copy returned with (currCOM, optCOM).
+    ground_h[nvar]: terrain height under each current CoM (projectToGround), None = no projection (flat script)."""
+    output = np.array(output, dtype=float)
+    nvar = output.shape[0]
+    curr = np.zeros((nvar, 3))
+    for i in range(nvar):
+        rot, tr = fk.bone_forward_kinematics(skel, output[i])
+        curr[i] = fk.calc_com(skel, rot, tr)
+    opt = np.zeros((nvar, 3))
+    for dim in range(3):
+        sq = []
+        for v in range(1, nvar - 1):
+            sq.append((1.5, [(-1.0, v - 1), (2.0, v), (-1.0, v + 1)], -1 * (-1 * com_srb[v - 1][dim] + 2 * com_srb[v][dim] - com_srb[v + 1][dim])))
+        con = [([(1.0, 0)], -curr[0][dim]), ([(1.0, 1)], -curr[1][dim]),
+               ([(1.0, i) for i in range(1, nvar)], -1 * float(np.sum(desired_com[0:nvar - 1, dim])))]
+        opt[:, dim] = hardcon_solve(nvar, sq, con)
+    if not fix_y_also:
+        opt[:, 1] = curr[:, 1]
+    for i in range(nvar):
+        delta = opt[i] - curr[i]
+        delta[1] = 0
+        axis = np.cross(delta, np.array([0.0, 1.0, 0.0]))
+        ln = math.sqrt(float(axis.dot(axis)))
+        axis = axis * (0.0 if ln == 0 else 1.0 / ln)
+        cy = curr[i, 1]
+        if ground_h is not None:
+            cy -= ground_h[i]
+        R = fk.qaxis(axis, -math.sqrt(float(delta.dot(delta))) * cy * 0.5)
+        # (plusCOM * R * minusCOM) * root: rotation R q, translation R (t - curr) + opt
+        q = output[i, 3:7].copy(); t = output[i, 0:3].copy()
+        output[i, 3:7] = fk.qmult(R, q)
+        output[i, 0:3] = fk.vrotate(R, t - curr[i]) + opt[i]
+    return output, curr, opt

@@ -128,3 +128,22 @@ def test_rejects_unsupported_configuration(opt):
     from ipcdnnwalk_b200.short_traj_opt import MmstoError
     with pytest.raises(MmstoError):
         opt.set("noSuchWeight", 1.0)
+
+
+@pytest.mark.parametrize("nvar,fix_y,ground", [(8, True, False), (8, False, True), (6, True, True)])
+def test_remove_com_sliding_matches_oracle(opt, skel, nvar, fix_y, ground):
+    """removeCOMsliding_online (DeltaExtractor.py:421-512) on a ragged batch of 19 windows: poses, currCOM, optCOM at 1e-10."""
+    import torch
+    from oracle import mmsto as mm
+    from test_oracle_mmsto_cpu import _com_slide_case
+    cases = [_com_slide_case(skel, 50 + s, nvar) for s in range(19)]
+    pose = torch.as_tensor(np.stack([c[0] for c in cases]), device="cuda").contiguous()
+    gh = np.random.default_rng(1).uniform(0, 0.4, (19, nvar)) if ground else None
+    com0 = opt.windowCOM(pose.clone()).cpu().numpy()
+    curr, op = opt.removeCOMsliding_online(np.stack([c[1] for c in cases]), np.stack([c[2] for c in cases]), pose, fix_y_also=fix_y, ground_h=gh)
+    pose = pose.cpu().numpy(); curr = curr.cpu().numpy(); op = op.cpu().numpy()
+    for i in (0, 7, 18):
+        out, c, o = mm.remove_com_sliding_online(skel, cases[i][1], cases[i][2], cases[i][0], fix_y_also=fix_y, ground_h=None if gh is None else gh[i])
+        assert np.abs(c - curr[i]).max() < 1e-12 and np.abs(c - com0[i]).max() < 1e-12
+        assert np.abs(o - op[i]).max() < 1e-10
+        assert np.abs(out - pose[i]).max() < 1e-10

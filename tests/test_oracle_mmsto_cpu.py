@@ -122,3 +122,39 @@ def test_solve_tracks_consistent_targets(skel):
     # the 25 degree clamp of the constant frames
     mot2 = mot.copy(); mot2[0, 10] += 1.0
     assert abs(o.initial_guess(mot2)[0, 10] - (start[0, 10] + np.radians(25))) < 1e-15
+
+
+def _com_slide_case(skel, seed, nvar=8):
+    from ipcdnnwalk_b200.short_traj_opt import _yzx_to_quat
+    rng = np.random.default_rng(seed)
+    q = hm.make_problem(seed, nf=nvar, skel=skel)["x_original"]
+    pose = np.concatenate([q[:, 0:3], _yzx_to_quat(q[:, 3:6]), q[:, 6:]], 1)
+    com_srb = np.cumsum(rng.normal(0, 0.02, (nvar, 3)), 0) + [0, 0.9, 0]
+    des = np.cumsum(rng.normal(0, 0.02, (nvar, 3)), 0) + [0.1, 0.9, 0]
+    return pose, com_srb, des
+
+
+def test_remove_com_sliding_satisfies_its_constraints(skel):
+    """removeCOMsliding_online: first two CoMs kept, sum of the rest equals the sum of the desired CoMs, the acceleration of
+    the optimised CoM follows com_srb up to the constraint forces (KKT), and the moved poses have the optimised CoM."""
+    pose, com_srb, des = _com_slide_case(skel, 3)
+    out, curr, opt = mm.remove_com_sliding_online(skel, com_srb, des, pose)
+    nvar = len(pose)
+    assert np.allclose(opt[:2], curr[:2], atol=1e-13)
+    assert np.allclose(opt[1:].sum(0), des[:nvar - 1].sum(0), atol=1e-12)
+    # stationarity on the unconstrained-by-position variables 2..nvar-1: gradient of the smoothness objective is the same
+    # constant (the multiplier of the sum constraint) for all of them
+    acc = lambda c: -c[:-2] + 2 * c[1:-1] - c[2:]
+    e = acc(opt) - acc(com_srb)                                      # [nvar-2, 3]
+    g = np.zeros((nvar, 3))
+    for v in range(1, nvar - 1):
+        g[v - 1] += -e[v - 1]; g[v] += 2 * e[v - 1]; g[v + 1] += -e[v - 1]
+    assert np.allclose(g[2:] - g[2], 0, atol=1e-9)
+    for i in (0, 3, nvar - 1):
+        rot, tr = fk.bone_forward_kinematics(skel, out[i])
+        assert np.allclose(fk.calc_com(skel, rot, tr), opt[i], atol=1e-12)
+    # fix_y_also = False keeps the heights; a ground height changes only the lean angle
+    out2, _, opt2 = mm.remove_com_sliding_online(skel, com_srb, des, pose, fix_y_also=False)
+    assert np.allclose(opt2[:, 1], curr[:, 1]) and np.allclose(opt2[:, [0, 2]], opt[:, [0, 2]])
+    out3, _, _ = mm.remove_com_sliding_online(skel, com_srb, des, pose, ground_h=np.full(nvar, 0.3))
+    assert not np.allclose(out3[4, 3:7], out[4, 3:7]) and np.allclose(out3[0], out[0])

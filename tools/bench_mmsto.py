@@ -36,4 +36,28 @@ if "--cpu" in sys.argv:
     t = time.perf_counter(); X, inf = o.solve(base[0]["euler_mot"], max_iterations=iters); dt = time.perf_counter() - t
     out["oracle_numpy_1core"] = {"s_per_window": dt, "evaluations": inf["evaluations"], "evaluations_per_s": inf["evaluations"] / dt}
 print(json.dumps(out))
+if "--comslide" in sys.argv:
+    # removeCOMsliding_online on windows of 8 poses: algorithmic bytes = poses in + root out + CoM targets in
+    from ipcdnnwalk_b200.short_traj_opt import _yzx_to_quat
+    nw = 1 << 17
+    q = np.stack([b["x_original"] for b in base])                           # [16, 7, 59]
+    q = np.concatenate([q, q[:, -1:]], 1)                                    # 8 frames
+    pose = np.concatenate([q[..., 0:3], _yzx_to_quat(q[..., 3:6]), q[..., 6:]], -1)
+    pose = torch.as_tensor(pose, device="cuda").repeat(nw // 16, 1, 1).contiguous()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    cs = (torch.randn(nw, 8, 3, device="cuda", generator=g, dtype=torch.float64) * 0.02).cumsum(1)
+    dc = (torch.randn(nw, 8, 3, device="cuda", generator=g, dtype=torch.float64) * 0.02).cumsum(1)
+    work = pose.clone()
+    for _ in range(3):
+        work.copy_(pose); opt.removeCOMsliding_online(cs, dc, work)
+    ts = []
+    for _ in range(10):
+        work.copy_(pose)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); opt.removeCOMsliding_online(cs, dc, work); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    by = nw * 8 * (60 + 7 + 6 + 6) * 8
+    print(json.dumps({"kernel": "comslide_kernel", "windows": nw, "poses_per_window": 8, "ms": ms, "windows_per_s": nw / ms * 1e3,
+                      "algorithmic_GBps": by / ms / 1e6, "note": "timing includes the two small output allocations of the Python mirror"}))
 opt.close()
