@@ -25,6 +25,7 @@ struct mmsto_solver {
   mmsto::Skel* d_sk = nullptr;
   mmsto::Prm* d_prm = nullptr;
   double* ws = nullptr; double* mc = nullptr; int ws_warps = 0;
+  double* d_kinv = nullptr; int kinv_nvar = 0;    // inverse KKT matrix of removeCOMsliding_online for kinv_nvar frames
   double* d_zero = nullptr; int zero_n = 0;       // all-zero velocity constraints / contacts when the caller passes none
   bool dirty = true;
   long long launches = 0;
@@ -157,7 +158,7 @@ int mmsto_create(int32_t device, int32_t nb, const int32_t* parent, const double
 int mmsto_destroy(mmsto_solver* s) {
   if (!s) return 0;
   cudaSetDevice(s->device);
-  cudaFree(s->d_sk); cudaFree(s->d_prm); cudaFree(s->ws); cudaFree(s->mc); cudaFree(s->d_zero);
+  cudaFree(s->d_sk); cudaFree(s->d_prm); cudaFree(s->ws); cudaFree(s->mc); cudaFree(s->d_zero); cudaFree(s->d_kinv);
   delete s;
   return 0;
 }
@@ -222,6 +223,14 @@ int mmsto_remove_com_sliding(mmsto_solver* s, int32_t n, int32_t nvar, double* p
   mmsto::ComSlideArgs A{};
   A.n = n; A.nvar = nvar; A.npose = s->sk.ndof + 1; A.fix_y = fix_y_also; A.com_only = 0; A.poses = poses; A.com_srb = com_srb;
   A.desired_com = desired_com; A.ground_h = ground_h; A.curr_out = curr_com_out; A.opt_out = opt_com_out; A.sk = s->d_sk;
+  if (!s->d_kinv) CK(cudaMalloc(&s->d_kinv, 11 * 11 * sizeof(double)));
+  if (s->kinv_nvar != nvar) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));       // an earlier launch may still read the previous inverse
+    mmsto::comslide_kkt_inverse_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(nvar, s->d_kinv);
+    CK(cudaGetLastError());
+    s->kinv_nvar = nvar; ++s->launches;
+  }
+  A.kinv = s->d_kinv;
   mmsto::comslide_kernel<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(A);
   CK(cudaGetLastError());
   ++s->launches;

@@ -735,7 +735,7 @@ namespace mmsto {
 struct ComSlideArgs {
   int n, nvar, npose, fix_y, com_only;
   double* poses;                 // [n][nvar][npose] in/out
-  const double *com_srb, *desired_com, *ground_h;
+  const double *com_srb, *desired_com, *ground_h, *kinv;
   double *curr_out, *opt_out;
   const Skel* sk;
 };
@@ -745,6 +745,37 @@ __device__ __forceinline__ void quat_mul(const double* a, const double* b, doubl
   o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
   o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
   o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+
+// inverse of the KKT matrix of removeCOMsliding_online's QuadraticFunctionHardCon (OperatorStitch.cpp:531-620): H = 2 sum c c^T
+// over the (-1, 2, -1) sqrt(1.5) stencils, constraints x0, x1, sum_{v>=1} x_v; Gauss-Jordan with partial pivoting, one thread
+__global__ void comslide_kkt_inverse_kernel(int nvar, double* kinv) {
+  const int N = nvar + 3;
+  double K[11][22];
+  for (int r = 0; r < N; ++r) for (int c = 0; c < 2 * N; ++c) K[r][c] = c == N + r ? 1.0 : 0.0;
+  const double s = sqrt(1.5);
+  for (int v = 1; v < nvar - 1; ++v) {
+    const double cf[3] = {s * -1.0, s * 2.0, s * -1.0};
+    for (int a = 0; a < 3; ++a) {
+      K[v - 1 + a][v - 1 + a] += 2.0 * cf[a] * cf[a];
+      for (int b = a + 1; b < 3; ++b) { K[v - 1 + a][v - 1 + b] += 2.0 * cf[a] * cf[b]; K[v - 1 + b][v - 1 + a] = K[v - 1 + a][v - 1 + b]; }
+    }
+  }
+  K[nvar][0] = 1.0; K[0][nvar] = 1.0; K[nvar + 1][1] = 1.0; K[1][nvar + 1] = 1.0;
+  for (int v = 1; v < nvar; ++v) { K[nvar + 2][v] = 1.0; K[v][nvar + 2] = 1.0; }
+  for (int col = 0; col < N; ++col) {
+    int piv = col; double best = fabs(K[col][col]);
+    for (int r = col + 1; r < N; ++r) if (fabs(K[r][col]) > best) { best = fabs(K[r][col]); piv = r; }
+    if (piv != col) for (int c = 0; c < 2 * N; ++c) { const double t = K[col][c]; K[col][c] = K[piv][c]; K[piv][c] = t; }
+    const double inv = 1.0 / K[col][col];
+    for (int c = 0; c < 2 * N; ++c) K[col][c] *= inv;
+    for (int r = 0; r < N; ++r) {
+      if (r == col) continue;
+      const double m = K[r][col];
+      if (m != 0.0) for (int c = 0; c < 2 * N; ++c) K[r][c] -= m * K[col][c];
+    }
+  }
+  for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) kinv[r * N + c] = K[r][N + c];
 }
 
 __global__ void __launch_bounds__(128) comslide_kernel(const ComSlideArgs A) {
@@ -813,42 +844,27 @@ __global__ void __launch_bounds__(128) comslide_kernel(const ComSlideArgs A) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) { c0[k] = __shfl_sync(0xffffffffu, com[k], (lane & ~7) + 0); c1[k] = __shfl_sync(0xffffffffu, com[k], (lane & ~7) + 1); }
   if (pvalid && f < 3) {
+    // The KKT matrix depends on nvar only: its inverse is built once (comslide_kkt_inverse_kernel) and each problem is the
+    // product of its first nvar rows with the right-hand side [-2 sum v c | curr0, curr1, sum desired].
     const int dim = f, N = nvar + 3;
-    double K[11][12];
-    for (int r = 0; r < N; ++r) for (int cc = 0; cc <= N; ++cc) K[r][cc] = 0.0;
+    double d[11];
+    for (int r = 0; r < N; ++r) d[r] = 0.0;
     const double* cs = A.com_srb + w64 * nvar * 3;
     const double s = sqrt(1.5);
     for (int v = 1; v < nvar - 1; ++v) {
-      const double cf[3] = {s * -1.0, s * 2.0, s * -1.0};
       const double cst = s * (-1 * (-1 * cs[(v - 1) * 3 + dim] + 2 * cs[v * 3 + dim] - cs[(v + 1) * 3 + dim]));
-      for (int a = 0; a < 3; ++a) {
-        K[v - 1 + a][v - 1 + a] += 2.0 * cf[a] * cf[a];
-        for (int b2 = a + 1; b2 < 3; ++b2) { K[v - 1 + a][v - 1 + b2] += 2.0 * cf[a] * cf[b2]; K[v - 1 + b2][v - 1 + a] = K[v - 1 + a][v - 1 + b2]; }
-        K[v - 1 + a][N] -= 2.0 * cst * cf[a];
-      }
+      d[v - 1] -= 2.0 * cst * (s * -1.0); d[v] -= 2.0 * cst * (s * 2.0); d[v + 1] -= 2.0 * cst * (s * -1.0);
     }
-    K[nvar][0] = 1.0; K[0][nvar] = 1.0; K[nvar][N] = dim == 0 ? c0[0] : dim == 1 ? c0[1] : c0[2];
-    K[nvar + 1][1] = 1.0; K[1][nvar + 1] = 1.0; K[nvar + 1][N] = dim == 0 ? c1[0] : dim == 1 ? c1[1] : c1[2];
+    d[nvar] = dim == 0 ? c0[0] : dim == 1 ? c0[1] : c0[2];
+    d[nvar + 1] = dim == 0 ? c1[0] : dim == 1 ? c1[1] : c1[2];
     double sum = 0.0;
     for (int v = 0; v < nvar - 1; ++v) sum += A.desired_com[(w64 * nvar + v) * 3 + dim];
-    for (int v = 1; v < nvar; ++v) { K[nvar + 2][v] = 1.0; K[v][nvar + 2] = 1.0; }
-    K[nvar + 2][N] = sum;
-    for (int col = 0; col < N; ++col) {                    // Gaussian elimination, partial pivoting
-      int piv = col; double best = fabs(K[col][col]);
-      for (int r = col + 1; r < N; ++r) if (fabs(K[r][col]) > best) { best = fabs(K[r][col]); piv = r; }
-      if (piv != col) for (int cc = col; cc <= N; ++cc) { const double tmp = K[col][cc]; K[col][cc] = K[piv][cc]; K[piv][cc] = tmp; }
-      const double inv = 1.0 / K[col][col];
-      for (int r = col + 1; r < N; ++r) {
-        const double m = K[r][col] * inv;
-        if (m != 0.0) for (int cc = col; cc <= N; ++cc) K[r][cc] -= m * K[col][cc];
-      }
+    d[nvar + 2] = sum;
+    for (int v = 0; v < nvar; ++v) {
+      double acc = 0.0;
+      for (int cc = 0; cc < N; ++cc) acc += A.kinv[v * N + cc] * d[cc];
+      xs[wl][dim][v] = acc;
     }
-    for (int r = N - 1; r >= 0; --r) {
-      double acc = K[r][N];
-      for (int cc = r + 1; cc < N; ++cc) acc -= K[r][cc] * K[cc][N];
-      K[r][N] = acc / K[r][r];
-    }
-    for (int v = 0; v < nvar; ++v) xs[wl][dim][v] = K[v][N];
   }
   __syncthreads();
   if (!valid) return;
