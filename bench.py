@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--precision", type=int, default=int(os.environ.get("SRB_BENCH_PRECISION", "32")), choices=[32, 64])
     ap.add_argument("--lanes", type=int, default=0)
-    ap.add_argument("--variant", default="test", choices=["test", "training"])
+    ap.add_argument("--variant", default="test", choices=["test", "training", "terrain"],
+                    help="terrain = BASELINE config 3 (SRBEnv5_mocap_list_terrain_window on the playground height fields); not the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flush", default="write", choices=["write", "read", "none"],
@@ -109,6 +110,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+TERRAIN_NPZ = os.path.join(ROOT, "tests", "golden", "terrain_playground.npz")
+# where the environments of the terrain workload stand on Characters/SRB5_playground.xml: flat plane, pyramid, hill and rough
+# height fields (the four regions the parity tests cover), jittered per environment
+TERRAIN_SPOTS = ((0.0, 0.0), (22.0, 24.0), (-42.0, 42.0), (42.0, -40.0))
+
+
+# The terrain env's `done` (absolute height < 0.5 or > 1.2 m, env/SRBEnv5_mocap_list_terrain_window.py:642-700) is true on
+# every elevated part of the playground and walk_SRBTrack2025_terrain_singlethreaded.py:421,724 ignores it, so the terrain
+# workload ignores it too: no auto-reset, all environments are re-seeded every TERRAIN_EPISODE steps outside the timed events.
+TERRAIN_EPISODE = 32
+
+
+def terrain_planar(n, seed):
+    rng = np.random.default_rng(seed)
+    spots = np.array(TERRAIN_SPOTS)[np.arange(n) % len(TERRAIN_SPOTS)]
+    return spots + rng.uniform(-1.5, 1.5, (n, 2))
+
+
 def usable_cores():
     """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
     try:
@@ -133,16 +152,29 @@ def _oracle_worker(args):
     rng = np.random.default_rng(1000 + wid)
     clips = helpers.fresh_clips()
     envs = []
-    for _ in range(n_env):
-        e = OracleSRBEnv(helpers.fresh_clips(), variant)
+    if variant == "terrain":
+        from oracle.terrain import Terrain
+        from oracle.srb_env import lift_clip_to_terrain
+        T = Terrain.load(TERRAIN_NPZ)
+        planar = terrain_planar(n_env, 500 + wid)
+        clips = helpers.fresh_clips(("aiming_show",))
+    for i in range(n_env):
+        if variant == "terrain":
+            e = OracleSRBEnv([lift_clip_to_terrain(helpers.load_clip("aiming_show"), T, tuple(planar[i]))], "terrain", terrain=T)
+        else:
+            e = OracleSRBEnv(helpers.fresh_clips(), variant)
         helpers.oracle_reset(e, helpers.random_plan(rng, clips))
         envs.append(e)
 
+    passes = [0]
+
     def one_pass():
+        passes[0] += 1
         for e in envs:
             a = helpers.tracking_action(e, rng, SIGMA)
             _, _, done, _, _ = e.step(a)
-            if done:
+            # terrain: `done` is ignored as the reference's terrain script does (see TERRAIN_EPISODE)
+            if (done and variant != "terrain") or (variant == "terrain" and passes[0] % TERRAIN_EPISODE == 0):
                 helpers.oracle_reset(e, helpers.random_plan(rng, clips))
     for _ in range(warmup):
         one_pass()
@@ -179,7 +211,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), bounded sample of {cores * per_core} envs per step on {cores} host cores"},
+        "config": {"workload": (f"SRBEnv5_mocap_list_terrain_window on the playground terrain, bounded sample of {cores * per_core} envs per step on {cores} host cores"
+                                if args.variant == "terrain" else
+                                f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), bounded sample of {cores * per_core} envs per step on {cores} host cores")},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -201,9 +235,16 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     N = args.envs
-    clips = helpers.fresh_clips()
-    env = SRBVecEnv(clips, N, variant=args.variant, precision=args.precision, lanes_per_env=args.lanes, auto_reset=True,
-                    device=local_rank, seed=1234 + rank)
+    if args.variant == "terrain":
+        from ipcdnnwalk_b200 import TerrainModel
+        clips = helpers.fresh_clips(("aiming_show",))
+        env = SRBVecEnv(clips, N, variant="terrain", precision=args.precision, lanes_per_env=args.lanes, auto_reset=False,
+                        device=local_rank, seed=1234 + rank, terrain=TerrainModel.from_npz(TERRAIN_NPZ),
+                        initial_pos_planar=terrain_planar(N, 77 + rank))
+    else:
+        clips = helpers.fresh_clips()
+        env = SRBVecEnv(clips, N, variant=args.variant, precision=args.precision, lanes_per_env=args.lanes, auto_reset=True,
+                        device=local_rank, seed=1234 + rank)
     env.reset()
     act = torch.zeros(N, ACT_DIM, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -211,7 +252,12 @@ def run_ours(args, rank, local_rank, world):
     acc = torch.zeros(1 + 2 * OBS_DIM, dtype=torch.float64, device=dev)
     K, W = args.steps, args.warmup
 
+    n_resets = [0]
+
     def one_step(k, timed):
+        if args.variant == "terrain" and k % TERRAIN_EPISODE == 0 and k > 0:
+            n_resets[0] += int(timed)
+            env.reset()                                                     # episode boundary of the terrain workload, untimed
         env.tracking_action(act, sigma=SIGMA, seed=99 + rank, step=k)      # the "policy": outside the timed events
         if args.flush == "write":
             flush.fill_(k & 0xFF)                                           # L2 flush between steps
@@ -262,7 +308,7 @@ def run_ours(args, rank, local_rank, world):
     coll_ms = float(sum(a.elapsed_time(b) for a, b in cevs))
     total_ms = float(step_ms.sum()) + coll_ms
     n_tracking = K
-    step_launches = env.launch_count() - launches0 - n_tracking - len(cevs)
+    step_launches = env.launch_count() - launches0 - n_tracking - len(cevs) - n_resets[0]
 
     # ---- end to end through the host-buffer C-ABI call (srb_step_host): pinned host actions in, obs/rew/done out
     e2e_ms = None
@@ -313,9 +359,14 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
-            "config": {"workload": f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), {N} envs per GPU x {world} GPU",
-                       "envs_per_gpu": N, "clips": "stand1 + aiming_show (shipped clips; walk/run clips are absent from the reference mount)",
-                       "actions": f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done",
+            "config": {"workload": (f"SRBEnv5_mocap_list_terrain_window on the playground terrain (plane / pyramid / hill / rough height field), {N} envs per GPU x {world} GPU"
+                                    if args.variant == "terrain" else
+                                    f"SRBEnv5_mocap_list_window flat ground ({args.variant} variant), {N} envs per GPU x {world} GPU"),
+                       "envs_per_gpu": N, "clips": ("aiming_show, lifted per environment in the kernel" if args.variant == "terrain" else
+                                                    "stand1 + aiming_show (shipped clips; walk/run clips are absent from the reference mount)"),
+                       "actions": (f"device-side reference-tracking controller + N(0,{SIGMA}^2); done ignored as walk_SRBTrack2025_terrain_singlethreaded.py does, "
+                                   f"all environments re-seeded every {TERRAIN_EPISODE} steps outside the timed events" if args.variant == "terrain" else
+                                   f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done"),
                        "l2": {"write": "flushed between steps (256 MiB write)", "read": "DIAGNOSTIC: evicted between steps by reading 256 MiB", "none": "DIAGNOSTIC: not flushed"}[args.flush] + "; per-step CUDA events on the launching stream",
                        "collective": f"obs-normaliser statistics kernel + NCCL all-reduce every {ROLLOUT} steps, inside the timed total",
                        "lanes_per_env": env_lanes(args), "median_step_ms": med_ms_max, "wall_s_timed_loop": t_wall,
