@@ -484,12 +484,14 @@ extern "C" int srb_upload_terrain(srb_env* h, const double plane_size[2], int32_
   for (int b = 0; b < n_body; b++) {
     TerrainBodyDev& o = T.body[b];
     o.cx = bodies[b].xpos[0]; o.cy = bodies[b].xpos[1]; o.snap = bodies[b].snap; o.body_id = bodies[b].body_id;
-    o.first = -1; o.count = 0; o.x0 = o.y0 = 1e300; o.x1 = o.y1 = -1e300;
+    o.first = -1; o.count = 0; o.x0 = o.y0 = 1e300; o.x1 = o.y1 = -1e300; o.nested = 1; o.pad = 0;
     for (int k = 0; k < n_box; k++) {
       if (boxes[k].body_id != bodies[b].body_id) continue;
       if (o.first < 0) o.first = k;
       if (k != o.first + o.count) return fail(-1, "srb_upload_terrain: the boxes of a body must be contiguous");
       if (o.count > 0 && bx[5 * k + 4] < bx[5 * (k - 1) + 4]) return fail(-1, "srb_upload_terrain: box tops must ascend inside a body");
+      if (o.count > 0 && (boxes[k].pos[0] != boxes[o.first].pos[0] || boxes[k].pos[1] != boxes[o.first].pos[1] ||
+                          boxes[k].size[0] > boxes[k - 1].size[0] || boxes[k].size[1] > boxes[k - 1].size[1])) o.nested = 0;
       o.count++;
       o.x0 = std::min(o.x0, boxes[k].pos[0] - boxes[k].size[0]); o.x1 = std::max(o.x1, boxes[k].pos[0] + boxes[k].size[0]);
       o.y0 = std::min(o.y0, boxes[k].pos[1] - boxes[k].size[1]); o.y1 = std::max(o.y1, boxes[k].pos[1] + boxes[k].size[1]);

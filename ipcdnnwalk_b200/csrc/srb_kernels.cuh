@@ -109,6 +109,23 @@ __device__ __forceinline__ real terrain_query(const TerrainDev& T, real x, real 
   for (int b = 0; b < T.n_body; b++) {
     const TerrainBodyDev& B = T.body[b];
     if ((double)x < B.x0 || (double)x > B.x1 || (double)y < B.y0 || (double)y > B.y1) continue;
+    if (B.nested) {
+      // concentric layers whose half sizes shrink with the index (a pyramid): "inside layer k" is monotone in k, so the
+      // highest layer under the point is found by bisection (7 probes for 81 layers) with the same comparisons as the scan
+      const double* b0 = T.box + (size_t)B.first * 5;
+      const real ax = num<real>::abs(x - (real)b0[0]), ay = num<real>::abs(y - (real)b0[1]);
+      int lo = B.first - 1, hi = B.first + B.count - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const double* bx = T.box + (size_t)mid * 5;
+        if (ax <= (real)bx[2] && ay <= (real)bx[3]) lo = mid; else hi = mid - 1;
+      }
+      if (lo >= B.first) {
+        real top = (real)T.box[(size_t)lo * 5 + 4];
+        if (!have || top > best) { best = top; gid = T.box_geom0 + lo; cc = cr = tri = -1; have = true; }
+      }
+      continue;
+    }
     for (int k = B.first + B.count - 1; k >= B.first; k--) {           // tops ascend in model order: highest first
       const double* bx = T.box + (size_t)k * 5;
       if (num<real>::abs(x - (real)bx[0]) <= (real)bx[2] && num<real>::abs(y - (real)bx[1]) <= (real)bx[3]) {

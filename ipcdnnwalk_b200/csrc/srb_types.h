@@ -56,7 +56,7 @@ enum Variant { VARIANT_TEST = 0, VARIANT_TRAINING = 1, VARIANT_TERRAIN = 2 };
 
 // ---- terrain of SRB5_playground.xml: plane + height fields + axis-aligned box stacks (pyramids) -------
 struct HFieldDev { const float* data; int nrow, ncol; double sx, sy, sz, px, py, pz; int geom_id; int pad; };
-struct TerrainBodyDev { double cx, cy; double x0, x1, y0, y1; int first, count, snap, body_id; };
+struct TerrainBodyDev { double cx, cy; double x0, x1, y0, y1; int first, count, snap, body_id; int nested, pad; };   // nested: concentric boxes, half sizes shrink with the index
 enum { MAX_HF = 4, MAX_TBODY = 16 };
 struct TerrainDev {
   int enabled, n_hf, n_body, n_box;
