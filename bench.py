@@ -393,7 +393,10 @@ def run_ours(args, rank, local_rank, world):
 
 
 def env_lanes(args):
-    return args.lanes if args.lanes else 8
+    if args.lanes:
+        return args.lanes
+    # the library's default (srb_create): by batch size
+    return 8 if args.envs <= 6144 else (4 if (args.envs <= 16384 or args.variant == "terrain") else 2)
 
 
 def main():

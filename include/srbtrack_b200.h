@@ -34,7 +34,7 @@ typedef struct srb_config {
   int32_t num_envs;       /* replaces make_vec_env(SRBEnv, n_envs=...)  walk_SRBTrack2025_train_delta.py:94-100 */
   int32_t variant;        /* SRB_VARIANT_*                                                                    */
   int32_t precision;      /* 64: fp64 state+arithmetic (reference precision); 32: fp32                        */
-  int32_t lanes_per_env;  /* 0 = default; 1,2,4,8,16,32 lanes of a warp cooperate on one environment           */
+  int32_t lanes_per_env;  /* 0 = by batch size (8 up to 6144 envs, 4 up to 16384, else 2); 1,2,4,8,16,32 lanes cooperate on one environment           */
   int32_t auto_reset;     /* 1: a terminated env is reset inside the step (SubprocVecEnv semantics)            */
   int32_t device;         /* CUDA device ordinal                                                               */
   uint64_t seed;          /* stream for device-side reset draws (random.randrange / np.random in SRBEnv.reset) */
