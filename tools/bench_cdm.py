@@ -19,6 +19,7 @@ ap.add_argument("--warmup", type=int, default=16)
 ap.add_argument("--lanes", default="4")
 ap.add_argument("--precision", default="32,64")
 ap.add_argument("--e2e", action="store_true")
+ap.add_argument("--policy", action="store_true", help="drive the environments with the reference's trained walk2-v1 policy (tests/golden/cdm_policy_walk2.npz), evaluated in torch outside the timed events, reset noise scaled to 20 %")
 a = ap.parse_args()
 peak = 6547.8
 try:
@@ -30,24 +31,39 @@ BYTES = {32: 108 + 40 + 8 + 2 * (61 * 4 + 16) + 2 * 32, 64: 108 + 40 + 8 + 2 * (
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for prec in [int(x) for x in a.precision.split(",")]:
     for lanes in [int(x) for x in a.lanes.split(",")]:
-        env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3)
-        env.reset()
+        params = {"noise_q": 0.1, "noise_pos": 0.01, "noise_dq": 0.1, "noise_vx": 0.01, "noise_vy": 0.1, "noise_vz": 0.01} if a.policy else None
+        env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3, params=params)
+        obs = env.reset()
+        if a.policy:
+            import helpers
+            pol = dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_walk2.npz")))
+            W = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device="cuda") for i in range(int(pol["n_layers"]))]
+            Bs = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device="cuda") for i in range(int(pol["n_layers"]))]
+            mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device="cuda")
+            istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device="cuda")
+
+            def policy_action(o):
+                h = torch.clamp((o - mean) * istd, -10.0, 10.0)
+                for w, b in zip(W, Bs):
+                    h = torch.tanh(h @ w.T + b)
+                return h
         g = torch.Generator(device="cuda"); g.manual_seed(3)
         acts = [(torch.rand(a.envs, 10, device="cuda", generator=g) * 2 - 1) for _ in range(32)]
-        for i in range(a.warmup):
-            env.step(acts[i % 32])
+        for i in range(a.warmup if not a.policy else max(a.warmup, 120)):     # policy: let the gait reach its steady state
+            obs = env.step(policy_action(obs) if a.policy else acts[i % 32])[0]
         torch.cuda.synchronize()
         env.episode_stats(clear=True)
         ts = []
         for i in range(a.steps):
             flush.fill_(i & 0xff)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); env.step(acts[i % 32]); e1.record()
+            act = policy_action(obs) if a.policy else acts[i % 32]
+            e0.record(); obs = env.step(act)[0]; e1.record()
             ts.append((e0, e1))
         torch.cuda.synchronize()
         ms = np.array([x.elapsed_time(y) for x, y in ts])
         st = env.episode_stats()
-        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes,
+        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "actions": "reference walk2-v1 policy (torch, untimed)" if a.policy else "U(-1,1)", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes,
                "steps": a.steps, "ms_per_step_mean": float(ms.mean()), "ms_per_step_median": float(np.median(ms)), "env_steps_per_s": a.envs / float(ms.mean()) * 1e3,
                "algorithmic_bytes_per_env_step": BYTES[prec], "achieved_GBps": BYTES[prec] * a.envs / float(ms.mean()) / 1e6, "peak_GBps": peak,
                "frac": BYTES[prec] * a.envs / float(ms.mean()) / 1e6 / peak, "episodes_finished": int(st[2]), "mean_episode_len": float(st[1] / max(st[2], 1)),
