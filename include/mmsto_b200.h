@@ -43,6 +43,8 @@ int mmsto_set_dof_weights(mmsto_solver* s, const double* w);
  *   con        [n] int32        contact bits, bit (marker*8 + frame); used when weightEEcon > 0
  *   velcon     [n][4][10]       velocity half-space constraints: frame (or -1), bone, min speed, normal 3, local pos 3, pad
  *   x_out      [n][nf][ndof]    solution; info [n][4] = final objective, libLBFGS return code, iterations, evaluations
+ *                               (a window whose objective turns NaN stops with LBFGSERR_UNKNOWNERROR = -1024 and its last
+ *                               finite point; libLBFGS itself has no such check)
  * stream = cudaStream_t as void*.  Returns 0, or a negative error code (mmsto_last_error has the text). */
 int mmsto_solve(mmsto_solver* s, int32_t n, const double* x_original, const double* dx, const double* ddx,
                 const double* euler_mot, const double* gpos_target, const double* com, const double* momentum,

@@ -21,7 +21,8 @@ enum { MAXB = 24, MAXD = 64, NFMAX = 8, NMARK = 4, MAXHS = 4, HS_W = 10, LB_M = 
        GM_CG = 144, GM_W = 152 };   // per-problem L-BFGS scalars in shared memory: Gram matrices 3 x 36, g.S, g.Y, coefficients, alpha, ys
 
 enum { LBFGS_SUCCESS = 0, LBFGS_ALREADY_MINIMIZED = 2, LBFGSERR_MINIMUMSTEP = -1000, LBFGSERR_MAXIMUMSTEP = -999,
-       LBFGSERR_MAXIMUMLINESEARCH = -998, LBFGSERR_MAXIMUMITERATION = -997, LBFGSERR_INCREASEGRADIENT = -994 };
+       LBFGSERR_MAXIMUMLINESEARCH = -998, LBFGSERR_MAXIMUMITERATION = -997, LBFGSERR_INCREASEGRADIENT = -994,
+       LBFGSERR_UNKNOWNERROR = -1024 };
 
 struct Skel {
   int nb, ndof;
@@ -584,6 +585,12 @@ __global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
     double dg, gg, xx;
     dots3(c, fr, nd, V_G, V_D, V_G, V_G, V_X, V_X, &dg, &gg, &xx);
     bool begin_ls = false, accepted = false;
+    if (phase != 2 && !(fv == fv)) {
+      // NaN containment (not in libLBFGS, which would keep iterating on NaNs): a window with non-finite inputs stops here with
+      // LBFGSERR_UNKNOWNERROR and the last finite point, it does not hold the other windows of its warp until the iteration cap
+      if (phase == 1 && fr) for (int j = 0; j < nd; ++j) { VEC(c, V_X, j) = VEC(c, V_XP, j); VEC(c, V_G, j) = VEC(c, V_GP, j); }
+      fx = fv; ret = LBFGSERR_UNKNOWNERROR; phase = 2; iters = k;
+    }
     if (phase == 0) {
       fx = fv;
       const double xnorm = fmax(sqrt(xx), 1.0), gnorm = sqrt(gg);

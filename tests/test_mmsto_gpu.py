@@ -147,3 +147,18 @@ def test_remove_com_sliding_matches_oracle(opt, skel, nvar, fix_y, ground):
         assert np.abs(c - curr[i]).max() < 1e-12 and np.abs(c - com0[i]).max() < 1e-12
         assert np.abs(o - op[i]).max() < 1e-10
         assert np.abs(out - pose[i]).max() < 1e-10
+
+
+def test_nan_window_is_contained(opt, skel):
+    """A window with a NaN target stops with LBFGSERR_UNKNOWNERROR (-1024) at once; its warp neighbours are solved as if alone."""
+    ps = [hm.make_problem(60 + s, skel=skel) for s in range(4)]
+    opt.set("max_iterations", 6)
+    args = [hm.stack(ps, k) for k in KEYS]
+    x0, i0 = opt.solveEndEffectors_euler(hm.stack(ps, "euler_mot"), *args, velcon=hm.stack(ps, "velcon"))
+    bad = [a.copy() for a in args]
+    bad[0][2, 3, 5] = np.nan                                  # gpos_target of window 2
+    x1, i1 = opt.solveEndEffectors_euler(hm.stack(ps, "euler_mot"), *bad, velcon=hm.stack(ps, "velcon"))
+    i0 = i0.cpu().numpy(); i1 = i1.cpu().numpy()
+    assert int(i1[2, 1]) == -1024 and int(i1[2, 3]) == 1
+    for w in (0, 1, 3):
+        assert np.array_equal(x0[w].cpu().numpy(), x1[w].cpu().numpy()) and np.array_equal(i0[w], i1[w])
