@@ -64,6 +64,15 @@ int mmsto_remove_com_sliding(mmsto_solver* s, int32_t n, int32_t nvar, double* p
                              int32_t fix_y_also, const double* ground_h, double* curr_com_out, double* opt_com_out, void* stream);
 /* CoM of every pose of every window (mLoader_full.setPoseDOF + calcCOM, DeltaExtractor.py:428-430): com_out [n][nvar][3] */
 int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* poses, double* com_out, void* stream);
+/* _extractSingleFrameFullbody (gym_trackSRB/taesooLib/DeltaExtractor.py:577-643): n items, each one decoded full-body row
+ * (DeltaExtractor.py:17-22: toPelvis 6 | toFeet 24 | toMomentum 9 | poses 53 | dx 59 | ddx 59 | con 4 = 214 doubles) plus the
+ * pack_obs_extra record of its frame (pose_tl 7 | dq 6 | two foot frames 7 | contacts 2 = 29 doubles).  srb_* describe the SRB
+ * segment of the caller's loader (mass, 3x3 inertia row-major, local CoM).  Outputs per item: human_pose 60 (root xyz, root
+ * quaternion, angles), dx_ddx 118, feetpos 24 (4 marker positions, 4 marker velocities), com 3, momentum 6 ([M, F] about the
+ * CoM), con_bin 4, con 4.  Hanyang_lowdof_T layout only (59 dofs), as mmsto_config fixes it. */
+int fullbody_extract(int32_t device, int32_t n, const double* extra, const double* row, double srb_mass, const double* srb_inertia9,
+                     const double* srb_local_com, double* human_pose, double* dx_ddx, double* feetpos, double* com, double* momentum,
+                     double* con_bin, double* con, void* stream);
 long long mmsto_launch_count(mmsto_solver* s);
 const char* mmsto_last_error(void);
 

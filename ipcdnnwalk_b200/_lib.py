@@ -111,6 +111,7 @@ _MMSTO_SIGNATURES = {       # include/mmsto_b200.h
     "mmsto_remove_com_sliding": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "mmsto_window_com": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmsto_launch_count": (C.c_int64, [_P]),
+    "fullbody_extract": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mmsto_last_error": (C.c_char_p, []),
 }
 MMSTO_EXPORTED_SYMBOLS = tuple(_MMSTO_SIGNATURES)

@@ -251,6 +251,26 @@ int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* pos
   return 0;
 }
 
+int fullbody_extract(int32_t device, int32_t n, const double* extra, const double* row, double srb_mass, const double* srb_inertia9,
+                     const double* srb_local_com, double* human_pose, double* dx_ddx, double* feetpos, double* com, double* momentum,
+                     double* con_bin, double* con, void* stream) {
+  if (n <= 0) return 0;
+  if (!extra || !row || !srb_inertia9 || !srb_local_com || !human_pose || !dx_ddx || !feetpos || !com || !momentum || !con_bin || !con)
+    return fail(-1, "fullbody_extract: null array");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(-3, "fullbody_extract: no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  mmsto::FullbodyArgs A{};
+  A.n = n; A.extra = extra; A.row = row; A.mass = srb_mass;
+  const double* I = srb_inertia9;
+  A.inertia[0] = I[0]; A.inertia[1] = I[4]; A.inertia[2] = I[8]; A.inertia[3] = I[1]; A.inertia[4] = I[2]; A.inertia[5] = I[5];
+  for (int k = 0; k < 3; ++k) { A.lcom[k] = srb_local_com[k]; A.r[k] = srb_mass * srb_local_com[k]; }
+  A.human = human_pose; A.dx_ddx = dx_ddx; A.feetpos = feetpos; A.com = com; A.momentum = momentum; A.con_bin = con_bin; A.con = con;
+  mmsto::fullbody_extract_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(A);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 long long mmsto_launch_count(mmsto_solver* s) { return s ? s->launches : 0; }
 
 }  // extern "C"

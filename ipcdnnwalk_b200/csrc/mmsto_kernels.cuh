@@ -906,3 +906,159 @@ __global__ void __launch_bounds__(128) comslide_kernel(const ComSlideArgs A) {
 }
 
 }  // namespace mmsto
+
+// ---------------------------------------------------------------------------------------------------------------------
+// _extractSingleFrameFullbody (gym_trackSRB/taesooLib/DeltaExtractor.py:577-643), SURVEY 8f rank 2: decoded full-body row +
+// SRB state of its frame -> the inputs of the MMSTO solve.  One warp per item: the row is staged in shared memory with
+// coalesced loads, the copy-and-scale parts (joint angles, dx, ddx, contacts) are written by all lanes, the handful of
+// small transforms (pelvis exp(se3), one-body momentum, foot markers, root velocity) by one lane each.
+namespace mmsto {
+
+enum { FB_TO_PELVIS = 6, FB_TO_FEET = 24, FB_TO_MOM = 9, FB_POSES = 53, FB_NDOF = 59, FB_ROW = 214, FB_EXTRA = 29,
+       FB_C_FEET = 6, FB_C_MOM = 30, FB_C_POSES = 39, FB_C_DX = 92, FB_C_DDX = 151, FB_C_CON = 210 };
+
+struct FullbodyArgs {
+  int n;
+  const double *extra, *row;           // [n][29], [n][214]
+  double mass, inertia[6], r[3];       // SRB segment: mass, Ixx Iyy Izz Ixy Ixz Iyz, mass * local CoM
+  double lcom[3];
+  double *human, *dx_ddx, *feetpos, *com, *momentum, *con_bin, *con;
+};
+
+// vector3::rotate(quater, v): (2 u.v) u + (s^2 - u.u) v + 2 s u x v   (no normalisation, as the reference)
+__device__ __forceinline__ void q_rotate(const double* q, const double* v, double* o) {
+  const double s = q[0], ux = q[1], uy = q[2], uz = q[3];
+  const double a = 2.0 * (ux * v[0] + uy * v[1] + uz * v[2]), b = s * s - (ux * ux + uy * uy + uz * uz), c2 = 2.0 * s;
+  o[0] = a * ux + b * v[0] + c2 * (uy * v[2] - uz * v[1]);
+  o[1] = a * uy + b * v[1] + c2 * (uz * v[0] - ux * v[2]);
+  o[2] = a * uz + b * v[2] + c2 * (ux * v[1] - uy * v[0]);
+}
+
+__global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArgs A) {
+  __shared__ double srow[4][FB_ROW + FB_EXTRA + 1];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int item = blockIdx.x * 4 + wi;
+  if (item >= A.n) return;
+  double* S = srow[wi];
+  const double* row = A.row + (size_t)item * FB_ROW;
+  const double* ex = A.extra + (size_t)item * FB_EXTRA;
+  for (int k = lane; k < FB_ROW; k += 32) S[k] = row[k];
+  if (lane < FB_EXTRA) S[FB_ROW + lane] = ex[lane];
+  __syncwarp();
+  const double* E = S + FB_ROW;                      // pose_tl 0..6 | dq 7..12 | foot0 13..19 | foot1 20..26 | con 27..28
+  const double* rq = E + 3;
+  double* human = A.human + (size_t)item * (7 + FB_POSES);
+  double* dxo = A.dx_ddx + (size_t)item * 2 * FB_NDOF;
+  for (int k = lane; k < FB_POSES; k += 32) human[7 + k] = S[FB_C_POSES + k];
+  for (int k = lane; k < FB_NDOF; k += 32) {
+    if (k >= 3) { dxo[k] = S[FB_C_DX + k] * 10.0; dxo[FB_NDOF + k] = S[FB_C_DDX + k] * 10.0; }
+  }
+  if (lane < 4) {
+    const double cv = S[FB_C_CON + lane];
+    A.con[(size_t)item * 4 + lane] = cv; A.con_bin[(size_t)item * 4 + lane] = cv > 0 ? 1.0 : 0.0;
+  }
+  if (lane == 4) {                                    // humanPose root = SRBroot * exp(toPelvis)
+    const double w0 = S[0], w1 = S[1], w2 = S[2];
+    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    double q2[4], p[3];
+    if (fabs(theta) < 1e-9) { q2[0] = 1.0; q2[1] = q2[2] = q2[3] = 0.0; p[0] = S[3]; p[1] = S[4]; p[2] = S[5];
+      // toBaseR of the identity: tr = 3 > 0 -> w = sqrt(4) / 2 = 1
+    } else {
+      const double it = 1.0 / theta;
+      const double s[6] = {it * w0, it * w1, it * w2, it * S[3], it * S[4], it * S[5]};
+      double st, ct;
+      sincos(theta, &st, &ct);
+      const double vt = 1.0 - ct, ut = (theta - st) * (s[0] * s[3] + s[1] * s[4] + s[2] * s[5]), t0 = s[2] * st, t1 = s[1] * st, t2 = s[0] * st;
+      double m[3][3];
+      m[0][0] = s[0] * s[0] * vt + ct; m[1][0] = s[0] * s[1] * vt + t0; m[2][0] = s[0] * s[2] * vt - t1;
+      m[0][1] = s[0] * s[1] * vt - t0; m[1][1] = s[1] * s[1] * vt + ct; m[2][1] = s[1] * s[2] * vt + t2;
+      m[0][2] = s[0] * s[2] * vt + t1; m[1][2] = s[1] * s[2] * vt - t2; m[2][2] = s[2] * s[2] * vt + ct;
+      p[0] = st * s[3] + ut * s[0] + vt * (s[1] * s[5] - s[2] * s[4]);
+      p[1] = st * s[4] + ut * s[1] + vt * (s[2] * s[3] - s[0] * s[5]);
+      p[2] = st * s[5] + ut * s[2] + vt * (s[0] * s[4] - s[1] * s[3]);
+      const double tr = m[0][0] + m[1][1] + m[2][2];   // toBaseR
+      if (tr > 0.0) {
+        double sq = sqrt(tr + 1.0);
+        q2[0] = sq * 0.5; sq = 0.5 / sq;
+        q2[1] = (m[2][1] - m[1][2]) * sq; q2[2] = (m[0][2] - m[2][0]) * sq; q2[3] = (m[1][0] - m[0][1]) * sq;
+      } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double sq = sqrt((m[i][i] - (m[j][j] + m[k][k])) + 1.0);
+        q2[i + 1] = sq * 0.5; sq = 0.5 / sq;
+        q2[0] = (m[k][j] - m[j][k]) * sq; q2[j + 1] = (m[j][i] + m[i][j]) * sq; q2[k + 1] = (m[k][i] + m[i][k]) * sq;
+      }
+    }
+    double hq[4], ht[3];
+    quat_mul(rq, q2, hq);
+    q_rotate(rq, p, ht);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) human[k] = ht[k] + E[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) human[3 + k] = hq[k];
+  }
+  if (lane == 5) {                                    // SRB momentum about its CoM + decoded corrections; CoM target
+    double inv[4], wb[3], vb[3], M[3], F[3], tmp[3];
+    const double n2 = rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3], il = 1.0 / sqrt(n2);
+    inv[0] = rq[0] * il; inv[1] = rq[1] * -1.0 * il; inv[2] = rq[2] * -1.0 * il; inv[3] = rq[3] * -1.0 * il;   // quater::inverse
+    q_rotate(inv, E + 7, wb); q_rotate(inv, E + 10, vb);
+    const double* I = A.inertia;
+    cross3(A.r, vb, tmp);
+    M[0] = I[0] * wb[0] + I[3] * wb[1] + I[4] * wb[2] + tmp[0];
+    M[1] = I[3] * wb[0] + I[1] * wb[1] + I[5] * wb[2] + tmp[1];
+    M[2] = I[4] * wb[0] + I[5] * wb[1] + I[2] * wb[2] + tmp[2];
+    cross3(wb, A.r, tmp);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) F[k] = tmp[k] + A.mass * vb[k];
+    // inv_dAd(T) then dAd(T(com)): world frame, about the CoM = R lcom + t
+    double inv2[4], tinv[3], rt[3], Fw[3], Mw[3], comw[3], mt[3];
+    q_rotate(inv, E, rt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tinv[k] = -rt[k];
+    cross3(tinv, F, tmp);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mt[k] = M[k] - tmp[k];
+    const double n3 = inv[0] * inv[0] + inv[1] * inv[1] + inv[2] * inv[2] + inv[3] * inv[3], il2 = 1.0 / sqrt(n3);
+    inv2[0] = inv[0] * il2; inv2[1] = inv[1] * -1.0 * il2; inv2[2] = inv[2] * -1.0 * il2; inv2[3] = inv[3] * -1.0 * il2;
+    q_rotate(inv2, mt, Mw); q_rotate(inv2, F, Fw);
+    q_rotate(rq, A.lcom, comw);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) comw[k] += E[k];
+    cross3(comw, Fw, tmp);
+    double eM[3], eF[3], eC[3];
+    q_rotate(rq, S + FB_C_MOM, eC); q_rotate(rq, S + FB_C_MOM + 3, eM); q_rotate(rq, S + FB_C_MOM + 6, eF);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      A.momentum[(size_t)item * 6 + k] = (Mw[k] - tmp[k]) + eM[k];
+      A.momentum[(size_t)item * 6 + 3 + k] = Fw[k] + eF[k];
+      A.com[(size_t)item * 3 + k] = E[k] + eC[k];
+    }
+  }
+  if (lane >= 6 && lane < 10) {                       // foot marker positions in the foot frames
+    const int ic = lane - 6;
+    const double* ft = E + 13 + 7 * (ic >> 1);
+    double g[3];
+    q_rotate(ft + 3, S + FB_C_FEET + ic * 3, g);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) A.feetpos[(size_t)item * 24 + ic * 3 + k] = g[k] + ft[k];
+  }
+  if (lane >= 10 && lane < 14) {                      // foot marker velocities
+    const int ic = lane - 10;
+    double g[3];
+    q_rotate(rq, S + FB_C_FEET + 12 + ic * 3, g);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) A.feetpos[(size_t)item * 24 + 12 + ic * 3 + k] = g[k] * 10.0 + E[10 + k];
+  }
+  if (lane == 14 || lane == 15) {                     // root translational velocity / acceleration: set_dx_ddx_v3
+    const int c0 = lane == 14 ? FB_C_DX : FB_C_DDX;
+    const double v[3] = {S[c0] * 10.0, S[c0 + 1] * 10.0, S[c0 + 2] * 10.0};
+    double g[3];
+    q_rotate(rq, v, g);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dxo[(lane == 14 ? 0 : FB_NDOF) + k] = g[k] + (lane == 14 ? E[10 + k] : 0.0);
+  }
+}
+
+}  // namespace mmsto

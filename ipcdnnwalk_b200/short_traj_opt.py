@@ -245,3 +245,34 @@ class ShortTrajOpt:
             self.close()
         except Exception:
             pass
+
+
+def extractSingleFrameFullbody(obs_extra, recon, srb_mass, srb_inertia, srb_local_com=(0.0, 0.0, 0.0), device=0):
+    """Batched `DeltaExtractor._extractSingleFrameFullbody` (DeltaExtractor.py:577-643).  obs_extra [n, 29] (pack_obs_extra
+    records), recon [n, 214] (decoder rows), the SRB segment's mass / 3x3 inertia / local CoM -> dict of torch.float64 device
+    tensors: humanPose [n, 60], dx_ddx [n, 118], feetpos [n, 24], com [n, 3], momentum [n, 6], con_bin [n, 4], con [n, 4]."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("ipcdnnwalk_b200.short_traj_opt needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+
+    def to_dev(a, w):
+        t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+        t = t.to(dev, torch.float64).contiguous()
+        if t.dim() != 2 or t.shape[1] != w:
+            raise ValueError(f"expected [n, {w}], got {tuple(t.shape)}")
+        return t
+    ex = to_dev(obs_extra, 29); rw = to_dev(recon, 214)
+    n = ex.shape[0]
+    if rw.shape[0] != n:
+        raise ValueError("obs_extra and recon must have the same number of rows")
+    out = {k: torch.empty(n, w, dtype=torch.float64, device=dev) for k, w in
+           (("humanPose", 60), ("dx_ddx", 118), ("feetpos", 24), ("com", 3), ("momentum", 6), ("con_bin", 4), ("con", 4))}
+    I = np.ascontiguousarray(np.asarray(srb_inertia, dtype=np.float64).reshape(3, 3))
+    lc = np.ascontiguousarray(np.asarray(srb_local_com, dtype=np.float64).reshape(3))
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib, lib.fullbody_extract(int(device), n, _ptr(ex), _ptr(rw), float(srb_mass), _ptr(I), _ptr(lc), _ptr(out["humanPose"]),
+                                     _ptr(out["dx_ddx"]), _ptr(out["feetpos"]), _ptr(out["com"]), _ptr(out["momentum"]),
+                                     _ptr(out["con_bin"]), _ptr(out["con"]), st))
+    return out

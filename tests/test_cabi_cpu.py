@@ -63,8 +63,8 @@ def test_mmsto_header_symbols_exported(built_lib):
     from ipcdnnwalk_b200 import _lib
     txt = open(os.path.join(helpers.ROOT, "include", "mmsto_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    names = sorted(set(re.findall(r"\b(mmsto_[a-z_0-9]+)\s*\(", txt)))
-    assert names == sorted(_lib.MMSTO_EXPORTED_SYMBOLS) and len(names) == 12
+    names = sorted(set(re.findall(r"\b((?:mmsto|fullbody)_[a-z_0-9]+)\s*\(", txt)))
+    assert names == sorted(_lib.MMSTO_EXPORTED_SYMBOLS) and len(names) == 13
     for n in names:
         assert hasattr(built_lib, n)
     import torch

@@ -162,3 +162,23 @@ def test_nan_window_is_contained(opt, skel):
     assert int(i1[2, 1]) == -1024 and int(i1[2, 3]) == 1
     for w in (0, 1, 3):
         assert np.array_equal(x0[w].cpu().numpy(), x1[w].cpu().numpy()) and np.array_equal(i0[w], i1[w])
+
+
+def test_extract_fullbody_matches_oracle():
+    """_extractSingleFrameFullbody (DeltaExtractor.py:577-643) on 37 items incl. a zero-rotation pelvis offset (small-angle branch
+    of Exp) and a half-turn one (the non-trace branches of the matrix -> quaternion conversion): every output at 1e-12."""
+    from ipcdnnwalk_b200.short_traj_opt import extractSingleFrameFullbody
+    from oracle import fullbody_map as fm
+    rng = np.random.default_rng(3)
+    n = 37
+    extra = rng.normal(0, 0.5, (n, fm.EXTRA_W)); row = rng.normal(0, 0.3, (n, fm.ROW_W))
+    for c in (3, 16, 23):
+        extra[:, c:c + 4] /= np.linalg.norm(extra[:, c:c + 4], axis=1, keepdims=True)
+    row[1, 0:3] = 0.0
+    row[2, 0:3] = np.array([0.0, 3.1, 0.2]); row[3, 0:3] = np.array([3.0, 0.1, 0.0]); row[4, 0:3] = np.array([0.1, 0.0, 3.05])
+    I = np.array([[3.0, 0.1, 0.0], [0.1, 1.5, -0.2], [0.0, -0.2, 2.5]]); lc = [0.01, -0.03, 0.02]
+    out = extractSingleFrameFullbody(extra, row, 60.0, I, lc)
+    for i in range(n):
+        ref = fm.extract_single_frame_fullbody(extra[i], row[i], 60.0, I, lc)
+        for k, v in ref.items():
+            assert np.abs(out[k][i].cpu().numpy() - v).max() < 1e-12, (i, k)

@@ -158,3 +158,37 @@ def test_remove_com_sliding_satisfies_its_constraints(skel):
     assert np.allclose(opt2[:, 1], curr[:, 1]) and np.allclose(opt2[:, [0, 2]], opt[:, [0, 2]])
     out3, _, _ = mm.remove_com_sliding_online(skel, com_srb, des, pose, ground_h=np.full(nvar, 0.3))
     assert not np.allclose(out3[4, 3:7], out[4, 3:7]) and np.allclose(out3[0], out[0])
+
+
+def test_extract_fullbody_building_blocks():
+    """Exp(se3) against scipy's matrix exponential (also across the small-angle branch), matrix -> quaternion on all four
+    branches, and the one-body momentum of _extractSingleFrameFullbody against m v / R I R^T w."""
+    from scipy.linalg import expm
+    from oracle import fullbody_map as fm
+    rng = np.random.default_rng(0)
+    for scale in (0.5, 3.0, 1e-12):
+        S = rng.normal(0, scale, 6)
+        R, p = fm.se3_exp(S)
+        X = np.zeros((4, 4)); w = S[:3]
+        X[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]; X[:3, 3] = S[3:]
+        E = expm(X)
+        assert np.allclose(E[:3, :3], R, atol=1e-9) and np.allclose(E[:3, 3], p, atol=1e-9)
+    branches = set()
+    for _ in range(200):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = np.array([fk.vrotate(q, e) for e in np.eye(3)]).T
+        q2 = fm.mat_to_quat(R)
+        tr = np.trace(R)
+        branches.add(-1 if tr > 0 else int(np.argmax(np.diag(R))))
+        assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 1e-12
+    assert branches == {-1, 0, 1, 2}
+    extra = np.zeros(fm.EXTRA_W); row = np.zeros(fm.ROW_W)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    extra[0:3] = [0.3, 0.9, -0.2]; extra[3:7] = q; extra[7:13] = rng.normal(size=6)
+    extra[16] = extra[23] = 1.0
+    I = np.diag([3.0, 1.5, 2.5])
+    out = fm.extract_single_frame_fullbody(extra, row, 60.0, I, [0, 0, 0])
+    R = np.array([fk.vrotate(q, e) for e in np.eye(3)]).T
+    assert np.allclose(out["momentum"][3:], 60.0 * extra[10:13], atol=1e-12)
+    assert np.allclose(out["momentum"][:3], R.dot(I).dot(R.T).dot(extra[7:10]), atol=1e-12)
+    assert np.allclose(out["humanPose"][:7], extra[:7]) and np.allclose(out["com"], extra[0:3])

@@ -60,4 +60,25 @@ if "--comslide" in sys.argv:
     by = nw * 8 * (60 + 7 + 6 + 6) * 8
     print(json.dumps({"kernel": "comslide_kernel", "windows": nw, "poses_per_window": 8, "ms": ms, "windows_per_s": nw / ms * 1e3,
                       "algorithmic_GBps": by / ms / 1e6, "note": "timing includes the two small output allocations of the Python mirror"}))
+if "--extract" in sys.argv:
+    from ipcdnnwalk_b200.short_traj_opt import extractSingleFrameFullbody
+    ni = 1 << 20
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    ex = torch.randn(ni, 29, device="cuda", generator=g, dtype=torch.float64) * 0.5
+    for c0 in (3, 16, 23):
+        ex[:, c0:c0 + 4] /= ex[:, c0:c0 + 4].norm(dim=1, keepdim=True)
+    rw = torch.randn(ni, 214, device="cuda", generator=g, dtype=torch.float64) * 0.3
+    I = np.diag([3.0, 1.5, 2.5])
+    for _ in range(3):
+        extractSingleFrameFullbody(ex, rw, 60.0, I)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); extractSingleFrameFullbody(ex, rw, 60.0, I); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    by = ni * (29 + 214 + 60 + 118 + 24 + 3 + 6 + 4 + 4) * 8
+    print(json.dumps({"kernel": "fullbody_extract_kernel", "items": ni, "ms": ms, "items_per_s": ni / ms * 1e3, "algorithmic_GBps": by / ms / 1e6,
+                      "note": "timing includes the seven output allocations of the Python mirror"}))
 opt.close()
