@@ -934,30 +934,13 @@ __device__ __forceinline__ void q_rotate(const double* q, const double* v, doubl
   o[2] = a * uz + b * v[2] + c2 * (ux * v[1] - uy * v[0]);
 }
 
-__global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArgs A) {
-  __shared__ double srow[4][FB_ROW + FB_EXTRA + 1];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int item = blockIdx.x * 4 + wi;
-  if (item >= A.n) return;
-  double* S = srow[wi];
-  const double* row = A.row + (size_t)item * FB_ROW;
-  const double* ex = A.extra + (size_t)item * FB_EXTRA;
-  for (int k = lane; k < FB_ROW; k += 32) S[k] = row[k];
-  if (lane < FB_EXTRA) S[FB_ROW + lane] = ex[lane];
-  __syncwarp();
+// task `task` of item `item` (S: its staged row followed by its SRB record)
+__device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, int task, size_t item, const double* S) {
   const double* E = S + FB_ROW;                      // pose_tl 0..6 | dq 7..12 | foot0 13..19 | foot1 20..26 | con 27..28
   const double* rq = E + 3;
-  double* human = A.human + (size_t)item * (7 + FB_POSES);
-  double* dxo = A.dx_ddx + (size_t)item * 2 * FB_NDOF;
-  for (int k = lane; k < FB_POSES; k += 32) human[7 + k] = S[FB_C_POSES + k];
-  for (int k = lane; k < FB_NDOF; k += 32) {
-    if (k >= 3) { dxo[k] = S[FB_C_DX + k] * 10.0; dxo[FB_NDOF + k] = S[FB_C_DDX + k] * 10.0; }
-  }
-  if (lane < 4) {
-    const double cv = S[FB_C_CON + lane];
-    A.con[(size_t)item * 4 + lane] = cv; A.con_bin[(size_t)item * 4 + lane] = cv > 0 ? 1.0 : 0.0;
-  }
-  if (lane == 4) {                                    // humanPose root = SRBroot * exp(toPelvis)
+  double* human = A.human + item * (7 + FB_POSES);
+  double* dxo = A.dx_ddx + item * 2 * FB_NDOF;
+  if (task == 0) {                                    // humanPose root = SRBroot * exp(toPelvis)
     const double w0 = S[0], w1 = S[1], w2 = S[2];
     const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
     double q2[4], p[3];
@@ -998,8 +981,7 @@ __global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArg
     for (int k = 0; k < 3; ++k) human[k] = ht[k] + E[k];
 #pragma unroll
     for (int k = 0; k < 4; ++k) human[3 + k] = hq[k];
-  }
-  if (lane == 5) {                                    // SRB momentum about its CoM + decoded corrections; CoM target
+  } else if (task == 1) {                             // SRB momentum about its CoM + decoded corrections; CoM target
     double inv[4], wb[3], vb[3], M[3], F[3], tmp[3];
     const double n2 = rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3], il = 1.0 / sqrt(n2);
     inv[0] = rq[0] * il; inv[1] = rq[1] * -1.0 * il; inv[2] = rq[2] * -1.0 * il; inv[3] = rq[3] * -1.0 * il;   // quater::inverse
@@ -1031,33 +1013,61 @@ __global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArg
     q_rotate(rq, S + FB_C_MOM, eC); q_rotate(rq, S + FB_C_MOM + 3, eM); q_rotate(rq, S + FB_C_MOM + 6, eF);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      A.momentum[(size_t)item * 6 + k] = (Mw[k] - tmp[k]) + eM[k];
-      A.momentum[(size_t)item * 6 + 3 + k] = Fw[k] + eF[k];
-      A.com[(size_t)item * 3 + k] = E[k] + eC[k];
+      A.momentum[item * 6 + k] = (Mw[k] - tmp[k]) + eM[k];
+      A.momentum[item * 6 + 3 + k] = Fw[k] + eF[k];
+      A.com[item * 3 + k] = E[k] + eC[k];
     }
-  }
-  if (lane >= 6 && lane < 10) {                       // foot marker positions in the foot frames
-    const int ic = lane - 6;
+  } else if (task < 6) {                              // foot marker positions in the foot frames
+    const int ic = task - 2;
     const double* ft = E + 13 + 7 * (ic >> 1);
     double g[3];
     q_rotate(ft + 3, S + FB_C_FEET + ic * 3, g);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) A.feetpos[(size_t)item * 24 + ic * 3 + k] = g[k] + ft[k];
-  }
-  if (lane >= 10 && lane < 14) {                      // foot marker velocities
-    const int ic = lane - 10;
+    for (int k = 0; k < 3; ++k) A.feetpos[item * 24 + ic * 3 + k] = g[k] + ft[k];
+  } else if (task < 10) {                             // foot marker velocities
+    const int ic = task - 6;
     double g[3];
     q_rotate(rq, S + FB_C_FEET + 12 + ic * 3, g);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) A.feetpos[(size_t)item * 24 + 12 + ic * 3 + k] = g[k] * 10.0 + E[10 + k];
-  }
-  if (lane == 14 || lane == 15) {                     // root translational velocity / acceleration: set_dx_ddx_v3
-    const int c0 = lane == 14 ? FB_C_DX : FB_C_DDX;
+    for (int k = 0; k < 3; ++k) A.feetpos[item * 24 + 12 + ic * 3 + k] = g[k] * 10.0 + E[10 + k];
+  } else {                                            // root translational velocity / acceleration: set_dx_ddx_v3
+    const bool vel = task == 10;
+    const int c0 = vel ? FB_C_DX : FB_C_DDX;
     const double v[3] = {S[c0] * 10.0, S[c0 + 1] * 10.0, S[c0 + 2] * 10.0};
     double g[3];
     q_rotate(rq, v, g);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dxo[(lane == 14 ? 0 : FB_NDOF) + k] = g[k] + (lane == 14 ? E[10 + k] : 0.0);
+    for (int k = 0; k < 3; ++k) dxo[(vel ? 0 : FB_NDOF) + k] = g[k] + (vel ? E[10 + k] : 0.0);
+  }
+}
+
+// 16 items per 128-thread CTA.  (1) rows and SRB records -> shared memory, coalesced; (2) the 12 small transforms of every
+// item as (task, item) pairs, 16 consecutive threads on the same task so a warp diverges two ways at most; (3) the
+// copy-and-scale columns (joint angles, dx, ddx, contacts) by all threads, coalesced.
+enum { FB_ITEMS = 16, FB_TASKS = 12, FB_STRIDE = FB_ROW + FB_EXTRA + 1 };
+__global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArgs A) {
+  __shared__ double srow[FB_ITEMS][FB_STRIDE];
+  const size_t item0 = (size_t)blockIdx.x * FB_ITEMS;
+  const int cnt = (int)min((size_t)FB_ITEMS, (size_t)A.n - item0);
+  for (int k = threadIdx.x; k < cnt * FB_ROW; k += 128) srow[k / FB_ROW][k % FB_ROW] = A.row[item0 * FB_ROW + k];
+  for (int k = threadIdx.x; k < cnt * FB_EXTRA; k += 128) srow[k / FB_EXTRA][FB_ROW + k % FB_EXTRA] = A.extra[item0 * FB_EXTRA + k];
+  __syncthreads();
+  for (int p = threadIdx.x; p < FB_TASKS * FB_ITEMS; p += 128) {
+    const int task = p / FB_ITEMS, it = p % FB_ITEMS;
+    if (it < cnt) fullbody_task(A, task, item0 + it, srow[it]);
+  }
+  for (int k = threadIdx.x; k < cnt * FB_POSES; k += 128) {
+    const int it = k / FB_POSES, c = k % FB_POSES;
+    A.human[(item0 + it) * (7 + FB_POSES) + 7 + c] = srow[it][FB_C_POSES + c];
+  }
+  for (int k = threadIdx.x; k < cnt * 2 * FB_NDOF; k += 128) {
+    const int it = k / (2 * FB_NDOF), c = k % (2 * FB_NDOF);
+    const int col = c < FB_NDOF ? c : c - FB_NDOF;
+    if (col >= 3) A.dx_ddx[(item0 + it) * 2 * FB_NDOF + c] = srow[it][(c < FB_NDOF ? FB_C_DX : FB_C_DDX) + col] * 10.0;
+  }
+  for (int k = threadIdx.x; k < cnt * 4; k += 128) {
+    const double cv = srow[k / 4][FB_C_CON + k % 4];
+    A.con[item0 * 4 + k] = cv; A.con_bin[item0 * 4 + k] = cv > 0 ? 1.0 : 0.0;
   }
 }
 
