@@ -95,6 +95,11 @@ int srb_set_state(srb_env* env, int32_t env_index, const double* reals, const in
 /* Running statistics for the one collective of the path (VecNormalize obs_rms, gym_cdm2/train_gym.py:98):
  * acc_dev[1 + 2*150] += (count, sum x, sum x^2) over the N rows of obs_dev.  The caller all-reduces acc. */
 int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* stream);
+
+/* pack_obs_extra (gym_trackSRB/taesooLib/DeltaExtractor.py:1015-1036): out_dev[N][29] doubles = the SRB state in taesooLib's
+ * Y-up convention: pose_tl 7 (translation, quaternion w x y z) | dq 6 (world angular, world linear velocity) | left / right
+ * foot frame 7 each (translation, quaternion) | left / right contact flag.  Input of fullbody_extract (include/mmsto_b200.h). */
+int srb_pack_obs_extra(srb_env* env, double* out_dev, void* stream);
 /* Episode statistics accumulated by auto-reset: out[3] = sum of returns, sum of lengths, count. */
 int srb_episode_stats(srb_env* env, double out[3], int32_t clear);
 

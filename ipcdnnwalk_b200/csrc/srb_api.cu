@@ -446,6 +446,58 @@ extern "C" int srb_obs_stats(srb_env* h, const float* obs_dev, double* acc_dev, 
   return 0;
 }
 
+// ---- pack_obs_extra (gym_trackSRB/taesooLib/DeltaExtractor.py:1015-1036): the SRB state in taesooLib's Y-up convention for the
+// SRB -> full-body mapping.  In the reference the foot-centre sites' xpos / xmat are overwritten with the feet of the action in
+// every sub-step (env/SRBEnv5_mocap_list_window.py:58-87), i.e. they ARE left/right_foot_contact_pos_global / _ori.
+// ZtoY (work/rendermodule.py:631-636): vector (x, y, z) -> (y, z, x), quaternion (w, x, y, z) -> (w, y, z, x).
+template <typename real>
+__global__ void srb_pack_obs_extra_kernel(const real* __restrict__ st, const int* __restrict__ ist, int N, int Npad, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+#define LD(f) (double)st[(size_t)(f) * Npad + e]
+  double* o = out + (size_t)e * 29;
+  // pose_tl: transf(quat, pos).ZtoY() written as translation, rotation
+  const double px = LD(F_POS), py = LD(F_POS + 1), pz = LD(F_POS + 2);
+  const double qw = LD(F_QUAT), qx = LD(F_QUAT + 1), qy = LD(F_QUAT + 2), qz = LD(F_QUAT + 3);
+  o[0] = py; o[1] = pz; o[2] = px; o[3] = qw; o[4] = qy; o[5] = qz; o[6] = qx;
+  // dq = [ q_yup * ZtoY(body angular velocity), ZtoY(world linear velocity) ]   (vector3::rotate, no normalisation)
+  const double wx = LD(F_QVEL + 4), wy = LD(F_QVEL + 5), wz = LD(F_QVEL + 3);          // ZtoY of qvel[3:6]
+  const double s = qw, ux = qy, uy = qz, uz = qx;
+  const double a = 2.0 * (ux * wx + uy * wy + uz * wz), b = s * s - (ux * ux + uy * uy + uz * uz), c2 = 2.0 * s;
+  o[7] = a * ux + b * wx + c2 * (uy * wz - uz * wy);
+  o[8] = a * uy + b * wy + c2 * (uz * wx - ux * wz);
+  o[9] = a * uz + b * wz + c2 * (ux * wy - uy * wx);
+  o[10] = LD(F_QVEL + 1); o[11] = LD(F_QVEL + 2); o[12] = LD(F_QVEL);
+  const int flags = ist[(size_t)I_FLAGS * Npad + e];
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const int fp = f == 0 ? F_FOOTL : F_FOOTR, fy = f == 0 ? F_FYAWL : F_FYAWR;
+    const double c = LD(fy), sn = LD(fy + 1);
+    // RE.toQuater(site_xmat) = quater::setRotation(matrix) on [[c,-s,0],[s,c,0],[0,0,1]] (quater.cpp:341-386), then ZtoY
+    double w, z;
+    const double tr = c + c + 1.0;
+    if (tr > 0.0) { double r = sqrt(tr + 1.0); w = r * 0.5; r = 0.5 / r; z = (sn - (-sn)) * r; }
+    else { double r = sqrt((1.0 - (c + c)) + 1.0); z = r * 0.5; r = 0.5 / r; w = (sn - (-sn)) * r; }
+    double* fo = o + 13 + 7 * f;
+    fo[0] = LD(fp + 1); fo[1] = LD(fp + 2); fo[2] = LD(fp);
+    fo[3] = w; fo[4] = 0.0; fo[5] = z; fo[6] = 0.0;
+  }
+  o[27] = (flags & FLAG_L) ? 1.0 : 0.0;
+  o[28] = (flags & FLAG_R) ? 1.0 : 0.0;
+#undef LD
+}
+
+extern "C" int srb_pack_obs_extra(srb_env* h, double* out_dev, void* stream) {
+  if (!h || !out_dev) return fail(-1, "srb_pack_obs_extra: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const int blocks = (h->N + 127) / 128;
+  if (h->cfg.precision == 64) srb_pack_obs_extra_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>((const double*)h->st, h->ist, h->N, h->Npad, out_dev);
+  else srb_pack_obs_extra_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>((const float*)h->st, h->ist, h->N, h->Npad, out_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int srb_episode_stats(srb_env* h, double out[3], int32_t clear) {
   if (!h || !out) return fail(-1, "srb_episode_stats: null argument");
   CK(cudaSetDevice(h->cfg.device));

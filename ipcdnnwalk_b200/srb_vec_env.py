@@ -256,6 +256,14 @@ class SRBVecEnv:
         """acc (float64 [1+2*150], device) += (count, sum, sum of squares) of the current observations."""
         check(self.lib.srb_obs_stats(self._h, _ptr(self.obs), _ptr(acc), self._stream()))
 
+    def pack_obs_extra(self, out=None):
+        """Batched `DeltaExtractor.pack_obs_extra(env)` (DeltaExtractor.py:1015-1036): [N, 29] float64 on the device."""
+        t = self.torch
+        if out is None:
+            out = t.empty(self.num_envs, 29, dtype=t.float64, device=self.device)
+        check(self.lib.srb_pack_obs_extra(self._h, _ptr(out), self._stream()))
+        return out
+
     def episode_stats(self, clear=False):
         out = np.zeros(3)
         check(self.lib.srb_episode_stats(self._h, _ptr(out), int(clear)))

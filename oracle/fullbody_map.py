@@ -107,3 +107,24 @@ def extract_single_frame_fullbody(extra, row, srb_mass, srb_inertia, srb_local_c
     ddx[0:3] = fk.vrotate(rq, ddx[0:3])
     return dict(humanPose=human, dx_ddx=np.concatenate([dx, ddx]), feetpos=feetpos, com=rt + com_error, momentum=mom,
                 con_bin=(con > 0).astype(float), con=con)
+
+
+def pack_obs_extra(env):
+    """DeltaExtractor.py:1015-1036 on an OracleSRBEnv.  data.site_xpos / site_xmat of the two foot-centre sites are what
+    set_feet_site_this_step_env wrote last (env/SRBEnv5_mocap_list_window.py:58-87): the feet of the action, i.e.
+    left/right_foot_contact_pos_global and left/right_foot_contact_ori.  ZtoY: work/rendermodule.py:631-636."""
+    d = env.data
+    qpos = np.asarray(d.qpos, dtype=float); qvel = np.asarray(d.qvel, dtype=float)
+
+    def v_ztoy(v):
+        return np.array([v[1], v[2], v[0]])
+
+    def q_ztoy(q):
+        return np.array([q[0], q[2], q[3], q[1]])
+    pose_q = q_ztoy(qpos[3:7]); pose_t = v_ztoy(qpos[0:3])
+    dq = np.concatenate([fk.vrotate(pose_q, v_ztoy(qvel[3:6])), v_ztoy(qvel[0:3])])
+    feet = []
+    for pos, ori in ((env.left_foot_contact_pos_global, env.left_foot_contact_ori), (env.right_foot_contact_pos_global, env.right_foot_contact_ori)):
+        feet.append(np.concatenate([v_ztoy(np.asarray(pos, dtype=float)), q_ztoy(mat_to_quat(np.asarray(ori, dtype=float)))]))
+    con = np.array([1.0 if env.left_foot_in_contact else 0.0, 1.0 if env.right_foot_in_contact else 0.0])
+    return np.concatenate([pose_t, pose_q, dq, feet[0], feet[1], con])

@@ -356,3 +356,34 @@ def test_single_env_proxy_has_reference_surface(built_lib):
     env.restoreFullState(st)
     assert env.current_frame == o.current_frame
     env.close()
+
+
+def test_pack_obs_extra_matches_oracle(built_lib):
+    """pack_obs_extra (DeltaExtractor.py:1015-1036): the Y-up SRB record of the SRB -> full-body mapping after a few steps."""
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv
+    from oracle.srb_env import OracleSRBEnv
+    from oracle import fullbody_map as fm
+    rng = np.random.default_rng(11)
+    clips = helpers.fresh_clips()
+    n = 6
+    plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
+    env = SRBVecEnv(clips, n, variant="test", precision=64, auto_reset=False)
+    env.reset(plan=plans)
+    oracles = []
+    for i in range(n):
+        o = OracleSRBEnv(helpers.fresh_clips(), "test")
+        helpers.oracle_reset(o, plans[i])
+        oracles.append(o)
+    for k in range(6):
+        acts = np.stack([helpers.tracking_action(o, rng, 0.05) for o in oracles])
+        env.step(torch.as_tensor(acts, device="cuda"))
+        ex = env.pack_obs_extra().cpu().numpy()
+        for i, o in enumerate(oracles):
+            o.step(acts[i])
+            ref = fm.pack_obs_extra(o)
+            both = np.isnan(ref) & np.isnan(ex[i])
+            assert ex[i].shape == (29,) and (np.isnan(ref) == np.isnan(ex[i])).all()
+            assert np.abs(np.where(both, 0.0, ex[i] - ref)).max() < 1e-5, (k, i)
+            assert (ex[i, 27:29] == ref[27:29]).all()
+    env.close()
