@@ -7,8 +7,9 @@
 // couples frames -- finite-difference velocities, the Gaussian-filtered marker / CoM residuals, the momentum Jacobian
 // averaged over the window, the L-BFGS dot products -- is an 8-lane shuffle.  The L-BFGS vectors (x, g, d, xp, gp, 6 s,
 // 6 y, the targets) live in a per-warp workspace laid out [vector][dof][32 lanes]: every access of the warp is one
-// contiguous 256-byte row.  Per-bone frames (R, t), the velocity / force accumulators and the middle hinge axes live in
-// shared memory as [bone][21][32 lanes] (105 kB per warp, bank-conflict free).
+// contiguous 256-byte row.  Shared memory per warp (53 kB, 4 warps per SM): bone frames as quaternion + origin
+// [bone][7][32 lanes], a depth-indexed stack [8][6][32 lanes] for parent velocities (forward sweep) and child force /
+// torque sums (reverse sweep), and the per-problem Gram matrices of the L-BFGS recursion.
 #pragma once
 #include <stdint.h>
 #include <math.h>
