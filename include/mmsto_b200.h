@@ -45,7 +45,9 @@ int mmsto_set_dof_weights(mmsto_solver* s, const double* w);
  *   x_out      [n][nf][ndof]    solution; info [n][4] = final objective, libLBFGS return code, iterations, evaluations
  *                               (a window whose objective turns NaN stops with LBFGSERR_UNKNOWNERROR = -1024 and its last
  *                               finite point; libLBFGS itself has no such check)
- * stream = cudaStream_t as void*.  Returns 0, or a negative error code (mmsto_last_error has the text). */
+ * stream = cudaStream_t as void*.  Returns 0, or a negative error code (mmsto_last_error has the text).
+ * A solver owns one workspace: calls on the same handle must be ordered (same stream, or synchronised by the caller); use one
+ * handle per concurrent stream. */
 int mmsto_solve(mmsto_solver* s, int32_t n, const double* x_original, const double* dx, const double* ddx,
                 const double* euler_mot, const double* gpos_target, const double* com, const double* momentum,
                 const int32_t* con, const double* velcon, double* x_out, double* info, void* stream);
