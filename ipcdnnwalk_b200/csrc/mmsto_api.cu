@@ -266,7 +266,11 @@ int fullbody_extract(int32_t device, int32_t n, const double* extra, const doubl
   A.inertia[0] = I[0]; A.inertia[1] = I[4]; A.inertia[2] = I[8]; A.inertia[3] = I[1]; A.inertia[4] = I[2]; A.inertia[5] = I[5];
   for (int k = 0; k < 3; ++k) { A.lcom[k] = srb_local_com[k]; A.r[k] = srb_mass * srb_local_com[k]; }
   A.human = human_pose; A.dx_ddx = dx_ddx; A.feetpos = feetpos; A.com = com; A.momentum = momentum; A.con_bin = con_bin; A.con = con;
-  mmsto::fullbody_extract_kernel<<<(n + mmsto::FB_ITEMS - 1) / mmsto::FB_ITEMS, 128, 0, (cudaStream_t)stream>>>(A);
+  // bulk copies need 16-byte aligned global addresses: every array base must be (cudaMalloc / torch allocations are 256-byte aligned)
+  const void* ptrs[] = {extra, row, human_pose, dx_ddx, feetpos, com, momentum, con_bin, con};
+  for (const void* q : ptrs) if (((uintptr_t)q & 15) != 0) return fail(-1, "fullbody_extract: arrays must be 16-byte aligned");
+  CK(cudaFuncSetAttribute(mmsto::fullbody_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mmsto::FullbodyTile)));
+  mmsto::fullbody_extract_kernel<<<(n + mmsto::FB_ITEMS - 1) / mmsto::FB_ITEMS, 128, sizeof(mmsto::FullbodyTile), (cudaStream_t)stream>>>(A);
   CK(cudaGetLastError());
   return 0;
 }

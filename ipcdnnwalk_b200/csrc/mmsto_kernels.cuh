@@ -11,6 +11,7 @@
 // [bone][7][32 lanes], a depth-indexed stack [8][6][32 lanes] for parent velocities (forward sweep) and child force /
 // torque sums (reverse sweep), and the per-problem Gram matrices of the L-BFGS recursion.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <math.h>
 
@@ -935,12 +936,14 @@ __device__ __forceinline__ void q_rotate(const double* q, const double* v, doubl
   o[2] = a * uz + b * v[2] + c2 * (ux * v[1] - uy * v[0]);
 }
 
-// task `task` of item `item` (S: its staged row followed by its SRB record)
-__device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, int task, size_t item, const double* S) {
-  const double* E = S + FB_ROW;                      // pose_tl 0..6 | dq 7..12 | foot0 13..19 | foot1 20..26 | con 27..28
+struct FullbodyOut { double *human, *dx_ddx, *feetpos, *com, *momentum, *con_bin, *con; };
+
+// task `task` of item `item` of the output arrays O (S: its staged row, E: its SRB record)
+__device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, const FullbodyOut& O, int task, size_t item, const double* S, const double* E) {
+  // E: pose_tl 0..6 | dq 7..12 | foot0 13..19 | foot1 20..26 | con 27..28
   const double* rq = E + 3;
-  double* human = A.human + item * (7 + FB_POSES);
-  double* dxo = A.dx_ddx + item * 2 * FB_NDOF;
+  double* human = O.human + item * (7 + FB_POSES);
+  double* dxo = O.dx_ddx + item * 2 * FB_NDOF;
   if (task == 0) {                                    // humanPose root = SRBroot * exp(toPelvis)
     const double w0 = S[0], w1 = S[1], w2 = S[2];
     const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
@@ -1014,9 +1017,9 @@ __device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, int task, s
     q_rotate(rq, S + FB_C_MOM, eC); q_rotate(rq, S + FB_C_MOM + 3, eM); q_rotate(rq, S + FB_C_MOM + 6, eF);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      A.momentum[item * 6 + k] = (Mw[k] - tmp[k]) + eM[k];
-      A.momentum[item * 6 + 3 + k] = Fw[k] + eF[k];
-      A.com[item * 3 + k] = E[k] + eC[k];
+      O.momentum[item * 6 + k] = (Mw[k] - tmp[k]) + eM[k];
+      O.momentum[item * 6 + 3 + k] = Fw[k] + eF[k];
+      O.com[item * 3 + k] = E[k] + eC[k];
     }
   } else if (task < 6) {                              // foot marker positions in the foot frames
     const int ic = task - 2;
@@ -1024,13 +1027,13 @@ __device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, int task, s
     double g[3];
     q_rotate(ft + 3, S + FB_C_FEET + ic * 3, g);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) A.feetpos[item * 24 + ic * 3 + k] = g[k] + ft[k];
+    for (int k = 0; k < 3; ++k) O.feetpos[item * 24 + ic * 3 + k] = g[k] + ft[k];
   } else if (task < 10) {                             // foot marker velocities
     const int ic = task - 6;
     double g[3];
     q_rotate(rq, S + FB_C_FEET + 12 + ic * 3, g);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) A.feetpos[item * 24 + 12 + ic * 3 + k] = g[k] * 10.0 + E[10 + k];
+    for (int k = 0; k < 3; ++k) O.feetpos[item * 24 + 12 + ic * 3 + k] = g[k] * 10.0 + E[10 + k];
   } else {                                            // root translational velocity / acceleration: set_dx_ddx_v3
     const bool vel = task == 10;
     const int c0 = vel ? FB_C_DX : FB_C_DDX;
@@ -1042,33 +1045,97 @@ __device__ __forceinline__ void fullbody_task(const FullbodyArgs& A, int task, s
   }
 }
 
-// 16 items per 128-thread CTA.  (1) rows and SRB records -> shared memory, coalesced; (2) the 12 small transforms of every
-// item as (task, item) pairs, 16 consecutive threads on the same task so a warp diverges two ways at most; (3) the
-// copy-and-scale columns (joint angles, dx, ddx, contacts) by all threads, coalesced.
-enum { FB_ITEMS = 16, FB_TASKS = 12, FB_STRIDE = FB_ROW + FB_EXTRA + 1 };
+// FB_ITEMS = 8 items per 128-thread CTA (29 kB of shared memory, 7 CTAs per SM; 16 items: fewer CTAs and 23 % slower, 4: too few
+// bytes per bulk copy).  (1) the 8 decoder rows (13.7 kB) and SRB records (1.9 kB) are contiguous in global memory and
+// arrive by two TMA bulk copies on an mbarrier; (2) the 12 small transforms of every item run as (task, item) pairs, 8
+// consecutive threads on the same task (a warp diverges four ways at most), and the copy-and-scale columns (joint angles, dx,
+// ddx, contacts) are produced by all threads -- everything into shared-memory output tiles; (3) the seven output tiles leave
+// by bulk stores.  The last, partly filled CTA of a launch uses plain loads / stores.
+enum { FB_ITEMS = 8, FB_TASKS = 12 };
+struct FullbodyTile {
+  double row[FB_ITEMS][FB_ROW];
+  double ext[FB_ITEMS][FB_EXTRA];
+  double human[FB_ITEMS][7 + FB_POSES];
+  double dx_ddx[FB_ITEMS][2 * FB_NDOF];
+  double feetpos[FB_ITEMS][24];
+  double com[FB_ITEMS][3];
+  double momentum[FB_ITEMS][6];
+  double con_bin[FB_ITEMS][4];
+  double con[FB_ITEMS][4];
+};
+static_assert(sizeof(double) * FB_ITEMS * FB_ROW % 16 == 0 && sizeof(double) * FB_ITEMS * FB_EXTRA % 16 == 0 &&
+              sizeof(double) * FB_ITEMS * 3 % 16 == 0 && offsetof(FullbodyTile, ext) % 16 == 0 && offsetof(FullbodyTile, human) % 16 == 0 &&
+              offsetof(FullbodyTile, dx_ddx) % 16 == 0 && offsetof(FullbodyTile, feetpos) % 16 == 0 && offsetof(FullbodyTile, com) % 16 == 0 &&
+              offsetof(FullbodyTile, momentum) % 16 == 0 && offsetof(FullbodyTile, con_bin) % 16 == 0 && offsetof(FullbodyTile, con) % 16 == 0,
+              "bulk copies need 16-byte multiples");
+
+__device__ __forceinline__ unsigned fb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(128) fullbody_extract_kernel(const FullbodyArgs A) {
-  __shared__ double srow[FB_ITEMS][FB_STRIDE];
+  extern __shared__ __align__(128) unsigned char fb_raw[];
+  FullbodyTile& T = *reinterpret_cast<FullbodyTile*>(fb_raw);
+  __shared__ __align__(8) unsigned long long mbar;
   const size_t item0 = (size_t)blockIdx.x * FB_ITEMS;
   const int cnt = (int)min((size_t)FB_ITEMS, (size_t)A.n - item0);
-  for (int k = threadIdx.x; k < cnt * FB_ROW; k += 128) srow[k / FB_ROW][k % FB_ROW] = A.row[item0 * FB_ROW + k];
-  for (int k = threadIdx.x; k < cnt * FB_EXTRA; k += 128) srow[k / FB_EXTRA][FB_ROW + k % FB_EXTRA] = A.extra[item0 * FB_EXTRA + k];
-  __syncthreads();
-  for (int p = threadIdx.x; p < FB_TASKS * FB_ITEMS; p += 128) {
+  const bool full = cnt == FB_ITEMS;
+  const int tid = threadIdx.x;
+  if (full) {
+    constexpr unsigned row_bytes = sizeof(double) * FB_ITEMS * FB_ROW, ext_bytes = sizeof(double) * FB_ITEMS * FB_EXTRA;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fb_smem_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb_smem_u32(&mbar)), "r"(row_bytes + ext_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(fb_smem_u32(T.row)), "l"(A.row + item0 * FB_ROW), "r"(row_bytes), "r"(fb_smem_u32(&mbar)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(fb_smem_u32(T.ext)), "l"(A.extra + item0 * FB_EXTRA), "r"(ext_bytes), "r"(fb_smem_u32(&mbar)) : "memory");
+    }
+    __syncthreads();
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred P; mbarrier.try_wait.parity.shared::cta.b64 P, [%1], 0; selp.u32 %0, 1, 0, P; }" : "=r"(ok) : "r"(fb_smem_u32(&mbar)) : "memory");
+  } else {
+    for (int k = tid; k < cnt * FB_ROW; k += 128) T.row[k / FB_ROW][k % FB_ROW] = A.row[item0 * FB_ROW + k];
+    for (int k = tid; k < cnt * FB_EXTRA; k += 128) T.ext[k / FB_EXTRA][k % FB_EXTRA] = A.extra[item0 * FB_EXTRA + k];
+    __syncthreads();
+  }
+  FullbodyOut O;
+  size_t base;
+  if (full) { O = {&T.human[0][0], &T.dx_ddx[0][0], &T.feetpos[0][0], &T.com[0][0], &T.momentum[0][0], &T.con_bin[0][0], &T.con[0][0]}; base = 0; }
+  else { O = {A.human, A.dx_ddx, A.feetpos, A.com, A.momentum, A.con_bin, A.con}; base = item0; }
+  for (int p = tid; p < FB_TASKS * FB_ITEMS; p += 128) {
     const int task = p / FB_ITEMS, it = p % FB_ITEMS;
-    if (it < cnt) fullbody_task(A, task, item0 + it, srow[it]);
+    if (it < cnt) fullbody_task(A, O, task, base + it, T.row[it], T.ext[it]);
   }
-  for (int k = threadIdx.x; k < cnt * FB_POSES; k += 128) {
+  for (int k = tid; k < cnt * FB_POSES; k += 128) {
     const int it = k / FB_POSES, c = k % FB_POSES;
-    A.human[(item0 + it) * (7 + FB_POSES) + 7 + c] = srow[it][FB_C_POSES + c];
+    O.human[(base + it) * (7 + FB_POSES) + 7 + c] = T.row[it][FB_C_POSES + c];
   }
-  for (int k = threadIdx.x; k < cnt * 2 * FB_NDOF; k += 128) {
+  for (int k = tid; k < cnt * 2 * FB_NDOF; k += 128) {
     const int it = k / (2 * FB_NDOF), c = k % (2 * FB_NDOF);
     const int col = c < FB_NDOF ? c : c - FB_NDOF;
-    if (col >= 3) A.dx_ddx[(item0 + it) * 2 * FB_NDOF + c] = srow[it][(c < FB_NDOF ? FB_C_DX : FB_C_DDX) + col] * 10.0;
+    if (col >= 3) O.dx_ddx[(base + it) * 2 * FB_NDOF + c] = T.row[it][(c < FB_NDOF ? FB_C_DX : FB_C_DDX) + col] * 10.0;
   }
-  for (int k = threadIdx.x; k < cnt * 4; k += 128) {
-    const double cv = srow[k / 4][FB_C_CON + k % 4];
-    A.con[item0 * 4 + k] = cv; A.con_bin[item0 * 4 + k] = cv > 0 ? 1.0 : 0.0;
+  for (int k = tid; k < cnt * 4; k += 128) {
+    const double cv = T.row[k / 4][FB_C_CON + k % 4];
+    O.con[base * 4 + k] = cv; O.con_bin[base * 4 + k] = cv > 0 ? 1.0 : 0.0;
+  }
+  if (full) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+#define FB_STORE(dst, src, bytes) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fb_smem_u32(src)), "r"((unsigned)(bytes)) : "memory")
+      FB_STORE(A.human + item0 * (7 + FB_POSES), T.human, sizeof(T.human));
+      FB_STORE(A.dx_ddx + item0 * 2 * FB_NDOF, T.dx_ddx, sizeof(T.dx_ddx));
+      FB_STORE(A.feetpos + item0 * 24, T.feetpos, sizeof(T.feetpos));
+      FB_STORE(A.com + item0 * 3, T.com, sizeof(T.com));
+      FB_STORE(A.momentum + item0 * 6, T.momentum, sizeof(T.momentum));
+      FB_STORE(A.con_bin + item0 * 4, T.con_bin, sizeof(T.con_bin));
+      FB_STORE(A.con + item0 * 4, T.con, sizeof(T.con));
+#undef FB_STORE
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
   }
 }
 
