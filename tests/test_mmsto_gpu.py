@@ -182,3 +182,29 @@ def test_extract_fullbody_matches_oracle():
         ref = fm.extract_single_frame_fullbody(extra[i], row[i], 60.0, I, lc)
         for k, v in ref.items():
             assert np.abs(out[k][i].cpu().numpy() - v).max() < 1e-12, (i, k)
+
+
+def test_full_batch_properties(opt, skel):
+    """4096 windows (the size of the throughput runs) built from 8 distinct problems: copies of a problem give bit-identical
+    solutions wherever they sit in the batch, the objective never ends above its starting value, frames 0 and 1 keep the clamped
+    input, and the solution of the copies equals the solution of the problem solved alone."""
+    import torch
+    base = [hm.make_problem(70 + s, skel=skel) for s in range(8)]
+    n = 4096
+    idx = np.arange(n) % 8
+    args = [torch.as_tensor(hm.stack(base, k), device="cuda")[idx].contiguous() for k in KEYS]
+    em = torch.as_tensor(hm.stack(base, "euler_mot"), device="cuda")[idx].contiguous()
+    vc = torch.as_tensor(hm.stack(base, "velcon"), device="cuda")[idx].contiguous()
+    opt.set("max_iterations", 8)
+    f0, _ = opt.evaluate(args[1], *args, velcon=vc)
+    x, info = opt.solveEndEffectors_euler(em, *args, velcon=vc)
+    x = x.cpu().numpy(); info = info.cpu().numpy()
+    assert np.isfinite(x).all()
+    for s in range(8):
+        sel = np.nonzero(idx == s)[0]
+        assert (x[sel] == x[sel[0]]).all() and (info[sel] == info[sel[0]]).all()
+    assert (info[:, 0] <= f0.cpu().numpy() * (1 + 1e-12)).all()
+    xo = args[1].cpu().numpy(); e = em.cpu().numpy()
+    assert np.array_equal(x[:, :2], np.clip(e[:, :2], xo[:, :2] - np.radians(25), xo[:, :2] + np.radians(25)))
+    x1, i1 = opt.solveEndEffectors_euler(em[3:4], *[a[3:4] for a in args], velcon=vc[3:4])
+    assert np.array_equal(x1[0].cpu().numpy(), x[3]) and np.array_equal(i1[0].cpu().numpy(), info[3])
