@@ -2,7 +2,7 @@
 
 Reference: the group-0 geoms of gym_trackSRB/Characters/SRB5_playground.xml that `terrain_height_ray`
 (env/testSRB_mujoco_original_viewer_terrain.py:741-752) ray-casts against -- one plane, PNG height fields, and the
-pyramid box stacks.  `TerrainModel.from_npz` reads the compact container written by tools/make_golden.py
+pyramid box stacks.  `TerrainModel.from_npz` reads the compact container written by tests/tools/make_golden.py
 (8-bit pixel arrays as stored in the PNG + geometry); pixels are converted the way mujoco stores hfield_data:
 image rows bottom-up, elevations normalised to [0,1] in float32."""
 import ctypes as C

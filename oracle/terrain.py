@@ -112,7 +112,7 @@ def normalise_png(pix):
 
 
 def load_playground(xml_path, terrain_dir):
-    """Parse SRB5_playground.xml (needs PIL for the PNGs; used only by tools/make_golden.py)."""
+    """Parse SRB5_playground.xml (needs PIL for the PNGs; used only by tests/tools/make_golden.py)."""
     from PIL import Image
     t = open(xml_path).read()
     hf_assets = {}

@@ -13,7 +13,7 @@ TABLE_KEYS = ("cdm", "dcdm", "cdm_d", "fullbody", "iframe_tab", "con", "touch_do
 
 
 def load_tables():
-    """tests/golden/cdm_walk_tables.npz (tools/make_golden_cdm.py) -> (tables dict, skeleton dict)."""
+    """tests/golden/cdm_walk_tables.npz (tests/tools/make_golden_cdm.py) -> (tables dict, skeleton dict)."""
     d = np.load(TABLES, allow_pickle=False)
     tab = {k: d[k].copy() for k in TABLE_KEYS}
     skel = json.loads(str(d["skeleton_json"]))

@@ -1,5 +1,5 @@
 """Closed-loop check of the AdaptiveSRB environment with the policy THE REFERENCE TRAINED on it
-(trained_models/ppo/walk2-v1.pt, flattened into tests/golden/cdm_policy_walk2.npz by tools/make_golden_cdm.py): a policy
+(trained_models/ppo/walk2-v1.pt, flattened into tests/golden/cdm_policy_walk2.npz by tests/tools/make_golden_cdm.py): a policy
 trained against the reference's environment only keeps walking in an environment that presents the same observation
 layout, action semantics, contact logic and dynamics.  Gait statistics are set beside those of the roll-out the
 reference recorded with the same policy (gym_cdm2/spec/refTraj_walk2-v1.dat); the reference tables used here are the

@@ -1,9 +1,9 @@
 """GPU throughput of the batched MMSTO solve: windows per second and objective evaluations per second at a
-fixed iteration budget, plus the numpy oracle on one host core for scale.  Usage: python tools/bench_mmsto.py [n] [max_iterations]"""
+fixed iteration budget, plus the numpy oracle on one host core for scale.  Usage: python tests/tools/bench_mmsto.py [n] [max_iterations]"""
 import json, os, sys, time
 import numpy as np
 import torch
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import helpers_mmsto as hm
 from ipcdnnwalk_b200 import ShortTrajOpt

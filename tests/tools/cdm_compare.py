@@ -3,7 +3,7 @@
 import os, sys
 import numpy as np
 import torch
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import helpers_cdm as hc
 from ipcdnnwalk_b200 import CDMVecEnv

@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
+import os; R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import helpers_mmsto as hm
 from ipcdnnwalk_b200 import ShortTrajOpt
 skel=hm.skeleton()

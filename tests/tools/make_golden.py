@@ -1,7 +1,7 @@
 """Generate the committed fixtures under tests/golden/ from the oracle and the reference's data files.
 
 Run HERE (needs /root/reference, which does not exist on the GPU box):
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 Writes:
   tests/golden/clip_<name>.npz        reference tables of the shipped clips (oracle/srbdata.py over
                                       gym_trackSRB/motiondata_mujoco_refined/<name>.txt + ref_contact/*.npz)
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.srbdata import SRBdata, load_mocap_txt          # noqa: E402

@@ -1,7 +1,7 @@
 """Generate the committed AdaptiveSRB fixtures under tests/golden/ from the oracle and the reference's data files.
 
 Run HERE (needs /root/reference, which does not exist on the GPU box):
-    python tools/make_golden_cdm.py
+    python tests/tools/make_golden_cdm.py
 Writes:
   tests/golden/cdm_walk_tables.npz   reference tables of walk2-v1 (ipcdnnwalk_b200/cdm_tables.py over
                                      work/taesooLib/Resource/motion/MOB1/hanyang_lowdof_T_lafan1_walk_2915.dof and
@@ -20,7 +20,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from ipcdnnwalk_b200 import cdm_tables as ct                 # noqa: E402

@@ -1,7 +1,7 @@
 """Every kernel family once at ragged batch sizes (last warp / CTA partly filled), all lane counts, device and host paths.
 Written for compute-sanitizer (memcheck / racecheck), which is closed on this GPU pool; runs plainly as a crash test."""
 import sys, os, numpy as np, torch
-R = os.environ.get("GRAFT_REPO_ROOT", "/root/repo")
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import helpers, helpers_mmsto as hm
 from ipcdnnwalk_b200 import SRBVecEnv, ShortTrajOpt, CDMVecEnv, Skeleton, vrml_skeleton, TerrainModel

@@ -3,12 +3,12 @@ statistics must be statistically indistinguishable over 1000 episodes").  Both s
 distributions) and tracking actions + N(0, 0.1^2); episodes end on `done`.  Prints one JSON line with means, standard
 deviations and Welch z-scores of episode return and length.
 
-  python tools/stat_compare.py [--episodes 1024] [--precision 32]"""
+  python tests/tools/stat_compare.py [--episodes 1024] [--precision 32]"""
 import argparse, json, math, os, sys, time
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
 import numpy as np
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 SIGMA = 0.1
 
