@@ -25,6 +25,7 @@ struct mmsto_solver {
   mmsto::Skel* d_sk = nullptr;
   mmsto::Prm* d_prm = nullptr;
   double* ws = nullptr; double* mc = nullptr; int ws_warps = 0;
+  int* d_queue = nullptr; int max_warps = 592;   // solve: persistent warps (4 per SM) pulling windows from a counter
   double* d_kinv = nullptr; int kinv_nvar = 0;    // inverse KKT matrix of removeCOMsliding_online for kinv_nvar frames
   double* d_zero = nullptr; int zero_n = 0;       // all-zero velocity constraints / contacts when the caller passes none
   bool dirty = true;
@@ -56,10 +57,17 @@ static int sync_params(mmsto_solver* s) {
   return 0;
 }
 
-static int prepare(mmsto_solver* s, int n) {
+static int prepare(mmsto_solver* s, int n, bool solve) {
   CK(cudaSetDevice(s->device));
   if (int r = sync_params(s)) return r;
-  const int warps = (n + mmsto::PPW - 1) / mmsto::PPW;
+  if (!s->d_queue) {
+    CK(cudaMalloc(&s->d_queue, sizeof(int)));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    s->max_warps = 4 * sms;
+  }
+  int warps = (n + mmsto::PPW - 1) / mmsto::PPW;
+  if (solve && warps > s->max_warps) warps = s->max_warps;
   if (warps > s->ws_warps) {
     cudaFree(s->ws); cudaFree(s->mc);
     const size_t wb = (size_t)warps * mmsto::NV * mmsto::MAXD * 32 * sizeof(double), mb = (size_t)warps * mmsto::MAXD * 6 * mmsto::PPW * sizeof(double);
@@ -80,10 +88,15 @@ static int prepare(mmsto_solver* s, int n) {
 }
 
 template <bool EVAL_ONLY> static int launch(mmsto_solver* s, mmsto::Args& A, void* stream) {
+  int warps = (A.n + mmsto::PPW - 1) / mmsto::PPW;
+  if (!EVAL_ONLY) {
+    if (warps > s->max_warps) warps = s->max_warps;
+    CK(cudaMemsetAsync(s->d_queue, 0, sizeof(int), (cudaStream_t)stream));
+    A.queue = s->d_queue;
+  }
   const size_t smem = (((size_t)s->sk.nb * mmsto::SM_W + mmsto::STK_LEVELS * mmsto::STK_W) * 32 + mmsto::PPW * mmsto::GM_W) * sizeof(double);
   auto kern = mmsto::mmsto_kernel<EVAL_ONLY>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int warps = (A.n + mmsto::PPW - 1) / mmsto::PPW;
   kern<<<warps, 32, smem, (cudaStream_t)stream>>>(A);
   CK(cudaGetLastError());
   ++s->launches;
@@ -158,7 +171,7 @@ int mmsto_create(int32_t device, int32_t nb, const int32_t* parent, const double
 int mmsto_destroy(mmsto_solver* s) {
   if (!s) return 0;
   cudaSetDevice(s->device);
-  cudaFree(s->d_sk); cudaFree(s->d_prm); cudaFree(s->ws); cudaFree(s->mc); cudaFree(s->d_zero); cudaFree(s->d_kinv);
+  cudaFree(s->d_sk); cudaFree(s->d_prm); cudaFree(s->ws); cudaFree(s->mc); cudaFree(s->d_zero); cudaFree(s->d_kinv); cudaFree(s->d_queue);
   delete s;
   return 0;
 }
@@ -191,7 +204,7 @@ int mmsto_solve(mmsto_solver* s, int32_t n, const double* x_original, const doub
   if (!s) return fail(-1, "mmsto_solve: null solver");
   if (n <= 0) return 0;
   if (!x_original || !dx || !ddx || !euler_mot || !gpos_target || !com || !momentum || !x_out || !info) return fail(-1, "mmsto_solve: null array");
-  if (int r = prepare(s, n)) return r;
+  if (int r = prepare(s, n, true)) return r;
   mmsto::Args A{};
   A.n = n; A.x_original = x_original; A.dx = dx; A.ddx = ddx; A.euler_mot = euler_mot; A.gpos_target = gpos_target; A.com = com;
   A.momentum = momentum; A.con = con; A.velcon = velcon ? velcon : s->d_zero; A.x_out = x_out; A.info = info;
@@ -205,7 +218,7 @@ int mmsto_evaluate(mmsto_solver* s, int32_t n, const double* x, const double* x_
   if (!s) return fail(-1, "mmsto_evaluate: null solver");
   if (n <= 0) return 0;
   if (!x || !x_original || !dx || !ddx || !gpos_target || !com || !momentum || !obj || !grad) return fail(-1, "mmsto_evaluate: null array");
-  if (int r = prepare(s, n)) return r;
+  if (int r = prepare(s, n, false)) return r;
   mmsto::Args A{};
   A.n = n; A.x_in = x; A.x_original = x_original; A.dx = dx; A.ddx = ddx; A.euler_mot = x; A.gpos_target = gpos_target; A.com = com;
   A.momentum = momentum; A.con = con; A.velcon = velcon ? velcon : s->d_zero; A.obj = obj; A.grad = grad;

@@ -49,6 +49,7 @@ struct Args {
   const int* con;
   double *x_out, *info, *obj, *grad;
   double *ws, *mc;
+  int* queue;                     // next unsolved problem (solve only): the 8-lane groups of the persistent warps pull from it
   const Skel* sk;
   const Prm* prm;
 };
@@ -170,8 +171,9 @@ __device__ __forceinline__ void bone_momentum(const Skel& sk, int b, const doubl
 }
 
 // One evaluation of LBFGS_opta's function at V_X: objective (same value on the 8 lanes of a problem) and, in V_G, the
-// gradient of this lane's frame.  `first`: rebuild the momentum-Jacobian cache (shortTermOptimizer.lua:669-684).
-__device__ double evaluate(Ctx& c, bool first) {
+// gradient of this lane's frame.  `first` (per problem; `any_first` = some problem of the warp): rebuild the momentum-Jacobian
+// cache (shortTermOptimizer.lua:669-684).
+__device__ double evaluate(Ctx& c, bool any_first, bool first) {
   const Skel& sk = *c.sk; const Prm& P = *c.P;
   const int nf = P.nf, nd = sk.ndof, f = c.f;
   const bool valid = c.valid, has_next = valid && f + 1 < nf;
@@ -253,7 +255,7 @@ __device__ double evaluate(Ctx& c, bool first) {
   for (int k = 0; k < 3; ++k) C[k] = comacc[k] * (1.0 / sk.total_mass);
 
   // ---------------- momentum Jacobian cache: mean over frames 0 .. nf-2 of calcMomentumJacobianTranspose
-  if (first && P.w_mom > 0) {
+  if (any_first && P.w_mom > 0) {                      // warp-uniform: every lane takes part in the reductions
     const bool use = valid && f < nf - 1;
     for (int j = 0; j < nd; ++j) {
       double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -288,7 +290,7 @@ __device__ double evaluate(Ctx& c, bool first) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const double s = grp_sum(use ? acc[k] : 0.0) * (1.0 / (nf - 1));
-        if (f == 0) c.MC[((size_t)j * 6 + k) * PPW + c.pg] = s;
+        if (first && f == 0) c.MC[((size_t)j * 6 + k) * PPW + c.pg] = s;
       }
     }
     __syncwarp();
@@ -527,46 +529,56 @@ __global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
   extern __shared__ double smem[];
   const Skel& sk = *A.sk; const Prm& P = *A.prm;
   const int lane = threadIdx.x, f = lane & 7, pg = lane >> 3, nf = P.nf, nd = sk.ndof;
-  const int prob = blockIdx.x * PPW + pg;
-  const bool pvalid = prob < A.n, valid = pvalid && f < nf;
   Ctx c;
-  c.sk = &sk; c.P = &P; c.sm = smem; c.gm = smem + ((size_t)sk.nb * SM_W + STK_LEVELS * STK_W) * 32 + pg * GM_W; c.lane = lane; c.f = f; c.pg = pg; c.valid = valid;
+  c.sk = &sk; c.P = &P; c.sm = smem; c.gm = smem + ((size_t)sk.nb * SM_W + STK_LEVELS * STK_W) * 32 + pg * GM_W; c.lane = lane; c.f = f; c.pg = pg;
   c.V = A.ws + (size_t)blockIdx.x * NV * MAXD * 32;
   c.MC = A.mc + (size_t)blockIdx.x * MAXD * 6 * PPW;
-  const size_t p64 = pvalid ? prob : 0;
-  c.velcon = A.velcon + p64 * MAXHS * HS_W;
-  c.con = A.con ? A.con[p64] : 0;
-#pragma unroll
-  for (int k = 0; k < 3 * NMARK; ++k) c.tgt[k] = valid ? A.gpos_target[(p64 * nf + f) * 3 * NMARK + k] : 0.0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) c.comt[k] = valid ? A.com[(p64 * nf + f) * 3 + k] : 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) c.momt[k] = (valid && f < nf - 1) ? A.momentum[(p64 * (nf - 1) + f) * 6 + k] : 0.0;
-
-  // ---- problem -> workspace.  Row f of V_DX holds dx[f-1], row f of V_DDX holds ddx[f-1] (the rows the terms centred at f use).
   const double thr = P.clamp * (3.14159265358979323846 / 180.0);
-  for (int j = 0; j < MAXD; ++j) {
-    double xo = 0, dxv = 0, ddxv = 0, x = 0;
-    if (valid && j < nd) {
-      xo = A.x_original[(p64 * nf + f) * nd + j];
-      if (f >= 1 && f - 1 < nf - 1) dxv = A.dx[(p64 * (nf - 1) + f - 1) * nd + j];
-      if (f >= 1 && f - 1 < nf - 2) ddxv = A.ddx[(p64 * (nf - 2) + f - 1) * nd + j];
-      if (EVAL_ONLY) x = A.x_in[(p64 * nf + f) * nd + j];
-      else if (f < 2) x = fmin(fmax(A.euler_mot[(p64 * nf + f) * nd + j], xo - thr), xo + thr);     // :829-838
-      else x = xo;
-    }
-    if (!EVAL_ONLY) {
+  int prob = -1;
+  bool pvalid = false, valid = false;
+  size_t p64 = 0;
+  // problem -> registers and workspace for the groups with `loading` set (called by the whole warp: the frame sums are
+  // shuffles).  Row f of V_DX holds dx[f-1], row f of V_DDX holds ddx[f-1] (the rows the terms centred at f use).
+  auto load_problem = [&](bool loading) {
+    if (loading) {
+      pvalid = prob >= 0 && prob < A.n; valid = pvalid && f < nf; c.valid = valid;
+      p64 = pvalid ? prob : 0;
+      c.velcon = A.velcon + p64 * MAXHS * HS_W;
+      c.con = A.con ? A.con[p64] : 0;
 #pragma unroll
-      for (int q = 0; q < 2 * LB_M; ++q) VEC(c, V_S + q, j) = 0.0;                 // stale history of an earlier solve
+      for (int k = 0; k < 3 * NMARK; ++k) c.tgt[k] = valid ? A.gpos_target[(p64 * nf + f) * 3 * NMARK + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c.comt[k] = valid ? A.com[(p64 * nf + f) * 3 + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c.momt[k] = (valid && f < nf - 1) ? A.momentum[(p64 * (nf - 1) + f) * 6 + k] : 0.0;
     }
-    VEC(c, V_XO, j) = xo; VEC(c, V_DX, j) = dxv; VEC(c, V_DDX, j) = ddxv; VEC(c, V_X, j) = x; VEC(c, V_G, j) = 0.0;
-    const double s = grp_sum(xo);                          // sum over the frames (:231-235); fixed order inside the shuffle tree
-    VEC(c, V_SUMO, j) = s;
-  }
-  __syncwarp();
+    for (int j = 0; j < MAXD; ++j) {
+      double xo = 0, dxv = 0, ddxv = 0, x = 0;
+      if (loading && valid && j < nd) {
+        xo = A.x_original[(p64 * nf + f) * nd + j];
+        if (f >= 1 && f - 1 < nf - 1) dxv = A.dx[(p64 * (nf - 1) + f - 1) * nd + j];
+        if (f >= 1 && f - 1 < nf - 2) ddxv = A.ddx[(p64 * (nf - 2) + f - 1) * nd + j];
+        if (EVAL_ONLY) x = A.x_in[(p64 * nf + f) * nd + j];
+        else if (f < 2) x = fmin(fmax(A.euler_mot[(p64 * nf + f) * nd + j], xo - thr), xo + thr);     // :829-838
+        else x = xo;
+      }
+      const double s = grp_sum(xo);                        // sum over the frames (:231-235); fixed order inside the shuffle tree
+      if (loading) {
+        if (!EVAL_ONLY) {
+#pragma unroll
+          for (int q = 0; q < 2 * LB_M; ++q) VEC(c, V_S + q, j) = 0.0;               // stale history of an earlier solve
+        }
+        VEC(c, V_XO, j) = xo; VEC(c, V_DX, j) = dxv; VEC(c, V_DDX, j) = ddxv; VEC(c, V_X, j) = x; VEC(c, V_G, j) = 0.0; VEC(c, V_D, j) = 0.0;
+        VEC(c, V_SUMO, j) = s;
+      }
+    }
+    __syncwarp();
+  };
 
   if (EVAL_ONLY) {
-    const double fx = evaluate(c, true);
+    prob = blockIdx.x * PPW + pg;
+    load_problem(true);
+    const double fx = evaluate(c, true, true);
     if (valid) {
       for (int j = 0; j < nd; ++j) A.grad[(p64 * nf + f) * nd + j] = VEC(c, V_G, j);
       if (f == 0) A.obj[p64] = fx;
@@ -575,13 +587,28 @@ __global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
   }
 
   // ---- lbfgs() (lbfgs.cpp:246-640) as a per-problem state machine; one evaluation per trip of the loop
-  const bool fr = valid && f >= 2;                         // the free variables (W2 of oracle/mmsto.py)
-  int phase = pvalid ? 0 : 2, k = 1, end = 0, count = 0, ret = 0, n_eval = 0, iters = 0;
+  // The warps are persistent: an 8-lane group that has finished its window pulls the next unsolved one from A.queue, so a
+  // warp never idles behind the slowest of four windows and a launch has no partly filled last wave.
+  bool fr = false;                                         // the free variables (W2 of oracle/mmsto.py)
+  int phase = 2, k = 1, end = 0, count = 0, ret = 0, n_eval = 0, iters = 0;
   double step = 0, finit = 0, dginit = 0, dgtest = 0, fx = 0;
-  bool firstev = true;
-  for (int trip = 0; trip < 1000000; ++trip) {
-    if (__all_sync(0xffffffffu, phase == 2)) break;
-    const double fv = evaluate(c, firstev);
+  bool firstev = false, need_load = true;
+  for (;;) {
+    if (__any_sync(0xffffffffu, need_load)) {
+      int idx = -1;
+      if (need_load && f == 0) idx = atomicAdd(A.queue, 1);
+      idx = __shfl_sync(0xffffffffu, idx, lane & ~7);
+      if (need_load) prob = idx;
+      load_problem(need_load);
+      if (need_load) {
+        fr = valid && f >= 2;
+        phase = pvalid ? 0 : 2; k = 1; end = 0; count = 0; ret = 0; n_eval = 0; iters = 0;
+        step = finit = dginit = dgtest = fx = 0;
+        firstev = pvalid; need_load = false;
+      }
+    }
+    if (__all_sync(0xffffffffu, phase == 2)) break;        // every group found the queue empty
+    const double fv = evaluate(c, __any_sync(0xffffffffu, firstev), firstev);
     firstev = false;
     if (phase != 2) ++n_eval;
     double dg, gg, xx;
@@ -720,13 +747,16 @@ __global__ void __launch_bounds__(32, 4) mmsto_kernel(const Args A) {
         }
       }
     }
-    __syncwarp();
-  }
-  if (valid) {
-    for (int j = 0; j < nd; ++j) A.x_out[(p64 * nf + f) * nd + j] = VEC(c, V_X, j);
-    if (f == 0) {
-      A.info[p64 * 4 + 0] = fx; A.info[p64 * 4 + 1] = ret; A.info[p64 * 4 + 2] = iters; A.info[p64 * 4 + 3] = n_eval;
+    if (phase == 2 && pvalid) {                            // this window is done: results out, next one at the top of the loop
+      if (valid) {
+        for (int j = 0; j < nd; ++j) A.x_out[(p64 * nf + f) * nd + j] = VEC(c, V_X, j);
+        if (f == 0) {
+          A.info[p64 * 4 + 0] = fx; A.info[p64 * 4 + 1] = ret; A.info[p64 * 4 + 2] = iters; A.info[p64 * 4 + 3] = n_eval;
+        }
+      }
+      pvalid = false; valid = false; c.valid = false; fr = false; need_load = true;
     }
+    __syncwarp();
   }
 }
 
