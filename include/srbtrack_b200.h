@@ -82,9 +82,11 @@ int srb_set_host_mode(srb_env* env, int32_t mode);
 int srb_set_aux(srb_env* env, const float* contact_prob_dev, float* term_obs_dev, const double* reset_plan_dev, double* dbg_dev);
 
 /* Reward weights (w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c; :561-569) and the external-push schedule
- * (impulse_interval / impulse_duration / force; :182-206). */
+ * (impulse_interval / impulse_duration / force; :182-206).  force[force_len], force_len <= 6, is what update_impulse copies into
+ * data.xfrc_applied[1] (`f[0:len(self.force)] = self.force`, :199): world-frame force at the body CoM and, for a 6-vector, a
+ * world-frame torque (the push of walk_SRBTrack2025_terrain_singlethreaded.py:117-119: torque = impulse_lpos x force). */
 int srb_set_reward_weights(srb_env* env, const double w[9]);
-int srb_set_impulse(srb_env* env, int32_t interval, int32_t duration, const double force[3]);
+int srb_set_impulse(srb_env* env, int32_t interval, int32_t duration, const double* force, int32_t force_len);
 
 /* SRBEnv.getFullState / restoreFullState (env/SRBEnv5_mocap_list_window.py:1005-1053) of one environment.
  * reals[srb_state_dims real count], ints[int count], hist[slots*width]; layout in srb_state_dims(). */

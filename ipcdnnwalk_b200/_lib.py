@@ -42,7 +42,7 @@ _SIGNATURES = {
     "srb_set_host_mode": (C.c_int, [_P, C.c_int32]),
     "srb_set_aux": (C.c_int, [_P, _P, _P, _P, _P]),
     "srb_set_reward_weights": (C.c_int, [_P, _P]),
-    "srb_set_impulse": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "srb_set_impulse": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32]),
     "srb_state_dims": (C.c_int, [C.POINTER(C.c_int32)] * 4),
     "srb_get_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "srb_set_state": (C.c_int, [_P, C.c_int32, _P, _P, _P]),

@@ -49,7 +49,8 @@ static const int MAX_CLIPS = 64;
 template <typename real> static Params<real> convert_params(const Params<double>& p) {
   Params<real> q;
   q.h = (real)p.h; q.nsub = p.nsub; q.mass = (real)p.mass;
-  for (int i = 0; i < 3; i++) { q.inertia[i] = (real)p.inertia[i]; q.impulse_force[i] = (real)p.impulse_force[i]; }
+  for (int i = 0; i < 3; i++) q.inertia[i] = (real)p.inertia[i];
+  for (int i = 0; i < 6; i++) q.impulse_force[i] = (real)p.impulse_force[i];
   q.armature = (real)p.armature; q.damping = (real)p.damping; q.grav = (real)p.grav; q.mu_b = (real)p.mu_b;
   q.kp = (real)p.kp; q.kd = (real)p.kd; q.w_lambda = (real)p.w_lambda; q.force_thr = (real)p.force_thr;
   for (int i = 0; i < 9; i++) q.w[i] = (real)p.w[i];
@@ -77,6 +78,7 @@ static void default_params(Params<double>& p, int variant) {
   p.kp = 120.0; p.kd = 35.0; p.w_lambda = 0.001; p.force_thr = 10000.0;
   p.max_frame = 512;
   p.use_terrain = 0;
+  for (int i = 0; i < 6; i++) p.impulse_force[i] = 0.0;
   if (variant == SRB_VARIANT_TEST || variant == SRB_VARIANT_TERRAIN) {
     const double w[9] = {5, 0.1, 0.5, 0, 50, 20, 700, 50, 1};
     memcpy(p.w, w, sizeof(w));
@@ -367,12 +369,13 @@ extern "C" int srb_set_reward_weights(srb_env* h, const double w[9]) {
   return 0;
 }
 
-extern "C" int srb_set_impulse(srb_env* h, int32_t interval, int32_t duration, const double force[3]) {
+extern "C" int srb_set_impulse(srb_env* h, int32_t interval, int32_t duration, const double* force, int32_t force_len) {
   if (!h || !force) return fail(-1, "srb_set_impulse: null argument");
   if (interval <= 0) return fail(-1, "srb_set_impulse: interval must be positive");
+  if (force_len < 0 || force_len > 6) return fail(-1, "srb_set_impulse: force has at most 6 components (force, torque)");
   h->p.impulse_interval = interval; h->p.impulse_duration = duration;
-  for (int i = 0; i < 3; i++) h->p.impulse_force[i] = force[i];
-  h->p.use_impulse = 1;
+  for (int i = 0; i < 6; i++) h->p.impulse_force[i] = i < force_len ? force[i] : 0.0;
+  h->p.use_impulse = h->cfg.variant != SRB_VARIANT_TRAINING;   // the training env never calls update_impulse (..._training.py:366-367)
   return 0;
 }
 

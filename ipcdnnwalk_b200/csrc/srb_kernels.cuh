@@ -1124,12 +1124,17 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     V3<real> bw = cross(s.vang, Iw);
     real bias[6] = {real(0), real(0), P.mass * P.grav, bw.x, bw.y, bw.z};
     // update_impulse (:191-206)
-    real xf[3] = {0, 0, 0};
+    real xf[6] = {0, 0, 0, 0, 0, 0};     // xfrc_applied: world force, world torque -> J^T: torque onto the body axes (mj_xfrcAccumulate)
     if (P.use_impulse) {
       bool trig = P.impulse_trigger_at_end ? (s.fcount % P.impulse_interval == P.impulse_interval - 1)
                                            : (s.fcount % P.impulse_interval == 0);
       if (trig) s.impulse = P.impulse_duration;
-      if (s.impulse > 0) { s.impulse -= 1; xf[0] = P.impulse_force[0]; xf[1] = P.impulse_force[1]; xf[2] = P.impulse_force[2]; }
+      if (s.impulse > 0) {
+        s.impulse -= 1;
+        xf[0] = P.impulse_force[0]; xf[1] = P.impulse_force[1]; xf[2] = P.impulse_force[2];
+        const V3<real> tq = mulT(R, V3<real>{P.impulse_force[3], P.impulse_force[4], P.impulse_force[5]});
+        xf[3] = tq.x; xf[4] = tq.y; xf[5] = tq.z;
+      }
       s.fcount += 1;
     }
     real qfrc[6] = {0, 0, 0, 0, 0, 0};
@@ -1223,11 +1228,10 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
       }
     }
     // mj_step2: acceleration + semi-implicit Euler with implicit joint damping
-    real xfq[6] = {xf[0], xf[1], xf[2], real(0), real(0), real(0)};
     real qv[6] = {s.vlin.x, s.vlin.y, s.vlin.z, s.vang.x, s.vang.y, s.vang.z};
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      real f = (-P.damping * qv[i]) - bias[i] + qfrc[i] + xfq[i];
+      real f = (-P.damping * qv[i]) - bias[i] + qfrc[i] + xf[i];
       qv[i] += P.h * (f * P.inv_Mh[i]);
     }
     s.vlin = {qv[0], qv[1], qv[2]};

@@ -78,7 +78,7 @@ template <typename real> struct Params {
   real w[9];            // w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c
   int use_filter, use_clamp, use_impulse, obs_after_inc, use_terrain;
   int impulse_interval, impulse_duration, impulse_trigger_at_end;
-  real impulse_force[3];
+  real impulse_force[6];   // xfrc_applied[1]: world-frame force, world-frame torque (f[0:len(self.force)] = self.force, :199)
   int max_frame;        // 512
 };
 

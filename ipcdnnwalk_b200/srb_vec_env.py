@@ -235,8 +235,10 @@ class SRBVecEnv:
         check(self.lib.srb_set_reward_weights(self._h, _ptr(w)))
 
     def set_impulse(self, interval, duration, force):
-        f = np.ascontiguousarray(force, dtype=np.float64)
-        check(self.lib.srb_set_impulse(self._h, int(interval), int(duration), _ptr(f)))
+        """impulse_interval / impulse_duration / force (:182-206); `force` has up to 6 components (world force, world torque:
+        `f[0:len(self.force)] = self.force`)."""
+        f = np.ascontiguousarray(np.asarray(force, dtype=np.float64).reshape(-1))
+        check(self.lib.srb_set_impulse(self._h, int(min(interval, 2**31 - 1)), int(duration), _ptr(f), int(f.shape[0])))
 
     def set_planar_offsets(self, xy):
         """initial_pos_planar per environment ([N,2]); used from each environment's next reset on."""

@@ -257,7 +257,7 @@ class OracleSRBEnv:
         f = np.zeros(6)
         if self.impulse > 0:
             self.impulse -= 1
-            f[0:3] = self.force[0:3]
+            f[0:len(self.force)] = self.force      # :199 -- a 6-vector carries a world-frame torque (driver :117-119)
         self.data.xfrc_applied = f.copy()
         self.f = f
         self.frame_counter += 1

@@ -108,7 +108,7 @@ def oracle_to_cuda_state(env, n_real=46, n_int=7, slots=32, width=8):
     r[17:20] = env.left_foot_contact_pos_global; r[20:23] = env.right_foot_contact_pos_global
     lo, ro = env.left_foot_contact_ori, env.right_foot_contact_ori
     r[23:27] = [lo[0, 0], lo[1, 0], ro[0, 0], ro[1, 0]]
-    inited = env.variant == "test" and env.contactFilter[0] is not None
+    inited = env.variant in ("test", "terrain") and env.contactFilter[0] is not None
     if inited:
         r[27:29] = [float(env.contactFilter[0]), float(env.contactFilter[1])]
         balls = [env.contactFilter[2][0], env.contactFilter[2][1], env.contactFilter[3][0], env.contactFilter[3][1]]

@@ -210,3 +210,48 @@ def test_luaenv_proxy(data):
     s, r, d, tr, info = e.step(np.zeros(10, dtype=np.float32))
     assert s.shape == (27,) and isinstance(r, float) and tr is False and info == {}
     e.close()
+
+
+@pytest.mark.parametrize("precision,rtol,atol", [(64, 1e-5, 1e-6), (32, 5e-3, 5e-3)])
+def test_sample_at_bench_size_16384(data, precision, rtol, atol):
+    """BASELINE configs[3] batch (16384 envs, default lane count = one thread per environment): 48 random environments
+    of the full batch against the oracle over 8 steps with U(-1,1) actions (the workload of tools/bench_cdm.py).
+    fp64 at the single-step tolerance; fp32 free-running, so the accumulated bound (5e-3); swing flags / replay length /
+    done bit exact in both."""
+    import torch
+    from ipcdnnwalk_b200 import CDMVecEnv
+    from oracle.cdm_env import OracleCDMEnv
+    tab, skel, _ = data
+    n = 16384
+    rng = np.random.default_rng(16384)
+    plans = np.stack([hc.random_plan(rng, 0.3) for _ in range(n)])      # 0.3 x the reset noise: most episodes outlive the 8 steps
+    env = CDMVecEnv(tab, skel, n, precision=precision, auto_reset=False)
+    env.reset(plan=plans)
+    sample = sorted(set(rng.choice(n, 46, replace=False).tolist() + [0, n - 1]))
+    oracles = {}
+    for i in sample:
+        o = OracleCDMEnv(tab, skel)
+        hc.oracle_reset(o, plans[i])
+        oracles[i] = o
+    alive = set(sample)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    idx = torch.as_tensor(sample, device="cuda")
+    for t in range(8):
+        act = torch.rand(n, 10, device="cuda", generator=gen) * 2 - 1
+        a = act[idx].cpu().numpy()
+        obs, rew, done, _ = env.step(act)
+        torch.cuda.synchronize()
+        o_s = obs[idx].cpu().numpy(); r_s = rew[idx].cpu().numpy(); d_s = done[idx].cpu().numpy()
+        for j, i in enumerate(sample):
+            if i not in alive:
+                continue
+            oo, rr, dd = oracles[i].step(a[j])
+            assert bool(d_s[j]) == dd, f"step {t} env {i}: done differs"
+            if dd:
+                alive.discard(i)              # NaN / terminal state: the reference returns zeros; not compared further
+                continue
+            _assert_close(o_s[j], oo, rtol, atol, f"step {t} env {i} obs")
+            _assert_close(float(r_s[j]), rr, rtol, atol, f"step {t} env {i} reward")
+            hc.compare_state(env.get_state(i), oracles[i], rtol, atol, f"step {t} env {i}")
+    assert len(alive) >= 24
+    env.close()
