@@ -1,0 +1,258 @@
+"""Pins against outputs of the REFERENCE ITSELF.
+
+tests/golden/ref_taesoolib.npz holds what the reference's own taesooLib C++ (BaseLib math / motion / IK_sdls / IK_lbfgs, compiled from
+/root/reference by oracle/ref_build/Makefile into oracle/_ref and driven by tests/tools/make_golden_ref.py) computes on seeded inputs.
+
+  * CPU tests: the oracle (oracle/bone_fk.py, mmsto.py, tl_math.py, tl_terrain.py) and the product's file readers reproduce those outputs.
+  * `live` tests re-run the compiled reference here when oracle/_ref exists (it does wherever /root/reference is mounted) and check that the
+    committed fixture is what it prints -- so the fixture cannot drift from the reference.
+  * GPU tests: the CUDA kernels (FK / CoM / momentum, taesooLib terrain height, MMSTO solve) are compared with the reference outputs DIRECTLY,
+    through the C-ABI, without the oracle in between."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+import helpers_mmsto as hm
+
+sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "tools"))
+import ref_harness as rh                    # noqa: E402
+from make_golden_ref import rosenbrock, mmsto_window, EU_MARKERS    # noqa: E402
+
+from ipcdnnwalk_b200 import vrml_skeleton
+from oracle import bone_fk as bk, mmsto as mm, tl_math as tm, tl_terrain as tt
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return dict(np.load(os.path.join(helpers.GOLDEN, "ref_taesoolib.npz")))
+
+
+@pytest.fixture(scope="module")
+def skel():
+    return vrml_skeleton.builtin()
+
+
+live = pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built (needs /root/reference): the committed fixture stands in")
+
+
+# ---------------------------------------------------------------------------------------------------------- a-22 / a-23
+def test_oracle_fk_and_momentum_equal_reference(ref, skel):
+    """BoneForwardKinematics frames, LoaderToTree frames, link velocities, calcCOM and calcMomentumCOM (Q13) of the reference."""
+    for r in range(ref["fk_pose"].shape[0]):
+        pose, dq = ref["fk_pose"][r], ref["fk_dq"][r]
+        rot, tr = bk.bone_forward_kinematics(skel, pose)
+        assert np.abs(rot - ref["fk_bfk"][r][:, 3:]).max() < 1e-14 and np.abs(tr - ref["fk_bfk"][r][:, :3]).max() < 1e-13
+        rot2, tr2, W, V = bk.loader_to_tree(skel, pose, dq)
+        assert np.abs(rot2 - ref["fk_tree"][r][:, 3:]).max() < 1e-14 and np.abs(tr2 - ref["fk_tree"][r][:, :3]).max() < 1e-13
+        for b in range(20):                                 # getWorldAngVel / getWorldVelocity = R * body velocity
+            assert np.abs(bk.vrotate(rot2[b], W[b]) - ref["fk_angvel"][r, b]).max() < 1e-12
+            assert np.abs(bk.vrotate(rot2[b], V[b]) - ref["fk_linvel"][r, b]).max() < 1e-12
+        com, H = bk.calc_momentum_com(skel, rot2, tr2, W, V)
+        assert np.abs(com - ref["fk_com"][r]).max() < 1e-13
+        assert np.abs(H - ref["fk_mom"][r]).max() < 1e-11 * max(1.0, np.abs(ref["fk_mom"][r]).max())
+
+
+# ---------------------------------------------------------------------------------------------------------- f-1 tree
+def test_oracle_euler_tree_equals_reference(ref, skel):
+    """ShortTrajOpt's Euler-root LoaderToTree: frames, CoM, momentum, and every Jacobian the MMSTO gradient is built from."""
+    T = mm.EulerTree(skel)
+    for r in range(ref["eu_q"].shape[0]):
+        T.set_q(ref["eu_q"][r]); T.set_dq(ref["eu_dq"][r])
+        assert np.abs(T.rot - ref["eu_frames"][r][:, 3:]).max() < 1e-14 and np.abs(T.tr - ref["eu_frames"][r][:, :3]).max() < 1e-13
+        assert np.abs(T.calc_com() - ref["eu_com"][r]).max() < 1e-13
+        assert np.abs(T.calc_momentum_com() - ref["eu_mom"][r]).max() < 1e-11 * max(1.0, np.abs(ref["eu_mom"][r]).max())
+        assert np.abs(T.calc_com_jacobian_T() - ref["eu_JT_com"][r]).max() < 1e-13
+        assert np.abs(T.calc_momentum_jacobian_T() - ref["eu_JT_mom"][r]).max() < 1e-11 * max(1.0, np.abs(ref["eu_JT_mom"][r]).max())
+        for k in range(ref["eu_marker_bone"].shape[0]):
+            b, l = int(ref["eu_marker_bone"][k]) - 1, ref["eu_marker_lpos"][k]
+            assert np.abs(T.global_pos(b, l) - ref["eu_mk_pos"][r, k]).max() < 1e-13
+            assert np.abs(T.jacobian_T_at(b, l) - ref["eu_mk_JT"][r, k]).max() < 1e-13
+            assert np.abs(T.rot_jacobian_T(b) - ref["eu_mk_JT_rot"][r, k]).max() < 1e-14
+            g = np.zeros(T.ndof)
+            T.update_grad_S_JT(g, ref["eu_dS"][r], b, l)
+            assert np.abs(g - ref["eu_mk_grad"][r, k]).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------- primitives
+def test_oracle_primitives_equal_reference(ref):
+    """quater / vector3 / transf / Liegroup / sop primitives that oracle/tl_math.py and oracle/bone_fk.py restate."""
+    rows = ref["q_rows"]
+    Y = tm.Y
+
+    def check(name, f, tol=2e-15):
+        for r in range(rows.shape[0]):
+            val = np.atleast_1d(f(ref["q_q1"][r], ref["q_q2"][r], rows[r, 8:11], rows[r, 11])).astype(float).reshape(-1)
+            assert np.abs(val - ref["q_" + name][r]).max() <= tol, (name, r)
+    check("mult", lambda a, b, v, t: tm.qmult(a, b)); check("inverse", lambda a, b, v, t: tm.qinv(a)); check("rotate", lambda a, b, v, t: tm.qrot(a, v))
+    for ch in ("YZX", "XYZ", "ZXY", "X"):                   # quater::setRotation(channels): right-multiplied single-axis rotations
+        check("euler_" + ch, lambda a, b, v, t, ch=ch: bk.local_rotation(ch, v[:len(ch)]))
+    check("axis_angle", lambda a, b, v, t: tm.qaxis(v, t)); check("exp", lambda a, b, v, t: tm.qexp(v)); check("log", lambda a, b, v, t: tm.qln(a))
+    check("rotation_vector", lambda a, b, v, t: tm.rotation_vector(a)); check("rotation_angle", lambda a, b, v, t: tm.rotation_angle(a))
+    check("difference", lambda a, b, v, t: tm.qdifference(a, b)); check("safe_slerp", lambda a, b, v, t: tm.safe_slerp(a, b, t))
+    check("rot_y", lambda a, b, v, t: tm.rotation_y(a)); check("offset", lambda a, b, v, t: tm.offset_q(a))
+    check("no_twist", lambda a, b, v, t: tm.decompose_notwist_twist(a, Y)[0]); check("twist_q", lambda a, b, v, t: tm.decompose_notwist_twist(a, Y)[1])
+    check("axis_to_axis", lambda a, b, v, t: tm.axis_to_axis(Y, tm.qrot(a, v)), 4e-15)
+    check("matrix", lambda a, b, v, t: tm.q2mat(a))
+    check("twist", lambda a, b, v, t: np.concatenate(tm.twist(a, v, b, np.array([v[1], v[2], v[0]]), 1 / 30)), 1e-12)
+    check("sop_map", lambda a, b, v, t: tm.sop_map(t, 0.2, 0.9, -3.0, 5.0)); check("sop_clamp_map", lambda a, b, v, t: tm.clamp_map(t * 2, 0.2, 0.9, -3.0, 5.0))
+    # Liegroup: Inertia * se3 (no parallel-axis term: the matrix is used as given, Q13), dAd, inv_dAd
+    for r in range(rows.shape[0]):
+        a = rows[r]
+        q1 = ref["q_q1"][r]; v = a[8:11]
+        m = a[11] + 2.0
+        I = np.array([[1.0 + a[0] ** 2, 0.1, 0.2], [0.1, 2.0 + a[1] ** 2, 0.3], [0.2, 0.3, 1.5 + a[2] ** 2]])
+        rr = m * v
+        w = np.array([a[0], a[5], a[10]]); vv = np.array([a[3], a[8], a[1]])
+        M = I.dot(w) + np.cross(rr, vv); F = np.cross(w, rr) + m * vv
+        assert np.abs(np.concatenate([M, F]) - ref["q_inertia_times_se3"][r]).max() < 1e-13
+        # inv_dAd(T, J) as oracle/bone_fk.calc_momentum_com applies it
+        Rinv = bk.qinv(q1); tinv = -bk.vrotate(Rinv, v)
+        out = np.concatenate([bk.vrotate(bk.qinv(Rinv), M - np.cross(tinv, F)), bk.vrotate(bk.qinv(Rinv), F)])
+        assert np.abs(out - ref["q_inv_dAd"][r]).max() < 1e-12 * max(1.0, np.abs(out).max())
+
+
+# ---------------------------------------------------------------------------------------------------------- a-21
+def test_oracle_terrain_height_equals_reference(ref):
+    """OBJloader::Terrain::height (the overload gym_cdm2 calls) on the gym_cdm2 height map: the loader's height table
+    (heightMax * v / 65536) and 605 queries inside, outside and on cell borders, tiled along Z and not."""
+    sx, sz, hmax = ref["tr_size"]
+    assert np.array_equal(ref["tr_heightmap"], hmax * ref["tr_image"].astype(np.float64) / 65536.0)
+    for tile in (1, 0):
+        T = tt.OracleTerrain(ref["tr_heightmap"], sx, sz, bool(tile))
+        got = np.array([T.height(x, z)[0] for x, z in ref["tr_xz"]])
+        assert np.abs(got - ref[f"tr_height_tile{tile}"]).max() < 1e-11
+        assert (ref[f"tr_height_tile{tile}"] != 0).sum() > 200
+
+
+# ---------------------------------------------------------------------------------------------------------- f-4
+def test_dof_reader_equals_reference(ref):
+    """MotionDOFcontainer's read of the .dof the gym_cdm2 tables come from (needs the file: skipped without /root/reference)."""
+    path = "/root/reference/work/taesooLib/Resource/motion/MOB1/hanyang_lowdof_T_lafan1_walk_2915.dof"
+    if not os.path.exists(path):
+        pytest.skip("reference mount absent")
+    from ipcdnnwalk_b200 import cdm_tables
+    assert np.array_equal(cdm_tables.read_dof(path), ref["dof_walk_2915"])
+
+
+# ---------------------------------------------------------------------------------------------------------- f-1 optimiser
+def test_oracle_lbfgs_equals_reference_liblbfgs(ref):
+    """libLBFGS itself (reference lbfgs.cpp, parameters as optimize.h:426-470): Rosenbrock sample and two MMSTO windows whose
+    objective is oracle/mmsto.py -- status code, iteration and evaluation counts exact, iterates to round-off."""
+    d = dict(zip(ref["lb_defaults_keys"], ref["lb_defaults"]))
+    assert (d["m"], d["ftol"], d["wolfe"], d["max_linesearch"], d["min_step"], d["max_step"], d["sizeof_float"]) == (6, 1e-4, 0.9, 40, 1e-20, 1e20, 8)
+    nev = [0]
+
+    def ev(x):
+        nev[0] += 1
+        return rosenbrock(x)
+    x, fx, ret, k = mm.lbfgs(ref["lb_rosen_x0"].copy(), ev, epsilon=1e-5)
+    assert (ret, k, nev[0]) == (int(ref["lb_rosen_ret"]), len(ref["lb_rosen_iter_fx"]), int(ref["lb_rosen_evaluations"]))
+    assert np.abs(x - ref["lb_rosen_x"]).max() < 1e-12
+    for seed in (3, 21):
+        p = hm.make_problem(seed)
+        o = hm.oracle_opt(p, dof_weights=hm.ankle_dof_weights())
+        X, info = o.solve(p["euler_mot"], epsilon=1e-9, max_iterations=int(ref[f"lb_mmsto{seed}_max_iterations"]))
+        pre = f"lb_mmsto{seed}_"
+        assert (info["ret"], info["iterations"], info["evaluations"]) == (int(ref[pre + "ret"]), len(ref[pre + "iter_fx"]), int(ref[pre + "evaluations"]))
+        assert np.abs(X.ravel()[2 * o.ndof:] - ref[pre + "x"]).max() < 1e-12
+        assert abs(info["fx"] - float(ref[pre + "fx"])) <= 1e-12 * abs(info["fx"])
+
+
+# ---------------------------------------------------------------------------------------------------------- live re-runs
+@live
+def test_live_reference_reproduces_the_fixture(ref):
+    r = rh.fk(ref["fk_pose"][:6], ref["fk_dq"][:6])
+    assert np.array_equal(r["bfk"], ref["fk_bfk"][:6]) and np.array_equal(r["mom"], ref["fk_mom"][:6]) and np.array_equal(r["com"], ref["fk_com"][:6])
+    e = rh.euler(ref["eu_q"][:2], ref["eu_dq"][:2], ref["eu_dS"][:2], EU_MARKERS)
+    assert np.array_equal(e[1]["JT_mom"], ref["eu_JT_mom"][1]) and np.array_equal(e[0]["markers"][2]["JT"], ref["eu_mk_JT"][0, 2])
+    Q = rh.quat(ref["q_rows"][:8])
+    assert all(np.array_equal(Q[k], ref["q_" + k][:8]) for k in Q)
+    sx, sz, hmax = ref["tr_size"]
+    hmap, h, _, _ = rh.terrain(ref["tr_image"], sx, sz, hmax, 1, ref["tr_xz"][:50])
+    assert np.array_equal(hmap, ref["tr_heightmap"]) and np.array_equal(h, ref["tr_height_tile1"][:50])
+    res = rh.lbfgs(ref["lb_rosen_x0"], rosenbrock, epsilon=1e-5)
+    assert res["ret"] == int(ref["lb_rosen_ret"]) and np.array_equal(res["x"], ref["lb_rosen_x"])
+
+
+@live
+def test_live_reference_lbfgs_on_a_fresh_mmsto_window():
+    """A window that is NOT in the fixture, both optimisers run here on the same objective."""
+    z0, nfix, ev = mmsto_window(77)
+    res = rh.lbfgs(z0[nfix:].copy(), ev, epsilon=1e-9, max_iterations=6)
+    p = hm.make_problem(77)
+    o = hm.oracle_opt(p, dof_weights=hm.ankle_dof_weights())
+    X, info = o.solve(p["euler_mot"], epsilon=1e-9, max_iterations=6)
+    assert (info["ret"], info["iterations"], info["evaluations"]) == (res["ret"], len(res["iterations"]), res["evaluations"])
+    assert np.abs(X.ravel()[nfix:] - res["x"]).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------- CUDA vs reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol_pos,tol_mom", [(64, 1e-12, 1e-10), (32, 1e-5, 2e-4)])
+def test_cuda_fk_equals_reference(built_lib, ref, skel, precision, tol_pos, tol_mom):
+    """FK kernel family vs the reference's BoneForwardKinematics / LoaderToTree outputs: joint positions within 1e-5 m in fp32
+    (BASELINE north star) and round-off in fp64; CoM and centroidal momentum likewise.  Every kernel variant."""
+    import torch
+    from ipcdnnwalk_b200 import Skeleton
+    dt = torch.float64 if precision == 64 else torch.float32
+    pose = torch.as_tensor(ref["fk_pose"], dtype=dt, device="cuda"); dq = torch.as_tensor(ref["fk_dq"], dtype=dt, device="cuda")
+    for generic, tma in ((True, -1), (False, 0), (False, 1), (False, 3)):
+        S = Skeleton(skel)
+        S.set_generic(generic)
+        if not generic:
+            S.set_tma(tma)
+        res = S.forward(pose, dq)
+        torch.cuda.synchronize()
+        xf = res["xform"].cpu().numpy().astype(np.float64); com = res["com"].cpu().numpy(); mom = res["momentum"].cpu().numpy()
+        q, t = xf[..., :4], xf[..., 4:]
+        assert np.abs(t - ref["fk_bfk"][..., :3]).max() <= tol_pos * (10 if precision == 32 else 1), (generic, tma)
+        sign = np.sign((q * ref["fk_bfk"][..., 3:]).sum(-1, keepdims=True))
+        assert np.abs(q * sign - ref["fk_bfk"][..., 3:]).max() <= (1e-6 if precision == 32 else 1e-13)
+        assert np.abs(com - ref["fk_com"]).max() <= tol_pos * (10 if precision == 32 else 1)
+        assert np.abs(mom - ref["fk_mom"]).max() <= tol_mom * max(1.0, np.abs(ref["fk_mom"]).max())
+        S.close()
+
+
+@pytest.mark.gpu
+def test_cuda_tl_terrain_equals_reference(built_lib, ref):
+    import torch
+    from ipcdnnwalk_b200.tl_terrain import Terrain
+    sx, sz, _ = ref["tr_size"]
+    for tile in (1, 0):
+        T = Terrain(ref["tr_heightmap"], sx, sz, bool(tile))
+        h = T.height(ref["tr_xz"])
+        torch.cuda.synchronize()
+        assert np.abs(h.cpu().numpy() - ref[f"tr_height_tile{tile}"]).max() < 1e-9
+        T.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [3, 21, 22])
+def test_cuda_mmsto_solve_equals_reference_liblbfgs(built_lib, ref, skel, seed):
+    """The batched MMSTO kernel against the REFERENCE's libLBFGS driving the same objective: status code, iteration and evaluation
+    counts bit exact; solution 1e-9 after <= 12 iterations.  Window 22 runs until libLBFGS stops by itself (294 iterations, 442
+    evaluations in the reference): the counts must still agree and the objective reached must match to 1e-6 relative."""
+    from ipcdnnwalk_b200 import ShortTrajOpt
+    keys = ("gpos_target", "x_original", "dx", "ddx", "com", "momentum")
+    p = hm.make_problem(seed, skel=skel)
+    o = ShortTrajOpt(skel, hm.NF, hm.MARKERS)
+    o.set_dof_weights(hm.ankle_dof_weights(skel))
+    pre = f"lb_mmsto{seed}_"
+    max_it = int(ref[pre + "max_iterations"])
+    o.set("max_iterations", max_it)
+    x, info = o.solveEndEffectors_euler(p["euler_mot"][None], *[p[k][None] for k in keys], velcon=p["velcon"][None])
+    x = x.cpu().numpy()[0]; info = info.cpu().numpy()[0]
+    nd = x.shape[1]
+    if max_it:
+        assert (int(info[1]), int(info[2]), int(info[3])) == (int(ref[pre + "ret"]), len(ref[pre + "iter_fx"]), int(ref[pre + "evaluations"]))
+        assert np.abs(x.ravel()[2 * nd:] - ref[pre + "x"]).max() < 1e-9
+        assert abs(info[0] - float(ref[pre + "fx"])) <= 1e-9 * abs(info[0])
+    else:
+        assert int(info[1]) == int(ref[pre + "ret"])
+        # hundreds of iterations amplify rounding differences of the 1e7-conditioned problem: the stopping iteration may shift slightly
+        assert abs(int(info[2]) - len(ref[pre + "iter_fx"])) <= 0.1 * len(ref[pre + "iter_fx"])
+        assert abs(info[0] - float(ref[pre + "fx"])) <= 1e-6 * abs(info[0])
+    o.close()
