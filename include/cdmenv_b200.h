@@ -73,7 +73,8 @@ int cdm_reset(cdm_env* env, const int32_t* env_idx_host, int32_t count, const do
 /* RagdollSim:step for all environments: act_dev[N][10] -> obs_dev[N][27], rew_dev[N], done_dev[N] (0/1).
  * The reference's NaN convention is kept per environment (NaN observation -> zeros, reward 0, done; :1557-1561). */
 int cdm_step(cdm_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream);
-/* Same through HOST buffers: H2D actions, kernel, D2H results on the handle's stream, synchronised. */
+/* Same through HOST buffers: H2D actions, kernel, D2H results on the handle's stream, synchronised.  That stream is ordered after
+ * every reset / step the handle launched on a caller stream (recorded event), so reset(); step_host() needs no caller-side sync. */
 int cdm_step_host(cdm_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host);
 int cdm_pinned_buffers(cdm_env* env, float** act, float** obs, float** rew, uint8_t** done);
 

@@ -65,7 +65,8 @@ int srb_reset(srb_env* env, const int32_t* env_idx_host, int32_t count, const do
 int srb_step(srb_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* rinfo_dev, void* stream);
 
 /* Same step through HOST buffers (what a per-process gym caller holds): copies actions host->device and
- * results device->host on the handle's own stream and synchronises.  NULL pointers = use the handle's
+ * results device->host on the handle's own stream and synchronises.  The handle orders that stream after every reset / step it
+ * was asked to launch on a caller stream (an event is recorded there), so reset(); step_host() needs no synchronisation by the caller.  NULL pointers = use the handle's
  * pinned staging buffers in place (see srb_pinned_buffers). */
 int srb_step_host(srb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host);
 int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint8_t** done, float** rinfo);

@@ -31,6 +31,7 @@ struct cdm_env {
   cdm_skeleton skel; bool have_skel = false;
   ResetConst<double> rc;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_state = nullptr;        // recorded after every state-mutating launch on a caller stream; cdm_step_host's stream waits on it
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t* d_done = nullptr;
   int64_t launches = 0;
@@ -162,6 +163,7 @@ extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   CK(cudaMalloc(&h->ep_stats, sizeof(double) * 3));
   CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -173,6 +175,7 @@ extern "C" int cdm_destroy(cdm_env* h) {
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev_state) cudaEventDestroy(h->ev_state);
   delete h;
   return 0;
 }
@@ -253,6 +256,7 @@ extern "C" int cdm_reset(cdm_env* h, const int32_t* env_idx_host, int32_t count,
   if (h->cfg.precision == 64) do_reset<double>(h, idx_dev, count, plan_dev, obs_dev, s);
   else do_reset<float>(h, idx_dev, count, plan_dev, obs_dev, s);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev_state, s));
   if (idx_dev || plan_dev) {
     CK(cudaStreamSynchronize(s));
     cudaFree(idx_dev); cudaFree(plan_dev);
@@ -292,6 +296,7 @@ extern "C" int cdm_step(cdm_env* h, const float* act_dev, float* obs_dev, float*
   int rc = h->cfg.precision == 64 ? dispatch_step<double>(h, act_dev, obs_dev, rew_dev, done_dev, s) : dispatch_step<float>(h, act_dev, obs_dev, rew_dev, done_dev, s);
   if (rc) return rc;
   CK(cudaGetLastError());
+  if (s != h->stream) CK(cudaEventRecord(h->ev_state, s));
   return 0;
 }
 
@@ -324,6 +329,7 @@ extern "C" int cdm_step_host(cdm_env* h, const float* act_host, float* obs_host,
   size_t N = h->N;
   if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
   cudaStream_t s = h->stream;
+  CK(cudaStreamWaitEvent(s, h->ev_state, 0));            // resets / device steps issued on caller streams come first
   CK(cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * N * ACT_W, cudaMemcpyHostToDevice, s));
   rc = cdm_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, s);
   if (rc) return rc;

@@ -36,6 +36,7 @@ struct srb_env {
   const float* contact_prob = nullptr; float* term_obs = nullptr; const double* reset_plan = nullptr; double* dbg = nullptr;
   Params<double> p;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_state = nullptr;        // recorded after every state-mutating launch on a caller stream; srb_step_host's stream waits on it
   // pinned host staging + device I/O for the host-buffer path
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
@@ -130,6 +131,7 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   CK(cudaMalloc(&h->ep_stats, sizeof(double) * 3));
   CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -144,6 +146,7 @@ extern "C" int srb_destroy(srb_env* h) {
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_rinfo); cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rinfo); cudaFree(h->d_done);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev_state) cudaEventDestroy(h->ev_state);
   delete h;
   return 0;
 }
@@ -226,6 +229,7 @@ extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count,
   if (h->cfg.precision == 64) do_reset<double>(h, idx_dev, count, plan_dev, obs_dev, s);
   else do_reset<float>(h, idx_dev, count, plan_dev, obs_dev, s);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev_state, s));
   if (idx_dev || plan_dev) {
     CK(cudaStreamSynchronize(s));
     cudaFree(idx_dev); cudaFree(plan_dev);
@@ -286,6 +290,7 @@ static int step_impl(srb_env* h, const float* act_dev, float* obs_dev, float* re
                                   : dispatch_step<float>(h, act_dev, obs_dev, rew_dev, done_dev, rinfo_dev, s, cio);
   if (rc) return rc;
   CK(cudaGetLastError());
+  if (s != h->stream) CK(cudaEventRecord(h->ev_state, s));
   return 0;
 }
 
@@ -322,6 +327,7 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   size_t N = h->N;
   if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
   cudaStream_t s = h->stream;
+  CK(cudaStreamWaitEvent(s, h->ev_state, 0));            // resets / device steps issued on caller streams come first
   if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
     // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
     // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions

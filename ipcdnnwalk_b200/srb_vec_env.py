@@ -61,6 +61,7 @@ class SRBVecEnv:
         self.num_envs = int(num_envs)
         self.variant = {"test": VARIANT_TEST, "training": VARIANT_TRAINING, "terrain": VARIANT_TERRAIN}[variant] if isinstance(variant, str) else int(variant)
         self.precision = int(precision)
+        self._seed = int(seed)
         cfg = SrbConfig(self.num_envs, self.variant, self.precision, int(lanes_per_env), int(bool(auto_reset)), int(device), int(seed))
         self._h = C.c_void_p()
         check(self.lib.srb_create(C.byref(cfg), C.byref(self._h)))
@@ -169,12 +170,45 @@ class SRBVecEnv:
         return [{"reward_info": dict(zip(REWARD_INFO_KEYS, map(float, row)))} for row in ri]
 
     def get_attr(self, name, indices=None):
-        idx = range(self.num_envs) if indices is None else indices
-        return [self._attr(name, i) for i in idx]
+        return [self._attr(name, i) for i in self._indices(indices)]
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        return [indices] if isinstance(indices, int) else indices
+
+    def set_attr(self, name, value, indices=None):
+        """VecEnv.set_attr for the attributes a driver writes on SRBEnv: per-environment `impulse` (remaining pushes) and the
+        batch-wide push schedule / reward weights (they are parameters of the one kernel launch)."""
+        if name == "impulse":
+            for i in self._indices(indices):
+                st = self.get_state(i)
+                st["ints"][5] = int(np.ceil(max(float(value), 0.0)))
+                self.set_state(i, st)
+        elif name in ("force", "impulse_interval", "impulse_duration"):
+            self._push = getattr(self, "_push", dict(force=[700, 700, -350], impulse_interval=1e9, impulse_duration=24))
+            self._push[name] = value
+            self.set_impulse(self._push["impulse_interval"], self._push["impulse_duration"], self._push["force"])
+        elif name == "reward_weights":
+            self.set_reward_weights(value)
+        else:
+            raise AttributeError(f"SRBVecEnv.set_attr: '{name}' is not a settable attribute of the batched environment")
 
     def env_method(self, name, *args, indices=None, **kw):
-        idx = range(self.num_envs) if indices is None else indices
-        return [getattr(self, "_m_" + name)(i, *args, **kw) for i in idx]
+        return [getattr(self, "_m_" + name)(i, *args, **kw) for i in self._indices(indices)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def seed(self, seed=None):
+        """The device reset stream is fixed at construction (srb_config.seed); returns it per environment like VecEnv.seed."""
+        return [self._seed for _ in range(self.num_envs)]
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode=None):
+        return None
 
     def close(self):
         if self._h:
@@ -278,3 +312,49 @@ class SRBVecEnv:
 
     def launch_count(self):
         return int(self.lib.srb_launch_count(self._h))
+
+
+class SB3VecEnv(SRBVecEnv):
+    """The SubprocVecEnv seam of the reference's trainer -- `make_vec_env(SRBEnv, n_envs=32, vec_env_cls=SubprocVecEnv)`
+    (walk_SRBTrack2025_train_delta.py:94-100), wrapped by VecNormalize (gym_cdm2/train_gym.py:98) -- as stable-baselines3 sees a
+    VecEnv: numpy in / numpy out, `reset() -> obs`, `step_wait() -> (obs, rewards, dones, infos)` with
+    infos[i]["terminal_observation"] on the step that ended an episode (the environment is reset inside the step, as SubprocVecEnv's
+    workers do), "reward_info" as SRBEnv.step returns it, and "episode" = {"r", "l"} as the Monitor wrapper of make_vec_env adds.
+    Data moves through the library's pinned host buffers (srb_step_host)."""
+
+    def __init__(self, clips, num_envs, variant="training", precision=32, **kw):
+        kw["auto_reset"] = True
+        super().__init__(clips, num_envs, variant=variant, precision=precision, **kw)
+        self.attach(term_obs=True)
+        self._ep_ret = np.zeros(self.num_envs); self._ep_len = np.zeros(self.num_envs, dtype=np.int64)
+        self.reward_info = True
+        try:                                              # pragma: no cover - gymnasium is not in the build image
+            import gymnasium as gym
+            self.action_space = gym.spaces.Box(low=-3.14, high=3.14, shape=(ACT_DIM,), dtype=np.float32)
+            self.observation_space = gym.spaces.Box(low=-np.inf, high=np.inf, shape=(OBS_DIM,), dtype=np.float32)
+        except Exception:                                 # noqa: BLE001
+            self.action_space = self.observation_space = None
+
+    def reset(self, env_idx=None, plan=None):
+        obs = super().reset(env_idx=env_idx, plan=plan)
+        self.torch.cuda.synchronize(self.device)
+        self._ep_ret[:] = 0; self._ep_len[:] = 0
+        return obs.cpu().numpy()
+
+    def step_wait(self):
+        a = np.ascontiguousarray(np.asarray(self._actions, dtype=np.float32).reshape(self.num_envs, ACT_DIM))
+        obs, rew, done, rinfo = self.step_host(a)
+        obs, rew, done = obs.copy(), rew.copy(), done.astype(bool)
+        self._ep_ret += rew; self._ep_len += 1
+        infos = [{"TimeLimit.truncated": False} for _ in range(self.num_envs)]
+        if self.reward_info:
+            for i, row in enumerate(rinfo):
+                infos[i]["reward_info"] = dict(zip(REWARD_INFO_KEYS, map(float, row)))
+        if done.any():
+            idx = np.nonzero(done)[0]
+            term = self.term_obs[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+            for k, i in enumerate(idx):
+                infos[i]["terminal_observation"] = term[k]
+                infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i])}
+            self._ep_ret[idx] = 0; self._ep_len[idx] = 0
+        return obs, rew, done, infos

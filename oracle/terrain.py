@@ -10,7 +10,7 @@ vertical `mj_ray` query the terrain env makes:
 mujoco is third party, un-vendored and unpinned; restated from its published algorithm (engine_ray.c:
 mj_ray / mju_rayGeom / mj_rayHfield, user_objects.cc: mjCHField::LoadPNG / Compile):
   * mj_ray keeps the geom with the strictly smallest distance (first geom wins ties), geoms in model order
-    (floor 0, cdm box 1 [group 1: excluded], hf_hill 2, hf_rough 3, pyramid boxes 4..327);
+    (body by body, the world body's geoms first: floor 0, hf_hill 1, hf_rough 2, cdm box 3 [group 1: excluded], pyramid boxes 4..327);
   * plane: hit only inside its rendered size; box: a vertical ray hits the top face iff |dx|<=hx and |dy|<=hy;
   * hfield: PNG rows are stored bottom-up (image row nrow-1-r -> data row r), elevations are normalised to
     [0,1] by (v-min)/(max-min) in float32, vertex (c,r) sits at (2*sx*c/(ncol-1)-sx, 2*sy*r/(nrow-1)-sy),
@@ -119,39 +119,39 @@ def load_playground(xml_path, terrain_dir):
     for m in re.finditer(r'<hfield name="(\w+)" size="([^"]+)" file="([^"]+)"', t):
         hf_assets[m.group(1)] = (np.array([float(x) for x in m.group(2).split()]), m.group(3).split("/")[-1])
     wb = t[t.index("<worldbody>"):]
+    # mujoco numbers geoms body by body (mjCModel::MakeLists): the world body's own geoms first, in document order, then each child
+    # body's.  Two passes over the flat element stream: pass 0 takes the geoms outside any <body>, pass 1 the geoms inside bodies.
     geom_id = 0
-    body_id = 0
     hfields, boxes, bodies = [], [], []
     plane_size, plane_geom = None, -1
-    # walk top-level elements of <worldbody> in document order
-    pos_re = re.compile(r'<(geom|body)\b([^>]*?)(/?)>')
-    i = 0
-    cur_body = None
-    for m in re.finditer(r'<(/?)(geom|body)\b([^>]*?)(/?)>', wb):
-        closing, tag, attrs, selfclose = m.group(1), m.group(2), m.group(3), m.group(4)
-        a = dict(re.findall(r'(\w+)="([^"]*)"', attrs))
-        if tag == "body":
-            if closing:
-                cur_body = None
-            else:
-                body_id += 1
-                cur_body = dict(body_id=body_id, name=a.get("name", ""), xpos=np.array([float(x) for x in a.get("pos", "0 0 0").split()]))
-                if cur_body["name"].startswith("pyramid"):
-                    bodies.append(cur_body)
-            continue
-        if closing:
-            continue
-        gtype = a.get("type", "sphere")
-        if gtype == "plane":
-            plane_size = np.array([float(x) for x in a["size"].split()][:2]); plane_geom = geom_id
-        elif gtype == "hfield":
-            size, fname = hf_assets[a["hfield"]]
-            pix = np.array(Image.open(f"{terrain_dir}/{fname}").convert("L"), dtype=np.uint8)
-            hfields.append(dict(pix=pix, data=normalise_png(pix), size=size, pos=np.array([float(x) for x in a["pos"].split()]), geom_id=geom_id))
-        elif gtype == "box" and cur_body is not None and cur_body["name"].startswith("pyramid"):
-            lp = np.array([float(x) for x in a["pos"].split()])
-            boxes.append(dict(pos=cur_body["xpos"] + lp, size=np.array([float(x) for x in a["size"].split()]), geom_id=geom_id, body_id=cur_body["body_id"]))
-        geom_id += 1
+    for want_inside in (False, True):
+        body_id = 0
+        cur_body = None
+        for m in re.finditer(r'<(/?)(geom|body)\b([^>]*?)(/?)>', wb):
+            closing, tag, attrs = m.group(1), m.group(2), m.group(3)
+            a = dict(re.findall(r'(\w+)="([^"]*)"', attrs))
+            if tag == "body":
+                if closing:
+                    cur_body = None
+                else:
+                    body_id += 1
+                    cur_body = dict(body_id=body_id, name=a.get("name", ""), xpos=np.array([float(x) for x in a.get("pos", "0 0 0").split()]))
+                    if want_inside and cur_body["name"].startswith("pyramid"):
+                        bodies.append(cur_body)
+                continue
+            if closing or (cur_body is not None) != want_inside:
+                continue
+            gtype = a.get("type", "sphere")
+            if gtype == "plane":
+                plane_size = np.array([float(x) for x in a["size"].split()][:2]); plane_geom = geom_id
+            elif gtype == "hfield":
+                size, fname = hf_assets[a["hfield"]]
+                pix = np.array(Image.open(f"{terrain_dir}/{fname}").convert("L"), dtype=np.uint8)
+                hfields.append(dict(pix=pix, data=normalise_png(pix), size=size, pos=np.array([float(x) for x in a["pos"].split()]), geom_id=geom_id))
+            elif gtype == "box" and cur_body is not None and cur_body["name"].startswith("pyramid"):
+                lp = np.array([float(x) for x in a["pos"].split()])
+                boxes.append(dict(pos=cur_body["xpos"] + lp, size=np.array([float(x) for x in a["size"].split()]), geom_id=geom_id, body_id=cur_body["body_id"]))
+            geom_id += 1
     for k, b in enumerate(bodies):
         nxt = [c for c in bodies if c["body_id"] == b["body_id"] + 1]
         b["snap"] = 1 if nxt else 0          # pyramid followed by a pyramid (the reference crashes on the last one)

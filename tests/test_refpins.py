@@ -114,6 +114,16 @@ def test_oracle_primitives_equal_reference(ref):
         assert np.abs(out - ref["q_inv_dAd"][r]).max() < 1e-12 * max(1.0, np.abs(out).max())
 
 
+def test_oracle_se3_exp_equals_reference(ref):
+    """Liegroup::se3::exp -> transf, the pelvis transform of _extractSingleFrameFullbody (oracle/fullbody_map.se3_exp + mat_to_quat)."""
+    from oracle import fullbody_map as fm
+    rows = ref["q_rows"]
+    for r in range(rows.shape[0]):
+        a = rows[r]
+        R, p = fm.se3_exp(np.array([a[0], a[5], a[10], a[3], a[8], a[1]]))
+        assert np.abs(p - ref["q_se3_exp"][r, :3]).max() < 1e-14 and np.abs(fm.mat_to_quat(R) - ref["q_se3_exp"][r, 3:]).max() < 1e-14
+
+
 # ---------------------------------------------------------------------------------------------------------- a-21
 def test_oracle_terrain_height_equals_reference(ref):
     """OBJloader::Terrain::height (the overload gym_cdm2 calls) on the gym_cdm2 height map: the loader's height table

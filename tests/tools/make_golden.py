@@ -78,8 +78,36 @@ def build_builder_case(name="aiming_show", frames=90):
     print("builder case", md.shape, s.mocap_com_humanoid.shape)
 
 
+def build_raw_clips():
+    """tests/golden/gym_trackSRB/ref_contact/<name>.motion.npz + <name>.constraint.npz: the shipped clips' raw mocap rows (41-float
+    qpos) and contact flags in the reference's own `.npz` clip layout ('motion' key; contact file = path[:-10] + 'constraint.npz',
+    env/testSRB_mujoco_original_viewer.py:795-809), so that SRBEnv(mocap_path_list) / ClipBuilder can run where /root/reference is absent."""
+    out = os.path.join(GOLDEN, "gym_trackSRB", "ref_contact")
+    os.makedirs(out, exist_ok=True)
+    for name in ("stand1", "aiming_show"):
+        md = load_mocap_txt(REF + f"motiondata_mujoco_refined/{name}.txt")
+        np.savez_compressed(os.path.join(out, f"{name}.motion.npz"), motion=np.asarray(md, dtype=np.float64))
+        c = np.load(REF + f"ref_contact/{name}.bvh.constraint.npz")
+        np.savez_compressed(os.path.join(out, f"{name}.constraint.npz"), **{k: c[k] for k in c})
+        print("raw clip", name, np.asarray(md).shape)
+
+
+def build_terrain():
+    """tests/golden/terrain_playground.npz: SRB5_playground.xml + its PNG height fields through the ORACLE's parser (PIL)."""
+    from oracle.terrain import load_playground
+    T = load_playground(REF + "Characters/SRB5_playground.xml", REF + "terrain")
+    T.save(os.path.join(GOLDEN, "terrain_playground.npz"))
+    print("terrain: plane geom", T.plane_geom, "hfield geoms", [h["geom_id"] for h in T.hfields], "boxes", len(T.boxes), "bodies", [b["body_id"] for b in T.bodies])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "terrain":
+        build_terrain()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "raw_clips":
+        build_raw_clips()
+        sys.exit(0)
     build_clip("stand1", True)
     build_clip("aiming_show", False)
     make_rollout("test")
