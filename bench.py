@@ -14,6 +14,14 @@ are produced outside the timed events, like a policy would.
 
 Timing: CUDA events on the launching stream around every step launch; L2 is flushed (256 MiB write)
 between steps because one step's working set (~6 MB) is far below the 126 MB L2; max over ranks.
+The path's one collective -- observation-normaliser statistics + episode counters, one NCCL all-reduce per
+rollout chunk -- runs every ROLLOUT steps and once more at the end of the timed loop, so it is inside the timed
+total whatever --steps is; its time is reported as `collective_ms`.
+
+The same JSON line carries `secondary` records (each timed the same way, after the headline loop): the fp64
+(reference precision) headline, BASELINE configs[2] (terrain, 8192 envs per GPU), configs[3] (gym_cdm2, 16384
+envs), configs[4] (FK of 1 M poses, split over the GPUs) and the batched MMSTO solve (4096 windows).
+Reference tables are built by the product's own ClipBuilder from the raw clips under tests/golden/gym_trackSRB.
 """
 import argparse
 import json
@@ -35,6 +43,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+RAW_CLIPS = ["ref_contact/stand1.motion.npz", "ref_contact/aiming_show.motion.npz"]   # tests/golden/gym_trackSRB/... (raw mocap + contact flags)
 ENVS_PER_GPU = 4096
 SIGMA = 0.1
 ROLLOUT = 128                 # steps between observation-statistics all-reduces (one per PPO rollout chunk)
@@ -55,6 +64,7 @@ def parse():
                     help="terrain = BASELINE config 3 (SRBEnv5_mocap_list_terrain_window on the playground height fields); not the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (fp64, terrain, gym_cdm2, FK, MMSTO)")
     ap.add_argument("--flush", default="write", choices=["write", "read", "none"],
                     help="L2 flush between steps: write a 256 MiB buffer (default, the timing rule), read it, or nothing (diagnostic)")
     return ap.parse_args()
@@ -235,21 +245,24 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     N = args.envs
+    # reference tables: the product's ClipBuilder (device FK of the MJCF humanoid) over the raw clips, SRBEnv.loadMocap's job
+    from ipcdnnwalk_b200.srb_env import build_clip_tables
+    all_clips = build_clip_tables(RAW_CLIPS, data_root=os.path.join(ROOT, "tests", "golden"), device=local_rank)
     if args.variant == "terrain":
         from ipcdnnwalk_b200 import TerrainModel
-        clips = helpers.fresh_clips(("aiming_show",))
+        clips = all_clips[1:]
         env = SRBVecEnv(clips, N, variant="terrain", precision=args.precision, lanes_per_env=args.lanes, auto_reset=False,
-                        device=local_rank, seed=1234 + rank, terrain=TerrainModel.from_npz(TERRAIN_NPZ),
+                        device=local_rank, seed=1234 + rank, terrain=TerrainModel.builtin_playground(),
                         initial_pos_planar=terrain_planar(N, 77 + rank))
     else:
-        clips = helpers.fresh_clips()
+        clips = all_clips
         env = SRBVecEnv(clips, N, variant=args.variant, precision=args.precision, lanes_per_env=args.lanes, auto_reset=True,
                         device=local_rank, seed=1234 + rank)
     env.reset()
     act = torch.zeros(N, ACT_DIM, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
-    acc = torch.zeros(1 + 2 * OBS_DIM, dtype=torch.float64, device=dev)
+    acc = torch.zeros(1 + 2 * OBS_DIM + 3, dtype=torch.float64, device=dev)   # (count, sum x, sum x^2) + episode (sum return, sum length, count)
     K, W = args.steps, args.warmup
 
     n_resets = [0]
@@ -271,13 +284,14 @@ def run_ours(args, rank, local_rank, world):
         if timed:
             ev[1].record()
         cev = None
-        if (k + 1) % ROLLOUT == 0:                                          # the path's one collective
-            if timed:
+        if (k + 1) % ROLLOUT == 0 or (timed and k == W + K - 1):           # the path's one collective: once per rollout
+            if timed:                                                       # chunk and at the end of the timed loop
                 cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 cev[0].record()
-            env.obs_stats(acc)
+            acc.zero_()                                                     # one rollout chunk's sufficient statistics
+            env.rollout_stats(acc)                                          # obs statistics kernel + episode counters (device copy)
             if dist is not None:
-                dist.all_reduce(acc)
+                dist.all_reduce(acc)                                        # NCCL over NVLink
             if timed:
                 cev[1].record()
         return ev, cev
@@ -333,7 +347,8 @@ def run_ours(args, rank, local_rank, world):
     if dist is not None:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_ms_max, med_ms_max = (float(x) for x in tvec.cpu())
-    ep = env.episode_stats()
+    ep = acc[301:304].cpu().numpy() if args.variant != "terrain" else np.zeros(3)   # all-reduced episode counters (whole job)
+    secondary = [] if args.no_secondary else run_secondary(args, rank, local_rank, world, dist, all_clips, flush)
 
     if rank == 0:
         peaks = {}
@@ -346,14 +361,21 @@ def run_ours(args, rank, local_rank, world):
         bytes_step = BYTES_PER_STEP[args.precision] * N
         kern_ms = float(step_ms.mean())
         achieved = bytes_step / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get(f"fp{args.precision}_n{N}")
-            except Exception:
-                traffic = None
+        traffic, traffic_detail = None, None
+        for tp in ("r02_traffic.json", "r01_traffic.json"):                # ncu --set full capture of the same command (constants, not measured in this run)
+            tp = os.path.join(ROOT, "profiles", tp)
+            if traffic is None and os.path.exists(tp):
+                try:
+                    tj = json.load(open(tp))
+                    tv = tj.get(f"fp{args.precision}_n{N}")
+                    if isinstance(tv, dict):
+                        traffic = float(tv["read"]) + float(tv["write"])
+                        traffic_detail = dict(tv, source=f"ncu constant from profiles/{os.path.basename(tp)} (dram__bytes_read.sum / dram__bytes_write.sum per launch, cold cache)")
+                    elif tv is not None:
+                        traffic = float(tv)
+                        traffic_detail = {"read": float(tv), "write": 0.0, "source": f"ncu constant from profiles/{os.path.basename(tp)}: reads only, write-backs leave the 126 MB L2 after the kernel"}
+                except Exception:
+                    traffic = None
         value = world * N * K / (total_ms_max * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -368,12 +390,13 @@ def run_ours(args, rank, local_rank, world):
                                    f"all environments re-seeded every {TERRAIN_EPISODE} steps outside the timed events" if args.variant == "terrain" else
                                    f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done"),
                        "l2": {"write": "flushed between steps (256 MiB write)", "read": "DIAGNOSTIC: evicted between steps by reading 256 MiB", "none": "DIAGNOSTIC: not flushed"}[args.flush] + "; per-step CUDA events on the launching stream",
-                       "collective": f"obs-normaliser statistics kernel + NCCL all-reduce every {ROLLOUT} steps, inside the timed total",
+                       "collective": f"obs-normaliser statistics kernel + episode counters, one NCCL all-reduce (304 doubles) every {ROLLOUT} steps and at the end of the timed loop: {len(cevs)} inside the timed total",
                        "lanes_per_env": env_lanes(args), "median_step_ms": med_ms_max, "wall_s_timed_loop": t_wall,
                        "episodes_finished": int(ep[2]), "mean_episode_len": float(ep[1] / max(ep[2], 1))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_env_step": BYTES_PER_STEP[args.precision],
-                         "kernel": "srb_step_kernel", "avg_launch_ms": kern_ms},
+                         "traffic_detail": traffic_detail, "kernel": "srb_step_kernel", "avg_launch_ms": kern_ms},
+            "collective_ms": coll_ms, "collectives_timed": len(cevs),
             "clocks": clocks,
             "gpu_launches": int(step_launches),
         }
@@ -381,6 +404,8 @@ def run_ours(args, rank, local_rank, world):
             line["e2e"] = {"value": world * N * Ke / (e2e_ms_max * 1e-3), "unit": "env-steps/s",
                            "h2d_bytes_per_step": N * ACT_DIM * 4, "d2h_bytes_per_step": N * (OBS_DIM * 4 + 4 + 1 + RINFO_DIM * 4),
                            "steps": Ke, "api": "srb_step_host, host buffers: the coalesced-I/O step kernel reads the actions from and writes obs/reward/done/info to mapped pinned host memory over PCIe inside the timed region (zero copy), then stream sync"}
+        if secondary:
+            line["secondary"] = secondary
         if not args.no_cpu_baseline:
             cores = usable_cores()
             v, total, tmax = cpu_oracle_throughput(cores, 1, 1, None, args.variant, budget_s=15.0)
@@ -390,6 +415,140 @@ def run_ours(args, rank, local_rank, world):
     env.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _timed(fn, steps, warmup, flush, dist, per_step_setup=None):
+    """CUDA-event time of `steps` calls of fn() after `warmup` calls, L2 flushed between calls; mean ms, max over ranks."""
+    import torch
+    for i in range(warmup):
+        if per_step_setup:
+            per_step_setup(i)
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    evs = []
+    for i in range(steps):
+        if per_step_setup:
+            per_step_setup(warmup + i)
+        flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_secondary(args, rank, local_rank, world, dist, all_clips, flush):
+    """The other BASELINE configurations and the MMSTO solve, each one record: value (whole job), roofline fraction of its kernel
+    (algorithmic bytes per unit from SURVEY 8d / DESIGN.md), kernel name.  Same timing rules as the headline loop."""
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv, CDMVecEnv, TerrainModel, Skeleton, ShortTrajOpt, vrml_skeleton
+    import helpers_cdm as hc
+    dev = torch.device("cuda", local_rank)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    S, Wm = 30, 5
+    recs = []
+
+    def rec(name, config, kernel, units_per_gpu, ms, bytes_per_unit, unit, scaling, dtype, extra=None):
+        value = units_per_gpu * world / (ms * 1e-3)
+        ach = bytes_per_unit * units_per_gpu / (ms * 1e-3) / 1e9
+        r = {"name": name, "config": config, "kernel": kernel, "value": value, "unit": unit, "ms_per_step": ms, "dtype": dtype, "n_gpus": world, "scaling": scaling,
+             "steps": S, "warmup": Wm, "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_unit": bytes_per_unit}}
+        if extra:
+            r.update(extra)
+        recs.append(r)
+
+    # ---- headline workload at the reference's precision (fp64)
+    N = args.envs
+    env = SRBVecEnv(all_clips, N, variant="test", precision=64, auto_reset=True, device=local_rank, seed=1234 + rank)
+    env.reset()
+    act = torch.zeros(N, 22, dtype=torch.float32, device=dev)
+    ms = _timed(lambda: env.step(act), S, Wm, flush, dist, lambda k: env.tracking_action(act, sigma=SIGMA, seed=5 + rank, step=k))
+    rec("flat_fp64", f"BASELINE configs[1] at reference precision: flat ground, {N} envs per GPU", "srb_step_kernel<double>", N, ms, BYTES_PER_STEP[64], "env-steps/s", "weak", "f64")
+    env.close()
+    # ---- configs[2]: terrain, 8192 envs per GPU (65536 on 8)
+    N = 8192
+    env = SRBVecEnv(all_clips[1:], N, variant="terrain", precision=32, auto_reset=False, device=local_rank, seed=99 + rank,
+                    terrain=TerrainModel.builtin_playground(), initial_pos_planar=terrain_planar(N, 77 + rank))
+    env.reset()
+    act = torch.zeros(N, 22, dtype=torch.float32, device=dev)
+
+    def terrain_setup(k):
+        if k % TERRAIN_EPISODE == 0 and k > 0:
+            env.reset()
+        env.tracking_action(act, sigma=SIGMA, seed=6 + rank, step=k)
+    ms = _timed(lambda: env.step(act), S, Wm, flush, dist, terrain_setup)
+    rec("terrain_fp32", f"BASELINE configs[2] per-GPU share: SRBEnv5_mocap_list_terrain_window on the playground (plane / pyramid / hill / rough), {N} envs per GPU, done ignored, re-seeded every {TERRAIN_EPISODE} steps",
+        "srb_step_kernel<float, TERRAIN>", N, ms, 1216, "env-steps/s", "weak", "f32")
+    env.close()
+    # ---- configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1), 16384 envs, driven by the reference's trained policy (evaluated in torch, untimed)
+    N = 16384
+    tab, skel = hc.load_tables()
+    params = {"noise_q": 0.1, "noise_pos": 0.01, "noise_dq": 0.1, "noise_vx": 0.01, "noise_vy": 0.1, "noise_vz": 0.01}
+    cenv = CDMVecEnv(tab, skel, N, precision=32, auto_reset=True, seed=3 + rank, params=params, device=local_rank)
+    pol = dict(np.load(os.path.join(ROOT, "tests", "golden", "cdm_policy_walk2.npz")))
+    Wt = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
+    Bt = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
+    mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device=dev)
+    istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device=dev)
+    state = {"obs": cenv.reset(), "act": None}
+
+    def policy(_k):
+        h = torch.clamp((state["obs"] - mean) * istd, -10.0, 10.0)
+        for w, b in zip(Wt, Bt):
+            h = torch.tanh(h @ w.T + b)
+        state["act"] = h
+
+    def cdm_step():
+        state["obs"] = cenv.step(state["act"])[0]
+    for k in range(100):                                   # let the gait reach its steady state
+        policy(k); cdm_step()
+    ms = _timed(cdm_step, S, Wm, flush, dist, policy)
+    rec("cdm_fp32", f"BASELINE configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1 constants), {N} envs per GPU, actions from the reference's trained walk2-v1 policy", "cdm_step_kernel<float>",
+        N, ms, 740, "env-steps/s", "weak", "f32")
+    cenv.close()
+    # ---- configs[4]: FK + CoM + centroidal momentum of 1 M poses, split over the GPUs (strong scaling)
+    sk = Skeleton(vrml_skeleton.builtin(), device=local_rank)
+    n = (1 << 20) // world
+    g = torch.Generator(device=dev); g.manual_seed(4 + rank)
+    q = torch.randn(n, 4, device=dev, generator=g); q = q / q.norm(dim=1, keepdim=True)
+    pose = torch.cat([torch.rand(n, 3, device=dev, generator=g) * 10 - 5, q, torch.rand(n, 53, device=dev, generator=g) * 2 - 1], 1).contiguous()
+    dq = (torch.rand(n, 59, device=dev, generator=g) * 2 - 1).contiguous()
+    out = sk.forward(pose, dq)
+    for mode, d, by in (("fk+com", None, 836 - 24), ("fk+com+momentum", dq, 836)):
+        ms = _timed(lambda: sk.forward(pose, d, out=out), 10, 3, flush, dist)
+        rec("fk_fp32_" + ("momentum" if d is not None else "com"), f"BASELINE configs[4]: BoneForwardKinematics ({mode}) of 2^20 hanyang poses split over {world} GPU", "fk_hanyang_tma_*_kernel<float>",
+            n, ms, by, "poses/s", "strong", "f32")
+    sk.close()
+    # ---- MMSTO: 4096 windows of 7 frames x 59 dofs per GPU, 30 L-BFGS iterations (online configuration)
+    P = dict(np.load(os.path.join(ROOT, "tests", "golden", "mmsto_bench_problems.npz")))
+    nw = 4096
+    markers = [dict(bone=int(b), lpos=list(map(float, l)), weight=float(w)) for b, l, w in zip(P["marker_bone"], P["marker_lpos"], P["marker_weight"])]
+    opt = ShortTrajOpt(vrml_skeleton.builtin(), 7, markers, device=local_rank)
+    opt.set_dof_weights(P["dof_weights"]); opt.set("max_iterations", 30)
+    tile = lambda a: torch.as_tensor(np.tile(a, (nw // a.shape[0],) + (1,) * (a.ndim - 1)), device=dev)
+    keys = ("gpos_target", "x_original", "dx", "ddx", "com", "momentum")
+    targs = [tile(P[k]) for k in keys]; em = tile(P["euler_mot"]); vc = tile(P["velcon"])
+    info = {}
+
+    def solve():
+        info["i"] = opt.solveEndEffectors_euler(em, *targs, velcon=vc)[1]
+    ms = _timed(solve, 3, 2, flush, dist)
+    evals = float(info["i"][:, 3].sum().item())
+    by = (7 * 59 * 2 + 7 * 12 + 6 * 59 + 5 * 59 + 7 * 3 + 6 * 6 + 7 * 59) * 8     # inputs + solution per window (the L-BFGS workspace stays on chip / in L2)
+    rec("mmsto_f64", f"ShortTrajOpt.solveEndEffectors (online configuration), {nw} windows per GPU, 30 L-BFGS iterations ({evals / nw:.1f} evaluations per window)", "mmsto_kernel",
+        nw, ms, by, "windows/s", "weak", "f64", {"evaluations_per_s": evals * world / (ms * 1e-3), "steps": 3, "warmup": 2})
+    opt.close()
+    return recs if rank == 0 else []
 
 
 def env_lanes(args):

@@ -70,8 +70,10 @@ int srb_step(srb_env* env, const float* act_dev, float* obs_dev, float* rew_dev,
  * pinned staging buffers in place (see srb_pinned_buffers). */
 int srb_step_host(srb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host);
 int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint8_t** done, float** rinfo);
-/* How srb_step_host moves data: 1 (default) = zero copy, the step kernel reads the actions from and writes its results to
- * the mapped pinned buffers directly (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies. */
+/* How srb_step_host moves data: 2 (default) = split: the look-ahead windows of the observation rows (known before the step) are
+ * gathered first and copied by a copy engine while the step kernel runs, the kernel writes the rest to the mapped pinned buffers;
+ * 1 = zero copy, the step kernel reads the actions from and writes all its results to the mapped pinned buffers directly
+ * (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies. */
 int srb_set_host_mode(srb_env* env, int32_t mode);
 
 /* Optional side channels (any may be NULL = detach):
@@ -105,6 +107,9 @@ int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* str
 int srb_pack_obs_extra(srb_env* env, double* out_dev, void* stream);
 /* Episode statistics accumulated by auto-reset: out[3] = sum of returns, sum of lengths, count. */
 int srb_episode_stats(srb_env* env, double out[3], int32_t clear);
+/* The same three sums copied to DEVICE memory on `stream` (no synchronisation): the tail of the vector the per-rollout all-reduce
+ * carries next to the observation statistics (episode-return / length counters). */
+int srb_episode_stats_device(srb_env* env, double* out_dev, void* stream);
 
 /* ---- terrain variant (env/SRBEnv5_mocap_list_terrain_window.py, model gym_trackSRB/Characters/SRB5_playground.xml) ----
  * The group-0 geoms the reference ray-casts against (terrain_height_ray, env/testSRB_mujoco_original_viewer_terrain.py:741-752):

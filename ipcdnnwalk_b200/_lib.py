@@ -49,6 +49,7 @@ _SIGNATURES = {
     "srb_obs_stats": (C.c_int, [_P, _P, _P, _P]),
     "srb_pack_obs_extra": (C.c_int, [_P, _P, _P]),
     "srb_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
+    "srb_episode_stats_device": (C.c_int, [_P, _P, _P]),
     "srb_tracking_action": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_uint32, _P, _P]),
     "srb_upload_terrain": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P]),
     "srb_set_planar_offsets": (C.c_int, [_P, _P]),

@@ -40,8 +40,12 @@ struct srb_env {
   // pinned host staging + device I/O for the host-buffer path
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
+  float* d_win = nullptr;               // [N][125] look-ahead windows staged for the copy engine (host mode 2)
+  cudaStream_t stream2 = nullptr;       // second stream of the host path: window gather + its D2H copy
+  cudaEvent_t ev_win = nullptr, ev_dma = nullptr;
+  int split_obs = 0; uint8_t* done_dev_arg = nullptr;   // per-launch arguments of the split host path
   int64_t launches = 0;
-  int host_mode = 1;                    // srb_step_host: 1 = kernel reads / writes the mapped pinned buffers directly, 0 = staged copies
+  int host_mode = 2;                    // srb_step_host: 2 = split (windows by copy engine, rest zero copy), 1 = zero copy, 0 = staged copies
   // terrain (variant 2)
   TerrainDev* terrain_dev = nullptr; std::vector<float*> hf_data; double* box_dev = nullptr;
 };
@@ -132,6 +136,9 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_win, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_dma, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -147,6 +154,10 @@ extern "C" int srb_destroy(srb_env* h) {
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rinfo); cudaFree(h->d_done);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev_state) cudaEventDestroy(h->ev_state);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_win) cudaEventDestroy(h->ev_win);
+  if (h->ev_dma) cudaEventDestroy(h->ev_dma);
+  cudaFree(h->d_win);
   delete h;
   return 0;
 }
@@ -245,6 +256,7 @@ template <typename real, int G, bool CIO = false, bool TERRAIN = false> static v
   A.act = act; A.obs = obs; A.rew = rew; A.done = done; A.rinfo = rinfo; A.term_obs = h->term_obs;
   A.contact_prob = h->contact_prob; A.reset_plan = h->reset_plan; A.dbg = h->dbg; A.ep_stats = h->ep_stats;
   A.seed = h->cfg.seed; A.auto_reset = h->cfg.auto_reset; A.p = convert_params<real>(h->p); A.terrain = h->terrain_dev;
+  A.split_obs = CIO ? h->split_obs : 0; A.done_dev = CIO ? h->done_dev_arg : nullptr;
   constexpr int EPW = 32 / G;
   int blocks = (h->N + EPW - 1) / EPW;
   srb_step_kernel<real, G, CIO, TERRAIN><<<blocks, 32, 0, s>>>(A);
@@ -307,7 +319,13 @@ static int ensure_host_buffers(srb_env* h) {
   CK(cudaMalloc(&h->d_rew, sizeof(float) * N));
   CK(cudaMalloc(&h->d_rinfo, sizeof(float) * N * RINFO_W));
   CK(cudaMalloc(&h->d_done, N));
+  CK(cudaMalloc(&h->d_win, sizeof(float) * N * 5 * FEAT_W));
   return 0;
+}
+
+template <typename real> static void launch_window(srb_env* h, int after_inc, const uint8_t* only_done, float* dst, int pitch, cudaStream_t s) {
+  srb_obs_window_kernel<real><<<h->N, 128, 0, s>>>(h->N, h->Npad, h->ist, (const ClipDesc<real>*)h->clips_dev, after_inc, only_done, dst, pitch);
+  h->launches++;
 }
 
 extern "C" int srb_pinned_buffers(srb_env* h, float** act, float** obs, float** rew, uint8_t** done, float** rinfo) {
@@ -328,7 +346,36 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   if (act_host && act_host != h->h_act) memcpy(h->h_act, act_host, sizeof(float) * N * ACT_W);
   cudaStream_t s = h->stream;
   CK(cudaStreamWaitEvent(s, h->ev_state, 0));            // resets / device steps issued on caller streams come first
-  if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
+  if (h->host_mode == 2 && cio_supported(h->G) && !h->p.use_terrain) {
+    // split: 83 % of an observation row is the look-ahead window, which depends on (clip, frame) only.  It is gathered first
+    // (3 us) and travels by copy engine on a second stream WHILE the step kernel computes; the kernel itself writes the 25 self
+    // features, reward, done and reward_info to the mapped pinned buffers (zero copy) and reads the actions from them.  Rows of
+    // environments that were auto-reset get their new window from a small fix-up launch ordered after the window copy.
+    float *a = nullptr, *o = nullptr, *r = nullptr, *ri = nullptr; uint8_t* d = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&a, h->h_act, 0)); CK(cudaHostGetDevicePointer((void**)&o, h->h_obs, 0));
+    CK(cudaHostGetDevicePointer((void**)&r, h->h_rew, 0)); CK(cudaHostGetDevicePointer((void**)&d, h->h_done, 0));
+    CK(cudaHostGetDevicePointer((void**)&ri, h->h_rinfo, 0));
+    const int W5 = 5 * FEAT_W;
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_state, 0));
+    if (h->cfg.precision == 64) launch_window<double>(h, h->p.obs_after_inc, nullptr, h->d_win, W5, h->stream2);
+    else launch_window<float>(h, h->p.obs_after_inc, nullptr, h->d_win, W5, h->stream2);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_win, h->stream2));
+    CK(cudaMemcpy2DAsync(h->h_obs + FEAT_W, sizeof(float) * OBS_W, h->d_win, sizeof(float) * W5, sizeof(float) * W5, N, cudaMemcpyDeviceToHost, h->stream2));
+    CK(cudaEventRecord(h->ev_dma, h->stream2));
+    CK(cudaStreamWaitEvent(s, h->ev_win, 0));            // the step must not advance the frame counters before they were read
+    h->split_obs = 1; h->done_dev_arg = h->cfg.auto_reset ? h->d_done : nullptr;
+    rc = step_impl(h, a, o, r, d, ri, s, true);
+    h->split_obs = 0; h->done_dev_arg = nullptr;
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, h->ev_dma, 0));
+    if (h->cfg.auto_reset) {                             // new windows of the environments that were reset in this step
+      if (h->cfg.precision == 64) launch_window<double>(h, 0, h->d_done, o + FEAT_W, OBS_W, s);
+      else launch_window<float>(h, 0, h->d_done, o + FEAT_W, OBS_W, s);
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));
+  } else if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
     // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
     // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions
     // that overlap the computation of the other warps instead of four copies serialised after it
@@ -358,7 +405,7 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
 
 extern "C" int srb_set_host_mode(srb_env* h, int32_t mode) {
   if (!h) return fail(-1, "srb_set_host_mode: null handle");
-  if (mode != 0 && mode != 1) return fail(-1, "srb_set_host_mode: mode must be 0 (staged copies) or 1 (zero copy)");
+  if (mode != 0 && mode != 1 && mode != 2) return fail(-1, "srb_set_host_mode: mode must be 0 (staged copies), 1 (zero copy) or 2 (split)");
   h->host_mode = mode;
   return 0;
 }
@@ -513,6 +560,13 @@ extern "C" int srb_episode_stats(srb_env* h, double out[3], int32_t clear) {
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, h->ep_stats, sizeof(double) * 3, cudaMemcpyDeviceToHost));
   if (clear) CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
+  return 0;
+}
+
+extern "C" int srb_episode_stats_device(srb_env* h, double* out_dev, void* stream) {
+  if (!h || !out_dev) return fail(-1, "srb_episode_stats_device: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out_dev, h->ep_stats, sizeof(double) * 3, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -1249,7 +1249,8 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 
   // ---- obs / reward / done (:477-494; training variant takes the obs after the frame increment)
   float* obs = CIO ? sio + (lane32 / G) * OBS_W : A.obs + (size_t)e * OBS_W;
-  if (!P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T);
+  const bool want_window = !(CIO && A.split_obs);        // split host path: the window travels by copy engine (srb_obs_window_kernel)
+  if (!P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T, want_window);
   float info[8];
   real r = real(0);
   if (T == nullptr) {
@@ -1260,7 +1261,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   }
   bool done = compute_done(s, cd, P, T);
   s.frame += 1;
-  if (P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T);
+  if (P.obs_after_inc) write_obs<real, G>(s, cd, obs, lane, active, T, want_window);
   s.ep_ret += r;
   if (!CIO) {
     if (active && lane == 0) {
@@ -1281,7 +1282,10 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     }
     const unsigned dbits = __ballot_sync(0xffffffffu, done);
     __syncwarp();
-    if (lane32 < nrows) { A.rew[env0 + lane32] = srew[lane32]; A.done[env0 + lane32] = (dbits >> (lane32 * G)) & 1u; }
+    if (lane32 < nrows) {
+      A.rew[env0 + lane32] = srew[lane32]; A.done[env0 + lane32] = (dbits >> (lane32 * G)) & 1u;
+      if (A.done_dev != nullptr) A.done_dev[env0 + lane32] = (dbits >> (lane32 * G)) & 1u;
+    }
     if (A.rinfo != nullptr)
       for (int i = lane32; i < nrows * RINFO_W; i += 32) A.rinfo[(size_t)env0 * RINFO_W + i] = sinfo[i];
   }
@@ -1320,7 +1324,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         for (int i = 0; i < HIST_W; i++) hist_env[i] = h0[i];
       }
       const ClipDesc<real> ncd = A.clips[s.clip];
-      write_obs<real, G>(s, ncd, obs, lane, active, T);
+      write_obs<real, G>(s, ncd, obs, lane, active, T, want_window);
       if (dbg != nullptr && lane == 0) dbg[DBG_SUB + 21] = (double)(clock64() - tk_r0);
     }
   }
@@ -1329,7 +1333,9 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   if (CIO) {                                             // the warp's observation rows: one contiguous block
     __syncwarp();
     float* dst = A.obs + (size_t)env0 * OBS_W;
-    if ((EPW % 2 == 0) && nrows == EPW) {
+    if (A.split_obs) {                                    // self part of every row only (25 floats = 100 bytes per row)
+      for (int i = lane32; i < nrows * FEAT_W; i += 32) { const int r = i / FEAT_W, c = i - r * FEAT_W; dst[r * OBS_W + c] = sio[r * OBS_W + c]; }
+    } else if ((EPW % 2 == 0) && nrows == EPW) {
       const float4* s4 = reinterpret_cast<const float4*>(sio);
       float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll 2
@@ -1339,6 +1345,27 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     }
   }
   if (dbg != nullptr && lane == 0) { dbg[21] = (double)(clock64() - tk0); dbg[22] = (double)(tk_pre - tk_entry); { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[23] = (double)gt; dbg[64 + 23] = (double)gt_entry; } }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Look-ahead window of the observation rows (get_obs_window :1096-1161: 5 precomputed 25-float records of the clip table), gathered
+// on its own: it depends on (clip, frame index) only, i.e. it is known BEFORE the step runs.  The host-buffer path launches this
+// first and lets a copy engine move the 500-byte windows to the host while the step kernel computes (srb_step_host, mode 2).
+// `after_inc`: the training variant takes the observation after current_frame += 1.  `only_done` != null: rows of environments
+// that were auto-reset in the step just finished (their window changed), written in place over the stale ones.
+// One 128-thread block per environment.
+template <typename real>
+__global__ void srb_obs_window_kernel(int N, int Npad, const int* __restrict__ ist, const ClipDesc<real>* __restrict__ clips, int after_inc,
+                                      const uint8_t* __restrict__ only_done, float* __restrict__ dst, int dst_pitch) {
+  const int e = blockIdx.x;
+  if (e >= N) return;
+  if (only_done != nullptr && !only_done[e]) return;
+  const int frame = ist[(size_t)I_FRAME * Npad + e], rif = ist[(size_t)I_RIF * Npad + e], clip = ist[(size_t)I_CLIP * Npad + e];
+  const ClipDesc<real> cd = clips[clip];
+  const int f0 = min(frame + rif + 1 + (after_inc ? 1 : 0), max(cd.nframes - 5, 0));
+  const float* __restrict__ src = cd.feat + (size_t)f0 * FEAT_W;
+  const int i = threadIdx.x;
+  if (i < 5 * FEAT_W) dst[(size_t)e * dst_pitch + i] = __ldg(src + i);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -97,6 +97,9 @@ template <typename real> struct StepArgs {
   unsigned long long seed;
   int auto_reset;
   const TerrainDev* terrain;     // device pointer (terrain variant) or null
+  int split_obs;                 // coalesced-I/O kernel only: the look-ahead window of the observation rows is delivered separately
+                                 // (srb_obs_window_kernel + copy engine); the kernel writes the 25 self features of every row only
+  uint8_t* done_dev;             // optional device copy of the done flags (the host path's window fix-up reads it) or null
   Params<real> p;
 };
 

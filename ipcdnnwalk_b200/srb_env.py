@@ -65,6 +65,14 @@ def read_contact_npz(path):
     return left, right
 
 
+def build_clip_tables(mocap_path_list, data_root=None, device=0):
+    """SRBEnv.loadMocap for a list of clip paths (relative to <data_root>/gym_trackSRB/): ClipBuilder tables ready for SRBVecEnv."""
+    env = SRBEnv(mocap_path_list, data_root=data_root, device=device)
+    for i in range(env.SRB_data_num):
+        env.loadMocap(i)
+    return env.SRB_data_list
+
+
 class _Model:
     def __init__(self, timestep):
         self.opt = types.SimpleNamespace(timestep=timestep)

@@ -300,6 +300,13 @@ class SRBVecEnv:
         check(self.lib.srb_pack_obs_extra(self._h, _ptr(out), self._stream()))
         return out
 
+    def rollout_stats(self, acc):
+        """acc (float64 [1 + 2*150 + 3], device): observation statistics accumulated into acc[:301] (obs_stats) and the episode
+        counters (sum of returns, sum of lengths, count) copied into acc[301:304] -- the vector of the path's one all-reduce."""
+        self.obs_stats(acc)
+        check(self.lib.srb_episode_stats_device(self._h, C.c_void_p(acc.data_ptr() + 301 * 8), self._stream()))
+        return acc
+
     def episode_stats(self, clear=False):
         out = np.zeros(3)
         check(self.lib.srb_episode_stats(self._h, _ptr(out), int(clear)))

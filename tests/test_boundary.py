@@ -202,7 +202,7 @@ def test_sb3_vecenv_seam(built_lib):
     clips = helpers.fresh_clips()
     rng = np.random.default_rng(3)
     plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
-    plans[::4, 4] = -8.0                                                      # some environments fall and terminate soon
+    plans[::2, 4] = -12.0                                                     # some environments fall and terminate soon
     venv = SB3VecEnv(clips, n, variant="training", precision=64, seed=11)
     twin = SRBVecEnv(clips, n, variant="training", precision=64, seed=11, auto_reset=True)
     twin.attach(term_obs=True)
@@ -210,7 +210,7 @@ def test_sb3_vecenv_seam(built_lib):
     assert isinstance(obs, np.ndarray) and obs.shape == (n, 150) and obs.dtype == np.float32 and venv.num_envs == n
     act = torch.zeros(n, 22, device="cuda")
     n_done = 0
-    for k in range(12):
+    for k in range(40):
         twin.tracking_action(act, sigma=0.1, seed=4, step=k)
         a = act.cpu().numpy()
         venv.step_async(a)
@@ -225,7 +225,7 @@ def test_sb3_vecenv_seam(built_lib):
                 assert np.array_equal(infos[i]["terminal_observation"], twin.term_obs[i].cpu().numpy())
                 assert infos[i]["episode"]["l"] >= 1 and np.isfinite(infos[i]["episode"]["r"])
                 n_done += 1
-    assert n_done >= 4
+    assert n_done >= 2
     assert venv.get_attr("current_frame", indices=[0, 5]) == [twin.named_state(0)["current_frame"], twin.named_state(5)["current_frame"]]
     assert venv.env_is_wrapped(object) == [False] * n and venv.seed() == [11] * n
     st = venv.env_method("getFullState", indices=[3])[0]
