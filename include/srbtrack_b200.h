@@ -70,11 +70,15 @@ int srb_step(srb_env* env, const float* act_dev, float* obs_dev, float* rew_dev,
  * pinned staging buffers in place (see srb_pinned_buffers). */
 int srb_step_host(srb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* rinfo_host);
 int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint8_t** done, float** rinfo);
-/* How srb_step_host moves data: 2 (default) = split: the look-ahead windows of the observation rows (known before the step) are
- * gathered first and copied by a copy engine while the step kernel runs, the kernel writes the rest to the mapped pinned buffers;
- * 1 = zero copy, the step kernel reads the actions from and writes all its results to the mapped pinned buffers directly
- * (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies. */
+/* How srb_step_host moves data: 1 (default) = zero copy, the step kernel reads the actions from and writes all its results to the
+ * mapped pinned buffers directly (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies; 2 = split: the
+ * look-ahead windows of the observation rows (known before the step) are gathered first and the observation array is copied by a
+ * copy engine while the step kernel runs, a patch launch then writes the self features over it (measured: the PCIe link, ~35 GB/s
+ * device-to-host either way, is the limit, so this does not beat mode 1 on one GPU; kept selectable). */
 int srb_set_host_mode(srb_env* env, int32_t mode);
+/* Device timeline of the last mode-2 host step, milliseconds after its first launch was enqueued: out_ms[1] window gather done,
+ * [2] observation copy done, [3] step kernel done, [4] patch launch done.  enable = 1 switches the timing events on. */
+int srb_host_timeline(srb_env* env, int32_t enable, float out_ms[5]);
 
 /* Optional side channels (any may be NULL = detach):
  *   contact_prob_dev[N][2]  Policy_prior_posterior_MoE_window._last_contact_prob hysteresis input

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "srb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "srb_pinned_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "srb_set_host_mode": (C.c_int, [_P, C.c_int32]),
+    "srb_host_timeline": (C.c_int, [_P, C.c_int32, _P]),
     "srb_set_aux": (C.c_int, [_P, _P, _P, _P, _P]),
     "srb_set_reward_weights": (C.c_int, [_P, _P]),
     "srb_set_impulse": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32]),

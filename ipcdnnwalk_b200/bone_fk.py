@@ -64,7 +64,7 @@ class Skeleton:
 
     def set_tma(self, use=True):
         """Specialised path: -1 / True = automatic choice, 0 / False = rows accessed directly, 1 = rolled loop on TMA tiles,
-        3 = unrolled sweep on TMA tiles (A/B runs, tests)."""
+        3 = unrolled sweep on TMA tiles, 4 = chain-wise unrolled bodies on TMA tiles (A/B runs, tests)."""
         if use is True:
             use = -1
         check(self.lib.fk_set_tma(self._h, int(use)))

@@ -115,15 +115,16 @@ static int fk_launch(fk_skeleton* s, int64_t n, const real* pose, const real* dq
     const bool al = ((uintptr_t)pose % 16 == 0) && (!xform || (uintptr_t)xform % 16 == 0) && (!dq || (uintptr_t)dq % 16 == 0) &&
                     (!com || (uintptr_t)com % 16 == 0) && (!mom || (uintptr_t)mom % 16 == 0);
     const bool momentum = dq && mom;
-    // fp64 + momentum: 119 doubles of inputs next to the sweep exceed the register file; the structure-agnostic kernel wins
-    if (al && !(s->tma_mode < 0 && momentum && sizeof(real) == 8)) {
+    if (al) {
       cudaStream_t st = (cudaStream_t)stream;
       // tma_mode: -1 auto (measured best per precision / outputs, tools/bench_fk.py), 0 direct rows, 1 rolled loop on TMA tiles,
-      //           3 unrolled sweep on TMA tiles.  (A per-bone CTA barrier to share instruction-cache lines was tried with
+      //           3 unrolled sweep on TMA tiles, 4 chain-wise unrolled bodies on TMA tiles.  (A per-bone CTA barrier to share instruction-cache lines was tried with
       //           128- and 256-pose tiles: 10-20 % slower than the plain unrolled tile kernel, removed.)
       int mode = s->tma_mode;
-      if (mode < 0) mode = sizeof(real) == 4 ? (momentum ? 1 : 3) : 0;
-      if (mode != 0 && mode != 1) mode = 3;
+      // measured on a B200, 1 M poses (profiles/r02_fk_bench.jsonl): with momentum the chain-wise kernel wins in both precisions
+      // (fp32 0.44 ms vs 0.60 rolled / 0.77 unrolled; fp64 0.94 ms vs 1.07 generic); FK + CoM alone: fp32 unrolled tiles, fp64 direct rows
+      if (mode < 0) mode = momentum ? 4 : (sizeof(real) == 4 ? 3 : 0);
+      if (mode != 0 && mode != 1 && mode != 4) mode = 3;
       const int TB = mode == 0 ? 1 : 64;
       const int64_t full = mode == 0 ? 0 : n / TB;
       if (full > 0) {
@@ -137,6 +138,9 @@ static int fk_launch(fk_skeleton* s, int64_t n, const real* pose, const real* dq
         if (mode == 1) {
           if (momentum) FK_LAUNCH_TILE((fk::fk_hanyang_tma_rolled_kernel<real, true, 64>), 64, 59);
           else FK_LAUNCH_TILE((fk::fk_hanyang_tma_rolled_kernel<real, false, 64>), 64, 0);
+        } else if (mode == 4) {                          // chain-wise unrolled bodies on TMA tiles
+          if (momentum) FK_LAUNCH_TILE((fk::fk_hanyang_tma_chain_kernel<real, true, 64>), 64, 59);
+          else FK_LAUNCH_TILE((fk::fk_hanyang_tma_chain_kernel<real, false, 64>), 64, 0);
         } else {
           if (momentum) FK_LAUNCH_TILE((fk::fk_hanyang_tma_unrolled_kernel<real, true, false, 64>), 64, 0);
           else FK_LAUNCH_TILE((fk::fk_hanyang_tma_unrolled_kernel<real, false, false, 64>), 64, 0);

@@ -538,6 +538,184 @@ __global__ void __launch_bounds__(BLOCK) fk_hanyang_tma_rolled_kernel(const Skel
   }
 }
 
+// Variant D (full tiles): TMA-staged rows as in variant B, CHAIN-WISE unrolled code.  The skeleton is five chains hanging off two
+// branch points: two legs (Hip YZX, Knee X, Ankle YZX), the spine (3 x YZX), two arms (Collar YZX, Shoulder XYZ, Elbow ZXY, Wrist
+// ZXY) and Neck / Head (2 x YZX).  Left and right limbs have the same channel structure, so ONE unrolled leg body and ONE unrolled
+// arm body run twice (side loop), and one YZX bone body serves the spine and Neck / Head (5 trips).  Channel axes are compile-time
+// constants inside a body (axis-specialised quaternion and velocity updates: the instruction count of the fully unrolled sweep,
+// 200 M warp instructions per 1 M poses instead of the rolled loop's 345 M), while the code is 22 channel bodies + 8 bone
+// epilogues instead of 53 + 20: ~40 % of the unrolled kernel's 104 / 146 kB, and every body's second trip hits the
+// instruction cache.  Bones are still visited in index order except Neck / Head, whose 14 output reals wait in registers
+// until the arms have consumed their angles (the in-place slot overwrite of variant B needs index order).
+template <typename real, bool MOM, int NC, int AX>
+__device__ __forceinline__ void bone_fixed(const BoneState<real>& par, BoneState<real>& cur, const real* __restrict__ ang, const real* __restrict__ rate, V3<real> off) {
+  Q4<real> lq = {real(1), real(0), real(0), real(0)};
+  V3<real> w = {0, 0, 0}, lv = {0, 0, 0};
+  if constexpr (MOM) { w = par.w; lv = par.lv + cross(par.w, off); }
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+    constexpr int dummy = 0; (void)dummy;
+    const int a = (AX >> (2 * k)) & 3;                       // compile-time after unrolling
+    real s, c;
+    num<real>::sincos(real(0.5) * ang[k], &s, &c);
+    Q4<real> r;
+    if (a == 0) r = {lq.w * c - lq.x * s, lq.x * c + lq.w * s, lq.y * c + lq.z * s, lq.z * c - lq.y * s};
+    else if (a == 1) r = {lq.w * c - lq.y * s, lq.x * c - lq.z * s, lq.y * c + lq.w * s, lq.z * c + lq.x * s};
+    else r = {lq.w * c - lq.z * s, lq.x * c + lq.y * s, lq.y * c - lq.x * s, lq.z * c + lq.w * s};
+    lq = r;
+    if constexpr (MOM) {
+      const real C = c * c - s * s, Sn = real(2) * s * c;
+      const real rt = rate[k];
+      if (a == 0) { w = {w.x, C * w.y + Sn * w.z, C * w.z - Sn * w.y}; lv = {lv.x, C * lv.y + Sn * lv.z, C * lv.z - Sn * lv.y}; w.x += rt; }
+      else if (a == 1) { w = {C * w.x - Sn * w.z, w.y, C * w.z + Sn * w.x}; lv = {C * lv.x - Sn * lv.z, lv.y, C * lv.z + Sn * lv.x}; w.y += rt; }
+      else { w = {C * w.x + Sn * w.y, C * w.y - Sn * w.x, w.z}; lv = {C * lv.x + Sn * lv.y, C * lv.y - Sn * lv.x, lv.z}; w.z += rt; }
+    }
+  }
+  cur.q = quat_mul(par.q, lq);
+  cur.t = qrot(par.q, off) + par.t;
+  cur.w = w; cur.lv = lv;
+}
+
+template <typename real, bool MOM> struct FkAccum {
+  V3<real> csum = {0, 0, 0};
+  real HM[3] = {0, 0, 0}, HF[3] = {0, 0, 0};
+  __device__ __forceinline__ void add(const BoneNum<real>& bn, int b, const BoneState<real>& B) {
+    const real m = bn.mass[b];
+    const V3<real> c = {bn.com[b][0], bn.com[b][1], bn.com[b][2]};
+    csum = csum + m * (qrot(B.q, c) + B.t);
+    if constexpr (MOM) {
+      const real Ixx = bn.inr[b][0], Iyy = bn.inr[b][1], Izz = bn.inr[b][2], Ixy = bn.inr[b][3], Ixz = bn.inr[b][4], Iyz = bn.inr[b][5];
+      const V3<real> r = m * c;
+      const V3<real> w = B.w, lv = B.lv;
+      V3<real> M = {Ixx * w.x + Ixy * w.y + Ixz * w.z + r.y * lv.z - r.z * lv.y,
+                    Ixy * w.x + Iyy * w.y + Iyz * w.z + r.z * lv.x - r.x * lv.z,
+                    Ixz * w.x + Iyz * w.y + Izz * w.z + r.x * lv.y - r.y * lv.x};
+      V3<real> F = {w.y * r.z - w.z * r.y + m * lv.x, w.z * r.x - w.x * r.z + m * lv.y, w.x * r.y - w.y * r.x + m * lv.z};
+      V3<real> Fw = qrot(B.q, F);
+      V3<real> Mw = qrot(B.q, M) + cross(B.t, Fw);
+      HM[0] += Mw.x; HM[1] += Mw.y; HM[2] += Mw.z; HF[0] += Fw.x; HF[1] += Fw.y; HF[2] += Fw.z;
+    }
+  }
+};
+
+template <typename real, bool MOM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fk_hanyang_tma_chain_kernel(const SkelConst* __restrict__ skp, const real* __restrict__ pose,
+                                                              const real* __restrict__ dq, real* __restrict__ xform,
+                                                              real* __restrict__ com_out, real* __restrict__ mom_out) {
+  using H = Hanyang;
+  constexpr int XW = H::NB * 7;
+  constexpr int PIN = XW - H::NPOSE;
+  constexpr int YZX = 9, XYZ = 36, ZXY = 18, X = 0;
+  extern __shared__ __align__(128) unsigned char fk_tile[];
+  real* sx = reinterpret_cast<real*>(fk_tile);                // [BLOCK][140]
+  real* sc = sx + BLOCK * XW;                                  // [BLOCK][3]
+  real* sm = sc + BLOCK * 3;                                   // [BLOCK][6]
+  real* sdq = sm + BLOCK * 6;                                  // [BLOCK][59]  (momentum only)
+  __shared__ BoneNum<real> bn;
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * BLOCK;
+  constexpr unsigned row_bytes = H::NPOSE * sizeof(real), dq_bytes = BLOCK * H::NDQ * sizeof(real);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(BLOCK * row_bytes + (MOM ? dq_bytes : 0u)) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sdq)), "l"(dq + row0 * H::NDQ), "r"(dq_bytes), "r"(smem_u32(&mbar)) : "memory");
+  }
+  load_bone_numbers<real, BLOCK>(bn, skp);
+  __syncthreads();
+  real* slot = sx + tid * XW;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(slot + PIN)), "l"(pose + (row0 + tid) * H::NPOSE), "r"(row_bytes), "r"(smem_u32(&mbar)) : "memory");
+  {
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred P; mbarrier.try_wait.parity.shared::cta.b64 P, [%1], 0; selp.u32 %0, 1, 0, P; }" : "=r"(ok) : "r"(smem_u32(&mbar)) : "memory");
+  }
+  const real* p = slot + PIN;
+  const real* v = sdq + tid * H::NDQ - 1;                      // rate of pose column c (c >= 7) = v[c]: dq index 6 + (c - 7)
+  const bool want_x = xform != nullptr;
+  FkAccum<real, MOM> acc;
+  auto offv = [&](int b) { return V3<real>{bn.off[b][0], bn.off[b][1], bn.off[b][2]}; };
+  auto put = [&](int b, const BoneState<real>& B) {
+    if (want_x) { real* o = slot + 7 * b; o[0] = B.q.w; o[1] = B.q.x; o[2] = B.q.y; o[3] = B.q.z; o[4] = B.t.x; o[5] = B.t.y; o[6] = B.t.z; }
+  };
+  BoneState<real> hips, chest2;
+  {                                                            // Hips: the free root
+    const V3<real> off = offv(0);
+    hips.q = {p[3], p[4], p[5], p[6]};
+    hips.t = {p[0] + off.x, p[1] + off.y, p[2] + off.z};
+    hips.w = {0, 0, 0}; hips.lv = {0, 0, 0};
+    if constexpr (MOM) {
+      Q4<real> qi = qconj_unit(hips.q);
+      hips.w = qrot(qi, V3<real>{sdq[tid * H::NDQ], sdq[tid * H::NDQ + 1], sdq[tid * H::NDQ + 2]});
+      hips.lv = qrot(qi, V3<real>{sdq[tid * H::NDQ + 3], sdq[tid * H::NDQ + 4], sdq[tid * H::NDQ + 5]});
+    }
+    put(0, hips); acc.add(bn, 0, hips);
+  }
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {                       // legs: bones 1-3 / 4-6, pose columns 7-13 / 14-20
+    const int b0 = 1 + 3 * side, st = 7 + 7 * side;
+    BoneState<real> hip, knee, ankle;
+    bone_fixed<real, MOM, 3, YZX>(hips, hip, p + st, v + st, offv(b0)); put(b0, hip); acc.add(bn, b0, hip);
+    bone_fixed<real, MOM, 1, X>(hip, knee, p + st + 3, v + st + 3, offv(b0 + 1)); put(b0 + 1, knee); acc.add(bn, b0 + 1, knee);
+    bone_fixed<real, MOM, 3, YZX>(knee, ankle, p + st + 4, v + st + 4, offv(b0 + 2)); put(b0 + 2, ankle); acc.add(bn, b0 + 2, ankle);
+  }
+  real pend[14];                                               // Neck / Head outputs, stored after the arms
+  {
+    BoneState<real> par = hips, cur;
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) {                              // Chest, Chest1, Chest2 (7-9, columns 21-29), then Neck, Head (18-19, columns 54-59)
+      const int b = k < 3 ? 7 + k : 15 + k, st = k < 3 ? 21 + 3 * k : 45 + 3 * k;
+      bone_fixed<real, MOM, 3, YZX>(par, cur, p + st, v + st, offv(b));
+      acc.add(bn, b, cur);
+      if (k < 3) put(b, cur);
+      else {
+        const int o = 7 * (k - 3);
+        if (k == 3) { pend[0] = cur.q.w; pend[1] = cur.q.x; pend[2] = cur.q.y; pend[3] = cur.q.z; pend[4] = cur.t.x; pend[5] = cur.t.y; pend[6] = cur.t.z; }
+        else { pend[7] = cur.q.w; pend[8] = cur.q.x; pend[9] = cur.q.y; pend[10] = cur.q.z; pend[11] = cur.t.x; pend[12] = cur.t.y; pend[13] = cur.t.z; }
+        (void)o;
+      }
+      if (k == 2) { chest2 = cur; par = chest2; } else par = cur;
+    }
+  }
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {                       // arms: bones 10-13 / 14-17, pose columns 30-41 / 42-53
+    const int b0 = 10 + 4 * side, st = 30 + 12 * side;
+    BoneState<real> collar, shoulder, elbow, wrist;
+    bone_fixed<real, MOM, 3, YZX>(chest2, collar, p + st, v + st, offv(b0)); put(b0, collar); acc.add(bn, b0, collar);
+    bone_fixed<real, MOM, 3, XYZ>(collar, shoulder, p + st + 3, v + st + 3, offv(b0 + 1)); put(b0 + 1, shoulder); acc.add(bn, b0 + 1, shoulder);
+    bone_fixed<real, MOM, 3, ZXY>(shoulder, elbow, p + st + 6, v + st + 6, offv(b0 + 2)); put(b0 + 2, elbow); acc.add(bn, b0 + 2, elbow);
+    bone_fixed<real, MOM, 3, ZXY>(elbow, wrist, p + st + 9, v + st + 9, offv(b0 + 3)); put(b0 + 3, wrist); acc.add(bn, b0 + 3, wrist);
+  }
+  if (want_x) {
+#pragma unroll
+    for (int i = 0; i < 14; i++) slot[7 * 18 + i] = pend[i];
+  }
+  const V3<real> com = bn.itm * acc.csum;
+  sc[tid * 3] = com.x; sc[tid * 3 + 1] = com.y; sc[tid * 3 + 2] = com.z;
+  if constexpr (MOM) {
+    V3<real> Fv = {acc.HF[0], acc.HF[1], acc.HF[2]};
+    V3<real> sh = cross(com, Fv);
+    real* o = sm + tid * 6;
+    o[0] = acc.HM[0] - sh.x; o[1] = acc.HM[1] - sh.y; o[2] = acc.HM[2] - sh.z; o[3] = acc.HF[0]; o[4] = acc.HF[1]; o[5] = acc.HF[2];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    if (want_x)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xform + row0 * XW), "r"(smem_u32(sx)), "r"((unsigned)(BLOCK * XW * sizeof(real))) : "memory");
+    if (com_out != nullptr)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(com_out + row0 * 3), "r"(smem_u32(sc)), "r"((unsigned)(BLOCK * 3 * sizeof(real))) : "memory");
+    if constexpr (MOM)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mom_out + row0 * 6), "r"(smem_u32(sm)), "r"((unsigned)(BLOCK * 6 * sizeof(real))) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
 // Variant C (full tiles): TMA-staged rows with the UNROLLED sweep.  Pose / dq tiles arrive by two bulk copies, every thread
 // pulls its row into registers with conflict-free 128-bit shared loads (pitch 240 / 560 bytes: the eight 16-byte spans of
 // a quarter-warp fall in distinct bank groups), the region is then reused for the output tile, which leaves by bulk stores.

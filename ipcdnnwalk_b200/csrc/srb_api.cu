@@ -40,12 +40,13 @@ struct srb_env {
   // pinned host staging + device I/O for the host-buffer path
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_rinfo = nullptr; uint8_t* h_done = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_rinfo = nullptr; uint8_t* d_done = nullptr;
-  float* d_win = nullptr;               // [N][125] look-ahead windows staged for the copy engine (host mode 2)
   cudaStream_t stream2 = nullptr;       // second stream of the host path: window gather + its D2H copy
   cudaEvent_t ev_win = nullptr, ev_dma = nullptr;
+  cudaEvent_t tl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // timeline of the last split host step (timing events)
+  int tl_on = 0; float tl_ms[6] = {0, 0, 0, 0, 0, 0};
   int split_obs = 0; uint8_t* done_dev_arg = nullptr;   // per-launch arguments of the split host path
   int64_t launches = 0;
-  int host_mode = 2;                    // srb_step_host: 2 = split (windows by copy engine, rest zero copy), 1 = zero copy, 0 = staged copies
+  int host_mode = 1;                    // srb_step_host: 1 = zero copy (default), 2 = split (windows by copy engine), 0 = staged copies
   // terrain (variant 2)
   TerrainDev* terrain_dev = nullptr; std::vector<float*> hf_data; double* box_dev = nullptr;
 };
@@ -139,6 +140,7 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_win, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_dma, cudaEventDisableTiming));
+  for (int i = 0; i < 5; i++) CK(cudaEventCreate(&h->tl[i]));
   *out = h;
   return 0;
 }
@@ -157,7 +159,7 @@ extern "C" int srb_destroy(srb_env* h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->ev_win) cudaEventDestroy(h->ev_win);
   if (h->ev_dma) cudaEventDestroy(h->ev_dma);
-  cudaFree(h->d_win);
+  for (int i = 0; i < 5; i++) if (h->tl[i]) cudaEventDestroy(h->tl[i]);
   delete h;
   return 0;
 }
@@ -319,12 +321,11 @@ static int ensure_host_buffers(srb_env* h) {
   CK(cudaMalloc(&h->d_rew, sizeof(float) * N));
   CK(cudaMalloc(&h->d_rinfo, sizeof(float) * N * RINFO_W));
   CK(cudaMalloc(&h->d_done, N));
-  CK(cudaMalloc(&h->d_win, sizeof(float) * N * 5 * FEAT_W));
   return 0;
 }
 
-template <typename real> static void launch_window(srb_env* h, int after_inc, const uint8_t* only_done, float* dst, int pitch, cudaStream_t s) {
-  srb_obs_window_kernel<real><<<h->N, 128, 0, s>>>(h->N, h->Npad, h->ist, (const ClipDesc<real>*)h->clips_dev, after_inc, only_done, dst, pitch);
+template <typename real> static void launch_window(srb_env* h, int after_inc, const uint8_t* only_done, const float* self_src, float* dst, cudaStream_t s) {
+  srb_obs_window_kernel<real><<<h->N, 160, 0, s>>>(h->N, h->Npad, h->ist, (const ClipDesc<real>*)h->clips_dev, after_inc, only_done, self_src, dst);
   h->launches++;
 }
 
@@ -348,33 +349,39 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   CK(cudaStreamWaitEvent(s, h->ev_state, 0));            // resets / device steps issued on caller streams come first
   if (h->host_mode == 2 && cio_supported(h->G) && !h->p.use_terrain) {
     // split: 83 % of an observation row is the look-ahead window, which depends on (clip, frame) only.  It is gathered first
-    // (3 us) and travels by copy engine on a second stream WHILE the step kernel computes; the kernel itself writes the 25 self
-    // features, reward, done and reward_info to the mapped pinned buffers (zero copy) and reads the actions from them.  Rows of
-    // environments that were auto-reset get their new window from a small fix-up launch ordered after the window copy.
+    // (3 us) into the device observation array, and that array travels to the host as ONE contiguous copy-engine transfer on a
+    // second stream WHILE the step kernel computes (SM-issued stores to mapped memory reach ~35 GB/s, the copy engine ~52 GB/s).
+    // The step kernel reads the actions from and writes reward / done / reward_info to the mapped pinned buffers (zero copy) and
+    // leaves the 25 self features of every row in the device array; a patch launch ordered after the big copy writes those self
+    // features, and the new windows of the environments that were auto-reset, over the rows in host memory.
     float *a = nullptr, *o = nullptr, *r = nullptr, *ri = nullptr; uint8_t* d = nullptr;
     CK(cudaHostGetDevicePointer((void**)&a, h->h_act, 0)); CK(cudaHostGetDevicePointer((void**)&o, h->h_obs, 0));
     CK(cudaHostGetDevicePointer((void**)&r, h->h_rew, 0)); CK(cudaHostGetDevicePointer((void**)&d, h->h_done, 0));
     CK(cudaHostGetDevicePointer((void**)&ri, h->h_rinfo, 0));
-    const int W5 = 5 * FEAT_W;
     CK(cudaStreamWaitEvent(h->stream2, h->ev_state, 0));
-    if (h->cfg.precision == 64) launch_window<double>(h, h->p.obs_after_inc, nullptr, h->d_win, W5, h->stream2);
-    else launch_window<float>(h, h->p.obs_after_inc, nullptr, h->d_win, W5, h->stream2);
+    if (h->tl_on) CK(cudaEventRecord(h->tl[0], h->stream2));
+    if (h->cfg.precision == 64) launch_window<double>(h, h->p.obs_after_inc, nullptr, nullptr, h->d_obs, h->stream2);
+    else launch_window<float>(h, h->p.obs_after_inc, nullptr, nullptr, h->d_obs, h->stream2);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev_win, h->stream2));
-    CK(cudaMemcpy2DAsync(h->h_obs + FEAT_W, sizeof(float) * OBS_W, h->d_win, sizeof(float) * W5, sizeof(float) * W5, N, cudaMemcpyDeviceToHost, h->stream2));
+    if (h->tl_on) CK(cudaEventRecord(h->tl[1], h->stream2));
+    CK(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * N * OBS_W, cudaMemcpyDeviceToHost, h->stream2));
     CK(cudaEventRecord(h->ev_dma, h->stream2));
+    if (h->tl_on) CK(cudaEventRecord(h->tl[2], h->stream2));
     CK(cudaStreamWaitEvent(s, h->ev_win, 0));            // the step must not advance the frame counters before they were read
-    h->split_obs = 1; h->done_dev_arg = h->cfg.auto_reset ? h->d_done : nullptr;
-    rc = step_impl(h, a, o, r, d, ri, s, true);
+    h->split_obs = 1; h->done_dev_arg = h->d_done;
+    rc = step_impl(h, a, h->d_obs, r, d, ri, s, true);
     h->split_obs = 0; h->done_dev_arg = nullptr;
     if (rc) return rc;
+    if (h->tl_on) CK(cudaEventRecord(h->tl[3], s));
     CK(cudaStreamWaitEvent(s, h->ev_dma, 0));
-    if (h->cfg.auto_reset) {                             // new windows of the environments that were reset in this step
-      if (h->cfg.precision == 64) launch_window<double>(h, 0, h->d_done, o + FEAT_W, OBS_W, s);
-      else launch_window<float>(h, 0, h->d_done, o + FEAT_W, OBS_W, s);
-      CK(cudaGetLastError());
-    }
+    const uint8_t* only_done = h->cfg.auto_reset ? h->d_done : nullptr;   // without auto-reset no window changes
+    if (h->cfg.precision == 64) launch_window<double>(h, 0, only_done, h->d_obs, o, s);
+    else launch_window<float>(h, 0, only_done, h->d_obs, o, s);
+    CK(cudaGetLastError());
+    if (h->tl_on) CK(cudaEventRecord(h->tl[4], s));
     CK(cudaStreamSynchronize(s));
+    if (h->tl_on) for (int i = 1; i < 5; i++) cudaEventElapsedTime(&h->tl_ms[i], h->tl[0], h->tl[i]);
   } else if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
     // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
     // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions
@@ -400,6 +407,15 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
   if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, sizeof(float) * N);
   if (done_host && done_host != h->h_done) memcpy(done_host, h->h_done, N);
   if (rinfo_host && rinfo_host != h->h_rinfo) memcpy(rinfo_host, h->h_rinfo, sizeof(float) * N * RINFO_W);
+  return 0;
+}
+
+// Timeline of the last split (mode 2) host step, milliseconds after the window gather was enqueued: [1] window gather done,
+// [2] observation copy done, [3] step kernel done, [4] patch launch done.  enable = 1 switches the timing events on.
+extern "C" int srb_host_timeline(srb_env* h, int32_t enable, float out_ms[5]) {
+  if (!h) return fail(-1, "srb_host_timeline: null handle");
+  h->tl_on = enable;
+  if (out_ms) for (int i = 0; i < 5; i++) out_ms[i] = h->tl_ms[i];
   return 0;
 }
 

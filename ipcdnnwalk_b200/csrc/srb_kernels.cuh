@@ -1349,23 +1349,29 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 
 // ------------------------------------------------------------------------------------------------
 // Look-ahead window of the observation rows (get_obs_window :1096-1161: 5 precomputed 25-float records of the clip table), gathered
-// on its own: it depends on (clip, frame index) only, i.e. it is known BEFORE the step runs.  The host-buffer path launches this
-// first and lets a copy engine move the 500-byte windows to the host while the step kernel computes (srb_step_host, mode 2).
-// `after_inc`: the training variant takes the observation after current_frame += 1.  `only_done` != null: rows of environments
-// that were auto-reset in the step just finished (their window changed), written in place over the stale ones.
-// One 128-thread block per environment.
+// on its own: it depends on (clip, frame index) only, i.e. it is known BEFORE the step runs.  The host-buffer path (srb_step_host,
+// mode 2) launches this first into the device copy of the observation array and lets a copy engine move the whole array to the host
+// as ONE contiguous transfer while the step kernel computes; a second launch after that copy patches what the step produced:
+// `self_src` != null (patch launch): the 25 self features of every row are copied from there (device rows) to dst, and the window
+// is rewritten only for environments flagged in `only_done` (auto-reset in the step just finished: their window changed; null =
+// no environment, i.e. auto-reset is off).
+// `after_inc`: the training variant takes the observation after current_frame += 1.  One 160-thread block per environment.
 template <typename real>
 __global__ void srb_obs_window_kernel(int N, int Npad, const int* __restrict__ ist, const ClipDesc<real>* __restrict__ clips, int after_inc,
-                                      const uint8_t* __restrict__ only_done, float* __restrict__ dst, int dst_pitch) {
+                                      const uint8_t* __restrict__ only_done, const float* __restrict__ self_src, float* __restrict__ dst) {
   const int e = blockIdx.x;
   if (e >= N) return;
-  if (only_done != nullptr && !only_done[e]) return;
+  const int i = threadIdx.x;
+  if (self_src != nullptr && i >= 5 * FEAT_W && i < 6 * FEAT_W) {
+    const int c = i - 5 * FEAT_W;
+    dst[(size_t)e * OBS_W + c] = self_src[(size_t)e * OBS_W + c];
+  }
+  if (self_src != nullptr && (only_done == nullptr || !only_done[e])) return;      // patch launch: windows of auto-reset environments only
+  if (i >= 5 * FEAT_W) return;
   const int frame = ist[(size_t)I_FRAME * Npad + e], rif = ist[(size_t)I_RIF * Npad + e], clip = ist[(size_t)I_CLIP * Npad + e];
   const ClipDesc<real> cd = clips[clip];
   const int f0 = min(frame + rif + 1 + (after_inc ? 1 : 0), max(cd.nframes - 5, 0));
-  const float* __restrict__ src = cd.feat + (size_t)f0 * FEAT_W;
-  const int i = threadIdx.x;
-  if (i < 5 * FEAT_W) dst[(size_t)e * dst_pitch + i] = __ldg(src + i);
+  dst[(size_t)e * OBS_W + FEAT_W + i] = __ldg(cd.feat + (size_t)f0 * FEAT_W + i);
 }
 
 // ------------------------------------------------------------------------------------------------

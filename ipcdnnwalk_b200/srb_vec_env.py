@@ -150,6 +150,12 @@ class SRBVecEnv:
         """step_host data movement: 1 = zero copy through mapped pinned memory (default), 0 = staged copies."""
         check(self.lib.srb_set_host_mode(self._h, int(mode)))
 
+    def host_timeline(self, enable=True):
+        """Device timeline (ms) of the last mode-2 step_host: window gather / observation copy / step kernel / patch launch done."""
+        out = (C.c_float * 5)()
+        check(self.lib.srb_host_timeline(self._h, int(bool(enable)), out))
+        return dict(zip(("t0", "window_gather", "obs_copy", "step_kernel", "patch"), list(out)))
+
     def pinned(self):
         if getattr(self, "_pinned", None) is None:
             ptrs = [C.c_void_p() for _ in range(5)]

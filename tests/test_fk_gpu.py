@@ -15,7 +15,7 @@ def _batch(rng, skel, n):
     return pose, dq
 
 
-@pytest.mark.parametrize("generic", [False, True, "no_tma", "tma1", "tma3"])
+@pytest.mark.parametrize("generic", [False, True, "no_tma", "tma1", "tma3", "tma4"])
 @pytest.mark.parametrize("dtype,tol_pos,tol_mom", [("float64", 1e-11, 1e-10), ("float32", 1e-5, 2e-4)])
 def test_fk_com_momentum_match_oracle(built_lib, dtype, tol_pos, tol_mom, generic):
     """FK joint positions within 1e-5 m (BASELINE.json); fp64 to round-off.  Both kernels: the skeleton-specialised

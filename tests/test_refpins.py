@@ -209,7 +209,7 @@ def test_cuda_fk_equals_reference(built_lib, ref, skel, precision, tol_pos, tol_
     from ipcdnnwalk_b200 import Skeleton
     dt = torch.float64 if precision == 64 else torch.float32
     pose = torch.as_tensor(ref["fk_pose"], dtype=dt, device="cuda"); dq = torch.as_tensor(ref["fk_dq"], dtype=dt, device="cuda")
-    for generic, tma in ((True, -1), (False, 0), (False, 1), (False, 3)):
+    for generic, tma in ((True, -1), (False, -1), (False, 0), (False, 1), (False, 3), (False, 4)):
         S = Skeleton(skel)
         S.set_generic(generic)
         if not generic:

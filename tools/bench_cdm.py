@@ -32,6 +32,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for prec in [int(x) for x in a.precision.split(",")]:
     for lanes in [int(x) for x in a.lanes.split(",")]:
         params = {"noise_q": 0.1, "noise_pos": 0.01, "noise_dq": 0.1, "noise_vx": 0.01, "noise_vy": 0.1, "noise_vz": 0.01} if a.policy else None
+        if a.policy and os.environ.get("CDM_NOISE_SCALE"):          # experiment: 0 = all environments identical (perfectly coherent warps)
+            params = {k: v * float(os.environ["CDM_NOISE_SCALE"]) for k, v in params.items()}
         env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3, params=params)
         obs = env.reset()
         if a.policy:

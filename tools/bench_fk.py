@@ -31,7 +31,7 @@ for dt, name in ((torch.float32, "f32"), (torch.float64, "f64")):
     pose = torch.cat([torch.rand(n, 3, device="cuda", generator=g, dtype=dt) * 10 - 5, q, torch.rand(n, 53, device="cuda", generator=g, dtype=dt) * 2 - 1], 1).contiguous()
     dq = (torch.rand(n, 59, device="cuda", generator=g, dtype=dt) * 2 - 1).contiguous()
     out = sk.forward(pose, dq)
-    for generic in (("auto",) if world > 1 else ("auto", "tma1", "tma3", "direct", "generic")):
+    for generic in (("auto",) if world > 1 else ("auto", "tma1", "tma3", "tma4", "direct", "generic")):
       sk.set_generic(generic == "generic"); sk.set_tma(int(generic[3:]) if generic.startswith("tma") else (-1 if generic == "auto" else 0))
       for mode, d in (("fk+com (no velocities)", None), ("fk+com+momentum", dq)):
         for _ in range(3):
@@ -51,7 +51,7 @@ for dt, name in ((torch.float32, "f32"), (torch.float64, "f64")):
         es = pose.element_size()
         alg = (60 + 140 + 3 + (6 if d is not None else 0)) * es
         tot = alg + (59 * es if d is not None else 0)
-        print(json.dumps({"kernel": {"generic": "fk_forward_kernel (structure-agnostic)", "tma1": "fk_hanyang_tma_rolled_kernel (64-pose TMA tiles)", "auto": "default dispatch", "tma3": "fk_hanyang_tma_unrolled_kernel (64-pose TMA tiles)", "direct": "fk_hanyang_kernel (skeleton-specialised, direct rows)"}[generic], "dtype": name, "mode": mode, "poses": n * world, "n_gpus": world, "ms": ms, "poses_per_s": n * world / ms * 1e3,
+        print(json.dumps({"kernel": {"generic": "fk_forward_kernel (structure-agnostic)", "tma1": "fk_hanyang_tma_rolled_kernel (64-pose TMA tiles)", "auto": "default dispatch", "tma3": "fk_hanyang_tma_unrolled_kernel (64-pose TMA tiles)", "tma4": "fk_hanyang_tma_chain_kernel (64-pose TMA tiles)", "direct": "fk_hanyang_kernel (skeleton-specialised, direct rows)"}[generic], "dtype": name, "mode": mode, "poses": n * world, "n_gpus": world, "ms": ms, "poses_per_s": n * world / ms * 1e3,
                           "algorithmic_bytes_per_pose": alg, "achieved_GBps_algorithmic_per_gpu": alg * n / ms / 1e6,
                           "achieved_GBps_incl_dq_per_gpu": tot * n / ms / 1e6, "peak_GBps": peak, "frac": alg * n / ms / 1e6 / peak}))
 sk.close()
