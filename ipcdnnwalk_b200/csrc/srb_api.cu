@@ -62,7 +62,7 @@ template <typename real> static Params<real> convert_params(const Params<double>
   for (int i = 0; i < 9; i++) q.w[i] = (real)p.w[i];
   q.use_filter = p.use_filter; q.use_clamp = p.use_clamp; q.use_impulse = p.use_impulse; q.obs_after_inc = p.obs_after_inc; q.use_terrain = p.use_terrain;
   q.impulse_interval = p.impulse_interval; q.impulse_duration = p.impulse_duration; q.impulse_trigger_at_end = p.impulse_trigger_at_end;
-  q.max_frame = p.max_frame;
+  q.max_frame = p.max_frame; q.aset_warm = p.aset_warm;
   q.inv_w_lambda = (real)(1.0 / p.w_lambda);
   const double Md[6] = {p.mass + p.armature, p.mass + p.armature, p.mass + p.armature,
                         p.inertia[0] + p.armature, p.inertia[1] + p.armature, p.inertia[2] + p.armature};
@@ -83,6 +83,7 @@ static void default_params(Params<double>& p, int variant) {
   p.mu_b = 1.2 * (1.2 * 1.0);                           // b = (1.2*mu, 0, 1), mu = 1.2 * floor friction
   p.kp = 120.0; p.kd = 35.0; p.w_lambda = 0.001; p.force_thr = 10000.0;
   p.max_frame = 512;
+  p.aset_warm = getenv("SRB_ASET_WARM") ? atoi(getenv("SRB_ASET_WARM")) : 1;
   p.use_terrain = 0;
   for (int i = 0; i < 6; i++) p.impulse_force[i] = 0.0;
   if (variant == SRB_VARIANT_TEST || variant == SRB_VARIANT_TERRAIN) {

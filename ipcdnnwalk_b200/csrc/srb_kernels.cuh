@@ -561,7 +561,11 @@ template <typename real, int G, int NCOLS = 40> struct QP {
   // the piece), is below rounding level, or decreases the dual objective phi; otherwise it is halved until phi
   // decreases (globally convergent; also keeps the iteration-count tail short, which matters because the
   // environments of a warp iterate in lock-step).
-  __device__ __forceinline__ int solve(int lane, const real y[6], real inv_w, real nu[6], real t[NC], real* sm) {
+  // S0 (optional): guess of the optimal active set (bit k = column k of this lane active), e.g. the active set the previous
+  // physics sub-step ended with.  The first Newton system is then built from S0 instead of from sign(A^T nu): when the guess
+  // is right the solve ends after ONE system (its solution reproduces S0 = exact optimum of that piece), otherwise the
+  // iteration continues from the usual state.  Acceptance tests are unchanged, so the result is the same exact optimum.
+  __device__ __forceinline__ int solve(int lane, const real y[6], real inv_w, real nu[6], real t[NC], real* sm, const unsigned* S0 = nullptr) {
     constexpr int MAX_IT = 48;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_id() / G) * G));
     const real invw = inv_w, inv2w = real(0.5) * invw;
@@ -572,16 +576,19 @@ template <typename real, int G, int NCOLS = 40> struct QP {
     real rhs[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) rhs[i] = -y[i];
+    real ts[NC];                                              // signs the next Hessian is built from / the new set is compared with
+#pragma unroll
+    for (int k = 0; k < NC; k++) ts[k] = S0 != nullptr ? (((*S0 >> k) & 1u) ? real(-1) : real(1)) : t[k];
     for (int it = 0; it < MAX_IT; it++) {
       if (!__any_sync(0xffffffffu, !done)) break;
       real H[21];
-      hessian(t, invw, H, sm);
+      hessian(ts, invw, H, sm);
       real nn[6], tn[NC];
       ldl_solve6(H, rhs, nn);
       tvals(nn, tn);
       bool same = true;
 #pragma unroll
-      for (int k = 0; k < NC; k++) same = same && ((tn[k] < 0) == (t[k] < 0));
+      for (int k = 0; k < NC; k++) same = same && ((tn[k] < 0) == (ts[k] < 0));
       unsigned bal = __ballot_sync(0xffffffffu, same);
       same = (bal & gmask) == gmask;
       real phn = phi(nn, y, tn, inv2w);
@@ -593,7 +600,8 @@ template <typename real, int G, int NCOLS = 40> struct QP {
         real av = nn[i] < 0 ? -nn[i] : nn[i];
         dmax = dd > dmax ? dd : dmax; nmax = av > nmax ? av : nmax;
       }
-      same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
+      // (with a guessed set the fixed-point shortcut is only valid once the Hessian came from sign(A^T nu) itself)
+      if (S0 == nullptr || it > 0) same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
       const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + (ph < 0 ? -ph : ph));   // phi resolution
       bool need_bt = !done && !same && !(phn < ph + ph_tol);
       if (__any_sync(0xffffffffu, need_bt)) {                 // rare
@@ -619,7 +627,7 @@ template <typename real, int G, int NCOLS = 40> struct QP {
 #pragma unroll
         for (int i = 0; i < 6; i++) nu[i] = nn[i];
 #pragma unroll
-        for (int k = 0; k < NC; k++) t[k] = tn[k];
+        for (int k = 0; k < NC; k++) { t[k] = tn[k]; ts[k] = tn[k]; }
         ph = phn;
         iters++;
         if (same) done = true;
@@ -1110,6 +1118,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 #pragma unroll
   for (int i = 0; i < 6; i++) nu[i] = s.nu[i];
   bool warm = (s.flags & FLAG_NU) != 0;
+  unsigned aset = 0; bool have_aset = false;              // active set of the previous sub-step's optimum (this lane's columns)
   double* dbg = (A.dbg != nullptr && active) ? A.dbg + (size_t)e * DBG_W : nullptr;
   long long tk0 = 0, tk_pre = 0;
   if (A.dbg != nullptr) { tk_pre = clock64(); tk0 = tk_pre; }   // phase clocks land in the debug record's pad slots
@@ -1159,8 +1168,12 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         for (int i = 0; i < 6; i++) nu[i] = -y[i];
       }
       real t[QP<real, G>::NC];
-      int iters = qp.solve(lane, y, P.inv_w_lambda, nu, t, hsm);
+      int iters = qp.solve(lane, y, P.inv_w_lambda, nu, t, hsm, (P.aset_warm && have_aset) ? &aset : nullptr);
       warm = true;
+      aset = 0;
+#pragma unroll
+      for (int k = 0; k < QP<real, G>::NC; k++) aset |= (t[k] < 0 ? 1u : 0u) << k;
+      have_aset = true;
       if (contact_mask != 0) {
         s.flags |= FLAG_NU;
 #pragma unroll

@@ -80,6 +80,7 @@ template <typename real> struct Params {
   int impulse_interval, impulse_duration, impulse_trigger_at_end;
   real impulse_force[6];   // xfrc_applied[1]: world-frame force, world-frame torque (f[0:len(self.force)] = self.force, :199)
   int max_frame;        // 512
+  int aset_warm;        // 1: a sub-step's QP starts from the active set the previous sub-step ended with (same optimum, fewer systems)
 };
 
 // debug record per env (doubles), only written when a debug buffer is attached
