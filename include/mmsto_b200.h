@@ -66,6 +66,22 @@ int mmsto_remove_com_sliding(mmsto_solver* s, int32_t n, int32_t nvar, double* p
                              int32_t fix_y_also, const double* ground_h, double* curr_com_out, double* opt_com_out, void* stream);
 /* CoM of every pose of every window (mLoader_full.setPoseDOF + calcCOM, DeltaExtractor.py:428-430): com_out [n][nvar][3] */
 int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* poses, double* com_out, void* stream);
+/* removeFootSliding_online / removeFootSliding_online_stair (gym_trackSRB/taesooLib/DeltaExtractor.py:650-760 / :763-893; called after
+ * the CoM step, walk_SRBTrack2025.py:631, walk_SRBTrack2025_terrain_singlethreaded.py:624) for n planning windows of nvar (<= 8) frames:
+ *   con_all [n][nvar][4]      contact targets toe L, heel L, toe R, heel R (> 0.5 = contact)
+ *   initial_feet [n][12]      the four marker positions the window must start from
+ *   marker_traj [n][nvar][12] smooth marker trajectories of the current full-body plan (fc.getMarkerTraj)
+ *   marker [n][nvar][12]      the jerky marker predictions (markerTarget columns 0:12)
+ *   desired_vel [n][nvar][12] marker velocity targets (markerTarget columns 12:24) or NULL = forward differences of marker_traj * 30
+ *   foot_center [n][2][nvar][3]  foot-centre trajectories: non-NULL selects the _stair variant (contact positions from them, hull pass)
+ *   ground_mode 0: no projectToGround; 1: flat ground at height ground_y (walk_SRBTrack2025.py:53-54); 2: the playground terrain of the
+ *               SRBTrack handle `srb_terrain_env` (an srb_env* of the terrain variant; Y-up query through the Z-up height fields)
+ *   out [n][nvar][12]         optMarkerTraj.
+ * fc.getContactPositions_v2 / _stair are not in the reference tree; the contact positions follow the stated stand-ins W5 / W6
+ * (oracle/foot_sliding.py). */
+int mmsto_remove_foot_sliding(int32_t device, int32_t n, int32_t nvar, double foot_len, const double* con_all, const double* initial_feet,
+                              const double* marker_traj, const double* marker, const double* desired_vel, const double* foot_center,
+                              int32_t ground_mode, double ground_y, void* srb_terrain_env, double* out, void* stream);
 /* _extractSingleFrameFullbody (gym_trackSRB/taesooLib/DeltaExtractor.py:577-643): n items, each one decoded full-body row
  * (DeltaExtractor.py:17-22: toPelvis 6 | toFeet 24 | toMomentum 9 | poses 53 | dx 59 | ddx 59 | con 4 = 214 doubles) plus the
  * pack_obs_extra record of its frame (pose_tl 7 | dq 6 | two foot frames 7 | contacts 2 = 29 doubles).  srb_* describe the SRB

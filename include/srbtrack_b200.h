@@ -130,6 +130,10 @@ int srb_set_planar_offsets(srb_env* env, const double* xy_host);
 /* Batched terrain_height_ray: xy_dev[n][2] -> height_dev[n]; hit_dev[n][4] (may be NULL) = geom id, hfield cell column, row, triangle. */
 int srb_terrain_height(srb_env* env, int32_t n, const double* xy_dev, double* height_dev, int32_t* hit_dev, void* stream);
 
+/* Device-side terrain description of this handle (NULL before srb_upload_terrain): lets the full-body mapping kernels of
+ * include/mmsto_b200.h evaluate projectToGround on the same playground (mmsto_remove_foot_sliding, ground_mode 2). */
+const void* srb_terrain_device(void* env);
+
 /* Benchmark / roll-out driver (not in the reference; stands in for the policy, walk_SRBTrack2025.py:424):
  * act_dev[N][22] = reference-tracking action for the next reference frame + N(0, sigma^2) noise. */
 int srb_tracking_action(srb_env* env, float sigma, uint64_t seed, uint32_t step, float* act_dev, void* stream);

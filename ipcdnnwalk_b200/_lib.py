@@ -55,6 +55,7 @@ _SIGNATURES = {
     "srb_upload_terrain": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P]),
     "srb_set_planar_offsets": (C.c_int, [_P, _P]),
     "srb_terrain_height": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "srb_terrain_device": (_P, [_P]),
     "srb_launch_count": (C.c_int64, [_P]),
 }
 _FK_SIGNATURES = {          # include/bonefk_b200.h
@@ -114,6 +115,7 @@ _MMSTO_SIGNATURES = {       # include/mmsto_b200.h
     "mmsto_remove_com_sliding": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "mmsto_window_com": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "mmsto_launch_count": (C.c_int64, [_P]),
+    "mmsto_remove_foot_sliding": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, _P, _P, _P]),
     "fullbody_extract": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mmsto_last_error": (C.c_char_p, []),
 }

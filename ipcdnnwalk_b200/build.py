@@ -25,7 +25,7 @@ EXTRA_FLAGS = {
 DEPS = {
     "srb_api.cu": ["srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/srbtrack_b200.h"],
     "fk_api.cu": ["fk_kernels.cuh", "srb_math.cuh", "../../include/bonefk_b200.h"],
-    "mmsto_api.cu": ["mmsto_kernels.cuh", "../../include/mmsto_b200.h"],
+    "mmsto_api.cu": ["mmsto_kernels.cuh", "footslide_kernels.cuh", "srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/mmsto_b200.h"],
     "cdm_api.cu": ["cdm_kernels.cuh", "cdm_types.h", "srb_kernels.cuh", "srb_math.cuh", "srb_types.h", "../../include/cdmenv_b200.h"],
 }
 

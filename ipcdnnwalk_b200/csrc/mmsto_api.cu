@@ -9,6 +9,9 @@
 
 #include "../../include/mmsto_b200.h"
 #include "mmsto_kernels.cuh"
+#include "footslide_kernels.cuh"
+
+extern "C" const void* srb_terrain_device(void* env);   // srb_api.cu: the TerrainDev of an SRBTrack handle (terrain variant)
 
 namespace {
 thread_local char g_err[512] = "";
@@ -261,6 +264,34 @@ int mmsto_window_com(mmsto_solver* s, int32_t n, int32_t nvar, const double* pos
   mmsto::comslide_kernel<<<(n + 15) / 16, 128, 0, (cudaStream_t)stream>>>(A);
   CK(cudaGetLastError());
   ++s->launches;
+  return 0;
+}
+
+int mmsto_remove_foot_sliding(int32_t device, int32_t n, int32_t nvar, double foot_len, const double* con_all, const double* initial_feet,
+                              const double* marker_traj, const double* marker, const double* desired_vel, const double* foot_center,
+                              int32_t ground_mode, double ground_y, void* srb_terrain_env, double* out, void* stream) {
+  if (n <= 0) return 0;
+  if (nvar < 3 || nvar > footslide::NV) return fail(-1, "mmsto_remove_foot_sliding: 3 <= nvar <= 8 required");
+  if (!con_all || !initial_feet || !marker_traj || !marker || !out) return fail(-1, "mmsto_remove_foot_sliding: null array");
+  if (ground_mode < 0 || ground_mode > 2) return fail(-1, "mmsto_remove_foot_sliding: ground_mode must be 0 (none), 1 (constant) or 2 (SRB terrain)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(-3, "mmsto_remove_foot_sliding: no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  footslide::Args A{};
+  A.n = n; A.nvar = nvar; A.stair = foot_center != nullptr; A.ground_mode = ground_mode; A.foot_len = foot_len; A.ground_y = ground_y;
+  A.con_all = con_all; A.initial_feet = initial_feet; A.marker_traj = marker_traj; A.marker = marker; A.desired_vel = desired_vel;
+  A.foot_center = foot_center; A.out = out; A.terrain = nullptr;
+  if (ground_mode == 2) {
+    A.terrain = (const srb::TerrainDev*)(srb_terrain_env ? srb_terrain_device(srb_terrain_env) : nullptr);
+    if (!A.terrain) return fail(-1, "mmsto_remove_foot_sliding: ground_mode 2 needs an SRBTrack handle with an uploaded terrain");
+  }
+  if (A.stair && ground_mode == 0) return fail(-1, "mmsto_remove_foot_sliding: the stair variant needs a ground (projectToGround is not optional there)");
+  footslide::footslide_kernel<<<(n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
+  CK(cudaGetLastError());
+  if (A.stair) {
+    footslide::footslide_hull_kernel<<<(n * 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 

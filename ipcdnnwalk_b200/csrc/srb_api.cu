@@ -645,6 +645,8 @@ extern "C" int srb_upload_terrain(srb_env* h, const double plane_size[2], int32_
   return 0;
 }
 
+extern "C" const void* srb_terrain_device(void* env) { return env ? ((srb_env*)env)->terrain_dev : nullptr; }
+
 extern "C" int srb_set_planar_offsets(srb_env* h, const double* xy_host) {
   if (!h || !xy_host) return fail(-1, "srb_set_planar_offsets: null argument");
   CK(cudaSetDevice(h->cfg.device));

@@ -276,3 +276,41 @@ def extractSingleFrameFullbody(obs_extra, recon, srb_mass, srb_inertia, srb_loca
                                      _ptr(out["dx_ddx"]), _ptr(out["feetpos"]), _ptr(out["com"]), _ptr(out["momentum"]),
                                      _ptr(out["con_bin"]), _ptr(out["con"]), st))
     return out
+
+
+def removeFootSliding_online(footLen, conAll, initialFeet, markerTraj, marker, desiredVel=None, projectToGround=None, footCenterTraj=None, device=0):
+    """Batched `DeltaExtractor.removeFootSliding_online` (DeltaExtractor.py:650-760) and, when `footCenterTraj` is given,
+    `removeFootSliding_online_stair` (:763-893).  conAll [n, nvar, 4], initialFeet [n, 12], markerTraj [n, nvar, 12] (the four smooth
+    marker trajectories side by side: toe L, heel L, toe R, heel R), marker [n, nvar, 12], desiredVel [n, nvar, 12] or None,
+    footCenterTraj [n, 2, nvar, 3] or None.  projectToGround: None (no projection), a float (flat ground at that height, what the flat
+    driver's `v.y = 0` does) or an SRBVecEnv of the terrain variant (the playground under the character).  -> optMarkerTraj [n, nvar, 12]
+    (torch.float64 on the device)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("ipcdnnwalk_b200.short_traj_opt needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+
+    def to_dev(a, shape):
+        if a is None:
+            return None
+        t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+        t = t.to(dev, torch.float64).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+    ca = conAll if torch.is_tensor(conAll) else torch.as_tensor(np.ascontiguousarray(conAll))
+    n, nvar = int(ca.shape[0]), int(ca.shape[1])
+    ca = to_dev(ca, (n, nvar, 4)); fi = to_dev(initialFeet, (n, 12)); mt = to_dev(markerTraj, (n, nvar, 12)); mk = to_dev(marker, (n, nvar, 12))
+    dv = to_dev(desiredVel, (n, nvar, 12)); fc = to_dev(footCenterTraj, (n, 2, nvar, 3))
+    mode, gy, henv = 0, 0.0, None
+    if projectToGround is not None:
+        if hasattr(projectToGround, "_h"):
+            mode, henv = 2, projectToGround._h
+        else:
+            mode, gy = 1, float(projectToGround)
+    out = torch.empty(n, nvar, 12, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib, lib.mmsto_remove_foot_sliding(int(device), n, nvar, float(footLen), _ptr(ca), _ptr(fi), _ptr(mt), _ptr(mk), _ptr(dv), _ptr(fc),
+                                              mode, gy, henv, _ptr(out), st))
+    return out

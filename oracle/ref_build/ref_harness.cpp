@@ -12,6 +12,8 @@
 //   quat     quater / vector3 / transf / Liegroup primitives  (BaseLib/math/quater.cpp, vector3.cpp, transf.cpp, Liegroup.cpp)
 //   terrain  OBJloader::Terrain::height                       (BaseLib/motion/Terrain.cpp:305-393)
 //   dof      MotionDOFcontainer / BinaryFile readers          (BaseLib/motion/MotionDOF.cpp, utility/tfile.cpp)
+//   hull     GrahamScan add_point / partition_points / build_hull / get_hull   (PhysicsLib/convexhull/graham.cpp), the hull
+//            under math.projectTrajectoryToItsHull (gym_cdm2/ConvexHull2D.lua:150-186,362)
 // Numbers travel as whitespace-separated %.17g text (round-trip exact for doubles).
 #include "stdafx.h"
 #include "motion/Mesh.h"
@@ -25,6 +27,7 @@
 #include "motion/Liegroup.h"
 #include "motion/IK_sdls/NodeWrap.h"
 #include "math/Operator.h"
+#include "../PhysicsLib/convexhull/graham.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -208,6 +211,24 @@ static int cmd_dof(int argc, char** argv) {
   return 0;
 }
 
+// hull <in> <out>: in = sets of points: n, then n (x, y) pairs, repeated -> per set: closed hull polygon as a matrix
+static int cmd_hull(int argc, char** argv) {
+  std::vector<double> in = read_all(argv[2]);
+  Out out(argv[3]);
+  size_t p = 0;
+  while (p < in.size()) {
+    const int n = (int)in[p++];
+    GrahamScan g;
+    for (int i = 0; i < n; i++) { g.add_point(std::make_pair(in[p], in[p + 1])); p += 2; }
+    g.partition_points();
+    g.build_hull();
+    matrixn h;
+    g.get_hull(h);
+    out.mat(h);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: taesoo_ref fk|euler|quat|terrain|dof ...\n"); return 1; }
   std::string c = argv[1];
@@ -216,6 +237,7 @@ int main(int argc, char** argv) {
   if (c == "quat" && argc >= 4) return cmd_quat(argc, argv);
   if (c == "terrain" && argc >= 4) return cmd_terrain(argc, argv);
   if (c == "dof" && argc >= 5) return cmd_dof(argc, argv);
+  if (c == "hull" && argc >= 4) return cmd_hull(argc, argv);
   fprintf(stderr, "bad command line\n");
   return 1;
 }

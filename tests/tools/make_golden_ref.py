@@ -9,6 +9,7 @@ Contents (inputs + reference outputs; nothing here is produced by oracle/ or by 
             updateGrad_S_JT                                                                                              (f-1)
   q_*       quater / vector3 / transf / Liegroup primitives                                                              (a-19, a-22, f-2)
   tr_*      OBJloader::Terrain::height on the gym_cdm2 height map (64 x 64 after the loader's decimation), tiled and not (a-21)
+  hull_*    GrahamScan hulls (PhysicsLib/convexhull/graham.cpp) of height profiles: what math.projectTrajectoryToItsHull builds on   (f-2)
   dof_*     MotionDOFcontainer read of hanyang_lowdof_T_lafan1_walk_2915.dof                                              (f-4)
   lb_*      libLBFGS (reference lbfgs.cpp, parameters as optimize.h:426-470 sets them) on its Rosenbrock sample and on MMSTO windows
             whose objective / gradient callback is oracle/mmsto.py (the missing Lua wrapper's role): status code, iteration and
@@ -102,6 +103,17 @@ def main():
         out[f"tr_heightmap"] = hm_; out[f"tr_height_tile{tile}"] = h; out[f"tr_height2_tile{tile}"] = h2; out[f"tr_normal_tile{tile}"] = nrm
     # ---- .dof reader
     out["dof_walk_2915"] = rh.dof(DOF)
+    # ---- GrahamScan (PhysicsLib/convexhull/graham.cpp) on height profiles over the frame index, incl. ties and collinear runs
+    sets = []
+    for k in range(160):
+        npt = int(rng.integers(3, 10))
+        y = np.round(rng.uniform(0, 1, npt) * [1, 4][k % 2]) / [1, 4][k % 2] if k % 3 == 0 else rng.uniform(0, 1, npt)
+        sets.append(np.stack([np.arange(npt, dtype=float), y], 1))
+    sets.append(np.stack([np.arange(7.0), np.zeros(7)], 1)); sets.append(np.stack([np.arange(7.0), [0, 0, 0.2, 0.2, 0.4, 0.4, 0.4]], 1))
+    hulls = rh.hull(sets)
+    out["hull_count"] = len(sets)
+    for k, (a, b) in enumerate(zip(sets, hulls)):
+        out[f"hull_in_{k}"] = a; out[f"hull_out_{k}"] = b
     # ---- libLBFGS
     d = rh.lbfgs_defaults()
     out["lb_defaults_keys"] = np.array(list(d.keys())); out["lb_defaults"] = np.array(list(d.values()))

@@ -113,6 +113,16 @@ def terrain(image, size_x, size_z, height_max, tile, xz):
     return hm, hn[:, 0].copy(), hn[:, 1].copy(), hn[:, 2:].copy()
 
 
+def hull(point_sets):
+    """GrahamScan of the reference on every point set ([n,2] arrays) -> list of closed hull polygons [m,2]."""
+    inp = []
+    for pts in point_sets:
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+        inp += [pts.shape[0]] + pts.reshape(-1).tolist()
+    c = _run(["hull", "@in", "@out"], inp)
+    return [c.mat().copy() for _ in point_sets]
+
+
 def dof(path, wrl=WRL):
     c = _run(["dof", wrl, path, "@out"], [0.0])
     r, k = int(c.scalar()), int(c.scalar())
