@@ -27,7 +27,31 @@ WALK4 = dict(touchDown=[[0, 16], [0, 32]], touchOff=[[2], [18]], start=0, stride
              minSwingPhase=0.25, filterFD=16, spread=15)
 FEET_CONFIG_TOE = np.array([0.0, -0.12, 0.15])       # input.limbs[1][3]  (module/info_hyunwooLowDOF.lua:38)
 FEET_CONFIG_HEEL = np.array([0.0, -0.15, -0.03])     # input.limbs[2][3]  (:39)
+# motionInfos.run4 (gym_cdm2/module/motionInfo.lua:133-183): no strideThr / maxContactLen / minSwingPhase, no makeCyclic
+# (fixDOF_part2 is empty), the CoM acceleration of the pendulum lean is low-passed (option_refCDMtraj.filterCDMacc = 12)
+RUN4 = dict(touchDown=[[11], [0, 23]], touchOff=[[20], [8]], start=0, strideThr=None, maxContactLen=None, minSwingPhase=None,
+            filterFD=16, filterCDMacc=12, spread=0)
 AX = {"X": 0, "Y": 1, "Z": 2}
+
+# The registered environments of gym_cdm2/__init__.py:9-11 whose clips ship with the reference: motion file (under
+# work/taesooLib/Resource/motion/MOB1/), motionInfo, and the overrides of the walk2-v1 defaults that cdm_create starts from
+# (cdm_set_param names).  `params` = the TRAINING configuration (no GUI: defaultRLsetting.lua:183-187 forces touchDownHeight 0
+# and unlimitedLeglen); `gui_params` = what the spec file itself sets and the Lua main-loop viewer keeps (test_cdm_deepmimic.lua: isMainloopInLua).
+#   run2-v1: spec/run2-v1.lua:14-19 (maxTurning, facingWeight, maxLegLen, contactThr, healthy_y_range), defaults where the spec
+#   and run4 are silent: k_p_ID 340 (defaultRLsetting.lua:43), EFdif_scale 1/8 (deepmimiccdm-v1.lua:2108), maxContactLen 2.0
+#   (:1246), minSwingPhase 0.4 (:615).  Not overridden although run4 names them: filterEndPhase (RagdollSim:filterContact hard-codes 0.4,
+#   deepmimiccdm-v1.lua:524 -- the recorded run reproduces only with 0.4) and maxContactY (never copied to the model: QPservo keeps 1.1); stride_thr < 0 = none.
+SPECS = {
+    "walk2-v1": dict(motion="hanyang_lowdof_T_lafan1_walk_2915.dof", info=WALK4, params={}, terrain=False,
+                     gui_params=dict(unlimited_leglen=0.0, touch_down_height=0.83)),
+    "walkterrain-v1": dict(motion="hanyang_lowdof_T_lafan1_walk_2915.dof", info=WALK4, params={}, terrain=True,
+                           gui_params=dict(unlimited_leglen=0.0, touch_down_height=0.83)),
+    "run2-v1": dict(motion="hanyang_lowdof_T_lafan1_run_3750.dof", info=RUN4, terrain=False,
+                    params=dict(k_p=340.0, ef_scale=0.125, max_leg_len=1.5, contact_thr=0.1, stride_thr=-1.0, max_contact_len=2.0,
+                                min_swing_phase=0.4, healthy_min=0.8, healthy_max=1.1, facing_weight=10.0,
+                                max_turning=0.4),
+                    gui_params=dict(unlimited_leglen=0.0, touch_down_height=0.7)),      # defaultRLsetting.lua:22 (the spec does not override it)
+}
 
 
 def read_dof(path):
@@ -157,9 +181,9 @@ def build_tables(mot, skel, info=WALK4, frame_rate=30.0, limit_length=300, defau
     nfr = mot.shape[0]
     names = skel["names"]
     # ---- makeCyclic stand-in: blend the end-of-cycle discontinuity of joint angles / height over `spread` frames
-    sp = info["spread"]
+    sp = info["spread"]                                            # 0: the clip is used as it is (run4)
     err = mot[-1] - mot[0]
-    for i in range(nfr - sp, nfr):
+    for i in range(nfr - sp if sp else nfr, nfr):
         w = (i - (nfr - 1 - sp)) / float(sp)
         mot[i, 7:] -= err[7:] * w
         mot[i, 1] -= err[1] * w
@@ -183,6 +207,12 @@ def build_tables(mot, skel, info=WALK4, frame_rate=30.0, limit_length=300, defau
     spl = CubicSpline(knots.astype(float), com[knots], bc_type="natural")
     tt = np.arange(knots[-1] + 1).astype(float)
     curve, acc = spl(tt), spl(tt, 2)
+    if info.get("filterCDMacc"):                                   # math.filter(newAcc, filterCDMacc) (CDMTraj.lua:738): Gaussian, odd kernel size
+        ka = info["filterCDMacc"] // 2 * 2 + 1
+        xa = np.linspace(-2.0, 2.0, ka)
+        kera = np.exp(-xa * xa); kera /= kera.sum()
+        pada = np.concatenate([np.repeat(acc[:1], ka, 0), acc, np.repeat(acc[-1:], ka, 0)])
+        acc = np.stack([np.convolve(pada[:, k], kera, mode="same") for k in range(3)], 1)[ka:-ka]
     cdm = np.zeros((nfr, 7))
     lean0 = _qaxis(np.array([1.0, 0.0, 0.0]), default_lean)
     for i in range(nfr):

@@ -96,6 +96,26 @@ class CDMVecEnv:
         self._actions = None
         self._pinned = None
 
+    @classmethod
+    def from_spec(cls, env_id, num_envs, tables=None, skel=None, motion_dir=None, gui=False, params=None, terrain=None, **kw):
+        """One of the registered environments (gym_cdm2/__init__.py:9-11: `walk2-v1`, `walkterrain-v1`, `run2-v1`) with the
+        parameter set its spec file selects (cdm_tables.SPECS).  Tables / skeleton are built from `motion_dir` (the reference's
+        work/taesooLib/Resource/motion/MOB1) unless passed in; `gui=True` adds what the Lua main-loop viewer (test_cdm_deepmimic.lua, isMainloopInLua) changes --
+        limited leg length, touchDownHeight -- the configuration the refTraj_*.dat roll-outs were recorded in; `terrain` as in the constructor (required for walkterrain-v1)."""
+        spec = cdm_tables.SPECS[env_id]
+        if skel is None or tables is None:
+            import os
+            from .vrml_skeleton import parse_wrl
+            skel = skel or parse_wrl(os.path.join(motion_dir, "hanyang_lowdof_T.wrl"))
+            tables = tables or cdm_tables.build_tables(cdm_tables.read_dof(os.path.join(motion_dir, spec["motion"])), skel, info=spec["info"])
+        if spec["terrain"] and terrain is None:
+            raise ValueError(env_id + " needs a terrain (heights, size_x, size_z, terrain_pos)")
+        p = dict(spec["params"])
+        if gui:
+            p.update(spec["gui_params"])
+        p.update(params or {})
+        return cls(tables, skel, num_envs, params=p, terrain=terrain, **kw)
+
     # ---- parameters (spec-file overrides) ----------------------------------------------------------
     def set_param(self, name, value):
         check(self.lib.cdm_set_param(self._h, name.encode(), float(value)))
@@ -229,12 +249,16 @@ class LuaEnv:
         from .vrml_skeleton import parse_wrl
         skel = getattr(args, "skel", None) or parse_wrl(args.skel_file)
         tables = getattr(args, "tables", None)
+        env_id = getattr(args, "env_name", None) or "walk2-v1"       # gym_cdm2/test_gym.py: args.env_name selects spec/<env_name>.lua
+        spec = cdm_tables.SPECS[env_id]
         if tables is None:
-            tables = cdm_tables.build_tables(cdm_tables.read_dof(args.mot_file), skel)
+            tables = cdm_tables.build_tables(cdm_tables.read_dof(args.mot_file), skel, info=spec["info"])
         self.renderMode = render_mode
         self.args = args
-        self._vec = CDMVecEnv(tables, skel, 1, precision=precision, auto_reset=False, device=device, seed=getattr(args, "seed", 0))
-        self.observation_space_shape = (CDM_OBS_DIM,)       # Box(-100, 100, (27,))   :62-65
+        # driven from Python, isMainloopInLua is unset: always the training configuration (defaultRLsetting.lua:177)
+        self._vec = CDMVecEnv.from_spec(env_id, 1, tables=tables, skel=skel, terrain=getattr(args, "terrain", None),
+                                        precision=precision, auto_reset=False, device=device, seed=getattr(args, "seed", 0))
+        self.observation_space_shape = (self._vec.obs_dim,)  # Box(-100, 100, (27,)), 31 on the terrain   :62-65
         self.action_space_shape = (CDM_ACT_DIM,)            # Box(-1, 1, (10,))
         self.actionSteps = 0
         self.step_counter = 0

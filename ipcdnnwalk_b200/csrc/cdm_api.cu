@@ -50,6 +50,7 @@ static void default_params(std::map<std::string, double>& p) {
   // cached in work/_LQR_CACHE_2.DAT for every 2x2 system (PhysicsLib/SDRE.cpp:136-154); the recorded reference roll-outs
   // reproduce only with it.  use_lqr_cache = 0 switches to the real ARE solution for (M=30, b=1e-3, k=1, Q=10^logQ).
   p["use_lqr_cache"] = 1.0; p["filter_K0"] = 9999.00005; p["filter_K1"] = 1095.39024412;
+  p["unlimited_leglen"] = 1.0; p["contact_thr"] = 0.0; p["touch_down_height"] = 0.0;   // training mode (defaultRLsetting.lua:183-187); contactThr 0 = motionInfos.walk4.contactThr (defaultRLsetting.lua:82)
   p["stride_thr"] = 0.45; p["max_contact_len"] = 0.9; p["min_swing_phase"] = 0.25; p["max_contact_y"] = 1.1;
   p["healthy_min"] = 0.8; p["healthy_max"] = 2.0; p["fall_angle"] = 20.0 * M_PI / 180.0;
   p["timing_mod_coef"] = 0.4; p["facing_weight"] = 1.5; p["ef_scale"] = 1.0; p["limit_length"] = 300.0;
@@ -79,6 +80,7 @@ template <typename real> static Params<real> make_params(cdm_env* h) {
   Params<real> q;
   memset(&q, 0, sizeof(q));
   q.k_p = (real)p["k_p"]; q.k_d = (real)p["k_d"]; q.acc_clamp = (real)p["acc_clamp"]; q.max_leg_len = (real)p["max_leg_len"];
+  q.unlimited_leglen = p["unlimited_leglen"] != 0.0; q.contact_thr = (real)p["contact_thr"]; q.touch_down_height = (real)p["touch_down_height"];
   q.max_foot_vel = (real)p["max_foot_vel"]; q.stride_thr = (real)p["stride_thr"]; q.max_contact_len = (real)p["max_contact_len"];
   q.min_swing_phase = (real)p["min_swing_phase"]; q.max_contact_y = (real)p["max_contact_y"]; q.healthy_min = (real)p["healthy_min"];
   q.healthy_max = (real)p["healthy_max"]; q.fall_angle = (real)p["fall_angle"]; q.timing_mod_coef = (real)p["timing_mod_coef"];

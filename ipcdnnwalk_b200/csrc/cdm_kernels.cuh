@@ -772,6 +772,13 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
     V3<real> cpt[2][2];
     real early[2] = {real(-1), real(-1)};
     bool has_early[2] = {false, false};
+    bool late = false;                                         // lateTouchDown (:702-709): only with a leg-length limit (run2-v1)
+    real ref_root_y = real(0);
+    if (!P.unlimited_leglen) {                                 // info.loader_ref:bone(1) height = motionDOF_cdm:sample(iframe) (setRefTree, :1043)
+      const RowMix<real> m0 = row_mix(s.iframe, F, false);
+      ref_root_y = m0.i0 == m0.i1 ? __ldg(tab + (size_t)m0.i0 * TAB_W + T_CDM + 1)
+                                  : m0.w0 * __ldg(tab + (size_t)m0.i0 * TAB_W + T_CDM + 1) + m0.w1 * __ldg(tab + (size_t)m0.i1 * TAB_W + T_CDM + 1);
+    }
 #pragma unroll
     for (int l = 0; l < 2; l++) {
       Leg<real>& li = s.leg[l];
@@ -795,16 +802,20 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
           com_height -= map_cos(ph, real(0), real(1), ground_y<real>(gr, p0.x, p0.z), ground_y<real>(gr, li.cpos.x, li.cpos.z));
         }
         if (rt <= 0) {
-          li.cpos.y = ground_y<real>(gr, li.cpos.x, li.cpos.z);       // unlimitedLeglen (training): projectToGround
-          start_spprt(li, rotY);
-        } else if (com_height < real(0) && li.swph > P.min_swing_phase) {     // touchDownHeight = 0 (training)
+          if (P.unlimited_leglen || com_height < ref_root_y + P.contact_thr) {
+            li.cpos.y = ground_y<real>(gr, li.cpos.x, li.cpos.z);     // projectToGround
+            start_spprt(li, rotY);
+          } else {
+            late = true;
+          }
+        } else if (com_height < P.touch_down_height && li.swph > P.min_swing_phase) {     // touchDownHeight: 0 in training
           has_early[l] = true; early[l] = real(rt);
         } else {
           const Leg<real>& oli = s.leg[1 - l];
           V3<real> a = li.bx, b = oli.bx;
           a.y = real(0); b.y = real(0);
           V3<real> d = a - (b + qrot(rotY, V3<real>{real(0), real(0), P.stride_thr}));
-          if (!oli.swing && norm(d) > P.stride_thr && li.swph > P.min_swing_phase) { has_early[l] = true; early[l] = real(rt); }
+          if (P.stride_thr >= real(0) && !oli.swing && norm(d) > P.stride_thr && li.swph > P.min_swing_phase) { has_early[l] = true; early[l] = real(rt); }
         }
       }
       V3<real> pos; Q4<real> ori;
@@ -812,8 +823,10 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
       cpt[l][0] = pos + qrot(ori, V3<real>{real(0), real(0), real(0.12)});
       cpt[l][1] = pos + qrot(ori, V3<real>{real(0), real(0), real(-0.12)});
     }
-    // ---- early touch-down -> advanceTime (:1150-1200); lateTouchDown never fires in training (unlimitedLeglen)
-    {
+    // ---- late touch-down: the reference frame does not advance this step; else early touch-down -> advanceTime (:1150-1200)
+    if (late) {
+      s.iframe += -(FRAME_RATE * RL_STEP);
+    } else {
       const real mspc = FRAME_RATE * RL_STEP;
       if (has_early[0] && has_early[1]) { if (early[0] < early[1]) has_early[1] = false; else has_early[0] = false; }
       bool have = false;

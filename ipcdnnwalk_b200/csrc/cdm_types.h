@@ -31,6 +31,7 @@ enum { FLAG_SW_R = 1, FLAG_SW_L = 2 };
 
 template <typename real> struct Params {
   real k_p, k_d, acc_clamp, max_leg_len, max_foot_vel, stride_thr, max_contact_len, min_swing_phase, max_contact_y;
+  real contact_thr, touch_down_height; int unlimited_leglen;   // deepmimiccdm-v1.lua:702 (late touch-down when the leg length is limited: spec/run2-v1.lua); stride_thr < 0 = no strideThr
   real healthy_min, healthy_max, fall_angle, timing_mod_coef, facing_weight, ef_scale, limit_length, max_turning, filter_end_phase;
   real K0, K1;                 // LQR gain of the contact filter (M=30, b=1e-3, k=1, Q=10^logQ): constant, see cdm_api.cu
   double inv_ridge2;           // 2 * w_ddq / w_lam : the ridge of the de-duplicated QP (Q7), always fp64

@@ -69,7 +69,16 @@ PARAMS = dict(k_p=120.0, k_d=35.0, w_ddq=10000.0, w_tau=0.0001, w_lam=0.0001, ac
               max_foot_vel=3.0, logQ=7.0, stride_thr=0.45, max_contact_len=0.9, min_swing_phase=0.25, max_contact_y=1.1,
               healthy_min=0.8, healthy_max=2.0, fall_angle=math.radians(20), timing_mod_coef=0.4, facing_weight=1.5,
               ef_scale=1.0, limit_length=300.0, max_turning=0.5, filter_end_phase=0.4, inv_fric=1.0,
-              filter_K=(9999.00005, 1095.39024412))
+              filter_K=(9999.00005, 1095.39024412),
+              unlimited_leglen=True, contact_thr=0.0, touch_down_height=0.0)        # training mode (defaultRLsetting.lua:183-187); contactThr: motionInfos.walk4 (:82)
+
+# spec/run2-v1.lua over motionInfos.run4 (gym_cdm2/module/motionInfo.lua:133-183): overrides of PARAMS in training mode; defaults
+# where both are silent: k_p_ID 340 (defaultRLsetting.lua:43), EFdif_scale 1/8 (deepmimiccdm-v1.lua:2108), maxContactLen 2.0 (:1246),
+# minSwingPhase 0.4 (:615).  RUN2_GUI: what a rendered run adds (the spec's own unlimitedLeglen=false, touchDownHeight 0.7 of
+# defaultRLsetting.lua:22) -- the configuration refTraj_run2-v1.dat was recorded in.
+RUN2_PARAMS = dict(k_p=340.0, ef_scale=0.125, max_leg_len=1.5, contact_thr=0.1, stride_thr=None, max_contact_len=2.0, min_swing_phase=0.4,
+                   healthy_min=0.8, healthy_max=1.1, facing_weight=10.0, max_turning=0.4)
+RUN2_GUI = dict(unlimited_leglen=False, touch_down_height=0.7)
 
 
 def lqr_gain(M, b, k, q, qd=0.0):
@@ -288,18 +297,23 @@ class OracleCDMEnv:
             if self.terrain is not None:                        # :686-692 height relative to the terrain between body and landing spot
                 com_height -= tl.map_cos(self.swing_phase(ileg), 0.0, 1.0, self.G(p), self.G(li.contactPos))
             if rt <= 0:
-                li.contactPos[1] = self.G(li.contactPos)        # unlimitedLeglen (training): projectToGround
-                self.start_spprt(li, rotY)
-            elif com_height < 0.0 and li.swingPhase > self.P["min_swing_phase"]:     # touchDownHeight = 0 (training)
+                # :702 -- with a leg-length limit the foot lands only once the body is low enough (reference CDM height + contactThr)
+                if self.P["unlimited_leglen"] or com_height < tl.sample_pose(self.tab["cdm"], self.iframe)[1] + self.P["contact_thr"]:
+                    li.contactPos[1] = self.G(li.contactPos)    # projectToGround
+                    self.start_spprt(li, rotY)
+                else:
+                    li.lateTouchDown = True
+            elif com_height < self.P["touch_down_height"] and li.swingPhase > self.P["min_swing_phase"]:     # touchDownHeight: 0 in training
                 li.earlyTouchDown = rt
             else:
                 oli = self.leg[ileg % 2 + 1]
                 st = self.P["stride_thr"]
-                a = li.contactFilter.copy(); a[1] = 0.0
-                b = oli.contactFilter.copy(); b[1] = 0.0
-                d = a - (b + tl.qrot(rotY, np.array([0.0, 0.0, st])))
-                if (not oli.isSwing) and math.sqrt(d.dot(d)) > st and li.swingPhase > self.P["min_swing_phase"]:
-                    li.earlyTouchDown = rt
+                if st is not None:                              # `if st then` (:718): run4 has no strideThr
+                    a = li.contactFilter.copy(); a[1] = 0.0
+                    b = oli.contactFilter.copy(); b[1] = 0.0
+                    d = a - (b + tl.qrot(rotY, np.array([0.0, 0.0, st])))
+                    if (not oli.isSwing) and math.sqrt(d.dot(d)) > st and li.swingPhase > self.P["min_swing_phase"]:
+                        li.earlyTouchDown = rt
 
     def filtered_foot_pos(self, gq, ilimb):
         li = self.leg[ilimb]
@@ -565,6 +579,7 @@ class OracleCDMEnv:
             pos, ori = self.filtered_foot_pos(Q, i)
             contact_pos[i] = [pos + tl.qrot(ori, np.array([0.0, 0.0, 0.12])), pos + tl.qrot(ori, np.array([0.0, 0.0, -0.12]))]
         mspc = FRAME_RATE * RL_STEP
+        self.debug["late"] = bool(self.leg[1].lateTouchDown or self.leg[2].lateTouchDown)
         if self.leg[1].lateTouchDown or self.leg[2].lateTouchDown:
             for i in (1, 2):
                 self.leg[i].lateTouchDown = None; self.leg[i].earlyTouchDown = None

@@ -12,9 +12,9 @@ TABLE_KEYS = ("cdm", "dcdm", "cdm_d", "fullbody", "iframe_tab", "con", "touch_do
               "feet_off", "nf", "leg_cols")
 
 
-def load_tables():
-    """tests/golden/cdm_walk_tables.npz (tests/tools/make_golden_cdm.py) -> (tables dict, skeleton dict)."""
-    d = np.load(TABLES, allow_pickle=False)
+def load_tables(clip="walk"):
+    """tests/golden/cdm_{walk,run}_tables.npz (tests/tools/make_golden_cdm.py) -> (tables dict, skeleton dict)."""
+    d = np.load(os.path.join(helpers.GOLDEN, f"cdm_{clip}_tables.npz"), allow_pickle=False)
     tab = {k: d[k].copy() for k in TABLE_KEYS}
     skel = json.loads(str(d["skeleton_json"]))
     return tab, skel

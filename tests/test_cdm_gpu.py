@@ -30,12 +30,12 @@ def _assert_close(a, b, rtol, atol, what):
         raise AssertionError(f"{what}: {(~ok).sum()} mismatches, first at {idx.tolist()} got {[float(a[tuple(i)]) for i in idx]} want {[float(b[tuple(i)]) for i in idx]}")
 
 
-def _run_golden(tab, skel, roll, lanes, precision=64, rtol=1e-5, atol=1e-7, steps=None, terrain=None):
+def _run_golden(tab, skel, roll, lanes, precision=64, rtol=1e-5, atol=1e-7, steps=None, terrain=None, params=None):
     import torch
     from ipcdnnwalk_b200 import CDMVecEnv
     n = roll["plans0"].shape[0]
     T = roll["acts"].shape[0] if steps is None else steps
-    env = CDMVecEnv(tab, skel, n, precision=precision, lanes_per_env=lanes, auto_reset=False, terrain=terrain)
+    env = CDMVecEnv(tab, skel, n, precision=precision, lanes_per_env=lanes, auto_reset=False, terrain=terrain, params=params)
     env.attach(dbg=True)
     obs = env.reset(plan=roll["plans0"])
     torch.cuda.synchronize()
@@ -80,9 +80,23 @@ def test_golden_rollout_terrain_fp64(data, lanes):
     """walkterrain-v1 variant (deepmimiccdmterrain-v1.lua): 31-float observation, projectToGround on the height field,
     terrain-following targets -- golden roll-out of the terrain oracle incl. resets."""
     tab, skel, _ = data
-    roll = dict(np.load(hc.ROLLOUT.replace("cdm_rollout", "cdm_rollout_terrain")))
+    roll = dict(np.load(hc.ROLLOUT.replace("cdm_rollout.npz", "cdm_rollout_terrain.npz")))
     assert roll["obs"].shape[2] == 31
     _run_golden(tab, skel, roll, lanes, terrain=hc.load_terrain())
+
+
+@pytest.mark.parametrize("mode,lanes", [("train", 1), ("train", 4), ("gui", 1), ("gui", 8)])
+def test_golden_rollout_run2_fp64(mode, lanes):
+    """run2-v1 (gym_cdm2/spec/run2-v1.lua over motionInfos.run4: k_p_ID 340, EFdif_scale 1/8, no strideThr, healthy range
+    0.8-1.1, ...) on the tables of the running clip, in the training configuration and in the GUI one (limited leg length: the
+    roll-out holds 9 late touch-downs, deepmimiccdm-v1.lua:702-709,1150-1159; touchDownHeight 0.7)."""
+    from ipcdnnwalk_b200 import cdm_tables as ct
+    tab, skel = hc.load_tables("run")
+    roll = dict(np.load(hc.ROLLOUT.replace("cdm_rollout.npz", f"cdm_rollout_run2_{mode}.npz")))
+    params = dict(ct.SPECS["run2-v1"]["params"])
+    if mode == "gui":
+        params.update(ct.SPECS["run2-v1"]["gui_params"], healthy_max=2.0)
+    _run_golden(tab, skel, roll, lanes, params=params)
 
 
 def test_fp32_single_step(data):

@@ -77,6 +77,74 @@ def test_reference_policy_walks_in_the_oracle(policy):
     assert np.mean(R) > 0.2 and min(np.array(P)[:, 1]) > 0.78
 
 
+def test_reference_run_policy_runs_in_the_oracle():
+    """run2-v1: trained_models/ppo/run2-v1.pt on the tables of the running clip with the run2-v1 parameter set; the roll-out the
+    reference recorded with it (gym_cdm2/spec/refTraj_run2-v1.dat) runs at 2.91 m/s, CoM height 0.889, 17.6-step swings, 2.3 %
+    double support."""
+    from oracle import cdm_env as ce
+    pol = dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_run2.npz")))
+    tab, skel = hc.load_tables("run")
+    env = ce.OracleCDMEnv(tab, skel, params=ce.RUN2_PARAMS)
+    obs = env.reset()
+    P, S, R = [], [], []
+    for t in range(360):
+        obs, r, d = env.step(act_numpy(pol, obs))
+        assert not d, f"the reference's run policy fell at step {t}"
+        P.append(env.p.copy()); S.append([env.leg[1].isSwing, env.leg[2].isSwing]); R.append(r)
+    speed, height, lat, swing_steps, dsup = gait_stats(np.array(P), np.array(S))
+    rs, rh, rl, rsw, rds = pol["recorded_gait"]
+    assert abs(speed - rs) < 0.05 * rs, (speed, rs)
+    assert abs(height - rh) < 0.01, (height, rh)
+    assert lat < 0.03 and abs(swing_steps - rsw) < 0.1 * rsw and abs(dsup - rds) < 0.02
+    assert np.mean(R) > 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [64, 32])
+def test_reference_run_policy_on_the_gpu(precision):
+    """run2-v1 closed loop on the device through CDMVecEnv.from_spec: the noise-free environment follows the oracle, the ensemble
+    keeps running at the recorded speed."""
+    import torch
+    from ipcdnnwalk_b200 import CDMVecEnv
+    from oracle import cdm_env as ce
+    pol = dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_run2.npz")))
+    tab, skel = hc.load_tables("run")
+    n, T = 256, 300
+    rng = np.random.default_rng(7)
+    plans = np.stack([hc.random_plan(rng, 0.2) for _ in range(n)])
+    plans[0] = 0.0
+    env = CDMVecEnv.from_spec("run2-v1", n, tables=tab, skel=skel, precision=precision, auto_reset=False)
+    assert env.get_param("k_p") == 340.0 and env.get_param("stride_thr") < 0 and env.get_param("healthy_max") == 1.1
+    obs = env.reset(plan=plans)
+    nl = int(pol["n_layers"])
+    W = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device="cuda") for i in range(nl)]
+    B = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device="cuda") for i in range(nl)]
+    mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device="cuda")
+    istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device="cuda")
+    oracle = ce.OracleCDMEnv(tab, skel, params=ce.RUN2_PARAMS)
+    o_obs = hc.oracle_reset(oracle, plans[0])
+    alive = torch.ones(n, dtype=torch.bool, device="cuda")
+    worst = 0.0
+    for t in range(T):
+        h = torch.clamp((obs - mean) * istd, -10.0, 10.0)
+        for i, (w, b) in enumerate(zip(W, B)):
+            h = h @ w.T + b
+            if i < nl - 1 or int(pol["final_tanh"]):
+                h = torch.tanh(h)
+        obs, rew, done, _ = env.step(h)
+        alive &= done == 0
+        if t < 100:
+            o_obs, o_r, o_d = oracle.step(act_numpy(pol, o_obs))
+            worst = max(worst, float(np.abs(obs[0].cpu().numpy() - o_obs).max()))
+    torch.cuda.synchronize()
+    assert worst < (2e-3 if precision == 64 else 5e-2), worst
+    assert float(alive.float().mean()) > 0.9
+    z = np.array([env.get_state(i)["reals"][2] for i in range(0, n, 8)])
+    speed = z[alive.cpu().numpy()[::8]] / (T / 60.0)
+    assert abs(speed.mean() - pol["recorded_gait"][0]) < 0.1 * pol["recorded_gait"][0], speed.mean()
+    env.close()
+
+
 def test_reference_terrain_policy_walks_over_the_terrain_in_the_oracle(policy_terrain):
     """walkterrain-v1 (deepmimiccdmterrain-v1.lua): the reference's terrain policy (31-float observation with 4 height
     samples) crosses the height field in the terrain oracle -- 8 s, ground under the path between 0.1 and 0.6 m."""

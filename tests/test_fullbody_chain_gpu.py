@@ -1,6 +1,6 @@
 """The online SRB -> full-body chain of walk_SRBTrack2025.py:440-620 on the device, end to end through the C-ABI pieces:
 SRBVecEnv.step -> pack_obs_extra -> [decoder rows: synthetic here, the FullbodyVAE is PyTorch and out of scope] ->
-fullbody_extract -> mmsto_solve -> mmsto_remove_com_sliding.  Each piece has its own parity test against the oracle; this test
+fullbody_extract -> mmsto_solve -> mmsto_remove_com_sliding -> mmsto_remove_foot_sliding.  Each piece has its own parity test against the oracle; this test
 checks that their layouts plug together (Y-up records, Euler-root conversion, window assembly) and the chain's invariants."""
 import numpy as np
 import pytest
@@ -76,4 +76,27 @@ def test_chain_runs_and_keeps_its_invariants(built_lib):
     # spot check of one window against the oracle chain
     o_out, o_curr, o_opt = mm.remove_com_sliding_online(skel, com_srb[0].cpu().numpy(), com[0], before[0].cpu().numpy())
     assert np.abs(o_out - poses[0].cpu().numpy()).max() < 1e-9
-    opt.close(); env.close()
+    # limb step (walk_SRBTrack2025.py:620-631): marker trajectories of the moved plan (fc.getMarkerTraj = FK of the four foot markers),
+    # contact targets and marker targets of the same frames -> sliding-free marker trajectories
+    from ipcdnnwalk_b200 import Skeleton
+    from ipcdnnwalk_b200.short_traj_opt import removeFootSliding_online
+    from oracle import foot_sliding as fs, bone_fk as bk
+    S = Skeleton(skel)
+    xf = S.forward(poses.reshape(-1, 60), None, want_com=False, want_momentum=False)["xform"].reshape(n, nf, 20, 7)
+    mk = []
+    for m in hm.MARKERS:                                              # frame * local position of every marker
+        qb = xf[:, :, m["bone"], 0:4].cpu().numpy(); tb = xf[:, :, m["bone"], 4:7].cpu().numpy()
+        mk.append(np.stack([[bk.vrotate(qb[i, f], np.array(m["lpos"])) + tb[i, f] for f in range(nf)] for i in range(n)]))
+    marker_traj = np.concatenate(mk, axis=-1)                         # [n, nf, 12]
+    con_all = (out["con"].reshape(n, nf + 1, 4)[:, 1:].cpu().numpy() > 0).astype(float)
+    marker_tgt = out["feetpos"].reshape(n, nf + 1, 24)[:, 1:].cpu().numpy()
+    initial = marker_traj[:, 0].copy()
+    foot_len = float(np.linalg.norm(np.array(hm.MARKERS[0]["lpos"]) - np.array(hm.MARKERS[1]["lpos"])))
+    feet = removeFootSliding_online(foot_len, con_all, initial, marker_traj, marker_tgt[..., :12], marker_tgt[..., 12:], projectToGround=0.0)
+    feet = feet.cpu().numpy()
+    assert np.isfinite(feet).all() and np.abs(feet[:, 0, 0::3] - initial[:, 0::3]).max() < 1e-12 and (feet[..., 1::3] >= -1e-15).all()
+    for i in (0, n - 1):
+        ref = fs.remove_foot_sliding_online(foot_len, con_all[i], initial[i], [marker_traj[i, :, 3 * k:3 * k + 3] for k in range(4)], marker_tgt[i, :, :12],
+                                            marker_tgt[i, :, 12:], ground=lambda pos: 0.0)
+        assert np.abs(feet[i] - ref).max() < 1e-10
+    S.close(); opt.close(); env.close()

@@ -60,10 +60,16 @@ def _new_leg(env, is_left, pos, yaw):
     return li
 
 
-def test_contact_filter_replays_the_recorded_walk(rec, env):
+@pytest.mark.parametrize("clip", ["walk2", "run2"])
+def test_contact_filter_replays_the_recorded_rollouts(rec, env, clip):
     """startSwing / filterContact('sw') / getFilteredFootPos (deepmimiccdm-v1.lua:441-599,1865-1903) through the oracle:
-    every swing row of the recorded walk, both feet, positions < 5e-6 m (float32 storage), foot yaw < 1e-7 rad."""
-    g, f, rf = rec["walk2_globalTraj"], rec["walk2_rawFootInfo"], rec["walk2_refFrames"]
+    every swing row of the recorded walk and of the recorded run (run tables, run2-v1 parameters; filterEndPhase is 0.4 for both, :524), both
+    feet, positions < 5e-6 m (float32 storage), foot yaw < 1e-7 rad."""
+    g, f, rf = rec[clip + "_globalTraj"], rec[clip + "_rawFootInfo"], rec[clip + "_refFrames"].ravel().copy()
+    if clip == "run2":
+        tab, skel = hc.load_tables("run")
+        env = ce.OracleCDMEnv(tab, skel, params=dict(ce.RUN2_PARAMS, **ce.RUN2_GUI))
+        rf = np.where(np.concatenate([[False], np.cumsum(np.diff(rf) < 0) > 0]), rf + int(tab["nf"]), rf)     # stitched frame index
     n = len(g)
     worst_p = worst_y = 0.0
     rows = 0
@@ -121,6 +127,32 @@ def test_gait_state_machine_matches_the_recorded_walk(rec, env):
         inc = np.diff(sw)[(sup[1:] == 0) & (sup[:-1] == 0)]
         assert np.allclose(inc, ce.RL_STEP, atol=1e-12)            # swingPhase advances by RL_step
     assert early <= 4
+
+
+def test_gait_state_machine_matches_the_recorded_run(rec):
+    """run2-v1: every swing start and touch-down of the roll-out the reference recorded (refTraj_run2-v1.dat, 700 rows) falls
+    where the rtt tables of the running clip (cdm_tables.RUN4 through build_tables) say -- including the right foot's
+    one-step touch-down at each loop boundary, which comes from the stitching code flagging touchDown[1] for both legs
+    (module/CDMTraj.lua:1506, kept as it is in cdm_tables.build_tables).  refFrames are recorded cycle-relative; the table
+    index is the stitched frame (cycle frame + cycle length after the first wrap, defaultRLsetting.lua:239-262)."""
+    tab, _ = hc.load_tables("run")
+    f, rf = rec["run2_rawFootInfo"], rec["run2_refFrames"].ravel().astype(int)
+    nf = int(tab["nf"])
+    wrapped = np.concatenate([[False], np.cumsum(np.diff(rf) < 0) > 0])
+    idx = np.where(wrapped, rf + nf, rf)
+    n_off = n_down = 0
+    for leg in (0, 1):
+        sup = f[:, leg]
+        for r in range(1, len(f)):
+            if sup[r - 1] == 1:
+                assert (tab["rtt_off"][leg][idx[r]] <= 0) == (sup[r] == 0), (leg, r)
+                n_off += int(sup[r] == 0)
+            else:
+                assert (tab["rtt_down"][leg][idx[r]] <= 0) == (sup[r] == 1), (leg, r)
+                n_down += int(sup[r] == 1)
+    assert n_off >= 45 and n_down >= 45
+    boundary = [r for r in range(1, len(f)) if rf[r] < rf[r - 1]]
+    assert len(boundary) >= 15 and all(f[r, 0] == 1 and f[r - 1, 0] == 0 and f[r + 1, 0] == 0 for r in boundary[:-1])
 
 
 def test_flight_substeps_replay_the_recorded_run(rec, env):

@@ -31,12 +31,12 @@ MOB1 = "/root/reference/work/taesooLib/Resource/motion/MOB1/"
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def make_tables():
+def make_tables(spec="walk2-v1", out="cdm_walk_tables.npz"):
     skel = parse_wrl(MOB1 + "hanyang_lowdof_T.wrl")
-    mot = ct.read_dof(MOB1 + "hanyang_lowdof_T_lafan1_walk_2915.dof")
-    tab = ct.build_tables(mot, skel)
-    np.savez_compressed(os.path.join(GOLDEN, "cdm_walk_tables.npz"), skeleton_json=np.array(json.dumps(skel)), **tab)
-    print("tables:", tab["cdm"].shape[0], "frames, cycle", int(tab["nf"]))
+    mot = ct.read_dof(MOB1 + ct.SPECS[spec]["motion"])
+    tab = ct.build_tables(mot, skel, info=ct.SPECS[spec]["info"])
+    np.savez_compressed(os.path.join(GOLDEN, out), skeleton_json=np.array(json.dumps(skel)), **tab)
+    print("tables:", spec, tab["cdm"].shape[0], "frames, cycle", int(tab["nf"]))
 
 
 def unique_lambda(lam, cmask):
@@ -50,18 +50,27 @@ def unique_lambda(lam, cmask):
     return out
 
 
-def make_rollout(n_envs=6, n_steps=90, seed=11, terrain=False):
+def make_rollout(n_envs=6, n_steps=90, seed=11, terrain=False, run2=None):
+    """run2: None = walk2-v1; "train" / "gui" = run2-v1 tables with oracle.cdm_env.RUN2_PARAMS (+ RUN2_GUI: limited leg length -> late
+    touch-downs, touchDownHeight 0.7 -> early ones)."""
     import helpers_cdm as hc
-    tab, skel = hc.load_tables()
+    from oracle import cdm_env as ce
+    tab, skel = hc.load_tables("run" if run2 else "walk")
     rng = np.random.default_rng(seed)
     scales = [0.0, 0.05, 0.1, 0.1, 0.3, 1.0][:n_envs]
     kw = {}
     if terrain:
         T, tpos = hc.load_terrain_oracle()
         kw = dict(terrain=T, terrain_pos=tpos)
+    if run2:
+        kw["params"] = dict(ce.RUN2_PARAMS, **(dict(ce.RUN2_GUI, healthy_max=2.0) if run2 == "gui" else {}))     # 2.0: high starts must live to a touch-down
     envs = [OracleCDMEnv(tab, skel, **kw) for _ in range(n_envs)]
+    late = 0
     OW = 31 if terrain else 27
     plans0 = np.stack([hc.random_plan(rng, scales[i]) for i in range(n_envs)])
+    if run2 == "gui":                                   # two bodies start high and are pushed up (late touch-downs), one starts low (touchDownHeight)
+        plans0[1, 5] += 0.2; plans0[2, 5] += 0.4; plans0[3, 5] -= 0.15
+        plans0[1, 14] = plans0[2, 14] = 2.0
     obs0 = np.stack([hc.oracle_reset(e, plans0[i]) for i, e in enumerate(envs)])
     reals0 = np.stack([hc.oracle_state_vectors(e)[0] for e in envs])
     T = n_steps
@@ -74,8 +83,11 @@ def make_rollout(n_envs=6, n_steps=90, seed=11, terrain=False):
         for i, e in enumerate(envs):
             amp = [0.0, 0.2, 0.5, 1.0, 0.5, 0.5][i]
             a = (rng.uniform(-1, 1, 10) * amp).astype(np.float32)
+            if run2 == "gui" and i in (1, 2):
+                a[5] = 1.0                                         # desired body position raised
             acts[t, i] = a
             o, r, d = e.step(a)
+            late += int(e.debug["late"])
             obs[t, i] = o; rew[t, i] = r; done[t, i] = d
             rr, ii, _ = hc.oracle_state_vectors(e)
             reals[t, i] = rr; ints[t, i] = ii
@@ -87,9 +99,10 @@ def make_rollout(n_envs=6, n_steps=90, seed=11, terrain=False):
             plans[t, i] = hc.random_plan(rng, scales[i])
             if d:
                 reset_obs[t, i] = hc.oracle_reset(e, plans[t, i])
-    np.savez_compressed(os.path.join(GOLDEN, "cdm_rollout_terrain.npz" if terrain else "cdm_rollout.npz"), plans0=plans0, obs0=obs0, reals0=reals0, acts=acts, plans=plans,
+    name = "cdm_rollout_terrain.npz" if terrain else (f"cdm_rollout_run2_{run2}.npz" if run2 else "cdm_rollout.npz")
+    np.savez_compressed(os.path.join(GOLDEN, name), plans0=plans0, obs0=obs0, reals0=reals0, acts=acts, plans=plans,
                         obs=obs, rew=rew, done=done, reals=reals, ints=ints, qdd=qdd, lam=lam, cmask=cm, scal=scal, reset_obs=reset_obs)
-    print("rollout: episodes finished", int(done.sum()), "mean reward", rew.mean(), "swing steps", int((ints[:, :, 0] != 0).sum()))
+    print("rollout:", name, "late touch-downs", late, "episodes finished", int(done.sum()), "mean reward", rew.mean(), "swing steps", int((ints[:, :, 0] != 0).sum()))
 
 
 
@@ -188,7 +201,18 @@ def make_policy_fixture(name="walk2"):
     print("policy:", [out[f"W{i}"].shape for i in range(len(layers))], "recorded gait [speed, height, lateral/m, swing steps, double support]:", out["recorded_gait"])
 
 
+def make_run2():
+    """run2-v1 (gym_cdm2/spec/run2-v1.lua over motionInfos.run4): tables, roll-outs in the training and the GUI configuration, trained policy."""
+    make_tables("run2-v1", "cdm_run_tables.npz")
+    make_rollout(n_envs=6, n_steps=70, seed=21, run2="train")
+    make_rollout(n_envs=6, n_steps=70, seed=22, run2="gui")
+    make_policy_fixture("run2")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "run2":
+        make_run2()
+        sys.exit(0)
     make_tables()
     make_rollout()
     make_reference_recordings()
@@ -196,3 +220,4 @@ if __name__ == "__main__":
     make_rollout(n_envs=6, n_steps=60, seed=12, terrain=True)
     make_policy_fixture("walk2")
     make_policy_fixture("walkterrain")
+    make_run2()
