@@ -56,6 +56,7 @@ static void default_params(std::map<std::string, double>& p) {
   p["timing_mod_coef"] = 0.4; p["facing_weight"] = 1.5; p["ef_scale"] = 1.0; p["limit_length"] = 300.0;
   p["max_turning"] = 0.5; p["filter_end_phase"] = 0.4; p["inv_fric"] = 1.0;
   p["mass"] = 60.0; p["inertia_x"] = 9.683; p["inertia_y"] = 2.056; p["inertia_z"] = 10.209; p["grav"] = 9.8;
+  p["envs_per_warp"] = 0.0;     // launch shape, not physics: 0 = full warps (see launch_step), else 1 .. 32 / lanes_per_env
   p["noise_q"] = 0.5; p["noise_pos"] = 0.05; p["noise_dq"] = 0.5; p["noise_vx"] = 0.05; p["noise_vy"] = 0.5; p["noise_vz"] = 0.05;
 }
 
@@ -275,7 +276,14 @@ template <typename real, int G> static void launch_step(cdm_env* h, const float*
   A.term_obs = h->term_obs; A.ep_stats = h->ep_stats; A.reset_plan = h->reset_plan; A.dbg = h->dbg;
   A.auto_reset = h->cfg.auto_reset; A.seed = h->cfg.seed; A.p = make_params<real>(h); A.rc = make_rc<real>(h);
   constexpr int EPW = 32 / G;
-  cdm_step_kernel<real, G><<<(h->N + EPW - 1) / EPW, 32, 0, s>>>(A);
+  // environments per warp: full warps unless envs_per_warp says otherwise.  Partially filled warps were measured as an answer to
+  // branch divergence (a warp runs the union of its environments' code paths) and LOSE: 16384 envs, policy workload, fp32:
+  // 32 per warp 131 us, 16: 169 us, 12: 236 us, 8: 292 us (profiles/r02_cdm_envs_per_warp.jsonl) -- the step is bound by
+  // instruction fetch / issue over all warps, not by the length of one warp's stream.
+  int gpw = (int)h->hp["envs_per_warp"];
+  if (gpw <= 0) gpw = EPW;
+  A.gpw = gpw < EPW ? gpw : EPW;
+  cdm_step_kernel<real, G><<<(h->N + A.gpw - 1) / A.gpw, 32, 0, s>>>(A);
   h->launches++;
 }
 template <typename real> static int dispatch_step(cdm_env* h, const float* act, float* obs, float* rew, uint8_t* done, cudaStream_t s) {

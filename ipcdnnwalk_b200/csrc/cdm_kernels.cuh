@@ -701,9 +701,13 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
   using QPT = srb::QP<double, G, NQCOL>;
   const int lane32 = threadIdx.x & 31;
   const int lane = lane32 % G;
-  const int e_raw = blockIdx.x * EPW + lane32 / G;
-  const bool active = e_raw < A.N;
-  const int e = active ? e_raw : A.N - 1;
+  // Partially filled warps (experiment switch, cdm_set_param "envs_per_warp"): with gpw < EPW only the first gpw lane groups of a
+  // warp carry an environment; the others shadow the warp's first environment (same branch decisions, no stores).
+  const int grp = lane32 / G;
+  const bool in_use = grp < A.gpw;
+  const int e_raw = blockIdx.x * A.gpw + (in_use ? grp : 0);
+  const bool active = in_use && e_raw < A.N;
+  const int e = e_raw < A.N ? e_raw : A.N - 1;
   const Params<real>& P = A.p;
   const real* __restrict__ tab = A.tab;
   const int F = A.nframes, nf = A.nf_cycle;

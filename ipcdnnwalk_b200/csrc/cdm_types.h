@@ -63,6 +63,7 @@ template <typename real> struct StepArgs {
   const float* act; float* obs; float* rew; uint8_t* done;
   float* term_obs; double* ep_stats; const double* reset_plan; double* dbg;
   int auto_reset;
+  int gpw;                      // lane groups (= environments) per warp actually used, <= 32 / G; the remaining lanes shadow group 0
   unsigned long long seed;
   Params<real> p;
   ResetConst<real> rc;

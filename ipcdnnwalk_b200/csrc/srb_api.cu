@@ -64,6 +64,7 @@ template <typename real> static Params<real> convert_params(const Params<double>
   q.impulse_interval = p.impulse_interval; q.impulse_duration = p.impulse_duration; q.impulse_trigger_at_end = p.impulse_trigger_at_end;
   q.max_frame = p.max_frame; q.aset_warm = p.aset_warm;
   q.inv_w_lambda = (real)(1.0 / p.w_lambda);
+  q.clamp_bound = (real)(1.01 * std::sqrt(1.0 + (double)q.mu_b * (double)q.mu_b));
   const double Md[6] = {p.mass + p.armature, p.mass + p.armature, p.mass + p.armature,
                         p.inertia[0] + p.armature, p.inertia[1] + p.armature, p.inertia[2] + p.armature};
   for (int i = 0; i < 6; i++) { q.inv_M[i] = (real)(1.0 / Md[i]); q.inv_Mh[i] = (real)(1.0 / (Md[i] + p.h * p.damping)); }

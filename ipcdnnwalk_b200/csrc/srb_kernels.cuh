@@ -471,6 +471,33 @@ template <typename real, int G, int NCOLS = 40> struct QP {
 
   __device__ __forceinline__ void build(int lane, const M3<real>& R, V3<real> p, const V3<real> foot[2], const real yc[2],
                                         const real ys[2], int contact_mask, real fx, real fy, real mu_b, const real Minv[6]) {
+    if constexpr (G == 8 && NCOLS == 40) {
+      // A lane's five columns share the foot f and the friction direction d and differ only in the site offset o_k in the foot's
+      // yaw frame (e1, e2): site_k = foot + ox_k e1 + oy_k e2, so the torque rows are affine in (ox_k, oy_k):
+      //   R^T((site_k - p) x B) = T0 + ox_k T1 + oy_k T2,  T0 = R^T((foot - p) x B), T1 = R^T(e1 x B), T2 = R^T(e2 x B)
+      // -- three cross products and rotations per lane instead of five.
+      const int f = (lane >> 2) & 1, d = lane & 3;
+      const real bx = d == 0 ? mu_b : (d == 1 ? -mu_b : real(0));
+      const real by = d == 2 ? mu_b : (d == 3 ? -mu_b : real(0));
+      const V3<real> B = {fx * bx - fy * by, fy * bx + fx * by, real(1)};
+      const V3<real> ft = f ? foot[1] : foot[0];
+      const real c_ = f ? yc[1] : yc[0], s_ = f ? ys[1] : ys[0];
+      const real m = ((contact_mask >> f) & 1) ? real(1) : real(0);
+      const real w3 = m * Minv[3], w4 = m * Minv[4], w5 = m * Minv[5];
+      V3<real> T0 = mulT(R, cross(ft - p, B));
+      V3<real> T1 = mulT(R, V3<real>{s_, -c_, c_ * B.y - s_ * B.x});           // e1 = (c, s, 0):  e1 x B
+      V3<real> T2 = mulT(R, V3<real>{c_, s_, -s_ * B.y - c_ * B.x});           // e2 = (-s, c, 0): e2 x B
+      T0 = {w3 * T0.x, w4 * T0.y, w5 * T0.z}; T1 = {w3 * T1.x, w4 * T1.y, w5 * T1.z}; T2 = {w3 * T2.x, w4 * T2.y, w5 * T2.z};
+      const real l0 = m * Minv[0] * B.x, l1 = m * Minv[1] * B.y, l2 = m * Minv[2] * B.z;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const real ox = k == 0 ? real(0) : ((k == 1 || k == 2) ? real(0.12) : real(-0.12));
+        const real oy = k == 0 ? real(0) : ((k == 1 || k == 3) ? real(0.06) : real(-0.06));
+        a[k][0] = l0; a[k][1] = l1; a[k][2] = l2;
+        a[k][3] = T0.x + ox * T1.x + oy * T2.x; a[k][4] = T0.y + ox * T1.y + oy * T2.y; a[k][5] = T0.z + ox * T1.z + oy * T2.z;
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < NC; k++) {
       int c = lane + k * G;
@@ -591,36 +618,41 @@ template <typename real, int G, int NCOLS = 40> struct QP {
       for (int k = 0; k < NC; k++) same = same && ((tn[k] < 0) == (ts[k] < 0));
       unsigned bal = __ballot_sync(0xffffffffu, same);
       same = (bal & gmask) == gmask;
-      real phn = phi(nn, y, tn, inv2w);
-      // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker)
-      real dmax = 0, nmax = 0;
+      // The acceptance tests (phi of the new point, rounding-level step, step halving) matter only where the active set changed;
+      // the last system of a solve -- every unfinished environment of the warp reproduced its set -- skips them.
+      real phn = ph;
+      if (__any_sync(0xffffffffu, !done && !same)) {
+        phn = phi(nn, y, tn, inv2w);
+        // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker)
+        real dmax = 0, nmax = 0;
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
-        real dd = nn[i] - nu[i]; dd = dd < 0 ? -dd : dd;
-        real av = nn[i] < 0 ? -nn[i] : nn[i];
-        dmax = dd > dmax ? dd : dmax; nmax = av > nmax ? av : nmax;
-      }
-      // (with a guessed set the fixed-point shortcut is only valid once the Hessian came from sign(A^T nu) itself)
-      if (S0 == nullptr || it > 0) same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
-      const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + (ph < 0 ? -ph : ph));   // phi resolution
-      bool need_bt = !done && !same && !(phn < ph + ph_tol);
-      if (__any_sync(0xffffffffu, need_bt)) {                 // rare
-        real alpha = real(0.5);
-        while (__any_sync(0xffffffffu, need_bt)) {
-          real nt[6], tt[NC];
+        for (int i = 0; i < 6; i++) {
+          real dd = nn[i] - nu[i]; dd = dd < 0 ? -dd : dd;
+          real av = nn[i] < 0 ? -nn[i] : nn[i];
+          dmax = dd > dmax ? dd : dmax; nmax = av > nmax ? av : nmax;
+        }
+        // (with a guessed set the fixed-point shortcut is only valid once the Hessian came from sign(A^T nu) itself)
+        if (S0 == nullptr || it > 0) same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
+        const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + (ph < 0 ? -ph : ph));   // phi resolution
+        bool need_bt = !done && !same && !(phn < ph + ph_tol);
+        if (__any_sync(0xffffffffu, need_bt)) {                 // rare
+          real alpha = real(0.5);
+          while (__any_sync(0xffffffffu, need_bt)) {
+            real nt[6], tt[NC];
 #pragma unroll
-          for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
-          tvals(nt, tt);
-          real pht = phi(nt, y, tt, inv2w);
-          if (need_bt && (pht < ph + ph_tol || alpha < real(1e-3))) {
+            for (int i = 0; i < 6; i++) nt[i] = nu[i] + alpha * (nn[i] - nu[i]);
+            tvals(nt, tt);
+            real pht = phi(nt, y, tt, inv2w);
+            if (need_bt && (pht < ph + ph_tol || alpha < real(1e-3))) {
 #pragma unroll
-            for (int i = 0; i < 6; i++) nn[i] = nt[i];
+              for (int i = 0; i < 6; i++) nn[i] = nt[i];
 #pragma unroll
-            for (int k = 0; k < NC; k++) tn[k] = tt[k];
-            phn = pht;
-            need_bt = false;
+              for (int k = 0; k < NC; k++) tn[k] = tt[k];
+              phn = pht;
+              need_bt = false;
+            }
+            alpha *= real(0.5);
           }
-          alpha *= real(0.5);
         }
       }
       if (!done) {
@@ -813,9 +845,9 @@ template <typename real> __device__ __forceinline__ real rot6_l1_full(const M3<r
   return s;
 }
 
-template <typename real>
+template <typename real, int G>
 __device__ __forceinline__ real compute_reward(const EnvState<real>& s, const ClipDesc<real>& cd, const real* __restrict__ hist_env,
-                                               int pred_contact, const Params<real>& p, float info[8]) {
+                                               int pred_contact, const Params<real>& p, float info[8], int lane) {
   const int cf = s.frame, f0 = cf + s.rif;
   M3<real> X = quat2mat_normalized(s.qlag);            // data.xmat (stale by one sub-step)
   real cx, cy;
@@ -860,33 +892,59 @@ __device__ __forceinline__ real compute_reward(const EnvState<real>& s, const Cl
     *hp = {h[0], h[1], h[2]};
     *hR = quat2mat_normalized(Q4<real>{h[3], h[4], h[5], h[6]});
   };
-  if (cf >= 15) {
+  if constexpr (G >= 4) {
+    // The three history terms are the same computation on different data (entry cf - {0, 5, 15}): lanes 0..2 of the group take one
+    // each (the other lanes repeat lane 0's), the sums are gathered by shuffles.  The -15 term projects with the full history
+    // matrices, the other two with their yaw frames; a yaw frame written as a matrix makes that one code path too.
+    const int j = lane < 3 ? lane : 0;
+    const int back = j == 0 ? 0 : (j == 1 ? 5 : 15);
+    const bool on = cf >= back;
     V3<real> hp; M3<real> hR;
-    hist_entry(cf - 15, &hp, &hR);
-    RefFrame<real> m15 = load_ref(cd, f0 - 15);
+    hist_entry(on ? cf - back : cf, &hp, &hR);
+    RefFrame<real> m = load_ref(cd, on ? f0 - back : f0);
     real hx, hy, mx, my;
     yaw_frame(hR, &hx, &hy);
-    yaw_frame(m15.R, &mx, &my);
-    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m15.pos));
-    dR += rot6_l1_full(hR, X, m15.R, nxt.R);
-  }
-  if (cf >= 5) {
-    V3<real> hp; M3<real> hR;
-    hist_entry(cf - 5, &hp, &hR);
-    RefFrame<real> m5 = load_ref(cd, f0 - 5);
-    real hx, hy, mx, my;
-    yaw_frame(hR, &hx, &hy);
-    yaw_frame(m5.R, &mx, &my);
-    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m5.pos));
-    dR += rot6_l1_yaw(hx, hy, X, mx, my, nxt.R);
-  }
-  {
-    V3<real> hp; M3<real> hR;
-    hist_entry(cf, &hp, &hR);
-    real hx, hy;
-    yaw_frame(hR, &hx, &hy);
-    dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mcx, mcy, nxt.pos - cur.pos));
-    dR += rot6_l1_yaw(hx, hy, X, mcx, mcy, nxt.R);
+    yaw_frame(m.R, &mx, &my);
+    real dpj = norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m.pos));
+    M3<real> Pa = hR, Pb = m.R;
+    if (back != 15) {
+      Pa.m[0] = hx; Pa.m[1] = -hy; Pa.m[2] = real(0); Pa.m[3] = hy; Pa.m[4] = hx; Pa.m[5] = real(0); Pa.m[6] = real(0); Pa.m[7] = real(0); Pa.m[8] = real(1);
+      Pb.m[0] = mx; Pb.m[1] = -my; Pb.m[2] = real(0); Pb.m[3] = my; Pb.m[4] = mx; Pb.m[5] = real(0); Pb.m[6] = real(0); Pb.m[7] = real(0); Pb.m[8] = real(1);
+    }
+    real dRj = rot6_l1_full(Pa, X, Pb, nxt.R);
+    if (!on) { dpj = real(0); dRj = real(0); }
+    const int base = (threadIdx.x & 31) & ~(G - 1);
+    dp = __shfl_sync(0xffffffffu, dpj, base + 2) + __shfl_sync(0xffffffffu, dpj, base + 1) + __shfl_sync(0xffffffffu, dpj, base);
+    dR = __shfl_sync(0xffffffffu, dRj, base + 2) + __shfl_sync(0xffffffffu, dRj, base + 1) + __shfl_sync(0xffffffffu, dRj, base);
+  } else {
+    if (cf >= 15) {
+      V3<real> hp; M3<real> hR;
+      hist_entry(cf - 15, &hp, &hR);
+      RefFrame<real> m15 = load_ref(cd, f0 - 15);
+      real hx, hy, mx, my;
+      yaw_frame(hR, &hx, &hy);
+      yaw_frame(m15.R, &mx, &my);
+      dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m15.pos));
+      dR += rot6_l1_full(hR, X, m15.R, nxt.R);
+    }
+    if (cf >= 5) {
+      V3<real> hp; M3<real> hR;
+      hist_entry(cf - 5, &hp, &hR);
+      RefFrame<real> m5 = load_ref(cd, f0 - 5);
+      real hx, hy, mx, my;
+      yaw_frame(hR, &hx, &hy);
+      yaw_frame(m5.R, &mx, &my);
+      dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mx, my, nxt.pos - m5.pos));
+      dR += rot6_l1_yaw(hx, hy, X, mx, my, nxt.R);
+    }
+    {
+      V3<real> hp; M3<real> hR;
+      hist_entry(cf, &hp, &hR);
+      real hx, hy;
+      yaw_frame(hR, &hx, &hy);
+      dp += norm(yawT(hx, hy, s.pos - hp) - yawT(mcx, mcy, nxt.pos - cur.pos));
+      dR += rot6_l1_yaw(hx, hy, X, mcx, mcy, nxt.R);
+    }
   }
   // absolute terms
   V3<real> pa = {real(0), real(0), s.pos.z}, pb = {real(0), real(0), nxt.pos.z};
@@ -939,9 +997,12 @@ template <typename real> __device__ __forceinline__ bool compute_done(const EnvS
 template <typename real, int G, bool CIO = false, bool TERRAIN = false>
 __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   constexpr int EPW = 32 / G;
-  const long long tk_entry = clock64();
-  unsigned long long gt_entry;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+  long long tk_entry = 0;                                  // phase clocks: only with a debug buffer attached (tools/phase_cycles.py)
+  unsigned long long gt_entry = 0;
+  if (A.dbg != nullptr) {
+    tk_entry = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+  }
   const int lane32 = threadIdx.x & 31;
   const int lane = lane32 % G;
   const int e_raw = (blockIdx.x * EPW) + lane32 / G;
@@ -950,6 +1011,12 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   const Params<real>& P = A.p;
 
   __shared__ __align__(16) real hsm[HReduce<real, G>::SMEM_WORDS];
+  float af[ACT_W];                                         // issued before the state loads: one DRAM round trip for both
+  if (!CIO) {
+    const float2* act2 = reinterpret_cast<const float2*>(A.act + (size_t)e * ACT_W);
+#pragma unroll
+    for (int i = 0; i < ACT_W / 2; i++) { const float2 v = __ldg(act2 + i); af[2 * i] = v.x; af[2 * i + 1] = v.y; }
+  }
   EnvState<real> s;
   load_state(s, A.st, A.ist, A.Npad, e);
   const ClipDesc<real> cd = A.clips[s.clip];
@@ -990,9 +1057,8 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     for (int i = 0; i < ACT_W; i++) a[i] = (real)sa[i];
     __syncwarp();                                        // sio is reused for the observation rows below
   } else {
-    const float* act = A.act + (size_t)e * ACT_W;
 #pragma unroll
-    for (int i = 0; i < ACT_W; i++) a[i] = (real)__ldg(act + i);
+    for (int i = 0; i < ACT_W; i++) a[i] = (real)af[i];
   }
   // ---- frames from the (stale) xmat, action decoding (SRBEnv.step :209-231)
   const M3<real> R0 = quat2mat_normalized(s.qlag);
@@ -1123,6 +1189,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   long long tk0 = 0, tk_pre = 0;
   if (A.dbg != nullptr) { tk_pre = clock64(); tk0 = tk_pre; }   // phase clocks land in the debug record's pad slots
 
+  int fc_mod = P.use_impulse ? s.fcount % P.impulse_interval : 0;
   for (int sub = 0; sub < P.nsub; sub++) {
     long long tk_sub = 0;
     if (A.dbg != nullptr) tk_sub = clock64();
@@ -1135,8 +1202,8 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
     // update_impulse (:191-206)
     real xf[6] = {0, 0, 0, 0, 0, 0};     // xfrc_applied: world force, world torque -> J^T: torque onto the body axes (mj_xfrcAccumulate)
     if (P.use_impulse) {
-      bool trig = P.impulse_trigger_at_end ? (s.fcount % P.impulse_interval == P.impulse_interval - 1)
-                                           : (s.fcount % P.impulse_interval == 0);
+      const bool trig = fc_mod == (P.impulse_trigger_at_end ? P.impulse_interval - 1 : 0);   // frame_counter % interval, kept incrementally
+      fc_mod = fc_mod + 1 == P.impulse_interval ? 0 : fc_mod + 1;
       if (trig) s.impulse = P.impulse_duration;
       if (s.impulse > 0) {
         s.impulse -= 1;
@@ -1181,7 +1248,11 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
       }
       const real invw = P.inv_w_lambda;
       bool clamped = false;
-      if (P.use_clamp) {
+      // Every friction-basis vector is (mu_b * unit horizontal, 1): a foot's force obeys |F_foot| <= sqrt(1 + mu_b^2) F_foot,z and
+      // F_foot,z <= F_total,z = M (nu + y)_z (all multipliers >= 0), so the per-foot sums are only needed when that bound can
+      // reach the threshold at all (never in a normal gait: 1e4 N).  Same decisions, three group reductions fewer per sub-step.
+      const bool may_clamp = Mdiag[2] * (nu[2] + y[2]) * P.clamp_bound > P.force_thr;
+      if (P.use_clamp && __any_sync(0xffffffffu, may_clamp && contact_mask != 0)) {
         // per-foot force sums and the 1e4 N clamp (:402-443, Q3)
         real FL[3] = {0, 0, 0};
 #pragma unroll
@@ -1267,7 +1338,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
   float info[8];
   real r = real(0);
   if (T == nullptr) {
-    r = compute_reward(s, cd, hist_env, pred_contact, P, info);
+    r = compute_reward<real, G>(s, cd, hist_env, pred_contact, P, info, lane);
   } else {                                               // terrain env: _get_reward returns (0, {}) (:525-526)
 #pragma unroll
     for (int i = 0; i < 8; i++) info[i] = 0.f;

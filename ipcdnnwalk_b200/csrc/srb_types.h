@@ -75,6 +75,7 @@ template <typename real> struct Params {
   real kp, kd, w_lambda;
   real inv_w_lambda, inv_M[6], inv_Mh[6];   // 1/w, 1/(M+armature), 1/(M+armature+h*damping)
   real force_thr;
+  real clamp_bound;     // 1.01 * sqrt(1 + mu_b^2): |F_foot| <= clamp_bound * F_total,z (see the force clamp in srb_step_kernel)
   real w[9];            // w_s w_m w_p w_e w_p1 w_p2 w_p3 w_p4 w_c
   int use_filter, use_clamp, use_impulse, obs_after_inc, use_terrain;
   int impulse_interval, impulse_duration, impulse_trigger_at_end;

@@ -19,6 +19,7 @@ ap.add_argument("--warmup", type=int, default=16)
 ap.add_argument("--lanes", default="4")
 ap.add_argument("--precision", default="32,64")
 ap.add_argument("--e2e", action="store_true")
+ap.add_argument("--epw", default="0", help="environments per warp (comma list; 0 = automatic)")
 ap.add_argument("--policy", action="store_true", help="drive the environments with the reference's trained walk2-v1 policy (tests/golden/cdm_policy_walk2.npz), evaluated in torch outside the timed events, reset noise scaled to 20 %")
 a = ap.parse_args()
 peak = 6547.8
@@ -30,10 +31,11 @@ tab, skel = hc.load_tables()
 BYTES = {32: 108 + 40 + 8 + 2 * (61 * 4 + 16) + 2 * 32, 64: 108 + 40 + 8 + 2 * (61 * 8 + 16) + 2 * 64}   # obs + act + rew/done + state r/w + replay entry r/w
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for prec in [int(x) for x in a.precision.split(",")]:
-    for lanes in [int(x) for x in a.lanes.split(",")]:
+    for lanes, epw in [(int(x), int(y)) for x in a.lanes.split(",") for y in a.epw.split(",")]:
         params = {"noise_q": 0.1, "noise_pos": 0.01, "noise_dq": 0.1, "noise_vx": 0.01, "noise_vy": 0.1, "noise_vz": 0.01} if a.policy else None
         if a.policy and os.environ.get("CDM_NOISE_SCALE"):          # experiment: 0 = all environments identical (perfectly coherent warps)
             params = {k: v * float(os.environ["CDM_NOISE_SCALE"]) for k, v in params.items()}
+        params = dict(params or {}, envs_per_warp=epw)
         env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3, params=params)
         obs = env.reset()
         if a.policy:
@@ -65,7 +67,7 @@ for prec in [int(x) for x in a.precision.split(",")]:
         torch.cuda.synchronize()
         ms = np.array([x.elapsed_time(y) for x, y in ts])
         st = env.episode_stats()
-        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "actions": "reference walk2-v1 policy (torch, untimed)" if a.policy else "U(-1,1)", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes,
+        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "actions": "reference walk2-v1 policy (torch, untimed)" if a.policy else "U(-1,1)", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes, "envs_per_warp": epw,
                "steps": a.steps, "ms_per_step_mean": float(ms.mean()), "ms_per_step_median": float(np.median(ms)), "env_steps_per_s": a.envs / float(ms.mean()) * 1e3,
                "algorithmic_bytes_per_env_step": BYTES[prec], "achieved_GBps": BYTES[prec] * a.envs / float(ms.mean()) / 1e6, "peak_GBps": peak,
                "frac": BYTES[prec] * a.envs / float(ms.mean()) / 1e6 / peak, "episodes_finished": int(st[2]), "mean_episode_len": float(st[1] / max(st[2], 1)),
