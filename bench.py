@@ -329,6 +329,9 @@ def run_ours(args, rank, local_rank, world):
     Ke = min(K, 200)
     if not args.no_e2e:
         pin = env.pinned()
+        host_mode = int(os.environ.get("SRB_HOST_MODE", "1"))     # experiment switch: 0 staged copies, 1 zero copy (library default), 2 split
+        if host_mode != 1:
+            env.set_host_mode(host_mode)
         for k in range(3):
             env.step_host()
         tt = 0.0
@@ -403,7 +406,10 @@ def run_ours(args, rank, local_rank, world):
         if e2e_ms is not None:
             line["e2e"] = {"value": world * N * Ke / (e2e_ms_max * 1e-3), "unit": "env-steps/s",
                            "h2d_bytes_per_step": N * ACT_DIM * 4, "d2h_bytes_per_step": N * (OBS_DIM * 4 + 4 + 1 + RINFO_DIM * 4),
-                           "steps": Ke, "api": "srb_step_host, host buffers: the coalesced-I/O step kernel reads the actions from and writes obs/reward/done/info to mapped pinned host memory over PCIe inside the timed region (zero copy), then stream sync"}
+                           "steps": Ke, "host_mode": host_mode,
+                           "api": "srb_step_host, host buffers: the coalesced-I/O step kernel reads the actions from and writes obs/reward/done/info to mapped pinned host memory over PCIe inside the timed region (zero copy), then stream sync" if host_mode == 1 else
+                                  ("srb_step_host, host buffers, staged copy-engine transfers (H2D actions, kernel, D2H obs/reward/done/info) inside the timed region" if host_mode == 0 else
+                                   "srb_step_host, host buffers, split mode (look-ahead windows by copy engine during the step kernel, the rest zero copy) inside the timed region")}
         if secondary:
             line["secondary"] = secondary
         if not args.no_cpu_baseline:

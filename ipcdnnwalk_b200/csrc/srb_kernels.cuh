@@ -623,16 +623,12 @@ template <typename real, int G, int NCOLS = 40> struct QP {
       real phn = ph;
       if (__any_sync(0xffffffffu, !done && !same)) {
         phn = phi(nn, y, tn, inv2w);
-        // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker)
-        real dmax = 0, nmax = 0;
+        // a step below rounding level is a fixed point (needed in fp32, where the sign of a ~0 t_j can flicker): |step|_2 <= eps (1 + |nu|_2)
+        real d2 = 0, n2 = 0;
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          real dd = nn[i] - nu[i]; dd = dd < 0 ? -dd : dd;
-          real av = nn[i] < 0 ? -nn[i] : nn[i];
-          dmax = dd > dmax ? dd : dmax; nmax = av > nmax ? av : nmax;
-        }
+        for (int i = 0; i < 6; i++) { const real dd = nn[i] - nu[i]; d2 += dd * dd; n2 += nn[i] * nn[i]; }
         // (with a guessed set the fixed-point shortcut is only valid once the Hessian came from sign(A^T nu) itself)
-        if (S0 == nullptr || it > 0) same = same || (dmax <= num<real>::eps_conv() * (real(1) + nmax));
+        if (S0 == nullptr || it > 0) same = same || (d2 <= num<real>::eps_conv() * num<real>::eps_conv() * (real(1) + n2));
         const real ph_tol = real(4) * num<real>::eps_conv() * (real(1) + (ph < 0 ? -ph : ph));   // phi resolution
         bool need_bt = !done && !same && !(phn < ph + ph_tol);
         if (__any_sync(0xffffffffu, need_bt)) {                 // rare
@@ -659,12 +655,14 @@ template <typename real, int G, int NCOLS = 40> struct QP {
 #pragma unroll
         for (int i = 0; i < 6; i++) nu[i] = nn[i];
 #pragma unroll
-        for (int k = 0; k < NC; k++) { t[k] = tn[k]; ts[k] = tn[k]; }
+        for (int k = 0; k < NC; k++) ts[k] = tn[k];
         ph = phn;
         iters++;
         if (same) done = true;
       }
     }
+#pragma unroll
+    for (int k = 0; k < NC; k++) t[k] = ts[k];                // A^T nu of the accepted iterate
     return iters;
   }
   // Same Newton iteration, globalised by an EXACT line search instead of step halving (the finite Newton method of

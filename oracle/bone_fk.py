@@ -10,9 +10,11 @@ SRB -> full-body momentum mapping:
   BaseLib/motion/IK_sdls/Node.cpp:58-99            Node::ComputeS / ComputeDS (one node per hinge dof)
   BaseLib/motion/Liegroup.cpp:45-75, Liegroup.h:131-147  dse3::dAd / inv_dAd, Inertia * se3 (Q13: no parallel-axis term)
 
-taesooLib cannot be compiled here (Eigen3 / FreeImage absent) and ships no expected values:
-PARITY UNPINNED; pinned by analytic checks in tests/test_oracle_fk_cpu.py (finite-difference velocities,
-momentum of a rigidly moving body, independence from the choice of the node chain).
+PARITY PINNED to the reference's own code: BaseLib math / motion / IK_sdls compile from /root/reference (oracle/ref_build/Makefile ->
+oracle/_ref/taesoo_ref); tests/test_refpins.py compares this file with what that binary computes on seeded poses (frames 1e-14,
+link velocities / CoM 1e-12, momentum 1e-11; fixture tests/golden/ref_taesoolib.npz, generator tests/tools/make_golden_ref.py).
+Analytic checks in addition: tests/test_oracle_fk_cpu.py (finite-difference velocities, momentum of a rigidly moving body,
+independence from the choice of the node chain).
 
 Pose layout (MotionDOF): [root xyz, root quaternion w x y z, joint angles in tree order]; dq layout
 (LoaderToTree): [root angular velocity (world), root linear velocity (world), joint rates]."""

@@ -17,16 +17,18 @@ gym_cdm2 -- SURVEY 8f rank 1 -- in the ONLINE configuration that walk_SRBTrack20
   BaseLib/motion/IK_lbfgs/lbfgs.cpp:114-119,246-640,646-738   libLBFGS defaults, main loop, backtracking (regular Wolfe) line search
   BaseLib/math/optimize.h:426-470              LBFGS_METHOD: linesearch = LBFGS_LINESEARCH_BACKTRACKING, epsilon from the caller
 
-PARITY UNPINNED.  taesooLib cannot be compiled here and the Lua wrapper `subRoutines/OptimizerLBFGS` that
-shortTermOptimizer.lua:1 requires is NOT in the reference tree.  It is restated from its call site
+PARITY: the Euler-root tree (frames, CoM, momentum, every Jacobian, updateGrad_S_JT) and the L-BFGS loop are PINNED to the reference's
+own compiled code (oracle/_ref: IK_sdls and libLBFGS built from /root/reference; tests/test_refpins.py -- libLBFGS driving this
+file's objective reproduces status code, iteration / evaluation counts exactly and the iterates at 1e-12).  UNPINNED: the Lua wrapper
+`subRoutines/OptimizerLBFGS` that shortTermOptimizer.lua:1 requires is NOT in the reference tree.  It is restated from its call site
 (`LBFGS_opta(nf*ndof, 1e-9, ndof*2, 0)`, `h:addWeighted`, `h.customGradientFunction`, `h:solve`) with these stated
 assumptions: (W1) the objective is the sum of the addWeighted squared terms and of customGradientFunction, the gradient
 likewise; (W2) the third / fourth constructor arguments are the numbers of leading / trailing variables that are held at
 their initial values (the Lua comments call frames 0 and 1 "constants"), L-BFGS runs on the remaining variables only;
 (W3) the second argument is lbfgs_parameter_t::epsilon, everything else is the libLBFGS default (m = 6, unlimited
 iterations, 40 line-search trials); (W4) tree joint numbers equal the dof indices (bones are stored depth first).
-Pinned by analytic checks only (tests/test_oracle_mmsto_cpu.py: finite differences of every term, momentum Jacobian
-against calcMomentumCOM, convergence on consistent targets).
+Analytic checks in addition (tests/test_oracle_mmsto_cpu.py): finite differences of every term, momentum Jacobian
+against calcMomentumCOM, convergence on consistent targets.
 
 Layout: q = [root xyz, root Euler YZX, joint angles in tree order] (ndof = 59 for hanyang_lowdof_T), x = nf stacked q."""
 import math
