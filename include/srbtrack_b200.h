@@ -73,8 +73,10 @@ int srb_pinned_buffers(srb_env* env, float** act, float** obs, float** rew, uint
 /* How srb_step_host moves data: 1 (default) = zero copy, the step kernel reads the actions from and writes all its results to the
  * mapped pinned buffers directly (contiguous 16-byte-vectorised blocks per warp); 0 = staged cudaMemcpyAsync copies; 2 = split: the
  * look-ahead windows of the observation rows (known before the step) are gathered first and the observation array is copied by a
- * copy engine while the step kernel runs, a patch launch then writes the self features over it (measured: the PCIe link, ~35 GB/s
- * device-to-host either way, is the limit, so this does not beat mode 1 on one GPU; kept selectable). */
+ * copy engine while the step kernel runs, a patch launch then writes the self features over it; 3 = as 2, but only the window
+ * columns travel by copy engine (one pitched copy) and the kernel stores the self features / reward / done / info to the mapped
+ * buffers itself.  Measured on one B200 (4096 envs, tools/exp_e2e_modes.py): mode 1 88 us per step, 3: 107 us, 0: 115 us, 2: 131 us --
+ * copy-engine traffic and SM-issued stores to host memory slow each other down, so the split forms do not pay; kept selectable. */
 int srb_set_host_mode(srb_env* env, int32_t mode);
 /* Device timeline of the last mode-2 host step, milliseconds after its first launch was enqueued: out_ms[1] window gather done,
  * [2] observation copy done, [3] step kernel done, [4] patch launch done.  enable = 1 switches the timing events on. */

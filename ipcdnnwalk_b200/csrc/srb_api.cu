@@ -326,8 +326,8 @@ static int ensure_host_buffers(srb_env* h) {
   return 0;
 }
 
-template <typename real> static void launch_window(srb_env* h, int after_inc, const uint8_t* only_done, const float* self_src, float* dst, cudaStream_t s) {
-  srb_obs_window_kernel<real><<<h->N, 160, 0, s>>>(h->N, h->Npad, h->ist, (const ClipDesc<real>*)h->clips_dev, after_inc, only_done, self_src, dst);
+template <typename real> static void launch_window(srb_env* h, int after_inc, const uint8_t* only_done, const float* self_src, float* dst, cudaStream_t s, int patch_only = 0) {
+  srb_obs_window_kernel<real><<<h->N, 160, 0, s>>>(h->N, h->Npad, h->ist, (const ClipDesc<real>*)h->clips_dev, after_inc, only_done, self_src, dst, patch_only);
   h->launches++;
 }
 
@@ -384,6 +384,35 @@ extern "C" int srb_step_host(srb_env* h, const float* act_host, float* obs_host,
     if (h->tl_on) CK(cudaEventRecord(h->tl[4], s));
     CK(cudaStreamSynchronize(s));
     if (h->tl_on) for (int i = 1; i < 5; i++) cudaEventElapsedTime(&h->tl_ms[i], h->tl[0], h->tl[i]);
+  } else if (h->host_mode == 3 && cio_supported(h->G) && !h->p.use_terrain) {
+    // split, second form: only the WINDOW columns (125 of 150 floats per row) travel by copy engine, as one pitched transfer that
+    // overlaps the step kernel; the kernel stores the 25 self features, reward / done / reward_info straight into the mapped host
+    // arrays (disjoint from what the copy engine writes), so nothing but the new windows of auto-reset environments is left to patch.
+    float *a = nullptr, *o = nullptr, *r = nullptr, *ri = nullptr; uint8_t* d = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&a, h->h_act, 0)); CK(cudaHostGetDevicePointer((void**)&o, h->h_obs, 0));
+    CK(cudaHostGetDevicePointer((void**)&r, h->h_rew, 0)); CK(cudaHostGetDevicePointer((void**)&d, h->h_done, 0));
+    CK(cudaHostGetDevicePointer((void**)&ri, h->h_rinfo, 0));
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_state, 0));
+    if (h->cfg.precision == 64) launch_window<double>(h, h->p.obs_after_inc, nullptr, nullptr, h->d_obs, h->stream2);
+    else launch_window<float>(h, h->p.obs_after_inc, nullptr, nullptr, h->d_obs, h->stream2);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_win, h->stream2));
+    CK(cudaMemcpy2DAsync(h->h_obs + FEAT_W, sizeof(float) * OBS_W, h->d_obs + FEAT_W, sizeof(float) * OBS_W, sizeof(float) * (OBS_W - FEAT_W), N,
+                         cudaMemcpyDeviceToHost, h->stream2));
+    CK(cudaEventRecord(h->ev_dma, h->stream2));
+    CK(cudaStreamWaitEvent(s, h->ev_win, 0));            // the step must not advance the frame counters before they were read
+    h->split_obs = 1; h->done_dev_arg = h->d_done;
+    rc = step_impl(h, a, o, r, d, ri, s, true);
+    h->split_obs = 0; h->done_dev_arg = nullptr;
+    if (rc) return rc;
+    if (h->cfg.auto_reset) {
+      CK(cudaStreamWaitEvent(s, h->ev_dma, 0));
+      if (h->cfg.precision == 64) launch_window<double>(h, 0, h->d_done, nullptr, o, s, 1);
+      else launch_window<float>(h, 0, h->d_done, nullptr, o, s, 1);
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(h->stream2));
   } else if (h->host_mode == 1 && cio_supported(h->G) && !h->p.use_terrain) {
     // zero copy: the step kernel loads the actions from and stores its results to the mapped pinned buffers; every such
     // access is a contiguous 16-byte-vectorised block per warp (see srb_step_kernel), i.e. full-size PCIe transactions
@@ -423,7 +452,7 @@ extern "C" int srb_host_timeline(srb_env* h, int32_t enable, float out_ms[5]) {
 
 extern "C" int srb_set_host_mode(srb_env* h, int32_t mode) {
   if (!h) return fail(-1, "srb_set_host_mode: null handle");
-  if (mode != 0 && mode != 1 && mode != 2) return fail(-1, "srb_set_host_mode: mode must be 0 (staged copies), 1 (zero copy) or 2 (split)");
+  if (mode < 0 || mode > 3) return fail(-1, "srb_set_host_mode: mode must be 0 (staged copies), 1 (zero copy), 2 (split) or 3 (split, window columns only)");
   h->host_mode = mode;
   return 0;
 }

@@ -1437,10 +1437,12 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
 // `self_src` != null (patch launch): the 25 self features of every row are copied from there (device rows) to dst, and the window
 // is rewritten only for environments flagged in `only_done` (auto-reset in the step just finished: their window changed; null =
 // no environment, i.e. auto-reset is off).
+// `patch_only` (mode 3, where the step kernel itself stores the self features to the host rows and only the window columns travel by
+// copy engine): windows of the `only_done` environments, no self features.
 // `after_inc`: the training variant takes the observation after current_frame += 1.  One 160-thread block per environment.
 template <typename real>
 __global__ void srb_obs_window_kernel(int N, int Npad, const int* __restrict__ ist, const ClipDesc<real>* __restrict__ clips, int after_inc,
-                                      const uint8_t* __restrict__ only_done, const float* __restrict__ self_src, float* __restrict__ dst) {
+                                      const uint8_t* __restrict__ only_done, const float* __restrict__ self_src, float* __restrict__ dst, int patch_only) {
   const int e = blockIdx.x;
   if (e >= N) return;
   const int i = threadIdx.x;
@@ -1448,7 +1450,7 @@ __global__ void srb_obs_window_kernel(int N, int Npad, const int* __restrict__ i
     const int c = i - 5 * FEAT_W;
     dst[(size_t)e * OBS_W + c] = self_src[(size_t)e * OBS_W + c];
   }
-  if (self_src != nullptr && (only_done == nullptr || !only_done[e])) return;      // patch launch: windows of auto-reset environments only
+  if ((self_src != nullptr || patch_only) && (only_done == nullptr || !only_done[e])) return;      // patch launch: windows of auto-reset environments only
   if (i >= 5 * FEAT_W) return;
   const int frame = ist[(size_t)I_FRAME * Npad + e], rif = ist[(size_t)I_RIF * Npad + e], clip = ist[(size_t)I_CLIP * Npad + e];
   const ClipDesc<real> cd = clips[clip];

@@ -147,7 +147,8 @@ class SRBVecEnv:
         return p["obs"], p["rew"], p["done"], p["rinfo"]
 
     def set_host_mode(self, mode):
-        """step_host data movement: 1 = zero copy through mapped pinned memory (default), 0 = staged copies."""
+        """step_host data movement: 1 = zero copy through mapped pinned memory (default), 0 = staged copies, 2 / 3 = split forms
+        (look-ahead windows by copy engine while the step kernel runs; see include/srbtrack_b200.h)."""
         check(self.lib.srb_set_host_mode(self._h, int(mode)))
 
     def host_timeline(self, enable=True):

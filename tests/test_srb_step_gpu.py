@@ -241,7 +241,7 @@ def test_tracking_action_kernel_matches_host_formula(built_lib):
     env.close()
 
 
-@pytest.mark.parametrize("mode,n,lanes", [(2, 64, 8), (2, 61, 8), (2, 37, 4), (1, 64, 8), (0, 64, 8), (1, 61, 8), (1, 37, 4), (1, 16, 2)])
+@pytest.mark.parametrize("mode,n,lanes", [(3, 64, 8), (3, 61, 8), (3, 37, 4), (2, 64, 8), (2, 61, 8), (2, 37, 4), (1, 64, 8), (0, 64, 8), (1, 61, 8), (1, 37, 4), (1, 16, 2)])
 def test_host_buffer_step_equals_device_step(built_lib, mode, n, lanes):
     """srb_step_host (host-buffer path used for the e2e number) returns what srb_step returns: zero-copy mode (the
     coalesced-I/O kernel writing mapped pinned memory, incl. ragged last warps and auto-resets), staged copies, and the

@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 clips = build_clip_tables(["ref_contact/stand1.motion.npz", "ref_contact/aiming_show.motion.npz"], data_root=os.path.join(R, "tests", "golden"))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for mode in (2, 1, 0, 2, 1):
+for mode in (3, 1, 2, 0, 3, 1):
     env = SRBVecEnv(clips, n, variant="test", precision=32, auto_reset=True, seed=1)
     env.set_host_mode(mode)
     env.reset()
