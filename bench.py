@@ -64,6 +64,9 @@ def parse():
                     help="terrain = BASELINE config 3 (SRBEnv5_mocap_list_terrain_window on the playground height fields); not the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="the per-rollout exchange: fused = statistics + all-reduce in ONE kernel over NVLink peer memory (srb_rollout_stats_allreduce); "
+                         "nccl = statistics kernel + torch.distributed all-reduce")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (fp64, terrain, gym_cdm2, FK, MMSTO)")
     ap.add_argument("--flush", default="write", choices=["write", "read", "none"],
                     help="L2 flush between steps: write a 256 MiB buffer (default, the timing rule), read it, or nothing (diagnostic)")
@@ -288,14 +291,40 @@ def run_ours(args, rank, local_rank, world):
             if timed:                                                       # chunk and at the end of the timed loop
                 cev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 cev[0].record()
-            acc.zero_()                                                     # one rollout chunk's sufficient statistics
-            env.rollout_stats(acc)                                          # obs statistics kernel + episode counters (device copy)
-            if dist is not None:
-                dist.all_reduce(acc)                                        # NCCL over NVLink
+            if fused:
+                env.rollout_stats_allreduce(acc)                            # statistics + all-reduce over NVLink peer memory: ONE kernel
+            else:
+                acc.zero_()                                                 # one rollout chunk's sufficient statistics
+                env.rollout_stats(acc)                                      # obs statistics kernel + episode counters (device copy)
+                if dist is not None:
+                    dist.all_reduce(acc)                                    # NCCL over NVLink
             if timed:
                 cev[1].record()
         return ev, cev
 
+    fused = args.collective == "fused"
+    fused_check = None
+    if fused:
+        # set-up (CUDA IPC handles of the ranks' exchange blocks) + untimed cross-check of the fused collective against the statistics
+        # kernel + NCCL on the same observations; any failure (no peer access on this box, ...) falls back to the NCCL form on ALL ranks
+        ok = 1
+        try:
+            env.connect_ranks(dist, rank, world)
+            ref = torch.zeros_like(acc)
+            env.rollout_stats(ref)
+            if dist is not None:
+                dist.all_reduce(ref)
+            env.rollout_stats_allreduce(acc)
+            torch.cuda.synchronize()
+            ok = int(bool(torch.allclose(acc, ref, rtol=1e-12, atol=1e-9)) and env.xchg_status() == 0)
+        except Exception as e:                                              # noqa: BLE001
+            print(f"[bench] rank {rank}: fused collective unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = 0
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        if dist is not None:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        fused = bool(int(okt.item()))
+        fused_check = fused
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -393,7 +422,8 @@ def run_ours(args, rank, local_rank, world):
                                    f"all environments re-seeded every {TERRAIN_EPISODE} steps outside the timed events" if args.variant == "terrain" else
                                    f"device-side reference-tracking controller + N(0,{SIGMA}^2), auto-reset on done"),
                        "l2": {"write": "flushed between steps (256 MiB write)", "read": "DIAGNOSTIC: evicted between steps by reading 256 MiB", "none": "DIAGNOSTIC: not flushed"}[args.flush] + "; per-step CUDA events on the launching stream",
-                       "collective": f"obs-normaliser statistics kernel + episode counters, one NCCL all-reduce (304 doubles) every {ROLLOUT} steps and at the end of the timed loop: {len(cevs)} inside the timed total",
+                       "collective": (f"ONE kernel: obs-normaliser statistics + episode counters + their all-reduce over NVLink peer memory (304 doubles, srb_rollout_stats_allreduce; checked against the NCCL path before timing: {fused_check})" if fused else
+                                      "obs-normaliser statistics kernel + episode counters, one NCCL all-reduce (304 doubles)") + f" every {ROLLOUT} steps and at the end of the timed loop: {len(cevs)} inside the timed total",
                        "lanes_per_env": env_lanes(args), "median_step_ms": med_ms_max, "wall_s_timed_loop": t_wall,
                        "episodes_finished": int(ep[2]), "mean_episode_len": float(ep[1] / max(ep[2], 1))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

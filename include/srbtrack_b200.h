@@ -107,6 +107,18 @@ int srb_set_state(srb_env* env, int32_t env_index, const double* reals, const in
  * acc_dev[1 + 2*150] += (count, sum x, sum x^2) over the N rows of obs_dev.  The caller all-reduces acc. */
 int srb_obs_stats(srb_env* env, const float* obs_dev, double* acc_dev, void* stream);
 
+/* The same statistics AND their all-reduce over the ranks of one node in ONE kernel over NVLink / NVSwitch peer memory (replaces
+ * srb_obs_stats + srb_episode_stats_device + an NCCL all-reduce, the per-rollout exchange of SURVEY 8e):
+ *   srb_xchg_create   allocates this rank's exchange block and returns its 64-byte CUDA IPC handle;
+ *   srb_xchg_connect  opens the blocks of all ranks (handles[world][64], gathered by the caller, e.g. with torch.distributed);
+ *   srb_rollout_stats_allreduce  acc_dev[1 + 2*150 + 3] = sum over ranks of (count, sum x, sum x^2 | episode return, length, count sums);
+ *                     a collective: every rank calls it the same number of times; results are bit-identical on all ranks;
+ *   srb_xchg_status   err = 1 if a peer's contribution never arrived (the kernel gives up after ~1 s instead of hanging). */
+int srb_xchg_create(srb_env* env, int32_t rank, int32_t world, void* handle_out);
+int srb_xchg_connect(srb_env* env, const void* handles);
+int srb_rollout_stats_allreduce(srb_env* env, const float* obs_dev, double* acc_dev, void* stream);
+int srb_xchg_status(srb_env* env, int32_t* err_out);
+
 /* pack_obs_extra (gym_trackSRB/taesooLib/DeltaExtractor.py:1015-1036): out_dev[N][29] doubles = the SRB state in taesooLib's
  * Y-up convention: pose_tl 7 (translation, quaternion w x y z) | dq 6 (world angular, world linear velocity) | left / right
  * foot frame 7 each (translation, quaternion) | left / right contact flag.  Input of fullbody_extract (include/mmsto_b200.h). */

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "srb_pack_obs_extra": (C.c_int, [_P, _P, _P]),
     "srb_episode_stats": (C.c_int, [_P, _P, C.c_int32]),
     "srb_episode_stats_device": (C.c_int, [_P, _P, _P]),
+    "srb_xchg_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "srb_xchg_connect": (C.c_int, [_P, _P]),
+    "srb_rollout_stats_allreduce": (C.c_int, [_P, _P, _P, _P]),
+    "srb_xchg_status": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "srb_tracking_action": (C.c_int, [_P, C.c_float, C.c_uint64, C.c_uint32, _P, _P]),
     "srb_upload_terrain": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P]),
     "srb_set_planar_offsets": (C.c_int, [_P, _P]),

@@ -22,6 +22,12 @@ int srb_set_error(int code, const std::string& msg) { return fail(code, msg); } 
     if (e_ != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
+// ---- exchange block of one rank: IPC-shared device memory, two slots used alternately (epoch parity) ----------------------------
+enum { XCHG_W = 1 + 2 * OBS_W + 3, XCHG_MAX_RANKS = 16 };
+struct XchgSlot { double v[XCHG_W]; unsigned long long flag; unsigned long long pad[7]; };
+struct XchgBlock { XchgSlot slot[2]; };
+struct XchgPeers { XchgBlock* p[XCHG_MAX_RANKS]; };
+
 struct ClipStore { void* frames = nullptr; float* feat = nullptr; int nframes = 0, cycle = 0, is_stand = 0; };
 
 struct srb_env {
@@ -49,6 +55,9 @@ struct srb_env {
   int host_mode = 1;                    // srb_step_host: 1 = zero copy (default), 2 = split (windows by copy engine), 0 = staged copies
   // terrain (variant 2)
   TerrainDev* terrain_dev = nullptr; std::vector<float*> hf_data; double* box_dev = nullptr;
+  // fused statistics + all-reduce over NVLink peer memory (srb_rollout_stats_allreduce)
+  int x_rank = -1, x_world = 0; unsigned long long x_epoch = 0;
+  XchgBlock* x_mine = nullptr; XchgBlock* x_peer[XCHG_MAX_RANKS] = {nullptr}; double* x_scratch = nullptr; int* x_err = nullptr;
 };
 static const int MAX_CLIPS = 64;
 
@@ -162,6 +171,8 @@ extern "C" int srb_destroy(srb_env* h) {
   if (h->ev_win) cudaEventDestroy(h->ev_win);
   if (h->ev_dma) cudaEventDestroy(h->ev_dma);
   for (int i = 0; i < 5; i++) if (h->tl[i]) cudaEventDestroy(h->tl[i]);
+  for (int r = 0; r < h->x_world; r++) if (r != h->x_rank && h->x_peer[r]) cudaIpcCloseMemHandle(h->x_peer[r]);
+  cudaFree(h->x_mine); cudaFree(h->x_scratch); cudaFree(h->x_err);
   delete h;
   return 0;
 }
@@ -546,6 +557,136 @@ extern "C" int srb_obs_stats(srb_env* h, const float* obs_dev, double* acc_dev, 
   srb_obs_stats_kernel<<<blocks, 160, 0, (cudaStream_t)stream>>>(obs_dev, h->N, acc_dev);
   h->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- the path's one collective as ONE kernel over NVLink / NVSwitch peer memory ------------------------------------------------
+// acc = sum over ranks of [count, sum x, sum x^2 of this rank's observation rows | episode return / length / count sums].
+// Phase 1 (all CTAs): column sums of the rank's obs rows into a scratch vector.  Phase 2 (the CTA that finishes last): publish the
+// vector in this rank's exchange slot (release store of the epoch into the slot's flag, system scope), then for every rank in rank
+// order: wait for that rank's flag (acquire load through the peer mapping) and add its vector with volatile peer loads -- every rank
+// sums in the same order, so all ranks hold bit-identical results.  Slots alternate with the epoch's parity: a rank can be at most
+// one collective ahead of the slowest reader of its slot (it needs that reader's NEXT flag to get further), so two slots suffice.
+// A flag that never arrives (a peer died) ends the wait after ~1 s and sets the error word instead of hanging the device.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void srb_stats_allreduce_kernel(const float* __restrict__ obs, int N, const double* __restrict__ ep_stats, double* __restrict__ scratch,
+                                           XchgPeers peers, int rank, int world, unsigned long long epoch, double* __restrict__ acc, int* __restrict__ err) {
+  const int j = threadIdx.x;
+  const int rows_per = (N + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(N, r0 + rows_per);
+  if (j < OBS_W) {
+    double s = 0, q = 0;
+    for (int r = r0; r < r1; r++) { double v = (double)obs[(size_t)r * OBS_W + j]; s += v; q += v * v; }
+    if (r1 > r0) { atomicAdd(scratch + 1 + j, s); atomicAdd(scratch + 1 + OBS_W + j, q); }
+  }
+  if (j == 0 && r1 > r0) atomicAdd(scratch, (double)(r1 - r0));
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (j == 0) last = atomicAdd(reinterpret_cast<int*>(scratch + XCHG_W), 1) == (int)gridDim.x - 1;     // ticket counter behind the vector
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int sl = (int)(epoch & 1ull);
+  XchgSlot* mine = &peers.p[rank]->slot[sl];
+  for (int k = j; k < XCHG_W; k += blockDim.x) {
+    const double v = k < 1 + 2 * OBS_W ? __ldcg(scratch + k) : ep_stats[k - (1 + 2 * OBS_W)];
+    mine->v[k] = v;
+    if (k < 1 + 2 * OBS_W) scratch[k] = 0.0;                       // ready for the next call
+  }
+  if (j == 0) *reinterpret_cast<int*>(scratch + XCHG_W) = 0;
+  __threadfence_system();
+  __syncthreads();
+  if (j == 0) st_release_sys(&mine->flag, epoch);
+  double tot[(XCHG_W + 159) / 160];
+#pragma unroll
+  for (int i = 0; i < (XCHG_W + 159) / 160; i++) tot[i] = 0.0;
+  __shared__ int bad;
+  if (j == 0) bad = 0;
+  for (int r = 0; r < world; r++) {
+    const XchgSlot* ps = &peers.p[r]->slot[sl];
+    if (j == 0 && r != rank) {
+      unsigned long long spins = 0;
+      while (ld_acquire_sys(&ps->flag) < epoch) {
+        __nanosleep(200);
+        if (++spins > (1ull << 22)) { bad = 1; break; }
+      }
+    }
+    __syncthreads();
+    if (bad) break;
+#pragma unroll
+    for (int i = 0; i < (XCHG_W + 159) / 160; i++) {
+      const int k = j + i * 160;
+      if (k < XCHG_W) tot[i] += *reinterpret_cast<const volatile double*>(&ps->v[k]);
+    }
+  }
+  if (bad) { if (j == 0) atomicExch(err, 1); return; }
+#pragma unroll
+  for (int i = 0; i < (XCHG_W + 159) / 160; i++) { const int k = j + i * 160; if (k < XCHG_W) acc[k] = tot[i]; }
+}
+
+extern "C" int srb_xchg_create(srb_env* h, int32_t rank, int32_t world, void* handle_out) {
+  if (!h || !handle_out) return fail(-1, "srb_xchg_create: null argument");
+  if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world) return fail(-1, "srb_xchg_create: rank / world out of range");
+  if (h->x_mine) return fail(-1, "srb_xchg_create: already created");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMalloc(&h->x_mine, sizeof(XchgBlock)));
+  CK(cudaMemset(h->x_mine, 0, sizeof(XchgBlock)));
+  CK(cudaMalloc(&h->x_scratch, sizeof(double) * (XCHG_W + 1)));
+  CK(cudaMemset(h->x_scratch, 0, sizeof(double) * (XCHG_W + 1)));
+  CK(cudaMalloc(&h->x_err, sizeof(int)));
+  CK(cudaMemset(h->x_err, 0, sizeof(int)));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mh;
+  CK(cudaIpcGetMemHandle(&mh, h->x_mine));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &mh, 64);
+  h->x_rank = rank; h->x_world = world; h->x_epoch = 0;
+  h->x_peer[rank] = h->x_mine;
+  return 0;
+}
+
+extern "C" int srb_xchg_connect(srb_env* h, const void* handles) {
+  if (!h || !handles || !h->x_mine) return fail(-1, "srb_xchg_connect: create the exchange first");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < h->x_world; r++) {
+    if (r == h->x_rank) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->x_peer[r] = (XchgBlock*)p;
+  }
+  return 0;
+}
+
+extern "C" int srb_rollout_stats_allreduce(srb_env* h, const float* obs_dev, double* acc_dev, void* stream) {
+  if (!h || !obs_dev || !acc_dev) return fail(-1, "srb_rollout_stats_allreduce: null argument");
+  if (!h->x_mine) return fail(-1, "srb_rollout_stats_allreduce: no exchange (srb_xchg_create / srb_xchg_connect)");
+  for (int r = 0; r < h->x_world; r++) if (!h->x_peer[r]) return fail(-1, "srb_rollout_stats_allreduce: exchange not connected");
+  CK(cudaSetDevice(h->cfg.device));
+  XchgPeers P;
+  for (int r = 0; r < XCHG_MAX_RANKS; r++) P.p[r] = r < h->x_world ? h->x_peer[r] : nullptr;
+  int blocks = h->N < 148 * 4 ? (h->N + 7) / 8 : 148 * 4;
+  if (blocks < 1) blocks = 1;
+  h->x_epoch += 1;
+  srb_stats_allreduce_kernel<<<blocks, 160, 0, (cudaStream_t)stream>>>(obs_dev, h->N, h->ep_stats, h->x_scratch, P, h->x_rank, h->x_world, h->x_epoch, acc_dev, h->x_err);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srb_xchg_status(srb_env* h, int32_t* err_out) {
+  if (!h || !err_out || !h->x_err) return fail(-1, "srb_xchg_status: no exchange");
+  CK(cudaSetDevice(h->cfg.device));
+  int e = 0;
+  CK(cudaMemcpy(&e, h->x_err, sizeof(int), cudaMemcpyDeviceToHost));
+  *err_out = e;
   return 0;
 }
 

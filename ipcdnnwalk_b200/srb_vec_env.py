@@ -314,6 +314,35 @@ class SRBVecEnv:
         check(self.lib.srb_episode_stats_device(self._h, C.c_void_p(acc.data_ptr() + 301 * 8), self._stream()))
         return acc
 
+    def connect_ranks(self, dist, rank, world):
+        """Set up the peer-memory exchange of `rollout_stats_allreduce` between the ranks of one node: every rank's exchange block is
+        exported as a CUDA IPC handle, the handles are all-gathered with torch.distributed (plumbing) and opened.  Call once per env."""
+        t = self.torch
+        buf = (C.c_ubyte * 64)()
+        check(self.lib.srb_xchg_create(self._h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+        mine = t.tensor(list(bytes(buf)), dtype=t.uint8, device=self.device)
+        if world > 1:
+            parts = [t.zeros(64, dtype=t.uint8, device=self.device) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            allh = t.stack(parts).cpu().numpy().tobytes()
+        else:
+            allh = bytes(buf)
+        self._xchg_handles = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+        check(self.lib.srb_xchg_connect(self._h, C.cast(self._xchg_handles, C.c_void_p)))
+        if world > 1:
+            dist.barrier()                                   # every rank has opened every block before the first collective
+
+    def rollout_stats_allreduce(self, acc):
+        """acc (float64 [304], device) = all-rank sum of this step's observation statistics and the episode counters, computed and
+        exchanged by ONE kernel over NVLink peer memory (collective: call on every rank).  Overwrites acc."""
+        check(self.lib.srb_rollout_stats_allreduce(self._h, _ptr(self.obs), _ptr(acc), self._stream()))
+        return acc
+
+    def xchg_status(self):
+        e = C.c_int32(0)
+        check(self.lib.srb_xchg_status(self._h, C.byref(e)))
+        return int(e.value)
+
     def episode_stats(self, clear=False):
         out = np.zeros(3)
         check(self.lib.srb_episode_stats(self._h, _ptr(out), int(clear)))
