@@ -139,6 +139,9 @@ __global__ void cdm_reset_const_kernel(const double* tab, int F, Params<double> 
   *out = r;
 }
 
+static int cdm_create_device_state(cdm_env* h);
+extern "C" int cdm_destroy(cdm_env* h);
+
 extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   if (!cfg || !out) return srb_set_error(-1, "cdm_create: null argument");
   if (cfg->num_envs <= 0) return srb_set_error(-1, "cdm_create: num_envs must be positive");
@@ -157,6 +160,13 @@ extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   default_params(h->hp);
   memset(&h->skel, 0, sizeof(h->skel));
   memset(&h->ground, 0, sizeof(h->ground));
+  const int rc = cdm_create_device_state(h);
+  if (rc) { cdm_destroy(h); return rc; }                   // nothing half-built survives a failed allocation
+  *out = h;
+  return 0;
+}
+
+static int cdm_create_device_state(cdm_env* h) {
   CK(cudaMalloc(&h->st, h->rsz * NF_REAL * h->Npad));
   CK(cudaMemset(h->st, 0, h->rsz * NF_REAL * h->Npad));
   CK(cudaMalloc(&h->ist, sizeof(int) * NF_INT * h->Npad));
@@ -167,7 +177,6 @@ extern "C" int cdm_create(const cdm_config* cfg, cdm_env** out) {
   CK(cudaMemset(h->ep_stats, 0, sizeof(double) * 3));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
-  *out = h;
   return 0;
 }
 
@@ -247,23 +256,26 @@ extern "C" int cdm_reset(cdm_env* h, const int32_t* env_idx_host, int32_t count,
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int* idx_dev = nullptr; double* plan_dev = nullptr;
+  // temporaries are released on every path, also when a later allocation or copy fails
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFree(idx_dev); cudaFree(plan_dev); return srb_set_error(-2, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   if (env_idx_host) {
     for (int i = 0; i < count; i++) if (env_idx_host[i] < 0 || env_idx_host[i] >= h->N) return srb_set_error(-1, "cdm_reset: env index out of range");
-    CK(cudaMalloc(&idx_dev, sizeof(int) * count));
-    CK(cudaMemcpyAsync(idx_dev, env_idx_host, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+    CKR(cudaMalloc(&idx_dev, sizeof(int) * count));
+    CKR(cudaMemcpyAsync(idx_dev, env_idx_host, sizeof(int) * count, cudaMemcpyHostToDevice, s));
   }
   if (plan_host) {
-    CK(cudaMalloc(&plan_dev, sizeof(double) * PLAN_W * count));
-    CK(cudaMemcpyAsync(plan_dev, plan_host, sizeof(double) * PLAN_W * count, cudaMemcpyHostToDevice, s));
+    CKR(cudaMalloc(&plan_dev, sizeof(double) * PLAN_W * count));
+    CKR(cudaMemcpyAsync(plan_dev, plan_host, sizeof(double) * PLAN_W * count, cudaMemcpyHostToDevice, s));
   }
   if (h->cfg.precision == 64) do_reset<double>(h, idx_dev, count, plan_dev, obs_dev, s);
   else do_reset<float>(h, idx_dev, count, plan_dev, obs_dev, s);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev_state, s));
+  CKR(cudaGetLastError());
+  CKR(cudaEventRecord(h->ev_state, s));
   if (idx_dev || plan_dev) {
-    CK(cudaStreamSynchronize(s));
+    CKR(cudaStreamSynchronize(s));
     cudaFree(idx_dev); cudaFree(plan_dev);
   }
+#undef CKR
   return 0;
 }
 
@@ -435,8 +447,11 @@ extern "C" int tlterrain_create(int32_t device, int32_t rows, int32_t cols, doub
   CK(cudaSetDevice(device));
   tl_terrain* t = new tl_terrain();
   t->device = device;
-  CK(cudaMalloc(&t->h, sizeof(double) * (size_t)rows * cols));
-  CK(cudaMemcpy(t->h, heights_host, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice));
+  {
+    cudaError_t ce = cudaMalloc(&t->h, sizeof(double) * (size_t)rows * cols);
+    if (ce == cudaSuccess) ce = cudaMemcpy(t->h, heights_host, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(t->h); delete t; return srb_set_error(-2, std::string("tlterrain_create: ") + cudaGetErrorString(ce)); }
+  }
   t->T.h = t->h; t->T.rows = rows; t->T.cols = cols; t->T.size_x = size_x; t->T.size_z = size_z; t->T.tile = tile_along_z ? 1 : 0;
   *out = t;
   return 0;

@@ -70,9 +70,12 @@ extern "C" int fk_create(int32_t device, int32_t nb, const int32_t* parent, cons
   }
   k.n_pose = 7 + nang; k.n_dq = 6 + nang; k.maxdepth = maxd;
   k.inv_total_mass = total > 0 ? 1.0 / total : 0.0;
-  FCK(cudaSetDevice(device));
-  FCK(cudaMalloc(&s->dev, sizeof(fk::SkelConst)));
-  FCK(cudaMemcpy(s->dev, &k, sizeof(k), cudaMemcpyHostToDevice));
+  {
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->dev, sizeof(fk::SkelConst));
+    if (ce == cudaSuccess) ce = cudaMemcpy(s->dev, &k, sizeof(k), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(s->dev); delete s; return srb_set_error(-2, std::string("fk_create: ") + cudaGetErrorString(ce)); }
+  }
   s->hanyang = fk::Hanyang::matches(k);
   *out = s;
   return 0;

@@ -30,7 +30,7 @@ struct mmsto_solver {
   double* ws = nullptr; double* mc = nullptr; int ws_warps = 0;
   int* d_queue = nullptr; int max_warps = 592;   // solve: persistent warps (4 per SM) pulling windows from a counter
   double* d_kinv = nullptr; int kinv_nvar = 0;    // inverse KKT matrix of removeCOMsliding_online for kinv_nvar frames
-  double* d_zero = nullptr; int zero_n = 0;       // all-zero velocity constraints / contacts when the caller passes none
+  double* d_zero = nullptr; size_t zero_n = 0;       // all-zero velocity constraints / contacts when the caller passes none
   bool dirty = true;
   long long launches = 0;
 };
@@ -78,12 +78,12 @@ static int prepare(mmsto_solver* s, int n, bool solve) {
     CK(cudaMemset(s->ws, 0, wb)); CK(cudaMemset(s->mc, 0, mb));
     s->ws_warps = warps;
   }
-  const int zn = n * mmsto::MAXHS * mmsto::HS_W;
+  const size_t zn = (size_t)n * mmsto::MAXHS * mmsto::HS_W;
   if (zn > s->zero_n) {
     cudaFree(s->d_zero);
     CK(cudaMalloc(&s->d_zero, zn * sizeof(double)));
     std::vector<double> z(zn, 0.0);
-    for (int i = 0; i < n * mmsto::MAXHS; ++i) z[(size_t)i * mmsto::HS_W] = -1.0;      // frame -1: no constraint
+    for (size_t i = 0; i < (size_t)n * mmsto::MAXHS; ++i) z[i * mmsto::HS_W] = -1.0;      // frame -1: no constraint
     CK(cudaMemcpy(s->d_zero, z.data(), zn * sizeof(double), cudaMemcpyHostToDevice));
     s->zero_n = zn;
   }

@@ -114,6 +114,9 @@ static void default_params(Params<double>& p, int variant) {
 
 extern "C" const char* srb_last_error(void) { return g_err.c_str(); }
 
+static int create_device_state(srb_env* h);
+extern "C" int srb_destroy(srb_env* h);
+
 extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   if (!cfg || !out) return fail(-1, "srb_create: null argument");
   if (cfg->num_envs <= 0) return fail(-1, "srb_create: num_envs must be positive");
@@ -135,6 +138,13 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   h->Npad = (h->N + 31) / 32 * 32;
   h->rsz = cfg->precision == 64 ? 8 : 4;
   default_params(h->p, cfg->variant);
+  const int rc = create_device_state(h);
+  if (rc) { srb_destroy(h); return rc; }                  // nothing half-built survives a failed allocation
+  *out = h;
+  return 0;
+}
+
+static int create_device_state(srb_env* h) {
   CK(cudaMalloc(&h->st, h->rsz * NF_REAL * h->Npad));
   CK(cudaMemset(h->st, 0, h->rsz * NF_REAL * h->Npad));
   CK(cudaMalloc(&h->ist, sizeof(int) * NF_INT * h->Npad));
@@ -152,7 +162,6 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   CK(cudaEventCreateWithFlags(&h->ev_win, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_dma, cudaEventDisableTiming));
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&h->tl[i]));
-  *out = h;
   return 0;
 }
 
@@ -243,23 +252,26 @@ extern "C" int srb_reset(srb_env* h, const int32_t* env_idx_host, int32_t count,
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int* idx_dev = nullptr; double* plan_dev = nullptr;
+  // temporaries are released on every path (CKR), also when a later allocation or copy fails
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFree(idx_dev); cudaFree(plan_dev); return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   if (env_idx_host) {
     for (int i = 0; i < count; i++) if (env_idx_host[i] < 0 || env_idx_host[i] >= h->N) return fail(-1, "srb_reset: env index out of range");
-    CK(cudaMalloc(&idx_dev, sizeof(int) * count));
-    CK(cudaMemcpyAsync(idx_dev, env_idx_host, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+    CKR(cudaMalloc(&idx_dev, sizeof(int) * count));
+    CKR(cudaMemcpyAsync(idx_dev, env_idx_host, sizeof(int) * count, cudaMemcpyHostToDevice, s));
   }
   if (plan_host) {
-    CK(cudaMalloc(&plan_dev, sizeof(double) * 9 * count));
-    CK(cudaMemcpyAsync(plan_dev, plan_host, sizeof(double) * 9 * count, cudaMemcpyHostToDevice, s));
+    CKR(cudaMalloc(&plan_dev, sizeof(double) * 9 * count));
+    CKR(cudaMemcpyAsync(plan_dev, plan_host, sizeof(double) * 9 * count, cudaMemcpyHostToDevice, s));
   }
   if (h->cfg.precision == 64) do_reset<double>(h, idx_dev, count, plan_dev, obs_dev, s);
   else do_reset<float>(h, idx_dev, count, plan_dev, obs_dev, s);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev_state, s));
+  CKR(cudaGetLastError());
+  CKR(cudaEventRecord(h->ev_state, s));
   if (idx_dev || plan_dev) {
-    CK(cudaStreamSynchronize(s));
+    CKR(cudaStreamSynchronize(s));
     cudaFree(idx_dev); cudaFree(plan_dev);
   }
+#undef CKR
   return 0;
 }
 
@@ -763,24 +775,13 @@ extern "C" int srb_upload_terrain(srb_env* h, const double plane_size[2], int32_
   if (!h || !plane_size) return fail(-1, "srb_upload_terrain: null argument");
   if (n_hf < 0 || n_hf > MAX_HF || n_body < 0 || n_body > MAX_TBODY || n_box < 0) return fail(-1, "srb_upload_terrain: too many height fields / bodies");
   if ((n_hf && !hfs) || (n_box && !boxes) || (n_body && !bodies)) return fail(-1, "srb_upload_terrain: null table");
-  CK(cudaSetDevice(h->cfg.device));
+  // 1. validate and build everything on the host; the installed terrain is untouched until the new one is complete
+  for (int i = 0; i < n_hf; i++)
+    if (!hfs[i].data_host || hfs[i].nrow < 2 || hfs[i].ncol < 2) return fail(-1, "srb_upload_terrain: bad height field");
   TerrainDev T;
   memset(&T, 0, sizeof(T));
   T.enabled = 1; T.n_hf = n_hf; T.n_body = n_body; T.n_box = n_box;
   T.plane_geom = plane_geom; T.plane_hx = plane_size[0]; T.plane_hy = plane_size[1];
-  for (auto p : h->hf_data) cudaFree(p);
-  h->hf_data.clear();
-  for (int i = 0; i < n_hf; i++) {
-    const srb_hfield& s = hfs[i];
-    if (!s.data_host || s.nrow < 2 || s.ncol < 2) return fail(-1, "srb_upload_terrain: bad height field");
-    float* d = nullptr;
-    CK(cudaMalloc(&d, sizeof(float) * (size_t)s.nrow * s.ncol));
-    CK(cudaMemcpy(d, s.data_host, sizeof(float) * (size_t)s.nrow * s.ncol, cudaMemcpyHostToDevice));
-    h->hf_data.push_back(d);
-    HFieldDev& o = T.hf[i];
-    o.data = d; o.nrow = s.nrow; o.ncol = s.ncol; o.sx = s.size[0]; o.sy = s.size[1]; o.sz = s.size[2];
-    o.px = s.pos[0]; o.py = s.pos[1]; o.pz = s.pos[2]; o.geom_id = s.geom_id;
-  }
   std::vector<double> bx((size_t)n_box * 5);
   for (int k = 0; k < n_box; k++) {
     if (k > 0 && boxes[k].geom_id != boxes[k - 1].geom_id + 1) return fail(-1, "srb_upload_terrain: boxes must be consecutive geoms in model order");
@@ -805,14 +806,36 @@ extern "C" int srb_upload_terrain(srb_env* h, const double plane_size[2], int32_
     }
     if (o.first < 0) o.first = 0;
   }
-  cudaFree(h->box_dev); h->box_dev = nullptr;
-  if (n_box) {
-    CK(cudaMalloc(&h->box_dev, sizeof(double) * bx.size()));
-    CK(cudaMemcpy(h->box_dev, bx.data(), sizeof(double) * bx.size(), cudaMemcpyHostToDevice));
+  // 2. new device buffers; on any failure they are released and the old terrain stays installed
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<float*> new_hf;
+  double* new_box = nullptr;
+  TerrainDev* new_dev = h->terrain_dev;
+  auto drop = [&]() { for (auto p : new_hf) cudaFree(p); cudaFree(new_box); if (new_dev != h->terrain_dev) cudaFree(new_dev); };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { drop(); return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  for (int i = 0; i < n_hf; i++) {
+    const srb_hfield& s = hfs[i];
+    float* d = nullptr;
+    CKT(cudaMalloc(&d, sizeof(float) * (size_t)s.nrow * s.ncol));
+    new_hf.push_back(d);
+    CKT(cudaMemcpy(d, s.data_host, sizeof(float) * (size_t)s.nrow * s.ncol, cudaMemcpyHostToDevice));
+    HFieldDev& o = T.hf[i];
+    o.data = d; o.nrow = s.nrow; o.ncol = s.ncol; o.sx = s.size[0]; o.sy = s.size[1]; o.sz = s.size[2];
+    o.px = s.pos[0]; o.py = s.pos[1]; o.pz = s.pos[2]; o.geom_id = s.geom_id;
   }
-  T.box = h->box_dev;
-  if (!h->terrain_dev) CK(cudaMalloc(&h->terrain_dev, sizeof(TerrainDev)));
-  CK(cudaMemcpy(h->terrain_dev, &T, sizeof(T), cudaMemcpyHostToDevice));
+  if (n_box) {
+    CKT(cudaMalloc(&new_box, sizeof(double) * bx.size()));
+    CKT(cudaMemcpy(new_box, bx.data(), sizeof(double) * bx.size(), cudaMemcpyHostToDevice));
+  }
+  T.box = new_box;
+  if (!new_dev) CKT(cudaMalloc(&new_dev, sizeof(TerrainDev)));
+  CKT(cudaDeviceSynchronize());                            // no launch may still read the tables that are about to be replaced
+  CKT(cudaMemcpy(new_dev, &T, sizeof(T), cudaMemcpyHostToDevice));
+#undef CKT
+  // 3. swap
+  for (auto p : h->hf_data) cudaFree(p);
+  cudaFree(h->box_dev);
+  h->hf_data = new_hf; h->box_dev = new_box; h->terrain_dev = new_dev;
   return 0;
 }
 

@@ -321,8 +321,17 @@ __device__ __forceinline__ void write_obs(const EnvState<real>& s, const ClipDes
       w[21] = c == 0 ? 1.f : 0.f; w[22] = c == 1 ? 1.f : 0.f; w[23] = c == 2 ? 1.f : 0.f; w[24] = c == 3 ? 1.f : 0.f;
     }
   } else if (active && window) {
-    // 5 consecutive frame records are contiguous in the feature table (clamped only at the table end)
-    int f0 = min(s.frame + s.rif + 1, max(cd.nframes - 5, 0));
+    // 5 consecutive frame records are contiguous in the feature table; at the table end every frame index is clamped on its own
+    // (min(f, nframes - 1)), the rule the terrain variant, the reward and the termination test use too.  The reference has no clamp
+    // (a clip shorter than start frame + 512 + 6 would raise IndexError there), so only consistency matters.
+    const int f0 = s.frame + s.rif + 1;
+    if (f0 + 4 > cd.nframes - 1) {
+      for (int i = lane; i < 5 * FEAT_W; i += G) {
+        const int wi = i / FEAT_W, c = i - wi * FEAT_W;
+        o[FEAT_W + i] = __ldg(cd.feat + (size_t)min(max(f0 + wi, 0), cd.nframes - 1) * FEAT_W + c);
+      }
+      return;
+    }
     const float* __restrict__ src = cd.feat + (size_t)f0 * FEAT_W;
     constexpr int PER = (5 * FEAT_W + G - 1) / G;
     if constexpr (PER <= 32) {
@@ -1042,7 +1051,7 @@ __global__ void __launch_bounds__(32) srb_step_kernel(const StepArgs<real> A) {
         ptr = (const char*)(cd.frames + (size_t)fr * CLIP_W) + ((id - 3) & 1) * 128;
         if (sizeof(real) == 4 && ((id - 3) & 1)) ptr -= 128;
       } else {
-        int fw = min(f0 + 1 + (P.obs_after_inc ? 1 : 0), max(cd.nframes - 5, 0));
+        int fw = min(f0 + 1 + (P.obs_after_inc ? 1 : 0), max(cd.nframes - 5, 0));      // (a prefetch hint only)
         ptr = (const char*)(cd.feat + (size_t)fw * FEAT_W) + (id - 11) * 128;
       }
       asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
@@ -1454,8 +1463,9 @@ __global__ void srb_obs_window_kernel(int N, int Npad, const int* __restrict__ i
   if (i >= 5 * FEAT_W) return;
   const int frame = ist[(size_t)I_FRAME * Npad + e], rif = ist[(size_t)I_RIF * Npad + e], clip = ist[(size_t)I_CLIP * Npad + e];
   const ClipDesc<real> cd = clips[clip];
-  const int f0 = min(frame + rif + 1 + (after_inc ? 1 : 0), max(cd.nframes - 5, 0));
-  dst[(size_t)e * OBS_W + FEAT_W + i] = __ldg(cd.feat + (size_t)f0 * FEAT_W + i);
+  const int f0 = frame + rif + 1 + (after_inc ? 1 : 0);
+  const int wi = i / FEAT_W, c = i - wi * FEAT_W;
+  dst[(size_t)e * OBS_W + FEAT_W + i] = __ldg(cd.feat + (size_t)min(max(f0 + wi, 0), cd.nframes - 1) * FEAT_W + c);   // per-frame clamp, as write_obs
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -158,8 +158,9 @@ class ShortTrajOpt:
                     k += 1
         return v
 
-    def solveEndEffectors_euler(self, euler_mot, gpos_target, x_original, dx, ddx, com, momentum, con=None, velcon=None, stream=None):
-        """All arrays [n, ...] as in include/mmsto_b200.h -> (x [n, nf, ndof] torch.float64 on the device, info [n, 4])."""
+    def solveEndEffectors_euler(self, euler_mot, gpos_target, x_original, dx, ddx, com, momentum, con=None, velcon=None):
+        """All arrays [n, ...] as in include/mmsto_b200.h -> (x [n, nf, ndof] torch.float64 on the device, info [n, 4]).  Runs on torch's
+        current stream (the staging tensors are created on it, so their copies are ordered before the kernel)."""
         torch = self.torch
         nf, nd = self.nf, self.ndof
         n = int(x_original.shape[0])
@@ -177,7 +178,7 @@ class ShortTrajOpt:
         vc = self._dev(velcon, (n, 4, 10)) if velcon is not None else None
         x = torch.empty(n, nf, nd, dtype=torch.float64, device=self.device)
         info = torch.empty(n, 4, dtype=torch.float64, device=self.device)
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _check(self.lib, self.lib.mmsto_solve(self._h, n, _ptr(xo), _ptr(dxd), _ptr(ddxd), _ptr(em), _ptr(gt), _ptr(cm), _ptr(mo), _ptr(cn), _ptr(vc),
                                               _ptr(x), _ptr(info), st))
         return x, info
