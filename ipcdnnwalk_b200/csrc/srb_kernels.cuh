@@ -477,6 +477,10 @@ template <typename real> __device__ __forceinline__ void ldl_solve6(const real* 
 template <typename real, int G, int NCOLS = 40> struct QP {
   static constexpr int NC = (NCOLS + G - 1) / G;
   real a[NC][6];
+  // G == 4 with the SRBTrack column order: a lane's ten columns are ONE friction direction over both feet (k even: left, k odd: right)
+  // and the five sites (k >> 1): their linear parts are bl (= M^-1 B, the same for both feet) times the foot's contact flag mf.
+  static constexpr bool SHARED_LIN4 = (G == 4 && NCOLS == 40);
+  real bl[3], mf[2];
 
   __device__ __forceinline__ void build(int lane, const M3<real>& R, V3<real> p, const V3<real> foot[2], const real yc[2],
                                         const real ys[2], int contact_mask, real fx, real fy, real mu_b, const real Minv[6]) {
@@ -504,6 +508,35 @@ template <typename real, int G, int NCOLS = 40> struct QP {
         const real oy = k == 0 ? real(0) : ((k == 1 || k == 3) ? real(0.06) : real(-0.06));
         a[k][0] = l0; a[k][1] = l1; a[k][2] = l2;
         a[k][3] = T0.x + ox * T1.x + oy * T2.x; a[k][4] = T0.y + ox * T1.y + oy * T2.y; a[k][5] = T0.z + ox * T1.z + oy * T2.z;
+      }
+      return;
+    }
+    if constexpr (SHARED_LIN4) {
+      // same affine form as above, per foot:  tau_k = T0_f + ox_k T1_f + oy_k T2_f,  f = k & 1, site = k >> 1
+      const int d = lane & 3;
+      const real bx = d == 0 ? mu_b : (d == 1 ? -mu_b : real(0));
+      const real by = d == 2 ? mu_b : (d == 3 ? -mu_b : real(0));
+      const V3<real> B = {fx * bx - fy * by, fy * bx + fx * by, real(1)};
+      bl[0] = Minv[0] * B.x; bl[1] = Minv[1] * B.y; bl[2] = Minv[2] * B.z;
+      V3<real> T0[2], T1[2], T2[2];
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const real m = ((contact_mask >> f) & 1) ? real(1) : real(0);
+        mf[f] = m;
+        const real w3 = m * Minv[3], w4 = m * Minv[4], w5 = m * Minv[5];
+        const real c_ = yc[f], s_ = ys[f];
+        V3<real> t0 = mulT(R, cross(foot[f] - p, B));
+        V3<real> t1 = mulT(R, V3<real>{s_, -c_, c_ * B.y - s_ * B.x});
+        V3<real> t2 = mulT(R, V3<real>{c_, s_, -s_ * B.y - c_ * B.x});
+        T0[f] = {w3 * t0.x, w4 * t0.y, w5 * t0.z}; T1[f] = {w3 * t1.x, w4 * t1.y, w5 * t1.z}; T2[f] = {w3 * t2.x, w4 * t2.y, w5 * t2.z};
+      }
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const int f = k & 1, site = k >> 1;
+        const real ox = site == 0 ? real(0) : ((site == 1 || site == 2) ? real(0.12) : real(-0.12));
+        const real oy = site == 0 ? real(0) : ((site == 1 || site == 3) ? real(0.06) : real(-0.06));
+        a[k][0] = mf[f] * bl[0]; a[k][1] = mf[f] * bl[1]; a[k][2] = mf[f] * bl[2];
+        a[k][3] = T0[f].x + ox * T1[f].x + oy * T2[f].x; a[k][4] = T0[f].y + ox * T1[f].y + oy * T2[f].y; a[k][5] = T0[f].z + ox * T1[f].z + oy * T2[f].z;
       }
       return;
     }
@@ -536,6 +569,11 @@ template <typename real, int G, int NCOLS = 40> struct QP {
       const real base = a[0][0] * nu[0] + a[0][1] * nu[1] + a[0][2] * nu[2];
 #pragma unroll
       for (int k = 0; k < NC; k++) t[k] = base + a[k][3] * nu[3] + a[k][4] * nu[4] + a[k][5] * nu[5];
+    } else if constexpr (SHARED_LIN4) {
+      const real base = bl[0] * nu[0] + bl[1] * nu[1] + bl[2] * nu[2];
+      const real bf[2] = {mf[0] * base, mf[1] * base};
+#pragma unroll
+      for (int k = 0; k < NC; k++) t[k] = bf[k & 1] + a[k][3] * nu[3] + a[k][4] * nu[4] + a[k][5] * nu[5];
     } else {
 #pragma unroll
       for (int k = 0; k < NC; k++)
@@ -555,8 +593,9 @@ template <typename real, int G, int NCOLS = 40> struct QP {
 
   // H (lower triangle, 21) = I + (1/w) sum_{k: t_k<0} a_k a_k^T, all-reduced over the group
   __device__ __forceinline__ void hessian(const real t[NC], real invw, real H[21], real* sm) const {
-    if constexpr (SHARED_LIN) {
+    if constexpr (SHARED_LIN || SHARED_LIN4) {
       // sum_k m_k [b; tau_k][b; tau_k]^T = [[n b b^T, b tsum^T], [tsum b^T, sum m_k tau_k tau_k^T]]   (80 instead of 135 ops)
+      // (G == 4: a column of a foot that is not in contact has t = 0 and is never active, so the unmasked b serves both feet)
       real n = 0, ts0 = 0, ts1 = 0, ts2 = 0, aa[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int k = 0; k < NC; k++) {
@@ -565,7 +604,7 @@ template <typename real, int G, int NCOLS = 40> struct QP {
         n += m; ts0 += t0; ts1 += t1; ts2 += t2;
         aa[0] += t0 * a[k][3]; aa[1] += t1 * a[k][3]; aa[2] += t1 * a[k][4]; aa[3] += t2 * a[k][3]; aa[4] += t2 * a[k][4]; aa[5] += t2 * a[k][5];
       }
-      const real b0 = a[0][0], b1 = a[0][1], b2 = a[0][2];
+      const real b0 = SHARED_LIN4 ? bl[0] : a[0][0], b1 = SHARED_LIN4 ? bl[1] : a[0][1], b2 = SHARED_LIN4 ? bl[2] : a[0][2];
       const real nb0 = n * b0, nb1 = n * b1, nb2 = n * b2;
       H[0] = nb0 * b0; H[1] = nb1 * b0; H[2] = nb1 * b1; H[3] = nb2 * b0; H[4] = nb2 * b1; H[5] = nb2 * b2;
       H[6] = ts0 * b0; H[7] = ts0 * b1; H[8] = ts0 * b2; H[9] = aa[0];
