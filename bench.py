@@ -591,7 +591,7 @@ def env_lanes(args):
     if args.lanes:
         return args.lanes
     # the library's default (srb_create): by batch size
-    return 8 if args.envs <= 6144 else (4 if (args.envs <= 16384 or args.variant == "terrain") else 2)
+    return 8 if args.envs <= (3072 if args.precision == 64 else 4096) else 4
 
 
 def main():

@@ -121,11 +121,12 @@ extern "C" int srb_create(const srb_config* cfg, srb_env** out) {
   if (!cfg || !out) return fail(-1, "srb_create: null argument");
   if (cfg->num_envs <= 0) return fail(-1, "srb_create: num_envs must be positive");
   if (cfg->precision != 32 && cfg->precision != 64) return fail(-1, "srb_create: precision must be 32 or 64");
-  // default lanes per environment by batch size (measured): 8 lanes keep the dependent chain short while the batch
-  // leaves schedulers idle (<= 6144 envs); beyond that the kernel is issue bound and fewer lanes amortise the scalar part
-  // of the step over more environments per warp
+  // default lanes per environment by batch size (measured, DESIGN 5 / profiles/r02_lanes_sweep.txt): 8 lanes keep the dependent chain
+  // of a warp short while the batch leaves schedulers idle; from ~3-4 k environments on, 4 lanes (structured QP: a lane's ten columns
+  // share their linear part) issue fewer instructions per environment and win at every larger size measured (up to 65536; 2 lanes
+  // never do).  fp32 switches after 4096 because the host-buffer path (coalesced-I/O kernel) still prefers 8 lanes there.
   int G = cfg->lanes_per_env;
-  if (G == 0) G = cfg->num_envs <= 6144 ? 8 : ((cfg->num_envs <= 16384 || cfg->variant == SRB_VARIANT_TERRAIN) ? 4 : 2);
+  if (G == 0) G = cfg->num_envs <= (cfg->precision == 64 ? 3072 : 4096) ? 8 : 4;
   if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(-1, "srb_create: lanes_per_env must be 1,2,4,8,16 or 32");
   if (cfg->variant != SRB_VARIANT_TEST && cfg->variant != SRB_VARIANT_TRAINING && cfg->variant != SRB_VARIANT_TERRAIN) return fail(-1, "srb_create: unknown variant");
   int ndev = 0;

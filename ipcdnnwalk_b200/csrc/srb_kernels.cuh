@@ -365,7 +365,8 @@ template <int G> __device__ __forceinline__ double gsum(double v) {
 // G == 8: staged through shared memory with 128-bit accesses -- every lane stores its 21 partials (padded row,
 // stride chosen so a quarter-warp's 16-byte chunks fall in distinct bank groups), lanes 0..5 of a group each sum
 // 4 entries over the 8 rows, the 24 sums are read back by all lanes: ~20 (fp32) / ~41 (fp64) LSU instructions
-// + 28 adds instead of 63 / 126 SHFL + 63 adds.
+// + 28 adds instead of 63 / 126 SHFL + 63 adds.  (The same staging for G == 4 was measured 4-6 % SLOWER than its 42-shuffle butterfly:
+// profiles/r02_ab_g4_smem_reduce_*.txt.)
 template <typename real, int G> struct HReduce {
   static constexpr int SMEM_WORDS = 1;
   static __device__ __forceinline__ void run(real H[21], real* sm, int lane32) {

@@ -290,11 +290,26 @@ def test_sample_at_bench_size_flat_4096(built_lib, precision, rtol):
 
 
 def test_sample_at_bench_size_two_lanes_32768(built_lib):
-    """32768 envs per GPU -> the 2-lane fp32 instantiation (the 8-GPU 1.8e9 figure): 32 sampled environments, 6 steps."""
+    """32768 envs per GPU with the 2-lane fp32 instantiation (the round-1 8-GPU 1.8e9 figure; since round 2 the default at this size
+    is 4 lanes, covered by test_sample_at_bench_size_default_lanes_32768): 32 sampled environments, 6 steps."""
     from ipcdnnwalk_b200 import SRBVecEnv
     n = 32768
     clips = helpers.fresh_clips()
     rng = np.random.default_rng(32768)
+    plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
+    env = SRBVecEnv(clips, n, variant="test", precision=32, auto_reset=False, lanes_per_env=2)
+    env.reset(plan=plans)
+    sample = sorted(set(rng.choice(n, 32, replace=False).tolist() + [0, n - 1]))
+    _sample_check(env, clips, plans, sample, "test", 6, 5e-3, 0.1)
+    env.close()
+
+
+def test_sample_at_bench_size_default_lanes_32768(built_lib):
+    """32768 envs per GPU with the library's default lane count (4: the structured 4-lane QP): 32 sampled environments, 6 steps."""
+    from ipcdnnwalk_b200 import SRBVecEnv
+    n = 32768
+    clips = helpers.fresh_clips()
+    rng = np.random.default_rng(32769)
     plans = np.stack([helpers.random_plan(rng, clips) for _ in range(n)])
     env = SRBVecEnv(clips, n, variant="test", precision=32, auto_reset=False)
     env.reset(plan=plans)
