@@ -1,0 +1,174 @@
+"""Pins of the SRBTrack path against the REFERENCE'S OWN ENVIRONMENT CODE.
+
+tests/golden/refenv_rollout_{test,training}.npz and refenv_special.npz are roll-outs of env/SRBEnv5_mocap_list_window.py /
+..._training.py themselves, executed from /root/reference through tests/tools/ref_srbenv_harness.py -- MuJoCo, Clarabel, controlmodule.SDS
+and SRBdata answered by stated stand-ins (restated MuJoCo free-body semantics, an exact QP solve, the SDS restatement, the committed clip
+tables), every other line the reference's code as it stands: action decoding, contact logic incl. the probability hysteresis, site
+placement, the assembly of the QP in solve_qp_for_contact_forces, force clamp, impulse schedule, history, get_obs_window, _get_reward,
+_get_done, reset / set_state.  Generator: tests/tools/make_golden_refenv.py.
+
+  * CPU: oracle/srb_env.py replays the same plans / actions and reproduces the reference code's outputs at 1e-10.
+  * `live` (where /root/reference is mounted): the harness re-runs the reference code and must print the committed fixture.
+  * GPU: the CUDA step, through the C-ABI, is compared with the reference code's roll-outs DIRECTLY (fp64 1e-5; done, contact flags and
+    frame counters bit exact), without the oracle in between."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+
+sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "tools"))
+import ref_srbenv_harness as rh            # noqa: E402
+
+RTOL64 = 1e-5
+live = pytest.mark.skipif(not rh.available(), reason="/root/reference is not mounted: the committed fixture stands in")
+
+
+def _fixture(variant):
+    return dict(np.load(os.path.join(helpers.GOLDEN, f"refenv_rollout_{variant}.npz")))
+
+
+def _special():
+    return dict(np.load(os.path.join(helpers.GOLDEN, "refenv_special.npz")))
+
+
+def _close(a, b, rtol, what):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    assert np.nanmax(err) <= rtol, f"{what}: max rel err {np.nanmax(err):.3e} at {np.unravel_index(np.nanargmax(err), err.shape)}"
+
+
+def _replay_oracle(g, variant, prob=None, impulse=None):
+    from oracle.srb_env import OracleSRBEnv
+    n_env, n_steps = g["actions"].shape[:2]
+    for e in range(n_env):
+        o = OracleSRBEnv(helpers.fresh_clips(), variant)
+        obs0, _ = helpers.oracle_reset(o, g["plans"][e])
+        _close(obs0, g["obs0"][e], 1e-10, f"env {e} reset obs")
+        if impulse is not None:
+            o.impulse_interval, o.impulse_duration, o.force = impulse
+            o.frame_counter = 0; o.impulse = 0
+        for k in range(n_steps):
+            if prob is not None:
+                p = prob[e, k]
+                o.contact_prob = [None, None] if np.isnan(p[0]) else [float(p[0]), float(p[1])]
+            obs, r, done, _, info = o.step(g["actions"][e, k])
+            what = f"env {e} step {k}"
+            assert bool(done) == bool(g["done"][e, k]), what + " done"
+            st = helpers.oracle_state_vector(o)
+            assert (st[23:26] == g["state"][e, k, 23:26]).all(), what + " contact flags / frame"
+            _close(st[:23], g["state"][e, k, :23], 1e-10, what + " state")
+            _close(obs, g["obs"][e, k], 1e-10, what + " obs")
+            _close(r, g["rew"][e, k], 1e-10, what + " reward")
+            ri = [info["reward_info"][k2] for k2 in ("reward_survive", "reward_contact", "reward_end_effector", "reward_delta_pos",
+                                                      "reward_delta_ori", "reward_pos", "reward_ori", "reward_total")]
+            _close(ri, g["rinfo"][e, k], 1e-10, what + " reward_info")
+            q = np.array([np.full(6, np.nan) if x is None else x for x in o.qdd_qp_list])
+            assert (np.isnan(q[:, 0]) == np.isnan(g["qdd"][e, k][:, 0])).all(), what + " which sub-steps ran the QP"
+            m = ~np.isnan(q[:, 0])
+            if m.any():
+                _close(q[m], g["qdd"][e, k][m], 1e-9, what + " QP accelerations")
+
+
+@pytest.mark.parametrize("variant", ["test", "training"])
+def test_oracle_equals_the_reference_environment_code(variant):
+    g = _fixture(variant)
+    assert g["done"].any() and not g["done"].all()
+    _replay_oracle(g, variant)
+
+
+def test_oracle_equals_the_reference_code_on_hysteresis_and_impulse():
+    s = _special()
+    h = {k[5:]: v for k, v in s.items() if k.startswith("hyst_")}
+    assert (np.diff(h["state"][:, :, 23:25], axis=1) != 0).sum() > 20          # the flags really switch
+    _replay_oracle(h, "test", prob=h["prob"])
+    i = {k[4:]: v for k, v in s.items() if k.startswith("imp_") and k not in ("imp_interval", "imp_duration", "imp_force")}
+    _replay_oracle(i, "test", impulse=(int(s["imp_interval"]), int(s["imp_duration"]), list(s["imp_force"])))
+
+
+@live
+@pytest.mark.parametrize("variant", ["test", "training"])
+def test_live_reference_code_reproduces_the_fixture(variant):
+    """Re-runs the reference's environment code here on the first environments of the fixture: plans, actions in -> identical outputs."""
+    g = _fixture(variant)
+    clips = helpers.fresh_clips()
+    ref, mod = rh.make_env(variant, clips)
+    for e in (0, 1):
+        plan = g["plans"][e]
+        if np.isnan(plan[5]):
+            obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]))
+        else:
+            obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]), plan[2:5], plan[5:9])
+        assert np.array_equal(np.asarray(obs0, float), g["obs0"][e])
+        for k in range(12):
+            obs, r, done, _, info = ref.step(g["actions"][e, k])
+            assert np.array_equal(np.asarray(obs, float), g["obs"][e, k]) and float(r) == g["rew"][e, k] and bool(done) == bool(g["done"][e, k])
+
+
+# --------------------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["test", "training"])
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_cuda_equals_the_reference_environment_code(built_lib, variant, lanes):
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv
+    g = _fixture(variant)
+    n_env, n_steps = g["actions"].shape[:2]
+    env = SRBVecEnv(helpers.fresh_clips(), n_env, variant=variant, precision=64, lanes_per_env=lanes, auto_reset=False)
+    env.attach(dbg=True)
+    obs0 = env.reset(plan=g["plans"]).cpu().numpy()
+    _close(obs0, g["obs0"], 2e-6, "reset obs")
+    for k in range(n_steps):
+        env.dbg.zero_()
+        obs, rew, done, rinfo = env.step(torch.as_tensor(g["actions"][:, k], device="cuda"))
+        torch.cuda.synchronize()
+        st = np.stack([helpers.cuda_state_vector(env.named_state(i)) for i in range(n_env)])
+        assert (done.cpu().numpy().astype(bool) == g["done"][:, k]).all(), f"done mismatch at step {k}"
+        assert (st[:, 23:26] == g["state"][:, k, 23:26]).all(), f"contact flags / frame mismatch at step {k}"
+        _close(st[:, :23], g["state"][:, k, :23], RTOL64, f"state step {k}")
+        _close(obs.cpu().numpy(), g["obs"][:, k], RTOL64, f"obs step {k}")
+        _close(rew.cpu().numpy(), g["rew"][:, k], RTOL64, f"reward step {k}")
+        _close(rinfo.cpu().numpy(), g["rinfo"][:, k], RTOL64, f"reward_info step {k}")
+        dbg = env.dbg.cpu().numpy().reshape(n_env, 4, 64)
+        m = ~np.isnan(g["qdd"][:, k][..., 0])
+        _close(dbg[..., :6][m], g["qdd"][:, k][m], RTOL64, f"QP qdd step {k}")
+    env.close()
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_reference_code_on_hysteresis_and_impulse(built_lib):
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv
+    s = _special()
+    # contact-probability hysteresis (SRBEnv5_mocap_list_window.py:239-275)
+    h = {k[5:]: v for k, v in s.items() if k.startswith("hyst_")}
+    n_env, n_steps = h["actions"].shape[:2]
+    env = SRBVecEnv(helpers.fresh_clips(), n_env, variant="test", precision=64, auto_reset=False)
+    env.attach(contact_prob=True)
+    env.reset(plan=h["plans"])
+    for k in range(n_steps):
+        env.contact_prob.copy_(torch.as_tensor(h["prob"][:, k].astype(np.float32)))
+        obs, rew, done, _ = env.step(torch.as_tensor(h["actions"][:, k], device="cuda"))
+        torch.cuda.synchronize()
+        st = np.stack([helpers.cuda_state_vector(env.named_state(i)) for i in range(n_env)])
+        assert (st[:, 23:26] == h["state"][:, k, 23:26]).all(), f"hysteresis: contact flags at step {k}"
+        assert (done.cpu().numpy().astype(bool) == h["done"][:, k]).all()
+        _close(obs.cpu().numpy(), h["obs"][:, k], RTOL64, f"hysteresis obs step {k}")
+        _close(rew.cpu().numpy(), h["rew"][:, k], RTOL64, f"hysteresis reward step {k}")
+    env.close()
+    # push impulse with a 6-component force (:191-206)
+    i = {k[4:]: v for k, v in s.items() if k.startswith("imp_") and k not in ("imp_interval", "imp_duration", "imp_force")}
+    n_env, n_steps = i["actions"].shape[:2]
+    env = SRBVecEnv(helpers.fresh_clips(), n_env, variant="test", precision=64, auto_reset=False)
+    env.set_impulse(int(s["imp_interval"]), int(s["imp_duration"]), s["imp_force"])
+    env.reset(plan=i["plans"])
+    for k in range(n_steps):
+        obs, rew, done, _ = env.step(torch.as_tensor(i["actions"][:, k], device="cuda"))
+        torch.cuda.synchronize()
+        st = np.stack([helpers.cuda_state_vector(env.named_state(j)) for j in range(n_env)])
+        assert (done.cpu().numpy().astype(bool) == i["done"][:, k]).all()
+        _close(st[:, :23], i["state"][:, k, :23], RTOL64, f"impulse state step {k}")
+        _close(obs.cpu().numpy(), i["obs"][:, k], RTOL64, f"impulse obs step {k}")
+    env.close()

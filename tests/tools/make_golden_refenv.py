@@ -1,0 +1,113 @@
+"""Record roll-outs of the REFERENCE'S OWN SRBEnv code (run through tests/tools/ref_srbenv_harness.py: MuJoCo / Clarabel / SDS /
+SRBdata answered by stated stand-ins, everything else the reference's code as it stands) as committed fixtures:
+
+    python tests/tools/make_golden_refenv.py        ->  tests/golden/refenv_rollout_test.npz, refenv_rollout_training.npz,
+                                                        tests/golden/refenv_special.npz
+
+Same layout as tests/golden/rollout_{test,training}.npz (tests/tools/make_golden.py, which records the ORACLE): per environment a
+reset plan, the reset observation, 40 float32 actions and per step the observation, reward, done, the eight reward_info terms, the
+state vector (helpers.oracle_state_vector) and the QP accelerations of the four sub-steps -- here read from the reference environment
+object (`q_ddot_QP` as solve_qp_for_contact_forces returns it).  The actions come from helpers.tracking_action on an oracle environment
+stepped alongside (it needs the state; the two agree to 1e-13, which this script asserts).
+refenv_special.npz: the policy-probability contact hysteresis (`_last_contact_prob` side channel, SRBEnv5_mocap_list_window.py:239-275)
+and the push-impulse schedule with a 6-component force (:191-206) -- branches the plain roll-outs do not reach."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import helpers                                   # noqa: E402
+import ref_srbenv_harness as rh                  # noqa: E402
+from oracle.srb_env import OracleSRBEnv          # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+RI_KEYS = ("reward_survive", "reward_contact", "reward_end_effector", "reward_delta_pos", "reward_delta_ori", "reward_pos", "reward_ori", "reward_total")
+
+
+def _capture_qdd(mod):
+    """wrap the reference's solve_qp_for_contact_forces so that q_ddot_QP of every call is kept"""
+    log = []
+    if not hasattr(mod, "_orig_solve_qp"):
+        mod._orig_solve_qp = mod.solve_qp_for_contact_forces
+
+    def wrapped(*a, **k):
+        r = mod._orig_solve_qp(*a, **k)
+        log.append(np.array(r[0], dtype=float))
+        return r
+    mod.solve_qp_for_contact_forces = wrapped
+    return log
+
+
+def rollout(variant, n_envs=6, n_steps=40, seed=17, contact_prob=False, impulse=None):
+    rng = np.random.default_rng(seed)
+    clips = helpers.fresh_clips()
+    ref, mod = rh.make_env(variant, clips)
+    qlog = _capture_qdd(mod)
+    pmod = sys.modules["env.Policy_prior_posterior_MoE_window"]
+    out = dict(plans=[], actions=[], obs=[], rew=[], done=[], rinfo=[], state=[], qdd=[], obs0=[], prob=[])
+    worst = 0.0
+    for e in range(n_envs):
+        orc = OracleSRBEnv(helpers.fresh_clips(), variant)
+        plan = helpers.random_plan(rng, clips, noise=(e % 3 != 0))
+        if np.isnan(plan[5]):
+            obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]))
+        else:
+            obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]), plan[2:5], plan[5:9])
+        o0, _ = helpers.oracle_reset(orc, plan)
+        worst = max(worst, float(np.abs(np.asarray(obs0, float) - o0).max()))
+        if impulse is not None:
+            for env_ in (ref, orc):
+                env_.impulse_interval = impulse["interval"]; env_.impulse_duration = impulse["duration"]; env_.force = list(impulse["force"])
+                env_.frame_counter = 0; env_.impulse = 0
+        A, O, Rw, D, RI, S, Q, PR = [], [], [], [], [], [], [], []
+        sigma = [0.02, 0.1, 0.3][e % 3]
+        for k in range(n_steps):
+            a = helpers.tracking_action(orc, rng, sigma)
+            prob = [None, None]
+            if contact_prob:
+                prob = [float(x) for x in rng.uniform(0, 1, 2)]
+            pmod._last_contact_prob = list(prob)
+            orc.contact_prob = list(prob)
+            del qlog[:]
+            obs, r, done, _, info = ref.step(a)
+            o2, r2, d2, _, _ = orc.step(a)
+            worst = max(worst, float(np.abs(np.asarray(obs, float) - o2).max()), abs(float(r) - float(r2)))
+            assert bool(done) == bool(d2)
+            q = [np.full(6, np.nan)] * 4
+            if qlog:
+                assert len(qlog) == 4
+                q = [x.copy() for x in qlog]
+            A.append(a); O.append(np.asarray(obs, float)); Rw.append(float(r)); D.append(bool(done))
+            RI.append([float(info["reward_info"][k2]) for k2 in RI_KEYS])
+            S.append(helpers.oracle_state_vector(ref)); Q.append(q)
+            PR.append([np.nan if p is None else p for p in prob])
+        out["plans"].append(plan); out["obs0"].append(np.asarray(obs0, float))
+        for key, v in zip(("actions", "obs", "rew", "done", "rinfo", "state", "qdd", "prob"), (A, O, Rw, D, RI, S, Q, PR)):
+            out[key].append(np.array(v))
+    pmod._last_contact_prob = [None, None]
+    assert worst < 1e-9, worst
+    return {k: np.array(v) for k, v in out.items()}, worst
+
+
+if __name__ == "__main__":
+    assert rh.available(), "needs /root/reference"
+    for variant in ("test", "training"):
+        g, worst = rollout(variant)
+        g.pop("prob")
+        np.savez_compressed(os.path.join(GOLDEN, f"refenv_rollout_{variant}.npz"), **g)
+        print(variant, "reference-code roll-out", {k: v.shape for k, v in g.items()}, "episodes done", int(g["done"].any(axis=1).sum()),
+              "| max |reference - oracle|", worst)
+    sp = {}
+    g, worst = rollout("test", n_envs=4, n_steps=30, seed=23, contact_prob=True)
+    sp.update({"hyst_" + k: v for k, v in g.items()})
+    print("hysteresis roll-out: contact flag changes", int((np.diff(g["state"][:, :, 23:25], axis=1) != 0).sum()), "| max |reference - oracle|", worst)
+    imp = dict(interval=8, duration=5, force=[300.0, -200.0, 100.0, 20.0, -30.0, 10.0])
+    g, worst = rollout("test", n_envs=3, n_steps=30, seed=29, impulse=imp)
+    sp.update({"imp_" + k: v for k, v in g.items()})
+    sp["imp_interval"] = np.array(imp["interval"]); sp["imp_duration"] = np.array(imp["duration"]); sp["imp_force"] = np.array(imp["force"])
+    print("impulse roll-out | max |reference - oracle|", worst)
+    np.savez_compressed(os.path.join(GOLDEN, "refenv_special.npz"), **sp)
