@@ -88,6 +88,41 @@ def test_oracle_equals_the_reference_code_on_hysteresis_and_impulse():
     _replay_oracle(i, "test", impulse=(int(s["imp_interval"]), int(s["imp_duration"]), list(s["imp_force"])))
 
 
+def test_oracle_equals_the_reference_terrain_environment_code():
+    """env/SRBEnv5_mocap_list_terrain_window.py on the playground (flat ground, pyramid with edge snapping, hill, rough height field);
+    mj_ray is answered by oracle/terrain.py, so this pins the environment logic (lifting, snapping, Q9 / Q10, terrain observations), not
+    the height-field semantics of MuJoCo."""
+    from oracle.srb_env import OracleSRBEnv, lift_clip_to_terrain
+    from oracle.terrain import Terrain
+    T = Terrain.load(os.path.join(helpers.GOLDEN, "terrain_playground.npz"))
+    g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_rollout_terrain.npz")))
+    for e in range(g["actions"].shape[0]):
+        planar = tuple(g["planar"][e])
+        o = OracleSRBEnv([lift_clip_to_terrain(helpers.load_clip("aiming_show"), T, planar)], "terrain", terrain=T)
+        plan = g["plans"][e]
+        obs0, _ = o.reset_explicit(0, int(plan[1]), plan[2:5].copy(), plan[5:9].copy())
+        _close(obs0, g["obs0"][e], 1e-10, f"terrain env {e} reset obs")
+        for k in range(g["actions"].shape[1]):
+            obs, r, done, _, _ = o.step(g["actions"][e, k])
+            st = helpers.oracle_state_vector(o)
+            assert bool(done) == bool(g["done"][e, k]) and (st[23:26] == g["state"][e, k, 23:26]).all(), (e, k)
+            _close(st[:23], g["state"][e, k, :23], 1e-10, f"terrain env {e} step {k} state")
+            _close(obs, g["obs"][e, k], 1e-10, f"terrain env {e} step {k} obs")
+
+
+@live
+def test_live_reference_terrain_code_reproduces_the_fixture():
+    g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_rollout_terrain.npz")))
+    e = 1                                                        # the pyramid
+    ref, mod = rh.make_env("terrain", helpers.fresh_clips(("aiming_show",)))
+    plan = g["plans"][e]
+    obs0 = rh.reset_explicit(ref, mod, 0, int(plan[1]), plan[2:5], plan[5:9], planar=tuple(g["planar"][e]))
+    assert np.array_equal(np.asarray(obs0, float), g["obs0"][e])
+    for k in range(15):
+        obs, r, done, _, _ = ref.step(g["actions"][e, k])
+        assert np.array_equal(np.asarray(obs, float), g["obs"][e, k]) and bool(done) == bool(g["done"][e, k])
+
+
 @live
 @pytest.mark.parametrize("variant", ["test", "training"])
 def test_live_reference_code_reproduces_the_fixture(variant):
@@ -171,4 +206,26 @@ def test_cuda_equals_the_reference_code_on_hysteresis_and_impulse(built_lib):
         assert (done.cpu().numpy().astype(bool) == i["done"][:, k]).all()
         _close(st[:, :23], i["state"][:, k, :23], RTOL64, f"impulse state step {k}")
         _close(obs.cpu().numpy(), i["obs"][:, k], RTOL64, f"impulse obs step {k}")
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_cuda_equals_the_reference_terrain_environment_code(built_lib, lanes):
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv, TerrainModel
+    g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_rollout_terrain.npz")))
+    n_env, n_steps = g["actions"].shape[:2]
+    env = SRBVecEnv(helpers.fresh_clips(("aiming_show",)), n_env, variant="terrain", precision=64, lanes_per_env=lanes, auto_reset=False,
+                    terrain=TerrainModel.from_npz(os.path.join(helpers.GOLDEN, "terrain_playground.npz")), initial_pos_planar=g["planar"])
+    obs0 = env.reset(plan=g["plans"]).cpu().numpy()
+    _close(obs0, g["obs0"], 2e-6, "terrain reset obs")
+    for k in range(n_steps):
+        obs, rew, done, _ = env.step(torch.as_tensor(g["actions"][:, k], device="cuda"))
+        torch.cuda.synchronize()
+        st = np.stack([helpers.cuda_state_vector(env.named_state(i)) for i in range(n_env)])
+        assert (done.cpu().numpy().astype(bool) == g["done"][:, k]).all(), f"terrain done mismatch at step {k}"
+        assert (st[:, 23:26] == g["state"][:, k, 23:26]).all(), f"terrain contact flags / frame mismatch at step {k}"
+        _close(st[:, :23], g["state"][:, k, :23], RTOL64, f"terrain state step {k}")
+        _close(obs.cpu().numpy(), g["obs"][:, k], RTOL64, f"terrain obs step {k}")
     env.close()

@@ -1,7 +1,7 @@
 """Record roll-outs of the REFERENCE'S OWN SRBEnv code (run through tests/tools/ref_srbenv_harness.py: MuJoCo / Clarabel / SDS /
 SRBdata answered by stated stand-ins, everything else the reference's code as it stands) as committed fixtures:
 
-    python tests/tools/make_golden_refenv.py        ->  tests/golden/refenv_rollout_test.npz, refenv_rollout_training.npz,
+    python tests/tools/make_golden_refenv.py        ->  tests/golden/refenv_rollout_{test,training,terrain}.npz,
                                                         tests/golden/refenv_special.npz
 
 Same layout as tests/golden/rollout_{test,training}.npz (tests/tools/make_golden.py, which records the ORACLE): per environment a
@@ -93,8 +93,43 @@ def rollout(variant, n_envs=6, n_steps=40, seed=17, contact_prob=False, impulse=
     return {k: np.array(v) for k, v in out.items()}, worst
 
 
+def rollout_terrain(planars=((0.0, 0.0), (22.0, 24.0), (-42.0, 42.0), (42.0, -40.0)), n_steps=50, seed=31):
+    """env/SRBEnv5_mocap_list_terrain_window.py on the playground: one environment per terrain patch (flat ground, the pyramid with
+    its edge snapping, the hill and the rough height field); reset(mocap_id, initial_pos_planar) as the terrain driver calls it."""
+    from oracle.srb_env import lift_clip_to_terrain
+    from oracle.terrain import Terrain
+    T = Terrain.load(os.path.join(GOLDEN, "terrain_playground.npz"))
+    rng = np.random.default_rng(seed)
+    out = dict(plans=[], planar=[], actions=[], obs=[], rew=[], done=[], state=[], obs0=[])
+    worst = 0.0
+    for planar in planars:
+        ref, mod = rh.make_env("terrain", helpers.fresh_clips(("aiming_show",)))
+        orc = OracleSRBEnv([lift_clip_to_terrain(helpers.load_clip("aiming_show"), T, planar)], "terrain", terrain=T)
+        frame = int(rng.integers(0, 300))
+        vn = rng.uniform(-.05, .05, 3); nq = np.array([1.0, 0.0, 0.0, 0.0])
+        obs0 = rh.reset_explicit(ref, mod, 0, frame, vn, nq, planar=planar)
+        o0, _ = orc.reset_explicit(0, frame, vn, nq)
+        worst = max(worst, float(np.abs(np.asarray(obs0, float) - o0).max()))
+        A, O, Rw, D, S = [], [], [], [], []
+        for k in range(n_steps):
+            a = helpers.tracking_action(orc, rng, 0.1)
+            obs, r, done, _, info = ref.step(a)
+            o2, r2, d2, _, _ = orc.step(a)
+            worst = max(worst, float(np.abs(np.asarray(obs, float) - o2).max()), abs(float(r) - float(r2)))
+            assert bool(done) == bool(d2)
+            A.append(a); O.append(np.asarray(obs, float)); Rw.append(float(r)); D.append(bool(done)); S.append(helpers.oracle_state_vector(ref))
+        out["plans"].append(np.concatenate([[0, frame], vn, nq])); out["planar"].append(planar); out["obs0"].append(np.asarray(obs0, float))
+        for key, v in zip(("actions", "obs", "rew", "done", "state"), (A, O, Rw, D, S)):
+            out[key].append(np.array(v))
+    assert worst < 1e-9, worst
+    return {k: np.array(v) for k, v in out.items()}, worst
+
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
+    g, worst = rollout_terrain()
+    np.savez_compressed(os.path.join(GOLDEN, "refenv_rollout_terrain.npz"), **g)
+    print("terrain reference-code roll-out", {k: v.shape for k, v in g.items()}, "| max |reference - oracle|", worst)
     for variant in ("test", "training"):
         g, worst = rollout(variant)
         g.pop("prob")

@@ -57,19 +57,38 @@ def _fake_mujoco():
             self.geom_friction = np.array([self._fb.floor_friction.copy()])      # geom 0 = 'floor'
             self.site_bodyid = np.ones(10, dtype=int)
             self.site_rgba = np.zeros((10, 4))
+            self._terrain = None; self._body_names = {0: "world", 1: "cdm"}; self._floor_geom = 0
 
         @staticmethod
         def from_xml_path(path):
-            assert path.endswith("SRB5.xml"), path
-            return MjModel()
+            mdl = MjModel()
+            if path.endswith("SRB5_playground.xml"):
+                # the terrain model: plane, two height fields, four pyramids of boxes -- geom / body numbering as MuJoCo compiles it
+                # (world 0, cdm 1, pyramid_1..4 2..5; geoms: floor 0, height fields 1-2, the cdm box 3, boxes 4..), held by the
+                # oracle's Terrain (tests/golden/terrain_playground.npz); mj_ray below answers from it
+                from oracle.terrain import Terrain
+                T = Terrain.load(os.path.join(ROOT, "tests", "golden", "terrain_playground.npz"))
+                mdl._terrain = T
+                ngeom = T.boxes[-1]["geom_id"] + 1
+                mdl.geom_bodyid = np.zeros(ngeom, dtype=int); mdl.geom_size = np.zeros((ngeom, 3))
+                mdl.geom_bodyid[3] = 1
+                for b in T.boxes:
+                    mdl.geom_bodyid[b["geom_id"]] = b["body_id"]; mdl.geom_size[b["geom_id"]] = b["size"]
+                mdl.geom_friction = np.tile(mdl._fb.floor_friction, (ngeom, 1))
+                mdl._body_names = {0: "world", 1: "cdm"}
+                mdl._body_names.update({b["body_id"]: b["name"] for b in T.bodies})
+                mdl._floor_geom = T.plane_geom
+            else:
+                assert path.endswith("SRB5.xml"), path
+            return mdl
 
     class MjData:
         def __init__(self, model):
             d = fb.FreeBodyData(model._fb)
             self.qpos = d.qpos.copy(); self.qvel = d.qvel.copy()
-            self.xpos = np.zeros((2, 3)); self.xmat = np.tile(np.eye(3).reshape(9), (2, 1))
+            self.xpos = np.zeros((6, 3)); self.xmat = np.tile(np.eye(3).reshape(9), (6, 1))
             self.site_xpos = np.zeros((10, 3)); self.site_xmat = np.zeros((10, 9))
-            self.qfrc_applied = np.zeros(6); self.xfrc_applied = np.zeros((2, 6))
+            self.qfrc_applied = np.zeros(6); self.xfrc_applied = np.zeros((6, 6))
             self.qfrc_bias = np.zeros(6); self.qfrc_passive = np.zeros(6); self.qacc = np.zeros(6)
             self.qM = np.zeros(21); self.time = 0.0
 
@@ -121,15 +140,26 @@ def _fake_mujoco():
 
     def mj_name2id(model, typ, name):
         if typ == mjtObj.mjOBJ_BODY:
-            return {"world": 0, "cdm": 1}[name]
+            return {v: k for k, v in model._body_names.items()}[name]
         if typ == mjtObj.mjOBJ_SITE:
             return SITES.index(name)
         if typ == mjtObj.mjOBJ_GEOM:
-            return {"floor": 0}[name]
+            return {"floor": model._floor_geom}[name]
         raise KeyError((typ, name))
 
+    def mj_id2name(model, typ, idx):
+        assert typ == mjtObj.mjOBJ_BODY
+        return model._body_names.get(int(idx))               # None past the last body, as mujoco
+
+    def mj_ray(model, data, pnt, vec, geomgroup=None, flg_static=1, bodyexclude=-1, geomid=None):
+        """vertical ray of terrain_height_ray (testSRB_mujoco_original_viewer_terrain.py:741-752) over the group-0 geoms"""
+        assert vec[0] == 0 and vec[1] == 0 and vec[2] == -1 and bodyexclude == 1
+        h, gid = model._terrain.height_ray(float(pnt[0]), float(pnt[1]))
+        geomid[0] = -1 if h is None else gid
+        return -1.0 if h is None else float(pnt[2]) - h
+
     for k, v in dict(MjModel=MjModel, MjData=MjData, mj_step1=mj_step1, mj_step2=mj_step2, mj_forward=mj_forward, mj_jac=mj_jac,
-                     mj_fullM=mj_fullM, mj_applyFT=mj_applyFT, mjtObj=mjtObj, mj_name2id=mj_name2id).items():
+                     mj_fullM=mj_fullM, mj_applyFT=mj_applyFT, mjtObj=mjtObj, mj_name2id=mj_name2id, mj_id2name=mj_id2name, mj_ray=mj_ray).items():
         setattr(m, k, v)
     return m
 
@@ -274,6 +304,8 @@ def reference_module(variant):
     import importlib
     if variant == "test":
         return importlib.import_module("env.SRBEnv5_mocap_list_window")
+    if variant == "terrain":
+        return importlib.import_module("env.SRBEnv5_mocap_list_terrain_window")
     name = "env.SRBEnv5_mocap_list_window_training"
     if name in sys.modules:
         return sys.modules[name]
@@ -301,13 +333,24 @@ def make_env(variant, clips, paths=None):
 
     class ClipTables:
         def __init__(self, mocap_path):
-            c = by_path[mocap_path]
-            self.dt = c["mocap_dt"]; self.cycle_length = c["cycle_length"]; self.mocap_com_humanoid = c["mocap_qpos"]
+            self._c = by_path[mocap_path]
+            self.dt = self._c["mocap_dt"]
+            self.mocap_data = np.zeros((1, 2))                 # the terrain env adds initial_pos_planar to columns 0:2 before humanoid2SRB
+            self._fill(self._c)
+
+        def _fill(self, c):
+            self.cycle_length = c["cycle_length"]; self.mocap_com_humanoid = c["mocap_qpos"]
             self.mocap_ori_com = c["mocap_ori_com"]; self.mocap_vel_com = c["mocap_vel_com"]
             self.feet_pos_list = c["feet_pos_list"]; self.feet_ori_list = c["feet_ori_list"]
+            if "feet_pos_list_original" in c:
+                self.feet_pos_list_original = c["feet_pos_list_original"]; self.mocap_height_com_terrain = c["mocap_height_com_terrain"]
 
         def humanoid2SRB(self, initial_frame=0, last_frame=None):
-            pass
+            if variant == "terrain":                           # tables lifted onto the terrain under the shifted clip (:1043-1065)
+                from oracle.srb_env import lift_clip_to_terrain
+                from oracle.terrain import Terrain
+                T = Terrain.load(os.path.join(ROOT, "tests", "golden", "terrain_playground.npz"))
+                self._fill(lift_clip_to_terrain(self._c, T, tuple(self.mocap_data[0, :2])))
 
     mod.SRBDataProcess = ClipTables
     cwd = os.getcwd()
@@ -315,21 +358,23 @@ def make_env(variant, clips, paths=None):
     try:
         env = mod.SRBEnv(paths)
         for i in range(len(paths)):
-            if hasattr(env, "loadMocap"):
-                env.loadMocap(i)                           # test variant: lazy loading (:1171-1197)
+            if hasattr(env, "loadMocap") and variant != "terrain":
+                env.loadMocap(i)                           # test variant: lazy loading (:1171-1197); terrain: at reset, with the planar shift
     finally:
         os.chdir(cwd)
     return env, mod
 
 
-def reset_explicit(env, mod, clip_id, frame, vel_noise=None, noise_quat=None):
-    """SRBEnv.reset (:805-845) with the random draws supplied: binds the clip as reset() does, then the reference's own set_state with
-    np.random.uniform / random_quaternion_perturbation answering `vel_noise` / `noise_quat` (None = testing_mode)."""
+def reset_explicit(env, mod, clip_id, frame, vel_noise=None, noise_quat=None, planar=None):
+    """SRBEnv.reset (:805-845; terrain :528-571) with the random draws supplied: binds the clip as reset() does, then the reference's
+    own set_state with np.random.uniform / random_quaternion_perturbation answering `vel_noise` / `noise_quat` (None = testing_mode).
+    `planar` (terrain variant): initial_pos_planar, handed to the reference's loadMocap as reset(mocap_id, initial_pos_planar) does."""
     env.contactFilter = [None] * 4
+    if planar is not None:
+        env.loadMocap(clip_id, np.asarray(planar, dtype=float))
     d = env.SRB_data_list[clip_id]
-    env.SRBdata = d["SRBdata"]; env.mocap_dt = d["mocap_dt"]; env.cycle_length = d["cycle_length"]; env.mocap_qpos = d["mocap_qpos"]
-    env.mocap_pos_com = d["mocap_pos_com"]; env.mocap_ori_com = d["mocap_ori_com"]; env.mocap_vel_com = d["mocap_vel_com"]
-    env.feet_pos_list = d["feet_pos_list"]; env.feet_ori_list = d["feet_ori_list"]
+    for k, v in d.items():                                    # SRBdata, mocap_dt, cycle_length, mocap_qpos, ... exactly the names reset() binds
+        setattr(env, k, v)
     env.is_stand = env.mocap_path_list[clip_id] == STAND_PATH            # training variant's reset (:643-645); unused by the test variant
     env.random_initial_frame = int(frame); env.current_frame = 0
     env.testing_mode = vel_noise is None
