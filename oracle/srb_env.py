@@ -14,8 +14,14 @@ Third-party arithmetic that is NOT in /root/reference and is restated instead:
     non-negative least squares problem is solved with scipy.optimize.nnls (Lawson-Hanson active set).
   * scipy.linalg.logm is available in this image and is called exactly as the reference does.
 
-PARITY UNPINNED: the reference has no tests / golden vectors for this path; the checks that pin this
-file are analytic (KKT residual of the un-eliminated QP, free-flight invariants) -- see tests/.
+PARITY: PINNED TO THE REFERENCE'S OWN ENVIRONMENT CODE for everything the reference itself wrote -- tests/tools/ref_srbenv_harness.py
+imports env/SRBEnv5_mocap_list_window.py, ..._window_training.py and ..._terrain_window.py from /root/reference and runs them with
+mujoco / clarabel / controlmodule.SDS / SRBdata answered by stand-ins (oracle/mj_freebody.py, an exact QP solve, oracle/sds_filter.py,
+the committed clip tables, oracle/terrain.py for mj_ray); their roll-outs (tests/golden/refenv_*.npz, generator
+tests/tools/make_golden_refenv.py) are reproduced by this file at 1e-13 (tests/test_refenv_pins.py), incl. the contact hysteresis, the
+6-component impulse and the terrain variant on all four playground patches.  UNPINNED: the third-party semantics behind those stand-ins
+(MuJoCo's mj_step1 / mj_step2 / mj_ray, Clarabel, taesooLib's SDS) -- checked analytically only (KKT residual of the un-eliminated QP,
+free-flight invariants; see tests/test_oracle_cpu.py).
 
 Every quirk listed in SURVEY.md section 8 (Q1,Q2,Q3,Q6,Q11,Q12,Q14) is reproduced deliberately.
 """
