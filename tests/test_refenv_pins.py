@@ -111,6 +111,21 @@ def test_oracle_equals_the_reference_terrain_environment_code():
 
 
 @live
+@pytest.mark.parametrize("name", ["aiming_show", "stand1"])
+def test_live_reference_srbdata_code_reproduces_the_clip_tables(name):
+    """Row a-13: the reference's own SRBdata(mocap_path).humanoid2SRB() (testSRB_mujoco_original_viewer.py:765-1031: frame stitching, the
+    yaw-aligned continuation of the cycle, CoM / velocity / foot-orientation / contact processing), run on the shipped clip with MuJoCo's
+    humanoid FK, subtree CoM, mj_differentiatePos and transformations.py answered by oracle/srbdata.py's restatements, yields the committed
+    clip tables tests/golden/clip_<name>.npz -- the tables the product's ClipBuilder is tested against -- exactly."""
+    s = rh.reference_srbdata(f"motiondata_mujoco_refined/{name}.txt")
+    c = helpers.load_clip(name)
+    assert s.cycle_length == c["cycle_length"] and abs(s.dt - c["mocap_dt"]) < 1e-15
+    for a, b in ((s.mocap_com_humanoid, c["mocap_qpos"]), (np.array(s.mocap_ori_com), c["mocap_ori_com"]), (s.mocap_vel_com, c["mocap_vel_com"]),
+                 (s.feet_pos_list, c["feet_pos_list"]), (np.array(s.feet_ori_list), c["feet_ori_list"])):
+        assert np.abs(np.asarray(a, dtype=float) - b).max() < 1e-12
+
+
+@live
 def test_live_reference_terrain_code_reproduces_the_fixture():
     g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_rollout_terrain.npz")))
     e = 1                                                        # the pyramid

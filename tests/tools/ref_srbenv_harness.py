@@ -11,8 +11,9 @@ the third-party back ends it cannot have here replaced by stated stand-ins:
               accessors the environment uses (test variant only; the training variant has no filter).
   gymnasium, transformations, work.settings / rendermodule, env.Policy_prior_posterior_MoE_window   import-time stubs (spaces.Box, Env,
               the `_last_contact_prob` side channel).
-  SRBdata (humanoid2SRB needs MuJoCo's humanoid FK)   `SRBDataProcess` is answered by a holder of the clip tables of
-              tests/golden/clip_*.npz, so loadMocap / __init__ fill SRB_data_list themselves.
+  SRBdata (humanoid2SRB needs MuJoCo's humanoid FK)   for the environments `SRBDataProcess` is answered by a holder of the clip tables
+              of tests/golden/clip_*.npz, so loadMocap / __init__ fill SRB_data_list themselves; `reference_srbdata` runs the reference's
+              own SRBdata.humanoid2SRB with the humanoid's mj_forward / mj_differentiatePos answered by oracle/srbdata.py's FK.
 
 Everything else -- action decoding, contact logic and hysteresis, site placement, the reference's own get_site_jacobians /
 apply_force_at_site / solve_qp_for_contact_forces problem assembly, force clamp, impulse schedule, history lists, get_obs_window,
@@ -61,6 +62,8 @@ def _fake_mujoco():
 
         @staticmethod
         def from_xml_path(path):
+            if path.endswith("humanoid_deepmimic_withpalm_Tpose.xml"):
+                return HumanoidMjModel(path)
             mdl = MjModel()
             if path.endswith("SRB5_playground.xml"):
                 # the terrain model: plane, two height fields, four pyramids of boxes -- geom / body numbering as MuJoCo compiles it
@@ -82,7 +85,32 @@ def _fake_mujoco():
                 assert path.endswith("SRB5.xml"), path
             return mdl
 
+    class HumanoidMjModel:
+        """the mocap humanoid of SRBdata.humanoid2SRB (testSRB_mujoco_original_viewer.py:871-1031): what mj_forward must deliver there is
+        subtree_com[0], xmat of bodies, geom_xpos / geom_xmat of the foot geoms and site_xpos -- from the oracle's MJCF reader / FK"""
+
+        def __init__(self, path):
+            from oracle.srbdata import HumanoidModel
+            self._h = HumanoidModel(path)
+            self._humanoid = True
+            self.nq = self._h.nq; self.nv = self._h.nq - 1
+            self._geoms = [g[0] for b in self._h.bodies for g in b["geoms"]]
+            self._sites = [st[0] for b in self._h.bodies for st in b["sites"]]
+
+    class HumanoidMjData:
+        def __init__(self, model):
+            nb = len(model._h.bodies) + 1
+            self.qpos = np.zeros(model.nq); self.qvel = np.zeros(model.nv)
+            self.xpos = np.zeros((nb, 3)); self.xmat = np.zeros((nb, 9)); self.subtree_com = np.zeros((nb, 3))
+            self.geom_xpos = np.zeros((len(model._geoms), 3)); self.geom_xmat = np.zeros((len(model._geoms), 9))
+            self.site_xpos = np.zeros((len(model._sites), 3))
+
     class MjData:
+        def __new__(cls, model):
+            if getattr(model, "_humanoid", False):
+                return HumanoidMjData(model)
+            return object.__new__(cls)
+
         def __init__(self, model):
             d = fb.FreeBodyData(model._fb)
             self.qpos = d.qpos.copy(); self.qvel = d.qvel.copy()
@@ -91,6 +119,7 @@ def _fake_mujoco():
             self.qfrc_applied = np.zeros(6); self.xfrc_applied = np.zeros((6, 6))
             self.qfrc_bias = np.zeros(6); self.qfrc_passive = np.zeros(6); self.qacc = np.zeros(6)
             self.qM = np.zeros(21); self.time = 0.0
+            self.subtree_com = np.zeros((6, 3))
 
     def _to(model, data):
         d = fb.FreeBodyData(model._fb)
@@ -105,6 +134,7 @@ def _fake_mujoco():
         data.qpos = d.qpos.copy(); data.qvel = d.qvel.copy()
         if kin:
             data.xpos[1] = d.xpos; data.xmat[1] = d.xmat
+            data.subtree_com[0] = d.xpos; data.subtree_com[1] = d.xpos      # one body, CoM at its origin
             data.site_xpos[:] = d.site_xpos; data.site_xmat[:] = d.site_xmat
         data.qfrc_bias[:] = d.qfrc_bias; data.qfrc_passive[:] = d.qfrc_passive; data.qacc[:] = d.qacc; data.time = d.time
 
@@ -115,7 +145,24 @@ def _fake_mujoco():
         d = _to(model, data); fb.mj_step2(model._fb, d); _back(d, data, False)
 
     def mj_forward(model, data):
+        if getattr(model, "_humanoid", False):
+            fk = model._h.forward(np.asarray(data.qpos, dtype=float))
+            data.xpos[1:] = fk["xpos"]; data.xmat[1:] = fk["xmat"].reshape(-1, 9)
+            data.subtree_com[0] = fk["com"]
+            for i, n in enumerate(model._geoms):
+                data.geom_xpos[i] = fk["geoms"][n][0]; data.geom_xmat[i] = fk["geoms"][n][1].reshape(9)
+            for i, n in enumerate(model._sites):
+                data.site_xpos[i] = fk["sites"][n]
+            return
         d = _to(model, data); fb.mj_forward(model._fb, d); _back(d, data, True)
+
+    def mj_differentiatePos(model, qvel, dt, qpos1, qpos2):
+        """mj_differentiatePos: free joint = position difference + quaternion difference as a rotation vector, hinges = angle difference"""
+        from oracle.srbdata import differentiate_pos_free
+        q1, q2 = np.asarray(qpos1, dtype=float), np.asarray(qpos2, dtype=float)
+        lin, ang = differentiate_pos_free(dt, q1, q2)
+        qvel[0:3] = lin; qvel[3:6] = ang
+        qvel[6:] = (q2[7:] - q1[7:]) / dt
 
     def mj_jac(model, data, jacp, jacr, point, body):
         assert body == 1
@@ -139,6 +186,10 @@ def _fake_mujoco():
         mjOBJ_BODY, mjOBJ_GEOM, mjOBJ_SITE = 1, 5, 6
 
     def mj_name2id(model, typ, name):
+        if getattr(model, "_humanoid", False):
+            if typ == mjtObj.mjOBJ_BODY:
+                return model._h.body_id[name] + 1
+            return (model._geoms if typ == mjtObj.mjOBJ_GEOM else model._sites).index(name)
         if typ == mjtObj.mjOBJ_BODY:
             return {v: k for k, v in model._body_names.items()}[name]
         if typ == mjtObj.mjOBJ_SITE:
@@ -159,7 +210,7 @@ def _fake_mujoco():
         return -1.0 if h is None else float(pnt[2]) - h
 
     for k, v in dict(MjModel=MjModel, MjData=MjData, mj_step1=mj_step1, mj_step2=mj_step2, mj_forward=mj_forward, mj_jac=mj_jac,
-                     mj_fullM=mj_fullM, mj_applyFT=mj_applyFT, mjtObj=mjtObj, mj_name2id=mj_name2id, mj_id2name=mj_id2name, mj_ray=mj_ray).items():
+                     mj_fullM=mj_fullM, mj_applyFT=mj_applyFT, mjtObj=mjtObj, mj_name2id=mj_name2id, mj_id2name=mj_id2name, mj_ray=mj_ray, mj_differentiatePos=mj_differentiatePos).items():
         setattr(m, k, v)
     return m
 
@@ -271,7 +322,53 @@ def install():
     mv = types.ModuleType("mujoco.viewer"); mj.viewer = mv
     sys.modules["mujoco.viewer"] = mv
     sys.modules["clarabel"] = _fake_clarabel()
-    sys.modules["transformations"] = types.ModuleType("transformations")
+    tr = types.ModuleType("transformations")                   # third-party transformations.py: the two functions SRBdata.get_frame_data calls
+    from oracle import srbdata as _sd
+
+    def quaternion_matrix(q):
+        M = np.eye(4); M[:3, :3] = _sd.quaternion_matrix3(q)
+        return M
+
+    tr.quaternion_matrix = quaternion_matrix
+    tr.quaternion_from_matrix = lambda M: _sd.quaternion_from_matrix3(np.asarray(M)[:3, :3])
+    import math
+    _NEXT = [1, 2, 0, 1]
+    _AXES = {"rxyz": (2, 1, 0, 1)}                                  # first axis, parity, repetition, frame
+
+    def euler_from_matrix(matrix, axes="sxyz"):
+        """transformations.py (Gohlke), the published algorithm, for the axes string the reference uses"""
+        first, parity, rep, frame = _AXES[axes]
+        i = first; j = _NEXT[i + parity]; k = _NEXT[i - parity + 1]
+        M = np.array(matrix, dtype=np.float64)[:3, :3]
+        cy = math.sqrt(M[i, i] * M[i, i] + M[j, i] * M[j, i])
+        if cy > np.finfo(float).eps * 4.0:
+            ax = math.atan2(M[k, j], M[k, k]); ay = math.atan2(-M[k, i], cy); az = math.atan2(M[j, i], M[i, i])
+        else:
+            ax = math.atan2(-M[j, k], M[j, j]); ay = math.atan2(-M[k, i], cy); az = 0.0
+        if parity:
+            ax, ay, az = -ax, -ay, -az
+        if frame:
+            ax, az = az, ax
+        return ax, ay, az
+
+    def euler_matrix(ai, aj, ak, axes="sxyz"):
+        first, parity, rep, frame = _AXES[axes]
+        i = first; j = _NEXT[i + parity]; k = _NEXT[i - parity + 1]
+        if frame:
+            ai, ak = ak, ai
+        if parity:
+            ai, aj, ak = -ai, -aj, -ak
+        si, sj, sk = math.sin(ai), math.sin(aj), math.sin(ak)
+        ci, cj, ck = math.cos(ai), math.cos(aj), math.cos(ak)
+        cc, cs, sc, ss = ci * ck, ci * sk, si * ck, si * sk
+        M = np.identity(4)
+        M[i, i] = cj * ck; M[i, j] = sj * sc - cs; M[i, k] = sj * cc + ss
+        M[j, i] = cj * sk; M[j, j] = sj * ss + cc; M[j, k] = sj * cs - sc
+        M[k, i] = -sj; M[k, j] = cj * si; M[k, k] = cj * ci
+        return M
+
+    tr.euler_from_matrix = euler_from_matrix; tr.euler_matrix = euler_matrix
+    sys.modules["transformations"] = tr
     g = types.ModuleType("gymnasium"); sp = types.ModuleType("gymnasium.spaces")
 
     class Box:
@@ -390,3 +487,20 @@ def reset_explicit(env, mod, clip_id, frame, vel_noise=None, noise_quat=None, pl
             np.random.uniform, mod.random_quaternion_perturbation = real_uniform, real_rqp
     env.testing_mode = False
     return env._get_obs()
+
+
+def reference_srbdata(mocap_path):
+    """The reference's own SRBdata(mocap_path).humanoid2SRB() (testSRB_mujoco_original_viewer.py:765-1031) on the shipped clip files:
+    MuJoCo's humanoid FK / subtree CoM / mj_differentiatePos and transformations.py answered by oracle/srbdata.py's restatements, the
+    reference's own frame stitching, yaw-aligned cycle continuation, velocity, foot-orientation and contact processing as it stands."""
+    install()
+    import importlib
+    mod = importlib.import_module("env.testSRB_mujoco_original_viewer")
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        s = mod.SRBdata(mocap_path)
+        s.humanoid2SRB()
+    finally:
+        os.chdir(cwd)
+    return s
