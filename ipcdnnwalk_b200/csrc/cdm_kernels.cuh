@@ -558,30 +558,6 @@ struct SQP {
     }
     return m;
   }
-  // along nu + alpha * dir: g-sum = sum_{r_j<0} r_j s_j, slope-sum = sum_{r_j<0} s_j^2, mask of r_j < 0   (r = t(nu + alpha dir), s = t(dir))
-  __device__ __forceinline__ unsigned line(const double nu[6], const double dir[6], double alpha, double* gsum, double* ssum) const {
-    double W[3], V[3], Wd[3], Vd[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      Wd[i] = dir[i] * Di[i]; Vd[i] = dir[3 + i] * Di[3 + i];
-      W[i] = (nu[i] + alpha * dir[i]) * Di[i]; V[i] = (nu[3 + i] + alpha * dir[3 + i]) * Di[3 + i];
-    }
-    unsigned m = 0;
-    double g = 0, sl = 0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const double u0 = V[0] + W[1] * r[c][2] - W[2] * r[c][1], u1 = V[1] + W[2] * r[c][0] - W[0] * r[c][2], u2 = V[2] + W[0] * r[c][1] - W[1] * r[c][0];
-      const double e0 = Vd[0] + Wd[1] * r[c][2] - Wd[2] * r[c][1], e1 = Vd[1] + Wd[2] * r[c][0] - Wd[0] * r[c][2], e2 = Vd[2] + Wd[0] * r[c][1] - Wd[1] * r[c][0];
-#pragma unroll
-      for (int d = 0; d < 5; d++) {
-        const double t = n[d][0] * u0 + n[d][1] * u1 + n[d][2] * u2;
-        const double sd = n[d][0] * e0 + n[d][1] * e1 + n[d][2] * e2;
-        if (t < 0 && ((valid >> c) & 1)) { m |= 1u << (5 * c + d); g += t * sd; sl += sd * sd; }
-      }
-    }
-    *gsum = g; *ssum = sl;
-    return m;
-  }
   // H (lower triangle, 21) = I + invw * sum_{j in mask} a_j a_j^T
   __device__ __forceinline__ void hessian(unsigned mask, double invw, double H[21]) const {
     double TT[6] = {0, 0, 0, 0, 0, 0};      // xx yy zz xy xz yz of the torque block
@@ -634,8 +610,73 @@ struct SQP {
     H[20] = 1.0 + invw * d5 * d5 * FF[2];
   }
   // returns the number of Newton systems; nu in: initial guess, out: solution
-  __device__ __forceinline__ int solve_ls(const double y[6], double invw, double nu[6]) const {
-    unsigned S = tmask(nu);
+  // ---- column values kept in shared memory (one slot per lane: element j of a lane at [j * 32]) ----------------------------------
+  // T0_j = t_j(nu) and Sd_j = t_j(direction) make every evaluation along the search line r_j(alpha) = T0_j + alpha Sd_j one FMA per
+  // column, so the columns (3 + 3 FMAs each plus the contact-point velocities) are formed ONCE per Newton system instead of once per
+  // probe: t(nn) doubles as line(1), line(0) and the probes read the two arrays, and T0 += alpha Sd replaces the re-evaluation of
+  // t(nu) after the step.  (Registers cannot hold the 40 values: that variant spilled and lost)
+  // T0_j = t_j(v); returns the mask of t < 0.  Columns of absent contacts are stored as +1 (never active).
+  __device__ __forceinline__ unsigned store_t(const double v[6], double* __restrict__ T0) const {
+    const double W[3] = {v[0] * Di[0], v[1] * Di[1], v[2] * Di[2]}, V[3] = {v[3] * Di[3], v[4] * Di[4], v[5] * Di[5]};
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double u0 = V[0] + W[1] * r[c][2] - W[2] * r[c][1], u1 = V[1] + W[2] * r[c][0] - W[0] * r[c][2], u2 = V[2] + W[0] * r[c][1] - W[1] * r[c][0];
+      const bool vc = (valid >> c) & 1;
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const double t = n[d][0] * u0 + n[d][1] * u1 + n[d][2] * u2;
+        T0[(5 * c + d) * 32] = vc ? t : 1.0;
+        if (t < 0 && vc) m |= 1u << (5 * c + d);
+      }
+    }
+    return m;
+  }
+  // Sd_j = t_j(v) - T0_j; returns the mask of t_j(v) < 0
+  __device__ __forceinline__ unsigned store_s(const double v[6], const double* __restrict__ T0, double* __restrict__ Sd) const {
+    const double W[3] = {v[0] * Di[0], v[1] * Di[1], v[2] * Di[2]}, V[3] = {v[3] * Di[3], v[4] * Di[4], v[5] * Di[5]};
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double u0 = V[0] + W[1] * r[c][2] - W[2] * r[c][1], u1 = V[1] + W[2] * r[c][0] - W[0] * r[c][2], u2 = V[2] + W[0] * r[c][1] - W[1] * r[c][0];
+      const bool vc = (valid >> c) & 1;
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const double t = n[d][0] * u0 + n[d][1] * u1 + n[d][2] * u2;
+        Sd[(5 * c + d) * 32] = vc ? t - T0[(5 * c + d) * 32] : 0.0;
+        if (t < 0 && vc) m |= 1u << (5 * c + d);
+      }
+    }
+    return m;
+  }
+  // along the line: g-sum = sum_{r_j<0} r_j s_j, slope-sum = sum_{r_j<0} s_j^2, mask of r_j < 0, r_j = T0_j + alpha Sd_j
+  static __device__ __forceinline__ unsigned line_s(const double* __restrict__ T0, const double* __restrict__ Sd, double alpha, double* gsum, double* ssum) {
+    unsigned m = 0;
+    double g = 0, sl = 0;
+#pragma unroll
+    for (int j = 0; j < 20; j++) {
+      const double sd = Sd[j * 32];
+      const double rr = fma(alpha, sd, T0[j * 32]);
+      if (rr < 0) { m |= 1u << j; g += rr * sd; sl += sd * sd; }
+    }
+    *gsum = g; *ssum = sl;
+    return m;
+  }
+  // T0 += alpha Sd (the new nu's column values); returns their mask of t < 0
+  static __device__ __forceinline__ unsigned advance(double* __restrict__ T0, const double* __restrict__ Sd, double alpha) {
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < 20; j++) {
+      const double t = fma(alpha, Sd[j * 32], T0[j * 32]);
+      T0[j * 32] = t;
+      if (t < 0) m |= 1u << j;
+    }
+    return m;
+  }
+
+  // T0, Sd: this lane's slots of two [20][32] shared-memory arrays
+  __device__ __forceinline__ int solve_ls(const double y[6], double invw, double nu[6], double* __restrict__ T0, double* __restrict__ Sd) const {
+    unsigned S = store_t(nu, T0);
     int iters = 0;
     double rhs[6];
 #pragma unroll
@@ -646,7 +687,7 @@ struct SQP {
       hessian(S, invw, H);
       srb::ldl_solve6<double>(H, rhs, nn);
       iters++;
-      const unsigned Sn = tmask(nn);
+      const unsigned Sn = store_s(nn, T0, Sd);
       if (Sn == S) {
 #pragma unroll
         for (int i = 0; i < 6; i++) nu[i] = nn[i];
@@ -660,10 +701,10 @@ struct SQP {
         nmax = fmax(nmax, fabs(nn[i]));
       }
       double gs, ss;
-      line(nu, dir, 1.0, &gs, &ss);
+      line_s(T0, Sd, 1.0, &gs, &ss);
       double alpha = 1.0;
       if (b0 + dd + invw * gs > 0) {                           // the full step overshoots: exact line search in (0, 1)
-        unsigned ml = line(nu, dir, 0.0, &gs, &ss);
+        unsigned ml = line_s(T0, Sd, 0.0, &gs, &ss);
         double gl = b0 + invw * gs, sl = dd + invw * ss, al = 0.0, lo = 0.0, hi = 1.0;
         if (!(gl < 0)) alpha = 0.0;
         else {
@@ -672,7 +713,7 @@ struct SQP {
             double cand = al - gl / sl;
             const bool newton = cand > lo && cand < hi;
             if (!newton) cand = 0.5 * (lo + hi);
-            const unsigned mc = line(nu, dir, cand, &gs, &ss);
+            const unsigned mc = line_s(T0, Sd, cand, &gs, &ss);
             const double gc = b0 + cand * dd + invw * gs, sc = dd + invw * ss;
             al = cand;
             if (newton && mc == ml) break;
@@ -687,7 +728,7 @@ struct SQP {
 #pragma unroll
       for (int i = 0; i < 6; i++) { const double dlt = alpha * dir[i]; nu[i] += dlt; stepn = fmax(stepn, fabs(dlt)); }
       if (stepn <= 1e-13 * (1.0 + nmax)) break;
-      S = tmask(nu);
+      S = advance(T0, Sd, alpha);
     }
     return iters;
   }
@@ -712,6 +753,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
   const real* __restrict__ tab = A.tab;
   const int F = A.nframes, nf = A.nf_cycle;
   __shared__ __align__(16) double hsm[srb::HReduce<double, G>::SMEM_WORDS];
+  __shared__ double sq_t0[G == 1 ? 20 * 32 : 1], sq_sd[G == 1 ? 20 * 32 : 1];      // SQP column values along the search line (one slot per lane)
 
   CdmState<real> s;
   load_state(s, A.st, A.ist, A.Npad, e);
@@ -958,7 +1000,7 @@ __global__ void __launch_bounds__(32) cdm_step_kernel(const StepArgs<real> A) {
 #pragma unroll
           for (int i = 0; i < 6; i++) sq.Di[i] = 1.0 / Md[i];
           sq.valid = (unsigned)use;
-          iters = sq.solve_ls(y, P.inv_ridge2, nu);
+          iters = sq.solve_ls(y, P.inv_ridge2, nu, sq_t0 + lane32, sq_sd + lane32);
           lam_mask = sq.tmask(nu);
         }
         if (A.dbg != nullptr && active) {
