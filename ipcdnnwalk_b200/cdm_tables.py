@@ -9,9 +9,13 @@ defaultRLsetting.lua:291-346,395-418.  This module restates that pipeline in Num
                        (fc.buildContactConstraints :576-603), loop stitching with planar alignment (:1451-1513),
                        DMotionDOF / CDM_DMotionDOF (MotionDOF.calcDerivative), rttTouchDown / rttTouchOff /
                        swingDuration, mocapFeetOffset (:1564-1606), CoM by FK over the WRL skeleton.
-  STAND-INS (stated)   `makeCyclic` (module/info_hyunwooLowDOF.lua:23-35, uses taesooLib's C++ stitch operator) is replaced
-                       by a linear blend of the end-of-cycle discontinuity over `spread` frames; `math.gaussFilter` and
-                       `math.NonuniformSpline` (C++) by a truncated Gaussian kernel and SciPy's natural cubic spline.
+                       `math.gaussFilter` / `math.filter` (BaseLib/math/Filter.cpp:25-31,257-277,347-389: kernel
+                       exp(-i^2 / size) over an odd size, end samples repeated) and `math.NonuniformSpline` with zero end
+                       accelerations (BaseLib/math/BSpline.cpp:143-414 = the natural cubic spline; SciPy's agrees with the
+                       compiled reference to 5e-15) -- both pinned against oracle/_ref in tests/test_refpins.py.
+  STAND-IN (stated)    `makeCyclic` (module/info_hyunwooLowDOF.lua:23-35: MotionDOF:Stitch twice, taesooLib's C++ stitch
+                       operators over an Eigen solve) is replaced by a linear blend of the end-of-cycle discontinuity over
+                       `spread` frames.
 The step kernel and its oracle consume the tables as inputs, so parity of the hot path does not depend on them.
 
 Table row (TAB_W reals per frame, see `pack_rows`): CDM pose 7, CDM body twist (v, w) 6, mocap feet offset 2x3,
@@ -176,6 +180,27 @@ def leg_chain_columns(skel):
     return cols
 
 
+def gauss_kernel(kernel_size):
+    """Filter::GetGaussFilter (BaseLib/math/Filter.cpp:257-277): an even size becomes the next odd one, w_i = exp(-i^2 / size), sum 1."""
+    if kernel_size % 2 == 0:
+        kernel_size = kernel_size // 2 * 2 + 1
+    i = np.arange(-(kernel_size // 2), kernel_size // 2 + 1, dtype=np.float64)
+    w = np.exp(-(i * i) / float(kernel_size))
+    return w / w.sum()
+
+
+def gauss_filter(kernel_size, x):
+    """math.gaussFilter / math.filter: Filter::LTIFilter(1, GetGaussFilter(size), x) per column (Filter.cpp:347-389,569-630) --
+    convolution with the first / last sample repeated beyond the ends."""
+    w = gauss_kernel(kernel_size)
+    k = len(w) // 2
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    assert len(w) < n, "LTIFilter: kernel is too large"
+    idx = np.clip(np.arange(n)[:, None] + np.arange(-k, k + 1)[None, :], 0, n - 1)      # [n, 2k+1]
+    return np.einsum("nm...,m->n...", x[idx], w)
+
+
 def build_tables(mot, skel, info=WALK4, frame_rate=30.0, limit_length=300, default_lean=0.28 * 0.5):
     mot = mot.copy()
     nfr = mot.shape[0]
@@ -196,23 +221,15 @@ def build_tables(mot, skel, info=WALK4, frame_rate=30.0, limit_length=300, defau
         across = (tr[iLS] - tr[iRS]) + (tr[iLH] - tr[iRH])
         v = np.cross(across, np.array([0.0, 1.0, 0.0])); v[1] = 0.0
         fwd[i] = v / np.linalg.norm(v)
-    ks = info["filterFD"]
-    x = np.linspace(-2.0, 2.0, ks)
-    ker = np.exp(-x * x); ker /= ker.sum()
-    pad = np.concatenate([np.repeat(fwd[:1], ks, 0), fwd, np.repeat(fwd[-1:], ks, 0)])
-    sm = np.stack([np.convolve(pad[:, k], ker, mode="same") for k in range(3)], 1)[ks:-ks]
+    sm = gauss_filter(info["filterFD"], fwd)                       # math.gaussFilter(filterFD, forwardDir) (CDMTraj.lua:875)
     rot_y = np.array([_qaxis(np.array([0.0, 1.0, 0.0]), math.atan2(f[0], f[2])) for f in sm])
     from scipy.interpolate import CubicSpline
     knots = np.arange(0, nfr, 7)
     spl = CubicSpline(knots.astype(float), com[knots], bc_type="natural")
     tt = np.arange(knots[-1] + 1).astype(float)
     curve, acc = spl(tt), spl(tt, 2)
-    if info.get("filterCDMacc"):                                   # math.filter(newAcc, filterCDMacc) (CDMTraj.lua:738): Gaussian, odd kernel size
-        ka = info["filterCDMacc"] // 2 * 2 + 1
-        xa = np.linspace(-2.0, 2.0, ka)
-        kera = np.exp(-xa * xa); kera /= kera.sum()
-        pada = np.concatenate([np.repeat(acc[:1], ka, 0), acc, np.repeat(acc[-1:], ka, 0)])
-        acc = np.stack([np.convolve(pada[:, k], kera, mode="same") for k in range(3)], 1)[ka:-ka]
+    if info.get("filterCDMacc"):                                   # math.filter(newAcc, filterCDMacc) (CDMTraj.lua:738)
+        acc = gauss_filter(info["filterCDMacc"], acc)
     cdm = np.zeros((nfr, 7))
     lean0 = _qaxis(np.array([1.0, 0.0, 0.0]), default_lean)
     for i in range(nfr):

@@ -12,6 +12,9 @@
 //   quat     quater / vector3 / transf / Liegroup primitives  (BaseLib/math/quater.cpp, vector3.cpp, transf.cpp, Liegroup.cpp)
 //   terrain  OBJloader::Terrain::height                       (BaseLib/motion/Terrain.cpp:305-393)
 //   dof      MotionDOFcontainer / BinaryFile readers          (BaseLib/motion/MotionDOF.cpp, utility/tfile.cpp)
+//   signal   Filter::GetGaussFilter / gaussFilter (BaseLib/math/Filter.cpp:25-31,257-277,347-389,569-630), NonuniformSpline with
+//            zero end accelerations: getCurve / getSecondDeriv (BaseLib/math/BSpline.cpp:143-414), matrixn::sampleRow
+//            (BaseLib/math/matrixn.cpp:781-805) -- the signal operators under fc.CDMTraj (gym_cdm2/module/CDMTraj.lua:709-775,875)
 //   hull     GrahamScan add_point / partition_points / build_hull / get_hull   (PhysicsLib/convexhull/graham.cpp), the hull
 //            under math.projectTrajectoryToItsHull (gym_cdm2/ConvexHull2D.lua:150-186,362)
 // Numbers travel as whitespace-separated %.17g text (round-trip exact for doubles).
@@ -27,12 +30,16 @@
 #include "motion/Liegroup.h"
 #include "motion/IK_sdls/NodeWrap.h"
 #include "math/Operator.h"
+#include "math/Filter.h"
+#include "math/BSpline.h"
 #include "../PhysicsLib/convexhull/graham.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
+
+void __noop(...) {}                 // BaseLib/stdafx.cpp:5 (the TRACE sink of release builds; stdafx.cpp itself is not among the compiled files)
 
 static std::vector<double> read_all(const char* path) {
   std::vector<double> v;
@@ -229,8 +236,43 @@ static int cmd_hull(int argc, char** argv) {
   return 0;
 }
 
+// signal <in> <out>: in = rows cols | matrix | nk | kernel sizes | delta | nt | sample times
+static int cmd_signal(int argc, char** argv) {
+  std::vector<double> in = read_all(argv[2]);
+  Out out(argv[3]);
+  size_t p = 0;
+  const int rows = (int)in[p++], cols = (int)in[p++];
+  matrixn M(rows, cols);
+  for (int i = 0; i < rows; i++) for (int j = 0; j < cols; j++) M(i, j) = in[p++];
+  const int nk = (int)in[p++];
+  for (int k = 0; k < nk; k++) {
+    const int ks = (int)in[p++];
+    vectorn kernel;
+    Filter::GetGaussFilter(ks, kernel);
+    out.vec(kernel);
+    matrixn F(M);
+    Filter::gaussFilter(ks, F);                      // math.gaussFilter; math.filter is GetGaussFilter + LTIFilter(1, ...), the same two calls
+    out.mat(F);
+  }
+  const int delta = (int)in[p++];
+  intvectorn frames; frames.colon(0, rows, delta);   // CT.colon(0, rows, delta)
+  vectorn timing(frames.size());
+  matrixn control(frames.size(), cols);
+  for (int i = 0; i < frames.size(); i++) { timing[i] = frames[i]; for (int j = 0; j < cols; j++) control(i, j) = M(frames[i], j); }
+  NonuniformSpline spl(timing, control);
+  const int nf = (int)timing[timing.size() - 1] + 1;
+  vectorn nt; nt.linspace(timing[0], nf - 1, nf);
+  matrixn curve, acc;
+  spl.getCurve(nt, curve); spl.getSecondDeriv(nt, acc);
+  out.vec(timing); out.mat(curve); out.mat(acc);
+  const int ns = (int)in[p++];
+  out.d(ns);
+  for (int k = 0; k < ns; k++) { vectorn r; M.sampleRow(in[p++], r); out.vec(r); }
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: taesoo_ref fk|euler|quat|terrain|dof ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: taesoo_ref fk|euler|quat|terrain|dof|hull|signal ...\n"); return 1; }
   std::string c = argv[1];
   if (c == "fk" && argc >= 5) return cmd_fk(argc, argv);
   if (c == "euler" && argc >= 6) return cmd_euler(argc, argv);
@@ -238,6 +280,7 @@ int main(int argc, char** argv) {
   if (c == "terrain" && argc >= 4) return cmd_terrain(argc, argv);
   if (c == "dof" && argc >= 5) return cmd_dof(argc, argv);
   if (c == "hull" && argc >= 4) return cmd_hull(argc, argv);
+  if (c == "signal" && argc >= 4) return cmd_signal(argc, argv);
   fprintf(stderr, "bad command line\n");
   return 1;
 }

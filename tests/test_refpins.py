@@ -171,6 +171,51 @@ def test_oracle_lbfgs_equals_reference_liblbfgs(ref):
         assert abs(info["fx"] - float(ref[pre + "fx"])) <= 1e-12 * abs(info["fx"])
 
 
+# ---------------------------------------------------------------------------------------------------------- signal operators (a-20, f-3)
+@pytest.fixture(scope="module")
+def sig():
+    return dict(np.load(os.path.join(helpers.GOLDEN, "ref_taesoolib_signal.npz")))
+
+
+@pytest.mark.parametrize("name", ["com", "rw"])
+def test_table_builder_filters_equal_reference(sig, name):
+    """cdm_tables.gauss_kernel / gauss_filter (product, host side of the table builder) against Filter::GetGaussFilter / gaussFilter, and
+    the natural cubic spline build_tables uses against NonuniformSpline's curve and second derivative (CDMTraj.lua:709-740,875)."""
+    from scipy.interpolate import CubicSpline
+    from ipcdnnwalk_b200 import cdm_tables as ct
+    M = sig[f"sg_{name}_in"]
+    for k in sig[f"sg_{name}_kernel_sizes"]:
+        assert np.abs(ct.gauss_kernel(int(k)) - sig[f"sg_{name}_kernel_{k}"]).max() < 1e-15
+        assert np.abs(ct.gauss_filter(int(k), M) - sig[f"sg_{name}_filtered_{k}"]).max() < 1e-13 * max(1.0, np.abs(M).max())
+    with pytest.raises(AssertionError):
+        ct.gauss_filter(2 * M.shape[0], M)                 # the reference refuses kernels longer than the signal (Filter.cpp:349)
+    knots = sig[f"sg_{name}_timing"]
+    assert np.array_equal(knots, np.arange(0, M.shape[0], int(sig[f"sg_{name}_delta"])).astype(float))
+    spl = CubicSpline(knots, M[knots.astype(int)], bc_type="natural")
+    tt_ = np.arange(knots[-1] + 1.0)
+    assert np.abs(spl(tt_) - sig[f"sg_{name}_curve"]).max() < 1e-12 * max(1.0, np.abs(M).max())
+    assert np.abs(spl(tt_, 2) - sig[f"sg_{name}_acc"]).max() < 1e-12 * max(1.0, np.abs(M).max())
+
+
+@pytest.mark.parametrize("name", ["com", "rw"])
+def test_oracle_sample_row_equals_reference(sig, name):
+    """matrixn::sampleRow (float32 fraction, snapping inside 0.005 of a row, extrapolating end segment): both restatements, bit exact."""
+    from oracle import sds_filter as sf
+    M = sig[f"sg_{name}_in"]
+    for t, want in zip(sig[f"sg_{name}_times"], sig[f"sg_{name}_samples"]):
+        assert np.array_equal(tm.sample_row(M, float(t)), want), t
+        assert np.array_equal(np.asarray(sf.sample_row(M, float(t))), want), t
+
+
+@live
+def test_live_reference_reproduces_the_signal_fixture(sig):
+    for name in ("com", "rw"):
+        r = rh.signal(sig[f"sg_{name}_in"], [int(k) for k in sig[f"sg_{name}_kernel_sizes"]], int(sig[f"sg_{name}_delta"]), sig[f"sg_{name}_times"])
+        assert np.array_equal(r["curve"], sig[f"sg_{name}_curve"]) and np.array_equal(r["acc"], sig[f"sg_{name}_acc"]) and np.array_equal(r["samples"], sig[f"sg_{name}_samples"])
+        for k, f in zip(sig[f"sg_{name}_kernel_sizes"], r["filtered"]):
+            assert np.array_equal(f, sig[f"sg_{name}_filtered_{k}"])
+
+
 # ---------------------------------------------------------------------------------------------------------- live re-runs
 @live
 def test_live_reference_reproduces_the_fixture(ref):

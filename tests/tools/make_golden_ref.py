@@ -11,6 +11,9 @@ Contents (inputs + reference outputs; nothing here is produced by oracle/ or by 
   tr_*      OBJloader::Terrain::height on the gym_cdm2 height map (64 x 64 after the loader's decimation), tiled and not (a-21)
   hull_*    GrahamScan hulls (PhysicsLib/convexhull/graham.cpp) of height profiles: what math.projectTrajectoryToItsHull builds on   (f-2)
   dof_*     MotionDOFcontainer read of hanyang_lowdof_T_lafan1_walk_2915.dof                                              (f-4)
+  (ref_taesoolib_signal.npz, `python tests/tools/make_golden_ref.py signal`)
+  sg_*      Filter::GetGaussFilter / gaussFilter, NonuniformSpline (zero end accelerations) curve + second derivative, matrixn::sampleRow --
+            the signal operators under fc.CDMTraj, on the CoM track of the walking clip (33 frames) and on a random walk       (a-20, f-3)
   lb_*      libLBFGS (reference lbfgs.cpp, parameters as optimize.h:426-470 sets them) on its Rosenbrock sample and on MMSTO windows
             whose objective / gradient callback is oracle/mmsto.py (the missing Lua wrapper's role): status code, iteration and
             evaluation counts, per-iteration fx / step / line-search count, final x                                      (f-1)
@@ -130,5 +133,33 @@ def main():
     print("wrote tests/golden/ref_taesoolib.npz:", {k: np.asarray(v).shape for k, v in out.items()})
 
 
+def main_signal():
+    """Inputs + reference outputs of the signal operators (separate file so that ref_taesoolib.npz stays as recorded)."""
+    assert rh.available(), "build oracle/_ref first: make -C oracle/ref_build"
+    from ipcdnnwalk_b200 import cdm_tables as ct
+    from ipcdnnwalk_b200.vrml_skeleton import parse_wrl
+    rng = np.random.default_rng(20251021)
+    skel = parse_wrl(rh.WRL)
+    mot = ct.read_dof(DOF)                                  # one cycle, 33 frames
+    com = np.stack([ct._com(skel, *ct.fk(skel, mot[i])) for i in range(len(mot))])
+    walk = np.cumsum(rng.standard_normal((90, 4)), 0)
+    out = {}
+    for name, M, delta in (("com", com, 7), ("rw", walk, 5)):
+        n = M.shape[0]
+        ks = [16, 17, 12, 13, 5, 20] + ([63] if n > 63 else [])     # LTIFilter refuses kernels longer than the signal
+        t = np.concatenate([rng.uniform(0, n - 1, 40), np.floor(rng.uniform(0, n - 2, 12)) + rng.choice([0.004, 0.0049, 0.0051, 0.006, 0.994, 0.9949, 0.9951, 0.996], 12),
+                            [0.0, n - 1.0, n - 1.4, n - 1.003, 3.3, 10.7, 0.1 + 0.2, 1.0 / 3.0]])
+        r = rh.signal(M, ks, delta, t)
+        out.update({f"sg_{name}_in": M, f"sg_{name}_kernel_sizes": np.array(ks), f"sg_{name}_delta": np.array(delta), f"sg_{name}_times": t,
+                    f"sg_{name}_timing": r["timing"], f"sg_{name}_curve": r["curve"], f"sg_{name}_acc": r["acc"], f"sg_{name}_samples": r["samples"]})
+        for k, ker, f in zip(ks, r["kernels"], r["filtered"]):
+            out[f"sg_{name}_kernel_{k}"] = ker; out[f"sg_{name}_filtered_{k}"] = f
+    np.savez_compressed(os.path.join(GOLDEN, "ref_taesoolib_signal.npz"), **out)
+    print("wrote tests/golden/ref_taesoolib_signal.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "signal":
+        main_signal()
+    else:
+        main()

@@ -123,6 +123,22 @@ def hull(point_sets):
     return [c.mat().copy() for _ in point_sets]
 
 
+def signal(mat, kernel_sizes, delta, sample_times):
+    """Filter::GetGaussFilter / gaussFilter per kernel size, NonuniformSpline (zero end accelerations) through every `delta`-th row
+    evaluated at the unit frames (curve, second derivative), matrixn::sampleRow at `sample_times`."""
+    mat = np.asarray(mat, dtype=np.float64)
+    inp = np.concatenate([[mat.shape[0], mat.shape[1]], mat.reshape(-1), [len(kernel_sizes)], np.asarray(kernel_sizes, dtype=np.float64), [delta],
+                          [len(sample_times)], np.asarray(sample_times, dtype=np.float64)])
+    c = _run(["signal", "@in", "@out"], inp)
+    out = {"kernels": [], "filtered": []}
+    for _ in kernel_sizes:
+        out["kernels"].append(c.vec().copy()); out["filtered"].append(c.mat().copy())
+    out["timing"] = c.vec().copy(); out["curve"] = c.mat().copy(); out["acc"] = c.mat().copy()
+    n = int(c.scalar())
+    out["samples"] = np.stack([c.vec().copy() for _ in range(n)])
+    return out
+
+
 def dof(path, wrl=WRL):
     c = _run(["dof", wrl, path, "@out"], [0.0])
     r, k = int(c.scalar()), int(c.scalar())
