@@ -15,6 +15,7 @@
 //   signal   Filter::GetGaussFilter / gaussFilter (BaseLib/math/Filter.cpp:25-31,257-277,347-389,569-630), NonuniformSpline with
 //            zero end accelerations: getCurve / getSecondDeriv (BaseLib/math/BSpline.cpp:143-414), matrixn::sampleRow
 //            (BaseLib/math/matrixn.cpp:781-805) -- the signal operators under fc.CDMTraj (gym_cdm2/module/CDMTraj.lua:709-775,875)
+//   samplepose  MotionDOF::samplePose / MotionDOFinfo::blend (BaseLib/motion/MotionDOF.cpp:237-257,593-620)
 //   hull     GrahamScan add_point / partition_points / build_hull / get_hull   (PhysicsLib/convexhull/graham.cpp), the hull
 //            under math.projectTrajectoryToItsHull (gym_cdm2/ConvexHull2D.lua:150-186,362)
 // Numbers travel as whitespace-separated %.17g text (round-trip exact for doubles).
@@ -271,8 +272,23 @@ static int cmd_signal(int argc, char** argv) {
   return 0;
 }
 
+// samplepose <wrl> <file.dof> <in> <out>: in = sample times -> MotionDOF::samplePose rows
+static int cmd_samplepose(int argc, char** argv) {
+  VRMLloader l(argv[2]);
+  MotionDOFcontainer c(l.dofInfo, argv[3]);
+  std::vector<double> in = read_all(argv[4]);
+  Out out(argv[5]);
+  out.d((double)in.size()); out.d(c.mot.numDOF());
+  for (size_t k = 0; k < in.size(); k++) {
+    vectorn pose;
+    c.mot.samplePose(in[k], pose);
+    for (int j = 0; j < pose.size(); j++) out.d(pose[j]);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: taesoo_ref fk|euler|quat|terrain|dof|hull|signal ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: taesoo_ref fk|euler|quat|terrain|dof|hull|signal|samplepose ...\n"); return 1; }
   std::string c = argv[1];
   if (c == "fk" && argc >= 5) return cmd_fk(argc, argv);
   if (c == "euler" && argc >= 6) return cmd_euler(argc, argv);
@@ -281,6 +297,7 @@ int main(int argc, char** argv) {
   if (c == "dof" && argc >= 5) return cmd_dof(argc, argv);
   if (c == "hull" && argc >= 4) return cmd_hull(argc, argv);
   if (c == "signal" && argc >= 4) return cmd_signal(argc, argv);
+  if (c == "samplepose" && argc >= 6) return cmd_samplepose(argc, argv);
   fprintf(stderr, "bad command line\n");
   return 1;
 }

@@ -19,7 +19,7 @@ import helpers_mmsto as hm
 
 sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "tools"))
 import ref_harness as rh                    # noqa: E402
-from make_golden_ref import rosenbrock, mmsto_window, EU_MARKERS    # noqa: E402
+from make_golden_ref import rosenbrock, mmsto_window, EU_MARKERS, DOF as rh_DOF    # noqa: E402
 
 from ipcdnnwalk_b200 import vrml_skeleton
 from oracle import bone_fk as bk, mmsto as mm, tl_math as tm, tl_terrain as tt
@@ -207,8 +207,16 @@ def test_oracle_sample_row_equals_reference(sig, name):
         assert np.array_equal(np.asarray(sf.sample_row(M, float(t))), want), t
 
 
+def test_oracle_sample_pose_equals_reference(sig, ref):
+    """MotionDOF::samplePose (MotionDOF.cpp:593-620 over MotionDOFinfo::blend :237-257) on the walking clip: tl_math.sample_pose at round-off."""
+    mot = ref["dof_walk_2915"]
+    for t, want in zip(sig["sg_pose_times"], sig["sg_pose_rows"]):
+        assert np.abs(tm.sample_pose(mot, float(t)) - want).max() < 5e-16 * max(1.0, np.abs(want).max()), t
+
+
 @live
 def test_live_reference_reproduces_the_signal_fixture(sig):
+    assert np.array_equal(rh.samplepose(rh_DOF, sig["sg_pose_times"]), sig["sg_pose_rows"])
     for name in ("com", "rw"):
         r = rh.signal(sig[f"sg_{name}_in"], [int(k) for k in sig[f"sg_{name}_kernel_sizes"]], int(sig[f"sg_{name}_delta"]), sig[f"sg_{name}_times"])
         assert np.array_equal(r["curve"], sig[f"sg_{name}_curve"]) and np.array_equal(r["acc"], sig[f"sg_{name}_acc"]) and np.array_equal(r["samples"], sig[f"sg_{name}_samples"])

@@ -13,7 +13,7 @@ Contents (inputs + reference outputs; nothing here is produced by oracle/ or by 
   dof_*     MotionDOFcontainer read of hanyang_lowdof_T_lafan1_walk_2915.dof                                              (f-4)
   (ref_taesoolib_signal.npz, `python tests/tools/make_golden_ref.py signal`)
   sg_*      Filter::GetGaussFilter / gaussFilter, NonuniformSpline (zero end accelerations) curve + second derivative, matrixn::sampleRow --
-            the signal operators under fc.CDMTraj, on the CoM track of the walking clip (33 frames) and on a random walk       (a-20, f-3)
+            the signal operators under fc.CDMTraj, on the CoM track of the walking clip (33 frames) and on a random walk; MotionDOF::samplePose on the clip   (a-20, f-3)
   lb_*      libLBFGS (reference lbfgs.cpp, parameters as optimize.h:426-470 sets them) on its Rosenbrock sample and on MMSTO windows
             whose objective / gradient callback is oracle/mmsto.py (the missing Lua wrapper's role): status code, iteration and
             evaluation counts, per-iteration fx / step / line-search count, final x                                      (f-1)
@@ -154,6 +154,10 @@ def main_signal():
                     f"sg_{name}_timing": r["timing"], f"sg_{name}_curve": r["curve"], f"sg_{name}_acc": r["acc"], f"sg_{name}_samples": r["samples"]})
         for k, ker, f in zip(ks, r["kernels"], r["filtered"]):
             out[f"sg_{name}_kernel_{k}"] = ker; out[f"sg_{name}_filtered_{k}"] = f
+    # MotionDOF::samplePose / MotionDOFinfo::blend on the walking clip (root quaternion by safeSlerp, everything else linear, double fraction)
+    nfr = mot.shape[0]
+    tp = np.concatenate([rng.uniform(0, nfr - 1, 30), np.floor(rng.uniform(0, nfr - 2, 8)) + rng.choice([0.0049, 0.0051, 0.9949, 0.9951], 8), [0.0, nfr - 1.0, nfr - 1.5, 5.5, 1.0 / 3.0]])
+    out["sg_pose_times"] = tp; out["sg_pose_rows"] = rh.samplepose(DOF, tp)
     np.savez_compressed(os.path.join(GOLDEN, "ref_taesoolib_signal.npz"), **out)
     print("wrote tests/golden/ref_taesoolib_signal.npz:", len(out), "arrays")
 

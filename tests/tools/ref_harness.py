@@ -139,6 +139,13 @@ def signal(mat, kernel_sizes, delta, sample_times):
     return out
 
 
+def samplepose(path, times, wrl=WRL):
+    """MotionDOF::samplePose of the clip at `times` -> [n, numDOF]."""
+    c = _run(["samplepose", wrl, path, "@in", "@out"], np.asarray(times, dtype=np.float64))
+    n, k = int(c.scalar()), int(c.scalar())
+    return c.take(n * k, (n, k))
+
+
 def dof(path, wrl=WRL):
     c = _run(["dof", wrl, path, "@out"], [0.0])
     r, k = int(c.scalar()), int(c.scalar())
