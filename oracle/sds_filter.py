@@ -9,7 +9,10 @@ Follows, line by line:
 
 Only the code path the SRBTrack env takes is restated: usePreset=True so `self.ct is None`, hence
 `updateCoef` always raises inside the try block and falls back to `useKpreset(Q)`.
-PARITY UNPINNED (the reference ships no expected values; libmainlib cannot be built here).
+PARITY PINNED against the reference's own class: tests/tools/ref_sds_harness.py imports work/controlmodule.py from /root/reference over
+NumPy-backed matrixn / vectorn objects (libmainlib cannot be built here) and tests/test_refenv_pins.py compares gains (exact) and filter
+states (1e-13) with it -- fixture tests/golden/refenv_sds.npz; `sample_row` is bit exact against the compiled matrixn.cpp
+(tests/test_refpins.py).  Not pinned: `piecewise_linear_map` (pure Lua in the reference, restated).
 """
 import math
 import numpy as np

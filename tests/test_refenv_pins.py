@@ -1,9 +1,9 @@
 """Pins of the SRBTrack path against the REFERENCE'S OWN ENVIRONMENT CODE.
 
 tests/golden/refenv_rollout_{test,training}.npz and refenv_special.npz are roll-outs of env/SRBEnv5_mocap_list_window.py /
-..._training.py themselves, executed from /root/reference through tests/tools/ref_srbenv_harness.py -- MuJoCo, Clarabel, controlmodule.SDS
-and SRBdata answered by stated stand-ins (restated MuJoCo free-body semantics, an exact QP solve, the SDS restatement, the committed clip
-tables), every other line the reference's code as it stands: action decoding, contact logic incl. the probability hysteresis, site
+..._training.py themselves, executed from /root/reference through tests/tools/ref_srbenv_harness.py -- MuJoCo, Clarabel and SRBdata
+answered by stated stand-ins (restated MuJoCo free-body semantics, an exact QP solve, the committed clip tables), controlmodule.SDS being the
+reference's own class over NumPy-backed matrixn / vectorn objects (tests/tools/ref_sds_harness.py), every other line the reference's code as it stands: action decoding, contact logic incl. the probability hysteresis, site
 placement, the assembly of the QP in solve_qp_for_contact_forces, force clamp, impulse schedule, history, get_obs_window, _get_reward,
 _get_done, reset / set_state.  Generator: tests/tools/make_golden_refenv.py.
 
@@ -108,6 +108,26 @@ def test_oracle_equals_the_reference_terrain_environment_code():
             assert bool(done) == bool(g["done"][e, k]) and (st[23:26] == g["state"][e, k, 23:26]).all(), (e, k)
             _close(st[:23], g["state"][e, k, :23], 1e-10, f"terrain env {e} step {k} state")
             _close(obs, g["obs"][e, k], 1e-10, f"terrain env {e} step {k} obs")
+
+
+def test_oracle_sds_equals_the_reference_filter_class():
+    """oracle/sds_filter.py against work/controlmodule.py's SDS / NonlinearController run from /root/reference (tests/tools/ref_sds_harness.py):
+    preset gains exact over logQ 5 ... 11, filter state after every singleStep at round-off."""
+    import ref_sds_harness as sh
+    from oracle.sds_filter import SDS
+    g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_sds.npz")))
+    plan = [(q, t, bool(z)) for q, t, z in g["plan"]]
+    xs, Ks = sh.drive(SDS, plan)
+    assert np.array_equal(Ks, g["K"])
+    assert np.abs(xs - g["x"]).max() < 1e-13 * max(1.0, np.abs(g["x"]).max())
+
+
+@live
+def test_live_reference_sds_class_reproduces_the_fixture():
+    import ref_sds_harness as sh
+    g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_sds.npz")))
+    xs, Ks = sh.drive(sh.load().SDS, [(q, t, bool(z)) for q, t, z in g["plan"]])
+    assert np.array_equal(Ks, g["K"]) and np.array_equal(xs, g["x"])
 
 
 @live

@@ -9,6 +9,8 @@ reset plan, the reset observation, 40 float32 actions and per step the observati
 state vector (helpers.oracle_state_vector) and the QP accelerations of the four sub-steps -- here read from the reference environment
 object (`q_ddot_QP` as solve_qp_for_contact_forces returns it).  The actions come from helpers.tracking_action on an oracle environment
 stepped alongside (it needs the state; the two agree to 1e-13, which this script asserts).
+refenv_sds.npz: the reference's swing-foot filter class by itself (work/controlmodule.py SDS through tests/tools/ref_sds_harness.py) driven
+the way SRBEnv.step drives it, over the whole gain range (logQ 5 ... 11, the environment uses 9 ... 11).
 refenv_special.npz: the policy-probability contact hysteresis (`_last_contact_prob` side channel, SRBEnv5_mocap_list_window.py:239-275)
 and the push-impulse schedule with a 6-component force (:191-206) -- branches the plain roll-outs do not reach."""
 import os
@@ -125,8 +127,24 @@ def rollout_terrain(planars=((0.0, 0.0), (22.0, 24.0), (-42.0, 42.0), (42.0, -40
     return {k: np.array(v) for k, v in out.items()}, worst
 
 
+def sds_plan(seed=5, n=80):
+    rng = np.random.default_rng(seed)
+    plan = [(10 ** rng.uniform(5, 10.99), rng.uniform(-1, 1), bool(rng.random() < 0.1)) for _ in range(n)]
+    plan[3] = (1e9, 0.3, False); plan[4] = (1e5, 0.2, False); plan[5] = (1e11, 0.1, False); plan[6] = (10 ** 7.003, 0.1, False); plan[7] = (10 ** 9.996, -0.4, True)
+    return plan
+
+
+def make_sds():
+    import ref_sds_harness as sh
+    plan = sds_plan()
+    xs, Ks = sh.drive(sh.load().SDS, plan)
+    np.savez_compressed(os.path.join(GOLDEN, "refenv_sds.npz"), plan=np.array([[q, t, float(z)] for q, t, z in plan]), x=xs, K=Ks)
+    print("SDS of the reference: ", xs.shape, "states,", Ks.shape, "gains")
+
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
+    make_sds()
     g, worst = rollout_terrain()
     np.savez_compressed(os.path.join(GOLDEN, "refenv_rollout_terrain.npz"), **g)
     print("terrain reference-code roll-out", {k: v.shape for k, v in g.items()}, "| max |reference - oracle|", worst)

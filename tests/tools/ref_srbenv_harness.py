@@ -7,8 +7,9 @@ the third-party back ends it cannot have here replaced by stated stand-ins:
               one-free-body model gym_trackSRB/Characters/SRB5.xml, implemented by oracle/mj_freebody.py (the restated MuJoCo semantics).
   clarabel    not installed.  `FakeClarabel.DefaultSolver` solves the QP it is handed EXACTLY (the problem is strictly convex, its optimum
               is unique, so any exact solver returns what an interior-point solver converges to): equality rows eliminated, NNLS on the rest.
-  work.controlmodule.SDS   needs taesooLib's libmainlib (matrixn / vectorn).  Stand-in: oracle/sds_filter.py behind the matrixn-style
-              accessors the environment uses (test variant only; the training variant has no filter).
+  work.controlmodule.SDS   the reference's OWN class (work/controlmodule.py:911-1086), imported by tests/tools/ref_sds_harness.py; only
+              libmainlib's matrixn / vectorn and two lua helpers under it are NumPy-backed stand-ins (test variant only; the training
+              variant has no filter).
   gymnasium, transformations, work.settings / rendermodule, env.Policy_prior_posterior_MoE_window   import-time stubs (spaces.Box, Env,
               the `_last_contact_prob` side channel).
   SRBdata (humanoid2SRB needs MuJoCo's humanoid FK)   for the environments `SRBDataProcess` is answered by a holder of the clip tables
@@ -282,33 +283,11 @@ def _fake_clarabel():
 
 # ------------------------------------------------------------------------------------------------ the rest of the import-time stubs
 def _fake_control():
-    from oracle.sds_filter import SDS as OracleSDS
-
-    class _Mat:
-        """the matrixn accessors the environment uses on SDS.x / SDS.xd: m.set(i, 0, v), m(i, 0)"""
-
-        def __init__(self, a):
-            self.a = a
-
-        def set(self, i, j, v):
-            self.a[i] = v
-
-        def __call__(self, i, j):
-            return self.a[i]
-
-    class SDS:
-        def __init__(self, mass, B, k, q, qd, dt, usePreset=False):
-            self._s = OracleSDS(mass, B, k, q, qd, dt, usePreset)
-            self.x = _Mat(self._s.x); self.xd = _Mat(self._s.xd)
-
-        def updateCoef(self, B, k, Q):
-            self._s.updateCoef(B, k, Q)
-
-        def singleStep(self):
-            self._s.singleStep()
-
+    """work.controlmodule as the environment sees it: the reference's OWN SDS / NonlinearController classes (work/controlmodule.py),
+    imported by tests/tools/ref_sds_harness.py over NumPy-backed matrixn / vectorn objects (libmainlib cannot be built here)."""
+    import ref_sds_harness as sh
     c = types.ModuleType("work.controlmodule")
-    c.SDS = SDS
+    c.SDS = sh.load().SDS
     return c
 
 
