@@ -9,8 +9,9 @@ full-body pose, Euler velocity / acceleration targets, foot marker targets, CoM 
   BaseLib/math/transf.cpp:98-103,178-183     transf::mult, toGlobalPos
   BaseLib/motion/IK_sdls/NodeWrap.cpp:325-371,548-573   calcMomentumCOM / setDQ of the one-body SRB tree (as oracle/bone_fk.py)
 PARITY: the primitives (Exp(se3), toBaseR, transf, inv_dAd / one-body momentum) are pinned to the reference's compiled BaseLib
-(tests/test_refpins.py: test_oracle_se3_exp_equals_reference, test_oracle_primitives_equal_reference); their composition in
-_extractSingleFrameFullbody has no recorded outputs (UNPINNED).  The SRB body's mass / inertia / local CoM are inputs: in the reference they come from
+(tests/test_refpins.py: test_oracle_se3_exp_equals_reference, test_oracle_primitives_equal_reference); their composition is pinned to the
+reference's own unpack_obs_extra / _extractSingleFrameFullbody / pack_obs_extra run from /root/reference (tests/tools/ref_delta_harness.py,
+tests/test_refenv_pins.py: exact, momentum 3e-14).  The SRB body's mass / inertia / local CoM are inputs: in the reference they come from
 `RE.MujocoLoader('gym_trackSRB/Characters/SRB4.xml', {convertToYUP=true})` (walk_SRBTrack2025.py:243-246), a file that is not
 in the reference tree."""
 import math

@@ -420,7 +420,8 @@ def lbfgs(x, evaluate, epsilon=1e-5, m=6, max_iterations=0):
 # online loop (walk_SRBTrack2025.py:617, walk_SRBTrack2025_terrain_singlethreaded.py:610).  SURVEY 8f rank 2.
 #   QuadraticFunctionHardCon: BaseLib/math/OperatorStitch.cpp:531-620 (H = 2 sum c c^T, R = -2 sum v c, KKT matrix),
 #   Resource/scripts/module.lua:2108-2124,2165-2207 (addWeighted, con, solve = math.LUsolve of the KKT system).
-# PARITY UNPINNED (no recorded outputs); pinned by the KKT conditions and constraint residuals in tests/test_oracle_mmsto_cpu.py.
+# PARITY PINNED to the reference's own removeCOMsliding_online run from /root/reference (tests/tools/ref_delta_harness.py, tests/test_refenv_pins.py:
+# 8e-16, flat and with projectToGround), besides the KKT conditions and constraint residuals in tests/test_oracle_mmsto_cpu.py.
 
 def hardcon_solve(nvar, sq_terms, con_terms):
     """sq_terms: (weight, [(coef, index)...], const); con_terms: ([(coef, index)...], const) -> x[nvar]."""

@@ -264,3 +264,89 @@ def test_cuda_equals_the_reference_terrain_environment_code(built_lib, lanes):
         _close(st[:, :23], g["state"][:, k, :23], RTOL64, f"terrain state step {k}")
         _close(obs.cpu().numpy(), g["obs"][:, k], RTOL64, f"terrain obs step {k}")
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------------- SRB -> full-body mapping (f-2a, f-2b, f-2c)
+def _delta():
+    return dict(np.load(os.path.join(helpers.GOLDEN, "refenv_delta.npz")))
+
+
+EX_KEYS = ("humanPose", "dx_ddx", "feetpos", "com", "momentum", "con_bin", "con")
+
+
+def test_oracle_equals_the_reference_fullbody_mapping_code():
+    """oracle/fullbody_map.py and oracle/mmsto.remove_com_sliding_online against gym_trackSRB/taesooLib/DeltaExtractor.py run from
+    /root/reference (tests/tools/ref_delta_harness.py): pack_obs_extra on the stepping reference environment, unpack_obs_extra +
+    _extractSingleFrameFullbody, removeCOMsliding_online (flat and with projectToGround)."""
+    from oracle import fullbody_map as fm, mmsto as mm
+    from oracle.srb_env import OracleSRBEnv
+    from ipcdnnwalk_b200 import vrml_skeleton
+    g = _delta()
+    for e in range(g["pk_plans"].shape[0]):
+        orc = OracleSRBEnv(helpers.fresh_clips(), "test")
+        helpers.oracle_reset(orc, g["pk_plans"][e])
+        for k in range(g["pk_actions"].shape[1]):
+            orc.step(g["pk_actions"][e, k])
+            _close(fm.pack_obs_extra(orc), g["pk_extra"][e, k], 1e-12, f"pack_obs_extra env {e} step {k}")
+    for i in range(g["ex_extra"].shape[0]):
+        o = fm.extract_single_frame_fullbody(g["ex_extra"][i], g["ex_row"][i], float(g["ex_mass"]), g["ex_inertia"], g["ex_local_com"])
+        for k in EX_KEYS:
+            _close(o[k], g["ex_" + k][i], 1e-12, f"extract item {i} {k}")
+    skel = vrml_skeleton.builtin()
+    for j in range(int(g["cs_count"])):
+        gh = g[f"cs{j}_ground_h"]
+        out, _, _ = mm.remove_com_sliding_online(skel, g[f"cs{j}_com_srb"], g[f"cs{j}_desired"], g[f"cs{j}_pose"], fix_y_also=bool(g[f"cs{j}_fix_y"]),
+                                                 ground_h=gh if gh.size else None)
+        _close(out, g[f"cs{j}_out"], 1e-12, f"removeCOMsliding_online case {j}")
+        assert np.abs(out - g[f"cs{j}_pose"]).max() > 1e-3
+
+
+def _delta_available():
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "tools"))
+    import ref_delta_harness as dh
+    return dh.available()
+
+
+@pytest.mark.skipif(not _delta_available(), reason="/root/reference or oracle/_ref is missing: the committed fixture stands in")
+def test_live_reference_fullbody_mapping_code_reproduces_the_fixture():
+    import ref_delta_harness as dh
+    g = _delta()
+    mod = dh.load()
+    for i in (0, 1, 4, 9):
+        r = dh.extract(mod, g["ex_extra"][i], g["ex_row"][i], float(g["ex_mass"]), g["ex_inertia"], g["ex_local_com"])
+        for k in EX_KEYS:
+            assert np.array_equal(r[k], g["ex_" + k][i]), (i, k)
+    for j in (1, 2):
+        gh = g[f"cs{j}_ground_h"]
+        new = dh.remove_com_sliding(mod, g[f"cs{j}_com_srb"], g[f"cs{j}_desired"], g[f"cs{j}_pose"], fix_y_also=bool(g[f"cs{j}_fix_y"]), ground_h=gh if gh.size else None)
+        _close(new, g[f"cs{j}_out"], 1e-13, f"removeCOMsliding_online case {j}")
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_reference_fullbody_mapping_code(built_lib):
+    """The CUDA side of rows f-2a / f-2b / f-2c against the reference code's outputs directly: srb_pack_obs_extra after the same steps,
+    fullbody_extract on the same rows, mmsto_remove_com_sliding on the same windows."""
+    import torch
+    import helpers_mmsto as hm
+    from ipcdnnwalk_b200 import SRBVecEnv, ShortTrajOpt, vrml_skeleton
+    from ipcdnnwalk_b200.short_traj_opt import extractSingleFrameFullbody
+    g = _delta()
+    n = g["pk_plans"].shape[0]
+    env = SRBVecEnv(helpers.fresh_clips(), n, variant="test", precision=64, auto_reset=False)
+    env.reset(plan=g["pk_plans"])
+    for k in range(g["pk_actions"].shape[1]):
+        env.step(torch.as_tensor(g["pk_actions"][:, k], device="cuda"))
+        ex = env.pack_obs_extra().cpu().numpy()
+        _close(ex, g["pk_extra"][:, k], RTOL64, f"pack_obs_extra step {k}")
+        assert np.array_equal(ex[:, 27:29], g["pk_extra"][:, k, 27:29])
+    env.close()
+    out = extractSingleFrameFullbody(g["ex_extra"], g["ex_row"], float(g["ex_mass"]), g["ex_inertia"], g["ex_local_com"])
+    for k in EX_KEYS:
+        _close(out[k].cpu().numpy(), g["ex_" + k], 1e-11, f"fullbody_extract {k}")
+    opt = ShortTrajOpt(vrml_skeleton.builtin(), hm.NF, hm.MARKERS)
+    for j in range(int(g["cs_count"])):
+        gh = g[f"cs{j}_ground_h"]
+        pose = torch.as_tensor(g[f"cs{j}_pose"][None], device="cuda").contiguous()
+        opt.removeCOMsliding_online(g[f"cs{j}_com_srb"][None], g[f"cs{j}_desired"][None], pose, fix_y_also=bool(g[f"cs{j}_fix_y"]), ground_h=gh[None] if gh.size else None)
+        _close(pose.cpu().numpy()[0], g[f"cs{j}_out"], 1e-10, f"mmsto_remove_com_sliding case {j}")
+    opt.close()

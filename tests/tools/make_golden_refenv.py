@@ -9,6 +9,9 @@ reset plan, the reset observation, 40 float32 actions and per step the observati
 state vector (helpers.oracle_state_vector) and the QP accelerations of the four sub-steps -- here read from the reference environment
 object (`q_ddot_QP` as solve_qp_for_contact_forces returns it).  The actions come from helpers.tracking_action on an oracle environment
 stepped alongside (it needs the state; the two agree to 1e-13, which this script asserts).
+refenv_delta.npz: the reference's SRB -> full-body mapping code (gym_trackSRB/taesooLib/DeltaExtractor.py through tests/tools/ref_delta_harness.py):
+pack_obs_extra on the reference environment while it steps, unpack_obs_extra + _extractSingleFrameFullbody on seeded decoder rows (SRB tree
+momentum by the compiled reference), removeCOMsliding_online on seeded windows (full-body CoM by the compiled reference).
 refenv_sds.npz: the reference's swing-foot filter class by itself (work/controlmodule.py SDS through tests/tools/ref_sds_harness.py) driven
 the way SRBEnv.step drives it, over the whole gain range (logQ 5 ... 11, the environment uses 9 ... 11).
 refenv_special.npz: the policy-probability contact hysteresis (`_last_contact_prob` side channel, SRBEnv5_mocap_list_window.py:239-275)
@@ -134,6 +137,58 @@ def sds_plan(seed=5, n=80):
     return plan
 
 
+DELTA_SRB = dict(mass=60.0, inertia=np.array([[3.0, 0.1, 0.0], [0.1, 1.5, -0.2], [0.0, -0.2, 2.5]]), local_com=np.array([0.01, -0.03, 0.02]))
+
+
+def make_delta(n_items=24, n_steps=14):
+    import ref_delta_harness as dh
+    from oracle import fullbody_map as fm
+    from ipcdnnwalk_b200 import vrml_skeleton
+    from test_oracle_mmsto_cpu import _com_slide_case
+    assert dh.available(), "needs /root/reference and oracle/_ref (make -C oracle/ref_build)"
+    mod = dh.load()
+    out = {}
+    # ---- pack_obs_extra on the reference environment (test variant), two environments
+    rng = np.random.default_rng(41)
+    clips = helpers.fresh_clips()
+    ref, emod = rh.make_env("test", clips)
+    P, A, E = [], [], []
+    for e in range(2):
+        orc = OracleSRBEnv(helpers.fresh_clips(), "test")
+        plan = helpers.random_plan(rng, clips, noise=True)
+        rh.reset_explicit(ref, emod, int(plan[0]), int(plan[1]), plan[2:5], plan[5:9]); helpers.oracle_reset(orc, plan)
+        acts, ex = [], []
+        for k in range(n_steps):
+            a = helpers.tracking_action(orc, rng, 0.1)
+            ref.step(a); orc.step(a)
+            acts.append(a); ex.append(mod.pack_obs_extra(ref).a.copy())
+        P.append(plan); A.append(np.array(acts)); E.append(np.array(ex))
+    out.update(pk_plans=np.array(P), pk_actions=np.array(A), pk_extra=np.array(E))
+    # ---- unpack_obs_extra + _extractSingleFrameFullbody
+    rng = np.random.default_rng(43)
+    extra = rng.normal(0, 0.5, (n_items, fm.EXTRA_W)); row = rng.normal(0, 0.3, (n_items, fm.ROW_W))
+    extra[:2] = E[0][3:5]                                    # two records the environment produced
+    for c in (3, 16, 23):
+        extra[:, c:c + 4] /= np.linalg.norm(extra[:, c:c + 4], axis=1, keepdims=True)
+    row[1, 0:3] = 0.0                                        # small-angle branch of Exp
+    row[2, 0:3] = [0.0, 3.1, 0.2]; row[3, 0:3] = [3.0, 0.1, 0.0]; row[4, 0:3] = [0.1, 0.0, 3.05]     # near half turns: the non-trace branches of matrix -> quaternion
+    res = [dh.extract(mod, extra[i], row[i], DELTA_SRB["mass"], DELTA_SRB["inertia"], DELTA_SRB["local_com"]) for i in range(n_items)]
+    out.update(ex_extra=extra, ex_row=row, ex_mass=np.array(DELTA_SRB["mass"]), ex_inertia=DELTA_SRB["inertia"], ex_local_com=DELTA_SRB["local_com"])
+    for k in res[0]:
+        out["ex_" + k] = np.stack([r[k] for r in res])
+    # ---- removeCOMsliding_online
+    skel = vrml_skeleton.builtin()
+    for j, (seed, nvar, fy, ground) in enumerate(((3, 8, True, False), (4, 8, False, True), (5, 6, True, True), (6, 8, True, False))):
+        pose, com_srb, des = _com_slide_case(skel, seed, nvar)
+        gh = np.random.default_rng(100 + seed).uniform(0, 0.4, nvar) if ground else None
+        new = dh.remove_com_sliding(mod, com_srb, des, pose, fix_y_also=fy, ground_h=gh)
+        out.update({f"cs{j}_pose": pose, f"cs{j}_com_srb": com_srb, f"cs{j}_desired": des, f"cs{j}_fix_y": np.array(int(fy)),
+                    f"cs{j}_ground_h": gh if gh is not None else np.zeros(0), f"cs{j}_out": new})
+    out["cs_count"] = np.array(4)
+    np.savez_compressed(os.path.join(GOLDEN, "refenv_delta.npz"), **out)
+    print("DeltaExtractor of the reference:", {k: np.asarray(v).shape for k, v in out.items() if k.startswith(("pk_", "ex_h", "ex_m", "cs0_out"))})
+
+
 def make_sds():
     import ref_sds_harness as sh
     plan = sds_plan()
@@ -145,6 +200,7 @@ def make_sds():
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
     make_sds()
+    make_delta()
     g, worst = rollout_terrain()
     np.savez_compressed(os.path.join(GOLDEN, "refenv_rollout_terrain.npz"), **g)
     print("terrain reference-code roll-out", {k: v.shape for k, v in g.items()}, "| max |reference - oracle|", worst)
