@@ -22,7 +22,9 @@ NOT IN THE REFERENCE TREE (restated from their call sites, stated stand-ins):
       the interval of the mid-sole point, where a frame with only the toe (heel) down rebuilds the other marker at footLen along the
       horizontal toe-heel direction; conDir = normalised horizontal sum of (toe - heel) over the interval.
   W6  fc.getContactPositions_stair(conToe, conHeel, footCenterTraj) -> conPos = mean of the foot-centre trajectory over each interval.
-PARITY UNPINNED for these two; the quadratic programmes, the hull projection and the post-processing follow the reference literally."""
+PARITY UNPINNED for these two.  The quadratic programmes, their hard constraints, the ground clamp and avoidHull are PINNED to the reference's own
+functions run from /root/reference with W5 / W6 / the hull projection plugged in as its Lua helpers (tests/tools/ref_delta_harness.py,
+tests/test_refenv_pins.py: 1e-15 over 40 windows)."""
 import math
 
 import numpy as np

@@ -350,3 +350,98 @@ def test_cuda_equals_the_reference_fullbody_mapping_code(built_lib):
         opt.removeCOMsliding_online(g[f"cs{j}_com_srb"][None], g[f"cs{j}_desired"][None], pose, fix_y_also=bool(g[f"cs{j}_fix_y"]), ground_h=gh[None] if gh.size else None)
         _close(pose.cpu().numpy()[0], g[f"cs{j}_out"], 1e-10, f"mmsto_remove_com_sliding case {j}")
     opt.close()
+
+
+def _foot_cases(g):
+    from test_foot_sliding import make_window
+    wavy = lambda p: 0.02 * np.sin(3 * p[0]) + 0.03 * np.cos(2 * p[2])          # noqa: E731
+    for k in range(int(g["fs_count"])):
+        w = make_window(int(g[f"fs{k}_seed"]))
+        yield k, w, bool(g[f"fs{k}_stair"]), (wavy if int(g[f"fs{k}_wavy"]) else (lambda p: 0.0)), bool(g[f"fs{k}_use_dv"]), g[f"fs{k}_out"]
+
+
+def test_oracle_equals_the_reference_foot_sliding_code():
+    """oracle/foot_sliding.py against removeFootSliding_online / removeFootSliding_online_stair / avoidHull of DeltaExtractor.py:650-897 run
+    from /root/reference: 24 windows over all contact patterns, flat and wavy ground, with and without the caller's desiredVel.  The Lua
+    helpers under it are stand-ins on both sides (W5 / W6, hull projection over the pinned GrahamScan); the programmes, their constraints,
+    the ground clamp and the hull passes are the reference's."""
+    from oracle import foot_sliding as fs
+    from test_foot_sliding import FOOT_LEN
+    for k, w, stair, ground, use_dv, want in _foot_cases(_delta()):
+        dv = w["desired_vel"] if use_dv else None
+        got = (fs.remove_foot_sliding_online_stair(FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["foot_center"], dv, ground) if stair
+               else fs.remove_foot_sliding_online(FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], dv, ground))
+        _close(got, want, 1e-12, f"foot sliding case {k}")
+
+
+def test_oracle_equals_the_reference_foot_sliding_code_on_the_playground():
+    """Both variants on the slope of the playground's pyramid (ground = terrain_height_ray): the hull passes of avoidHull act here."""
+    from oracle import foot_sliding as fs
+    from test_foot_sliding import FOOT_LEN
+    from make_golden_refenv import playground_ground, playground_window
+    g = _delta()
+    ground = playground_ground()
+    lifted = 0
+    for j in range(int(g["pg_count"])):
+        w = playground_window(j)
+        st = fs.remove_foot_sliding_online_stair(FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["foot_center"], w["desired_vel"], ground)
+        _close(st, g[f"pg{j}_stair_out"], 1e-12, f"stair case {j}")
+        base = fs._marker_qps(FOOT_LEN, np.asarray(w["con"]), np.asarray(w["initial"]), w["marker_traj"], w["marker"], w["desired_vel"], ground, True, w["foot_center"])
+        lifted += int((g[f"pg{j}_stair_out"][:, 1::3] > base[:, 1::3] + 1e-9).any())
+        pl = fs.remove_foot_sliding_online(FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["desired_vel"], ground)
+        _close(pl, g[f"pg{j}_plain_out"], 1e-12, f"plain case {j}")
+    assert lifted >= 1, "the hull pass should act on some window"
+
+
+@pytest.mark.skipif(not _delta_available(), reason="/root/reference or oracle/_ref is missing: the committed fixture stands in")
+def test_live_reference_foot_sliding_code_reproduces_the_fixture():
+    import ref_delta_harness as dh
+    from test_foot_sliding import FOOT_LEN
+    mod = dh.load()
+    for k, w, stair, ground, use_dv, want in _foot_cases(_delta()):
+        if k % 5 == 0:
+            r = dh.remove_foot_sliding(mod, FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["foot_center"] if stair else None, ground,
+                                       w["desired_vel"] if use_dv else None)
+            _close(r, want, 1e-13, f"foot sliding case {k}")
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_reference_foot_sliding_code(built_lib):
+    """mmsto_remove_foot_sliding against the reference code's outputs directly, flat-ground cases (the batched API takes a constant height or
+    an SRBTrack terrain; the wavy ground of the CPU cases is neither)."""
+    import torch
+    from ipcdnnwalk_b200.short_traj_opt import removeFootSliding_online
+    from test_foot_sliding import FOOT_LEN
+    n = 0
+    for k, w, stair, ground, use_dv, want in _foot_cases(_delta()):
+        if stair or ground(np.zeros(3)) != 0.0 or ground(np.ones(3)) != 0.0:
+            continue
+        mt = np.concatenate(w["marker_traj"], axis=1)[None]
+        out = removeFootSliding_online(FOOT_LEN, w["con"][None], w["initial"][None], mt, w["marker"][None], w["desired_vel"][None] if use_dv else None, projectToGround=0.0)
+        torch.cuda.synchronize()
+        _close(out.cpu().numpy()[0], want, 1e-10, f"mmsto_remove_foot_sliding case {k}")
+        n += 1
+    assert n >= 5
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_reference_foot_sliding_code_on_the_playground(built_lib):
+    """Both variants with projectToGround = the SRBTrack playground terrain on the device, against the reference code's outputs directly."""
+    import torch
+    from ipcdnnwalk_b200 import SRBVecEnv, TerrainModel
+    from ipcdnnwalk_b200.short_traj_opt import removeFootSliding_online
+    from test_foot_sliding import FOOT_LEN
+    from make_golden_refenv import playground_window
+    g = _delta()
+    env = SRBVecEnv(helpers.fresh_clips(("aiming_show",)), 1, variant="terrain", precision=64, terrain=TerrainModel.from_npz(os.path.join(helpers.GOLDEN, "terrain_playground.npz")))
+    ws = [playground_window(j) for j in range(int(g["pg_count"]))]
+    stack = lambda k: np.stack([w[k] for w in ws])                  # noqa: E731
+    mt = np.stack([np.concatenate(w["marker_traj"], axis=1) for w in ws])
+    fc = np.stack([np.stack(w["foot_center"]) for w in ws])
+    for stair in (True, False):
+        out = removeFootSliding_online(FOOT_LEN, stack("con"), stack("initial"), mt, stack("marker"), stack("desired_vel"), projectToGround=env, footCenterTraj=fc if stair else None)
+        torch.cuda.synchronize()
+        out = out.cpu().numpy()
+        for j in range(len(ws)):
+            _close(out[j], g[f"pg{j}_{'stair' if stair else 'plain'}_out"], 1e-10, f"playground {'stair' if stair else 'plain'} case {j}")
+    env.close()

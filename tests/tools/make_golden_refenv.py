@@ -140,6 +140,22 @@ def sds_plan(seed=5, n=80):
 DELTA_SRB = dict(mass=60.0, inertia=np.array([[3.0, 0.1, 0.0], [0.1, 1.5, -0.2], [0.0, -0.2, 2.5]]), local_com=np.array([0.01, -0.03, 0.02]))
 
 
+def playground_ground():
+    from oracle.terrain import Terrain
+    T = Terrain.load(os.path.join(GOLDEN, "terrain_playground.npz"))
+    return lambda pos: T.height_ray(pos[2], pos[0])[0]              # Y-up (a, b, c) <-> Z-up (c, a, b)
+
+
+def playground_window(j):
+    from test_foot_sliding import make_window
+    w = make_window(100 + j)
+    shift = np.array([4.0 + 0.37 * j, 0.0, 20.0])                  # on the slope of pyramid_1 (as tests/test_foot_sliding.py)
+    for key in ("marker_traj", "foot_center"):
+        w[key] = [t + shift for t in w[key]]
+    w["marker"] = w["marker"] + np.tile(shift, 4); w["initial"] = w["initial"] + np.tile(shift, 4)
+    return w
+
+
 def make_delta(n_items=24, n_steps=14):
     import ref_delta_harness as dh
     from oracle import fullbody_map as fm
@@ -185,6 +201,30 @@ def make_delta(n_items=24, n_steps=14):
         out.update({f"cs{j}_pose": pose, f"cs{j}_com_srb": com_srb, f"cs{j}_desired": des, f"cs{j}_fix_y": np.array(int(fy)),
                     f"cs{j}_ground_h": gh if gh is not None else np.zeros(0), f"cs{j}_out": new})
     out["cs_count"] = np.array(4)
+    # ---- removeFootSliding_online / _stair: every contact pattern of tests/test_foot_sliding.make_window, flat (y = 0, what
+    #      walk_SRBTrack2025.py:53 passes) and on a wavy ground, with the caller's desiredVel and with derivative_forward
+    from test_foot_sliding import make_window, FOOT_LEN
+    wavy = lambda p: 0.02 * np.sin(3 * p[0]) + 0.03 * np.cos(2 * p[2])          # noqa: E731
+    k = 0
+    for seed in range(12):
+        w = make_window(seed)
+        for stair in (False, True):
+            kind = seed % 2                                   # 0: flat ground, 1: wavy
+            use_dv = seed % 3 != 0
+            g = wavy if kind else (lambda p: 0.0)
+            r = dh.remove_foot_sliding(mod, FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["foot_center"] if stair else None, g,
+                                       w["desired_vel"] if use_dv else None)
+            out.update({f"fs{k}_seed": np.array(seed), f"fs{k}_stair": np.array(int(stair)), f"fs{k}_wavy": np.array(kind), f"fs{k}_use_dv": np.array(int(use_dv)), f"fs{k}_out": r})
+            k += 1
+    out["fs_count"] = np.array(k)
+    # ---- the _stair variant (and the plain one) on the SRBTrack playground: the slope of pyramid_1, ground = terrain_height_ray
+    ground_pg = playground_ground()
+    for j in range(8):
+        w = playground_window(j)
+        for stair in (True, False):
+            r = dh.remove_foot_sliding(mod, FOOT_LEN, w["con"], w["initial"], w["marker_traj"], w["marker"], w["foot_center"] if stair else None, ground_pg, w["desired_vel"])
+            out[f"pg{j}_{'stair' if stair else 'plain'}_out"] = r
+    out["pg_count"] = np.array(8)
     np.savez_compressed(os.path.join(GOLDEN, "refenv_delta.npz"), **out)
     print("DeltaExtractor of the reference:", {k: np.asarray(v).shape for k, v in out.items() if k.startswith(("pk_", "ex_h", "ex_m", "cs0_out"))})
 

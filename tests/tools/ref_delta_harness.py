@@ -1,6 +1,7 @@
 """Run the REFERENCE'S OWN full-body mapping code (gym_trackSRB/taesooLib/DeltaExtractor.py: _extractSingleFrameFullbody :577-643,
-unpack_obs_extra :1037-1043, pack_obs_extra :1015-1035, removeCOMsliding_online :421-512) here, so that oracle/fullbody_map.py and the
-CoM-sliding restatement are compared with the reference code instead of being trusted (rows f-2a, f-2b, f-2c).
+unpack_obs_extra :1037-1043, pack_obs_extra :1015-1035, removeCOMsliding_online :421-512, removeFootSliding_online / _stair + avoidHull
+:650-897) here, so that oracle/fullbody_map.py, the CoM-sliding and the foot-sliding restatements are compared with the reference code instead
+of being trusted (rows f-2a ... f-2d).
 
 DeltaExtractor.py is Python over taesooLib's libmainlib (`m = lua.taesooLib()`) and `lua.*` / `RE.*` helpers; libmainlib cannot be built in
 this image.  The file is imported as it stands from /root/reference with
@@ -14,6 +15,9 @@ this image.  The file is imported as it stands from /root/reference with
         hanyang_lowdof_T_sh.wrl) -- SRB4.xml, where the reference takes the body from, is not in the tree;
   lua.new('QuadraticFunctionHardCon')     the Lua wrapper (module.lua:2090-2199) over OperatorStitch.cpp:468-620 restated: squared terms
         and hard constraints collected as written, the KKT system built as buildSystem builds it, solved by numpy (the reference: LU);
+  lua.F('fc.getContactPositions_v2' / '_stair' / 'math.projectTrajectoryToItsHull')   see _lua_F: the first two are NOT in the reference tree
+        (oracle stand-ins W5 / W6), the third is pure Lua restated over the pinned GrahamScan; what IS pinned for row f-2d is everything the
+        Python function does with them -- the four x three quadratic programmes, their hard constraints, the ground clamp, avoidHull;
   RE.toVector3 / toQuater / ZtoY          the definitions of work/rendermodule.py:505-675 restated (three lines each).
 Test infrastructure only."""
 import importlib.util
@@ -73,6 +77,16 @@ class vector3:
 
     def copy(self):
         return vector3(self.x, self.y, self.z)
+
+    def normalized(self):
+        v = self.copy(); v.normalize()
+        return v
+
+    def assign(self, o):
+        self.x, self.y, self.z = o.x, o.y, o.z
+
+    def __call__(self, i):
+        return (self.x, self.y, self.z)[i]
 
     def ZtoY(self):                                       # rendermodule.py:633
         return vector3(self.y, self.z, self.x)
@@ -164,6 +178,9 @@ class vectorn:
     def setAllValue(self, v):
         self.a[:] = v
 
+    def rmult(self, s):
+        self.a *= s
+
     def sum(self):
         return float(self.a.sum())
 
@@ -171,7 +188,7 @@ class vectorn:
         return vectorn(_a=self.a[s:e])
 
     def slice(self, s, e):
-        return vectorn(_a=self.a[s:e].copy())
+        return vectorn(_a=self.a[_span(s, e, self.a.shape[0])].copy())
 
     def __or__(self, o):
         return vectorn(_a=np.concatenate([self.a, o.a]))
@@ -223,6 +240,108 @@ class matrixn:
     def ref(self):
         return self.a
 
+    def set(self, i, j, v):
+        self.a[i, j] = v
+
+    def sub(self, r0, r1, c0, c1):                        # matrixn:sub: negative = from the end, end 0 = to the end (view)
+        return matrixn(_a=self.a[_span(r0, r1, self.a.shape[0]), _span(c0, c1, self.a.shape[1])])
+
+    def assign(self, o):
+        self.a[:, :] = o.a
+
+    def __or__(self, o):
+        return matrixn(_a=np.concatenate([self.a, o.a], axis=1))
+
+    def __sub__(self, o):
+        return matrixn(_a=self.a - o.a)
+
+    def derivative_forward(self, rate):                   # forward difference, last row repeated (binding-level helper, assumed)
+        d = np.zeros_like(self.a)
+        d[:-1] = (self.a[1:] - self.a[:-1]) * rate
+        d[-1] = d[-2]
+        return matrixn(_a=d)
+
+
+def _span(s, e, n):
+    if s < 0:
+        s += n
+    if e <= 0:
+        e += n
+    return slice(s, e)
+
+
+class vector3N:
+    """rows of vector3 sharing one [n, 3] array; v(i) is a reference to row i."""
+
+    def __init__(self, n=0, _a=None):
+        self.a = np.zeros((int(n), 3)) if _a is None else _a
+
+    def size(self):
+        return self.a.shape[0]
+
+    rows = size
+
+    class _Row(vector3):
+        """v(i): a vector3 that lives in row i (assignments write through)"""
+
+        def __init__(self, a):
+            self._a = a
+        x = property(lambda s: float(s._a[0]), lambda s, v: s._a.__setitem__(0, v))
+        y = property(lambda s: float(s._a[1]), lambda s, v: s._a.__setitem__(1, v))
+        z = property(lambda s: float(s._a[2]), lambda s, v: s._a.__setitem__(2, v))
+
+    def __call__(self, i):
+        return vector3N._Row(self.a[i])
+
+    def slice(self, s, e):
+        return vector3N(_a=self.a[_span(s, e, self.a.shape[0])])
+
+    def matView(self):
+        return matrixn(_a=self.a)
+
+    def __add__(self, o):
+        return vector3N(_a=self.a + o.a)
+
+    def __sub__(self, o):
+        return vector3N(_a=self.a - o.a)
+
+    def __mul__(self, s):
+        return vector3N(_a=self.a * s)
+
+
+class boolN:
+    def __init__(self, a):
+        self.a = np.asarray(a, dtype=bool)
+
+    def __call__(self, i):
+        return bool(self.a[i])
+
+    def slice(self, s, e):
+        return boolN(self.a[_span(s, e, self.a.shape[0])])
+
+    def __or__(self, o):
+        return boolN(self.a | o.a)
+
+    def count(self):
+        return int(self.a.sum())
+
+    def size(self):
+        return self.a.shape[0]
+
+
+class intIntervals:
+    def __init__(self, runs):
+        self.runs = list(runs)
+
+    def size(self):
+        return len(self.runs)
+
+    def startI(self, i):
+        return self.runs[i][0]
+
+    def endI(self, i):
+        return self.runs[i][1]
+
 
 class intvectorn:
     def __init__(self, n=0):
@@ -253,6 +372,9 @@ class QuadraticFunctionHardCon:
 
     def add(self, *p):
         self.sq.append(self._pairs(p))
+
+    def addSquared(self, index, coef):
+        self.sq.append((index.a.copy(), coef.a.copy()))
 
     def con(self, *p):
         self.cons.append(self._pairs(p))
@@ -337,15 +459,39 @@ class FullBodyLoader:
         return vector3.of(self._com[self._cur])
 
 
+def _lua_F(name, *a):
+    """The three Lua functions removeFootSliding_online(_stair) calls.  fc.getContactPositions_v2 / _stair are NOT in the reference tree
+    (stand-ins W5 / W6 of oracle/foot_sliding.py, restated from their call sites); math.projectTrajectoryToItsHull is pure Lua
+    (gym_cdm2/ConvexHull2D.lua:362-455, restated in oracle/foot_sliding.py over the GrahamScan that tests/test_refpins.py pins to graham.cpp)
+    and changes the heights of its argument in place."""
+    from oracle import foot_sliding as fs
+    if name == "fc.getContactPositions_v2":
+        foot_len, con_toe, con_heel, toe, heel = a
+        pos, dr, ii = fs.get_contact_positions_v2(foot_len, con_toe.a, con_heel.a, toe.a, heel.a)
+        return vector3N(_a=np.array(pos, dtype=float).reshape(-1, 3).copy()), vector3N(_a=np.array(dr, dtype=float).reshape(-1, 3).copy()), intIntervals(ii)
+    if name == "fc.getContactPositions_stair":
+        con_toe, con_heel, center = a
+        pos, ii = fs.get_contact_positions_stair(con_toe.a, con_heel.a, center.a)
+        return vector3N(_a=np.array(pos, dtype=float).reshape(-1, 3).copy()), intIntervals(ii)
+    if name == "math.projectTrajectoryToItsHull":
+        tpos, = a
+        changed, y = fs.project_trajectory_to_its_hull(tpos.a[:, 1].copy())
+        tpos.a[:, 1] = y
+        return changed
+    raise KeyError(name)
+
+
 # ------------------------------------------------------------------------------------------------ import of the reference file
 def load():
     """-> the reference's DeltaExtractor module."""
     lua = types.ModuleType("work.luamodule")
-    mm = types.SimpleNamespace(vector3=vector3, quater=quater, transf=transf, vectorn=vectorn, matrixn=matrixn, intvectorn=intvectorn)
+    mm = types.SimpleNamespace(vector3=vector3, quater=quater, transf=transf, vectorn=vectorn, matrixn=matrixn, intvectorn=intvectorn, vector3N=vector3N)
     lua.taesooLib = lambda: mm
     lua.zeros = lambda n, c=None: vectorn(n) if c is None else matrixn(n, c)
     lua.vec = lambda v: vectorn(_a=np.asarray(v, dtype=float).copy())
     lua.new = lambda name, *a: {"QuadraticFunctionHardCon": QuadraticFunctionHardCon}[name](*a)
+    lua.ivec = lambda a: boolN(a)
+    lua.F = _lua_F
     RE = types.ModuleType("work.rendermodule")
     RE.toVector3 = lambda v: vector3(v[0], v[1], v[2])                                         # rendermodule.py:550-563
 
@@ -399,4 +545,20 @@ def remove_com_sliding(mod, com_srb, desired_com, poses, fix_y_also=True, ground
         def project(cc):
             cc.y = float(next(it))
     mod.removeCOMsliding_online(FullBodyLoader(poses), matrixn(_a=np.asarray(com_srb, dtype=float).copy()), matrixn(_a=np.asarray(desired_com, dtype=float).copy()), out, fix_y_also, project)
+    return out.a
+
+
+def remove_foot_sliding(mod, foot_len, con_all, initial_feet, marker_traj, marker, foot_center=None, ground=None, desired_vel=None):
+    """removeFootSliding_online (foot_center None) / removeFootSliding_online_stair of the reference -> optMarkerTraj [nvar, 12].
+    ground(p[3]) -> height under p (what projectToGround sets p.y to; the reference's call sites always pass one)."""
+    def project(v):
+        v.y = float(ground(np.array([v.x, v.y, v.z])))
+    mt = [vector3N(_a=np.asarray(t, dtype=float).copy()) for t in marker_traj]
+    dv = None if desired_vel is None else matrixn(_a=np.asarray(desired_vel, dtype=float).copy())
+    args = [foot_len, matrixn(_a=np.asarray(con_all, dtype=float).copy()), vectorn(_a=np.asarray(initial_feet, dtype=float).copy()), mt,
+            matrixn(_a=np.asarray(marker, dtype=float).copy())]
+    if foot_center is None:
+        out = mod.removeFootSliding_online(*args, dv, project)
+    else:
+        out = mod.removeFootSliding_online_stair(*args, [vector3N(_a=np.asarray(c, dtype=float).copy()) for c in foot_center], dv, project)
     return out.a
