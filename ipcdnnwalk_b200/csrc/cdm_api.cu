@@ -295,7 +295,8 @@ template <typename real, int G> static void launch_step(cdm_env* h, const float*
   int gpw = (int)h->hp["envs_per_warp"];
   if (gpw <= 0) gpw = EPW;
   A.gpw = gpw < EPW ? gpw : EPW;
-  cdm_step_kernel<real, G><<<(h->N + A.gpw - 1) / A.gpw, 32, 0, s>>>(A);
+  if (h->ground.T.h != nullptr) cdm_step_kernel<real, G, true><<<(h->N + A.gpw - 1) / A.gpw, 32, 0, s>>>(A);
+  else cdm_step_kernel<real, G, false><<<(h->N + A.gpw - 1) / A.gpw, 32, 0, s>>>(A);
   h->launches++;
 }
 template <typename real> static int dispatch_step(cdm_env* h, const float* act, float* obs, float* rew, uint8_t* done, cudaStream_t s) {
