@@ -210,9 +210,13 @@ __device__ __forceinline__ double tl_terrain_height(const TLTerrainDev& T, doubl
 
 // Ground under a world point: RagdollSim:projectToGround / OBJloader.Terrain:getTerrainPos (deepmimiccdm-v1.lua:415-424,2171-2177).
 // `Ground` with T.h == nullptr is flat ground (walk2-v1); otherwise the gym_cdm2 terrain (walkterrain-v1), metres <-> cm.
+// One copy of the height query per kernel, CALLED from its 20 sites: inlined, the copies were 45 % of the SASS and every one of them was
+// fetched once per step (terrain) or jumped over (flat ground inside the shared helpers); as a function the body stays in the instruction
+// cache.  16384 envs, walkterrain-v1 policy: 209.8 -> 163.9 us per step, U(-1,1) actions 348.6 -> 256.2 us (profiles/r02_cdm_terrain_call_ab.txt).
+__device__ __noinline__ double tl_terrain_height_call(const TLTerrainDev& T, double x0, double x1) { return tl_terrain_height(T, x0, x1, nullptr); }
 template <typename real> __device__ __forceinline__ real ground_y(const Ground* g, real x, real z) {
   if (g == nullptr || g->T.h == nullptr) return real(0);
-  return (real)(tl_terrain_height(g->T, ((double)x - g->px) * 100.0, ((double)z - g->pz) * 100.0, nullptr) / 100.0 + g->py);
+  return (real)(tl_terrain_height_call(g->T, ((double)x - g->px) * 100.0, ((double)z - g->pz) * 100.0) / 100.0 + g->py);
 }
 
 // ---- state in registers ------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ ap.add_argument("--lanes", default="4")
 ap.add_argument("--precision", default="32,64")
 ap.add_argument("--e2e", action="store_true")
 ap.add_argument("--epw", default="0", help="environments per warp (comma list; 0 = automatic)")
+ap.add_argument("--terrain", action="store_true", help="walkterrain-v1: the gym_cdm2 height field attached (31-float observation); with --policy the reference's walkterrain-v1 policy")
 ap.add_argument("--policy", action="store_true", help="drive the environments with the reference's trained walk2-v1 policy (tests/golden/cdm_policy_walk2.npz), evaluated in torch outside the timed events, reset noise scaled to 20 %")
 a = ap.parse_args()
 peak = 6547.8
@@ -36,11 +37,11 @@ for prec in [int(x) for x in a.precision.split(",")]:
         if a.policy and os.environ.get("CDM_NOISE_SCALE"):          # experiment: 0 = all environments identical (perfectly coherent warps)
             params = {k: v * float(os.environ["CDM_NOISE_SCALE"]) for k, v in params.items()}
         params = dict(params or {}, envs_per_warp=epw)
-        env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3, params=params)
+        env = CDMVecEnv(tab, skel, a.envs, precision=prec, lanes_per_env=lanes, auto_reset=True, seed=3, params=params, **({"terrain": hc.load_terrain()} if a.terrain else {}))
         obs = env.reset()
         if a.policy:
             import helpers
-            pol = dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_walk2.npz")))
+            pol = dict(np.load(os.path.join(helpers.GOLDEN, "cdm_policy_walkterrain.npz" if a.terrain else "cdm_policy_walk2.npz")))
             W = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device="cuda") for i in range(int(pol["n_layers"]))]
             Bs = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device="cuda") for i in range(int(pol["n_layers"]))]
             mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device="cuda")
@@ -67,7 +68,7 @@ for prec in [int(x) for x in a.precision.split(",")]:
         torch.cuda.synchronize()
         ms = np.array([x.elapsed_time(y) for x, y in ts])
         st = env.episode_stats()
-        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "actions": "reference walk2-v1 policy (torch, untimed)" if a.policy else "U(-1,1)", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes, "envs_per_warp": epw,
+        out = {"kernel": "cdm_step_kernel", "workload": "gym_cdm2 deepmimiccdmterrain-v1 (walkterrain-v1), height field" if a.terrain else "gym_cdm2 deepmimiccdm-v1 (walk2-v1), flat ground", "actions": ("reference walkterrain-v1 policy (torch, untimed)" if a.terrain else "reference walk2-v1 policy (torch, untimed)") if a.policy else "U(-1,1)", "envs": a.envs, "dtype": f"f{prec}", "lanes_per_env": lanes, "envs_per_warp": epw,
                "steps": a.steps, "ms_per_step_mean": float(ms.mean()), "ms_per_step_median": float(np.median(ms)), "env_steps_per_s": a.envs / float(ms.mean()) * 1e3,
                "algorithmic_bytes_per_env_step": BYTES[prec], "achieved_GBps": BYTES[prec] * a.envs / float(ms.mean()) / 1e6, "peak_GBps": peak,
                "frac": BYTES[prec] * a.envs / float(ms.mean()) / 1e6 / peak, "episodes_finished": int(st[2]), "mean_episode_len": float(st[1] / max(st[2], 1)),
