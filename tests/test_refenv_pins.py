@@ -23,6 +23,7 @@ sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "tools"))
 import ref_srbenv_harness as rh            # noqa: E402
 
 RTOL64 = 1e-5
+LIVE_RTOL = 1e-10          # live re-runs reproduce the fixtures bit for bit on the box that recorded them; the QP solves go through BLAS / LAPACK, whose kernels depend on the CPU
 live = pytest.mark.skipif(not rh.available(), reason="/root/reference is not mounted: the committed fixture stands in")
 
 
@@ -118,7 +119,7 @@ def test_oracle_sds_equals_the_reference_filter_class():
     g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_sds.npz")))
     plan = [(q, t, bool(z)) for q, t, z in g["plan"]]
     xs, Ks = sh.drive(SDS, plan)
-    assert np.array_equal(Ks, g["K"])
+    _close(Ks, g["K"], 1e-15, "SDS gains")
     assert np.abs(xs - g["x"]).max() < 1e-13 * max(1.0, np.abs(g["x"]).max())
 
 
@@ -127,7 +128,7 @@ def test_live_reference_sds_class_reproduces_the_fixture():
     import ref_sds_harness as sh
     g = dict(np.load(os.path.join(helpers.GOLDEN, "refenv_sds.npz")))
     xs, Ks = sh.drive(sh.load().SDS, [(q, t, bool(z)) for q, t, z in g["plan"]])
-    assert np.array_equal(Ks, g["K"]) and np.array_equal(xs, g["x"])
+    _close(Ks, g["K"], 1e-15, "SDS gains"); _close(xs, g["x"], 1e-13, "SDS states")     # identical on the box that recorded them; a BLAS with other kernels may differ in the last bit
 
 
 @live
@@ -152,10 +153,11 @@ def test_live_reference_terrain_code_reproduces_the_fixture():
     ref, mod = rh.make_env("terrain", helpers.fresh_clips(("aiming_show",)))
     plan = g["plans"][e]
     obs0 = rh.reset_explicit(ref, mod, 0, int(plan[1]), plan[2:5], plan[5:9], planar=tuple(g["planar"][e]))
-    assert np.array_equal(np.asarray(obs0, float), g["obs0"][e])
+    _close(obs0, g["obs0"][e], LIVE_RTOL, "terrain reset obs")
     for k in range(15):
         obs, r, done, _, _ = ref.step(g["actions"][e, k])
-        assert np.array_equal(np.asarray(obs, float), g["obs"][e, k]) and bool(done) == bool(g["done"][e, k])
+        _close(obs, g["obs"][e, k], LIVE_RTOL, f"terrain obs step {k}")
+        assert bool(done) == bool(g["done"][e, k])
 
 
 @live
@@ -171,10 +173,11 @@ def test_live_reference_code_reproduces_the_fixture(variant):
             obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]))
         else:
             obs0 = rh.reset_explicit(ref, mod, int(plan[0]), int(plan[1]), plan[2:5], plan[5:9])
-        assert np.array_equal(np.asarray(obs0, float), g["obs0"][e])
+        _close(obs0, g["obs0"][e], LIVE_RTOL, "reset obs")
         for k in range(12):
             obs, r, done, _, info = ref.step(g["actions"][e, k])
-            assert np.array_equal(np.asarray(obs, float), g["obs"][e, k]) and float(r) == g["rew"][e, k] and bool(done) == bool(g["done"][e, k])
+            _close(obs, g["obs"][e, k], LIVE_RTOL, f"obs env {e} step {k}"); _close(r, g["rew"][e, k], LIVE_RTOL, "reward")
+            assert bool(done) == bool(g["done"][e, k])
 
 
 # --------------------------------------------------------------------------------------------------------------------- GPU
@@ -315,7 +318,7 @@ def test_live_reference_fullbody_mapping_code_reproduces_the_fixture():
     for i in (0, 1, 4, 9):
         r = dh.extract(mod, g["ex_extra"][i], g["ex_row"][i], float(g["ex_mass"]), g["ex_inertia"], g["ex_local_com"])
         for k in EX_KEYS:
-            assert np.array_equal(r[k], g["ex_" + k][i]), (i, k)
+            _close(r[k], g["ex_" + k][i], 1e-13, f"extract {i} {k}")
     for j in (1, 2):
         gh = g[f"cs{j}_ground_h"]
         new = dh.remove_com_sliding(mod, g[f"cs{j}_com_srb"], g[f"cs{j}_desired"], g[f"cs{j}_pose"], fix_y_also=bool(g[f"cs{j}_fix_y"]), ground_h=gh if gh.size else None)
