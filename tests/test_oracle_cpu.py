@@ -174,7 +174,7 @@ def test_oracle_reproduces_golden_rollout(variant):
     for e in (0, 1):
         env = E.OracleSRBEnv(helpers.fresh_clips(), variant)
         obs0, _ = helpers.oracle_reset(env, g["plans"][e])
-        assert np.array_equal(obs0, g["obs0"][e])
+        assert np.abs(obs0 - g["obs0"][e]).max() < 1e-12
         for k in range(8):
             obs, r, done, _, info = env.step(g["actions"][e, k])
             assert np.allclose(obs, g["obs"][e, k], rtol=0, atol=1e-6)
