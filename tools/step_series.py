@@ -1,3 +1,4 @@
+"""GPU: per-step kernel times of a short run of the SRBTrack step (series, not the mean) -- shows warm-up and outliers."""
 import sys, os
 import numpy as np, torch
 R=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
