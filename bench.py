@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="the per-rollout exchange: fused = statistics + all-reduce in ONE kernel over NVLink peer memory (srb_rollout_stats_allreduce); "
                          "nccl = statistics kernel + torch.distributed all-reduce")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (fp64, terrain, gym_cdm2, FK, MMSTO)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (fp64, terrain, gym_cdm2 flat + terrain, FK, MMSTO)")
     ap.add_argument("--flush", default="write", choices=["write", "read", "none"],
                     help="L2 flush between steps: write a 256 MiB buffer (default, the timing rule), read it, or nothing (diagnostic)")
     return ap.parse_args()
@@ -526,32 +526,41 @@ def run_secondary(args, rank, local_rank, world, dist, all_clips, flush):
     rec("terrain_fp32", f"BASELINE configs[2] per-GPU share: SRBEnv5_mocap_list_terrain_window on the playground (plane / pyramid / hill / rough), {N} envs per GPU, done ignored, re-seeded every {TERRAIN_EPISODE} steps",
         "srb_step_kernel<float, TERRAIN>", N, ms, 1216, "env-steps/s", "weak", "f32")
     env.close()
-    # ---- configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1), 16384 envs, driven by the reference's trained policy (evaluated in torch, untimed)
+    # ---- configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1) and its terrain variant (walkterrain-v1), 16384 envs, driven by the reference's
+    #      trained policies (evaluated in torch, untimed)
     N = 16384
     tab, skel = hc.load_tables()
     params = {"noise_q": 0.1, "noise_pos": 0.01, "noise_dq": 0.1, "noise_vx": 0.01, "noise_vy": 0.1, "noise_vz": 0.01}
-    cenv = CDMVecEnv(tab, skel, N, precision=32, auto_reset=True, seed=3 + rank, params=params, device=local_rank)
-    pol = dict(np.load(os.path.join(ROOT, "tests", "golden", "cdm_policy_walk2.npz")))
-    Wt = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
-    Bt = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
-    mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device=dev)
-    istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device=dev)
-    state = {"obs": cenv.reset(), "act": None}
 
-    def policy(_k):
-        h = torch.clamp((state["obs"] - mean) * istd, -10.0, 10.0)
-        for w, b in zip(Wt, Bt):
-            h = torch.tanh(h @ w.T + b)
-        state["act"] = h
+    def cdm_record(name, config, kernel, policy_file, bytes_per_step, **env_kw):
+        cenv = CDMVecEnv(tab, skel, N, precision=32, auto_reset=True, seed=3 + rank, params=params, device=local_rank, **env_kw)
+        pol = dict(np.load(os.path.join(ROOT, "tests", "golden", policy_file)))
+        Wt = [torch.as_tensor(pol[f"W{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
+        Bt = [torch.as_tensor(pol[f"b{i}"], dtype=torch.float32, device=dev) for i in range(int(pol["n_layers"]))]
+        mean = torch.as_tensor(pol["obs_mean"], dtype=torch.float32, device=dev)
+        istd = torch.as_tensor(1.0 / np.sqrt(pol["obs_var"] + 1e-8), dtype=torch.float32, device=dev)
+        state = {"obs": cenv.reset(), "act": None}
 
-    def cdm_step():
-        state["obs"] = cenv.step(state["act"])[0]
-    for k in range(100):                                   # let the gait reach its steady state
-        policy(k); cdm_step()
-    ms = _timed(cdm_step, S, Wm, flush, dist, policy)
-    rec("cdm_fp32", f"BASELINE configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1 constants), {N} envs per GPU, actions from the reference's trained walk2-v1 policy", "cdm_step_kernel<float>",
-        N, ms, 740, "env-steps/s", "weak", "f32")
-    cenv.close()
+        def policy(_k):
+            h = torch.clamp((state["obs"] - mean) * istd, -10.0, 10.0)
+            for w, b in zip(Wt, Bt):
+                h = torch.tanh(h @ w.T + b)
+            state["act"] = h
+
+        def cdm_step():
+            state["obs"] = cenv.step(state["act"])[0]
+        for k in range(100):                                   # let the gait reach its steady state
+            policy(k); cdm_step()
+        ms = _timed(cdm_step, S, Wm, flush, dist, policy)
+        rec(name, config, kernel, N, ms, bytes_per_step, "env-steps/s", "weak", "f32")
+        cenv.close()
+    cdm_record("cdm_fp32", f"BASELINE configs[3]: gym_cdm2 deepmimiccdm-v1 (walk2-v1 constants), {N} envs per GPU, actions from the reference's trained walk2-v1 policy",
+               "cdm_step_kernel<float>", "cdm_policy_walk2.npz", 740)
+    try:                                                       # the terrain variant is an extra record: never let it take the bench line down
+        cdm_record("cdm_terrain_fp32", f"gym_cdm2 deepmimiccdmterrain-v1 (walkterrain-v1): the same step on the gym_cdm2 height field, {N} envs per GPU, actions from the reference's "
+                   "trained walkterrain-v1 policy", "cdm_step_kernel<float, TERRAIN>", "cdm_policy_walkterrain.npz", 740 + 16, terrain=hc.load_terrain())
+    except Exception as exc:                                   # noqa: BLE001
+        print(f"[bench] walkterrain-v1 record skipped: {exc!r}", file=sys.stderr)
     # ---- configs[4]: FK + CoM + centroidal momentum of 1 M poses, split over the GPUs (strong scaling)
     sk = Skeleton(vrml_skeleton.builtin(), device=local_rank)
     n = (1 << 20) // world
