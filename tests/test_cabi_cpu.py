@@ -141,3 +141,38 @@ def test_bad_config_rejected(built_lib):
     for cfg in (_lib.SrbConfig(0, 0, 64, 8, 1, 0, 0), _lib.SrbConfig(4, 0, 16, 8, 1, 0, 0), _lib.SrbConfig(4, 0, 64, 3, 1, 0, 0),
                 _lib.SrbConfig(4, 7, 64, 8, 1, 0, 0)):
         assert built_lib.srb_create(C.byref(cfg), C.byref(h)) != 0
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the product package (nor the product arm of bench.py) may import it, and importing the
+    whole package must not pull it in as a side effect."""
+    import ast
+    import subprocess
+    import sys
+    root = helpers.ROOT
+    pkg = os.path.join(root, "ipcdnnwalk_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+                assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{fn} imports the oracle"
+    code = ("import sys; sys.path.insert(0, %r); import ipcdnnwalk_b200 as p; "
+            "from ipcdnnwalk_b200 import SRBVecEnv, SRBEnv, SB3VecEnv, CDMVecEnv, LuaEnv, Skeleton, ShortTrajOpt, TerrainModel; "
+            "import ipcdnnwalk_b200.clip_builder, ipcdnnwalk_b200.tl_binary, ipcdnnwalk_b200.mjcf_humanoid; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported by the product package'" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_product_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback: constructing an environment / optimiser on a box without CUDA raises instead of computing something else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    from ipcdnnwalk_b200 import SRBVecEnv
+    from ipcdnnwalk_b200.short_traj_opt import extractSingleFrameFullbody
+    with pytest.raises(Exception):
+        SRBVecEnv(helpers.fresh_clips(), 4, variant="test", precision=64)
+    with pytest.raises(RuntimeError):
+        extractSingleFrameFullbody(np.zeros((1, 29)), np.zeros((1, 214)), 60.0, np.eye(3))
