@@ -107,7 +107,8 @@ int tlterrain_height(tl_terrain* t, int64_t n, const double* xz_dev, double* hei
  * RagdollSim:projectToGround goes to this height field (terrain_pos = g_terrainPos in metres, heights / sizes in cm,
  * deepmimiccdm-v1.lua:368-424), the targets follow the terrain (:1205-1238), the observation grows to CDM_OBS_DIM_TERRAIN.
  * t == NULL returns to flat ground.  The terrain must outlive the environment.  Spec values that differ from walk2-v1
- * (healthy_min 0.7) are set with cdm_set_param.  Call before cdm_reset. */
+ * (healthy_min 0.7) are set with cdm_set_param.  Call before cdm_reset.  cdm_step launches the terrain instantiation of the step kernel
+ * while a terrain is attached and the flat-ground one (no terrain code at all) otherwise; results on flat ground are the same either way. */
 int cdm_set_terrain(cdm_env* env, tl_terrain* t, const double terrain_pos[3]);
 int cdm_obs_dim(cdm_env* env);   /* CDM_OBS_DIM or CDM_OBS_DIM_TERRAIN: row length of obs_dev / term_obs_dev */
 
